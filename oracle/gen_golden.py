@@ -1,0 +1,324 @@
+"""TEST INFRASTRUCTURE — pins `oracle/restated.py` against the UNMODIFIED reference and writes
+`tests/golden/*.npz`.
+
+Run in the build container only (needs /root/reference):   python -m oracle.gen_golden
+
+What is executed is the reference's own code: `models/dit.py` is imported as-is (two dependency shims,
+see ref_loader.py) and the `Diffusion` methods `q_xt`, `_sample_t`, `_subs_parameterization`, `forward`,
+`compute_loss` (model.py) plus `_sample_categorical`, `_ddpm_forward`, `_ddpm_update`,
+`_ddpm_caching_update`, `adap_sche`, `_maskgit_update` (model_utils.py / model_eval.py) are pulled out of
+the source files with `ast` and exec'd against a minimal fake `self`.  Each block below (1) runs the
+reference, (2) asserts the restatement matches (bit-exact for integer outputs, tight tolerance for fp32),
+(3) stores inputs + reference outputs as fixtures.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader as RL  # noqa: E402
+from oracle import restated as R  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(t):
+    if isinstance(t, torch.Tensor):
+        if t.dtype == torch.bfloat16:
+            return t.float().numpy()
+        return t.detach().cpu().numpy()
+    return np.asarray(t)
+
+
+def make_fake_self(cfgd, ref_dit=None, *, training=True, mask_entire_modality=None, img_loss_weight=0.6,
+                   softmin_snr=None, eval_cfg=None):
+    noise_mod = RL.load_reference_noise()
+    M = RL.load_reference_diffusion_methods()
+    s = SimpleNamespace()
+    s.config = RL.to_attrdict(dict(
+        backbone="dit", mode="train", parameterization="subs",
+        trainer=dict(mask_entire_modality=mask_entire_modality, multimodal_batches=True, interleaved=False,
+                     joint_ar_nar_prob=None, add_label=False, first_token_dropout=None,
+                     joint_ar_nar_timestep_warmup_steps=None, force_timestep=None, image_mode="discrete",
+                     ar_llm_loss=False, allow_null_sigma=True, force_null_sigma=True,
+                     disable_forward_autocast_during_eval=False, compile=False, force_bf16_eval=False,
+                     ar_shift=False, low_precision_loss=False, log_seperate_modal_losses=True,
+                     text_loss_weight=1.0, img_loss_weight=img_loss_weight, softmin_snr=softmin_snr,
+                     interleaved_training_flex_attention=False),
+        model=dict(force_argmax_valid_indices=True, use_attention_mask=False, length=cfgd["txt"] + cfgd["img"],
+                   flex_attention_img_masking_prob=None, flex_attention_txt_masking_prob=None,
+                   txt_length=cfgd["txt"], img_length=cfgd["img"]),
+        eval=dict(ar_inpainting_force_val=None, cfg=eval_cfg),
+        noise=dict(type="loglinear"),
+    ))
+    s.backbone = ref_dit if ref_dit is not None else SimpleNamespace(training=training)
+    s.training = training
+    s.mask_index = cfgd["mask_index"]
+    s.text_vocab_size = cfgd["text_vocab_size"]
+    s.vocab_size = cfgd["vocab_size"]
+    s.parameterization = "subs"
+    s.antithetic_sampling = True
+    s.importance_sampling = False
+    s.change_of_variables = False
+    s.sampling_eps = 1e-3
+    s.allow_slicing = False
+    s.neg_infinity = -1_000_000.0
+    s.time_conditioning = False
+    s.T = 0
+    s.dtype = torch.float32
+    s.device = torch.device("cpu")
+    s.is_compiled = True          # skips utils.print_nans (model.py:943)
+    s.current_run_fwd_bwd_pass = 1
+    s.noise = noise_mod.LogLinearNoise()
+    s.global_step = 0
+    s.visualize_samples = lambda *a, **k: None
+    s._maybe_sub_sample = lambda x0, am: (x0, None, am)
+    for name in ["q_xt", "_sample_t", "_subs_parameterization", "_process_sigma", "_ddpm_forward", "_ddpm_update",
+                 "_ddpm_caching_update", "get_cfg_weight", "_maskgit_update", "_sample_prior"]:
+        fn = getattr(M, name)
+        setattr(s, name, (lambda f: (lambda *a, **k: f(s, *a, **k)))(fn))
+    return s, M
+
+
+def gen_dit():
+    """Backbone: reference DIT (fp32 and CPU-bf16-autocast) vs restatement; stores params+io."""
+    cfgd = dict(D=128, H=2, L=2, txt=64, img=64, text_vocab_size=97, vocab_size=160, mask_index=96)
+    ref_cfg = RL.make_ref_config(cfgd["D"], cfgd["H"], cfgd["L"], cfgd["txt"], cfgd["img"])
+    torch.manual_seed(0)
+    dit = RL.build_reference_dit(ref_cfg, cfgd["vocab_size"], cfgd["text_vocab_size"], cfgd["mask_index"], dtype=torch.float32)
+    dit.eval()
+    # perturb norm weights / LN bias away from the (1, 0) init so that they are actually exercised
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in dit.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                p.add_((torch.rand(p.shape, generator=g) - 0.5) * 0.4)
+            if "norm" in n and n.endswith("bias"):
+                p.add_((torch.rand(p.shape, generator=g) - 0.5) * 0.2)
+            if n == "output_layer.linear.bias":
+                p.add_((torch.rand(p.shape, generator=g) - 0.5) * 0.2)
+    P = {k: v.detach().clone() for k, v in dit.state_dict().items()}
+    ids, modality = R.synthetic_batch(2, cfgd["txt"], cfgd["img"], cfgd["text_vocab_size"], cfgd["vocab_size"], seed=42)
+    ids_clean = ids.clone()
+    ids[0, 3] = cfgd["mask_index"]
+    ids[1, 70:90] = cfgd["mask_index"]
+    with torch.no_grad():
+        ref_logits = dit(ids, None, modality=modality)
+    ocfg = R.OracleConfig(cfgd["D"], cfgd["H"], cfgd["L"], cfgd["txt"], cfgd["img"], cfgd["vocab_size"],
+                          cfgd["text_vocab_size"], cfgd["mask_index"])
+    mine = R.dit_forward(ocfg, P, ids, modality, mode="fp32")
+    err = (mine - ref_logits).abs().max().item()
+    print(f"[dit fp32] max|restated - reference| = {err:.3e}  (ref absmax {ref_logits.abs().max():.3f})")
+    assert err < 2e-5, err
+    # rope tables
+    rc, rs = R.rope_table_2d(ocfg.head_dim, ocfg.img_length)
+    assert torch.equal(rc, dit.rotary_cos_emb_img) and torch.equal(rs, dit.rotary_sin_emb_img)
+    tc, ts = R.rope_table_1d(ocfg.head_dim, ocfg.length)
+    assert torch.equal(tc, dit.rotary_cos_emb_txt) and torch.equal(ts, dit.rotary_sin_emb_txt)
+
+    # reference's default CPU mode: bf16 autocast vs restated bf16 mode — loose check only
+    torch.manual_seed(0)
+    dit_bf = RL.build_reference_dit(ref_cfg, cfgd["vocab_size"], cfgd["text_vocab_size"], cfgd["mask_index"], dtype=torch.bfloat16)
+    dit_bf.load_state_dict(P)
+    dit_bf.eval()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        ref_bf = dit_bf(ids, None, modality=modality).float()
+    mine_bf = R.dit_forward(ocfg, P, ids, modality, mode="bf16").float()
+    e_bf = (mine_bf - ref_bf).abs().max().item()
+    e_bf32 = (mine_bf - ref_logits).abs().max().item()
+    print(f"[dit bf16] restated-bf16 vs reference-cpu-autocast: {e_bf:.3e}; restated-bf16 vs reference-fp32: {e_bf32:.3e}")
+    assert e_bf < 0.15, e_bf
+
+    # gradient of a scalar through the reference (out-of-place qk-norm shim not needed in fp32 w/ clone? it is) —
+    # reference eager backward raises on the in-place q/k norm write, so gradients are pinned
+    # through the restatement only.
+    np.savez_compressed(os.path.join(OUT, "dit_small.npz"),
+                        cfg=np.array([cfgd[k] for k in ["D", "H", "L", "txt", "img", "vocab_size", "text_vocab_size", "mask_index"]]),
+                        ids=_np(ids), modality=_np(modality), ref_logits_fp32=_np(ref_logits), ref_logits_cpu_bf16=_np(ref_bf),
+                        rope_cos_img=_np(dit.rotary_cos_emb_img), rope_sin_img=_np(dit.rotary_sin_emb_img),
+                        **{"P::" + k: _np(v) for k, v in P.items()})
+    return cfgd, dit, P, ids, modality, ocfg, ids_clean
+
+
+def gen_diffusion_fns(cfgd, dit, P, ids, modality, ocfg, ids_clean):
+    out = {}
+    s, M = make_fake_self(cfgd, ref_dit=dit, mask_entire_modality=None)
+    B, N = ids.shape
+
+    # ---- _sample_t (model.py:589-619)
+    torch.manual_seed(11)
+    t_ref = s._sample_t(8, torch.device("cpu"))
+    torch.manual_seed(11)
+    u = torch.rand(8)
+    assert torch.equal(R.sample_t(u), t_ref)
+    out.update(sample_t_u=_np(u), sample_t_ref=_np(t_ref))
+
+    # ---- noise (noise_schedule.py:142-150)
+    sig_ref, dsig_ref = s.noise(t_ref)
+    sig, dsig = R.loglinear_noise(t_ref)
+    assert torch.equal(sig, sig_ref) and torch.equal(dsig, dsig_ref)
+    out.update(sigma_ref=_np(sig_ref), dsigma_ref=_np(dsig_ref))
+
+    # ---- q_xt plain (model.py:439,579)
+    x0 = ids_clean.clone()
+    mc = torch.tensor([[0.3], [0.9]])
+    torch.manual_seed(12)
+    xt_ref, ign, _, smt, smi, mv_ref = s.q_xt(x0, mc, return_ignore_batch_mask_for_metrics=True, batch=None)
+    torch.manual_seed(12)
+    rand = torch.rand(B, N)
+    xt, mv, _ = R.q_xt(x0, mc, rand, cfgd["mask_index"])
+    assert torch.equal(xt, xt_ref) and torch.equal(mv, mv_ref)
+    out.update(qxt_x0=_np(x0), qxt_mc=_np(mc), qxt_rand=_np(rand), qxt_ref=_np(xt_ref), qxt_move_ref=_np(mv_ref))
+
+    # ---- q_xt with mask_entire_modality (model.py:470-529)
+    s2, _ = make_fake_self(cfgd, ref_dit=SimpleNamespace(training=True), mask_entire_modality=0.9)
+    Bm = 8
+    x0m = x0[:1].repeat(Bm, 1)
+    modm = modality[:1].repeat(Bm, 1)
+    mm = torch.stack([modm == 0, modm == 1], dim=-1)
+    mcm = torch.full((Bm, 1), 0.5)
+    torch.manual_seed(13)
+    xt_ref2, ign2, _, smt2, smi2, mv2 = s2.q_xt(x0m, mcm, return_ignore_batch_mask_for_metrics=True, batch=dict(modality_mask=mm))
+    torch.manual_seed(13)
+    randm = torch.rand(Bm, N)
+    rt, ri = torch.rand(Bm, 1), torch.rand(Bm, 1)
+    xt2, mv2_, ign2_ = R.q_xt(x0m, mcm, randm, cfgd["mask_index"], modality_mask=mm, mask_entire_modality=0.9, rand_txt=rt, rand_img=ri)
+    assert torch.equal(xt2, xt_ref2) and torch.equal(mv2_, mv2) and torch.equal(ign2_, ign2)
+    assert ign2.any() and not ign2.all()
+    out.update(qxtm_x0=_np(x0m), qxtm_mod=_np(modm), qxtm_mc=_np(mcm), qxtm_rand=_np(randm), qxtm_rt=_np(rt), qxtm_ri=_np(ri),
+               qxtm_ref=_np(xt_ref2), qxtm_ignore_ref=_np(ign2))
+
+    # ---- _subs_parameterization (model.py:621-658): fp32 and bf16 logits, with and without xt
+    torch.manual_seed(14)
+    logits = torch.randn(B, N, cfgd["vocab_size"]) * 3
+    for tag, lg in (("f32", logits), ("bf16", logits.bfloat16())):
+        ref_a = s._subs_parameterization(lg.clone(), xt=xt_ref, batch=None, modality=modality)
+        ref_b = s._subs_parameterization(lg.clone(), xt=None, batch=None, modality=modality)
+        a = R.subs_parameterization(lg, xt_ref, modality, cfgd["mask_index"], cfgd["text_vocab_size"])
+        b = R.subs_parameterization(lg, None, modality, cfgd["mask_index"], cfgd["text_vocab_size"])
+        assert torch.equal(a, ref_a) and torch.equal(b, ref_b), tag
+        out[f"subs_{tag}_ref_xt"] = _np(ref_a)
+        out[f"subs_{tag}_ref_noxt"] = _np(ref_b)
+    out.update(subs_logits=_np(logits), subs_xt=_np(xt_ref), subs_modality=_np(modality))
+
+    # ---- compute_loss (model.py:797-1173) through the reference forward + reference DIT (fp32)
+    found = RL._extract_functions(os.path.join(RL.REFERENCE_ROOT, "model.py"), ["forward", "compute_loss", "get_cond_dict"])
+    g = RL._exec_functions(found, dict(Loss=lambda **k: SimpleNamespace(**k), utils=SimpleNamespace(print_nans=lambda *a: None),
+                                      get_block_mask=None, get_interleaved_block_mask=None, shard_output=None))
+    for img_w, snr in ((0.6, None), (0.5, 5.0)):
+        s3, _ = make_fake_self(cfgd, ref_dit=dit, img_loss_weight=img_w, softmin_snr=snr)
+        s3.forward = lambda *a, **k: g["forward"](s3, *a, **k)
+        s3.get_cond_dict = lambda b: g["get_cond_dict"](s3, b)
+        am = torch.ones(B, N, dtype=torch.bool)
+        am[1, 10:14] = False
+        batch = dict(input_ids=x0, attention_mask=am, modality=modality,
+                     modality_mask=torch.stack([modality == 0, modality == 1], dim=-1))
+        torch.manual_seed(15)
+        with torch.no_grad():
+            L = g["compute_loss"](s3, batch, prefix="train", batch_idx=-1)
+        torch.manual_seed(15)
+        u_t = torch.rand(B)
+        rand_move = torch.rand(B, N)
+        mine = R.training_loss(ocfg, P, x0, modality, am, u_t, rand_move, mode="fp32", img_loss_weight=img_w, softmin_snr=snr)
+        e = abs(mine["loss"].item() - L.loss.item())
+        print(f"[compute_loss w_img={img_w} snr={snr}] ref {L.loss.item():.6f} restated {mine['loss'].item():.6f} |d|={e:.2e}")
+        assert e < 1e-4 * max(1.0, abs(L.loss.item()))
+        assert torch.allclose(mine["nlls"], L.nlls, rtol=1e-4, atol=1e-3)
+        tag = f"loss_w{int(img_w*10)}_snr{0 if snr is None else int(snr)}"
+        out.update({tag + "_ref": np.array([L.loss.item(), L.txt_loss.item(), L.img_loss.item()]), tag + "_nlls_ref": _np(L.nlls)})
+    out.update(loss_x0=_np(x0), loss_am=_np(am), loss_u_t=_np(u_t), loss_rand_move=_np(rand_move))
+
+    # ---- _sample_categorical (model_utils.py:95-97)
+    torch.manual_seed(16)
+    probs = torch.softmax(torch.randn(B, N, cfgd["vocab_size"]) * 2, -1)
+    torch.manual_seed(17)
+    sc_ref = M._sample_categorical(probs)
+    torch.manual_seed(17)
+    uu = torch.rand_like(probs)
+    assert torch.equal(R.sample_categorical(probs, uu), sc_ref)
+    out.update(sc_probs=_np(probs), sc_u=_np(uu), sc_ref=_np(sc_ref))
+
+    # ---- _ddpm_caching_update / _ddpm_update given p_x0 (model_eval.py:2042-2104)
+    xcur = x0.clone()
+    xcur[:, ::3] = cfgd["mask_index"]
+    tt = torch.full((B, 1), 0.7)
+    dt = (1 - 1e-5) / 16
+    torch.manual_seed(18)
+    _, xn_ref, _ = M._ddpm_caching_update(s, xcur, tt, dt, p_x0=probs.clone())
+    torch.manual_seed(18)
+    u2 = torch.rand_like(probs)
+    xn = R.ddpm_caching_update(xcur, tt, dt, probs.clone(), u2, cfgd["mask_index"])
+    assert torch.equal(xn, xn_ref)
+    out.update(ddpm_x=_np(xcur), ddpm_t=_np(tt), ddpm_dt=np.array(dt), ddpm_u=_np(u2), ddpm_cache_ref=_np(xn_ref))
+    s._ddpm_forward = lambda *a, **k: probs.clone()
+    torch.manual_seed(19)
+    xn2_ref, _ = M._ddpm_update(s, xcur, tt, dt)
+    torch.manual_seed(19)
+    u3 = torch.rand_like(probs)
+    xn2 = R.ddpm_update(xcur, tt, dt, probs.clone(), u3, cfgd["mask_index"])
+    assert torch.equal(xn2, xn2_ref)
+    out.update(ddpm_u3=_np(u3), ddpm_ref=_np(xn2_ref))
+
+    # ---- _ddpm_forward end-to-end through the reference DIT, no CFG (model_eval.py:1761-1833)
+    s4, _ = make_fake_self(cfgd, ref_dit=dit)
+    s4.forward = lambda *a, **k: g["forward"](s4, *a, **k)
+    with torch.no_grad():
+        p_ref = M._ddpm_forward(s4, xcur, tt, None, x0=None, x0_unmask=None, modality=modality)
+    lg = R.dit_forward(ocfg, P, xcur, modality, mode="fp32")
+    p_mine = R.subs_parameterization(lg, xcur, modality, cfgd["mask_index"], cfgd["text_vocab_size"]).exp()
+    assert torch.allclose(p_mine, p_ref, rtol=1e-4, atol=1e-6), (p_mine - p_ref).abs().max()
+    out.update(ddpmfwd_p_ref=_np(p_ref))
+    # with CFG (model_eval.py:1763-1818)
+    s5, _ = make_fake_self(cfgd, ref_dit=dit, eval_cfg=2.5)
+    s5.forward = lambda *a, **k: g["forward"](s5, *a, **k)
+    x0_unmask = torch.zeros(B, N, dtype=torch.bool)
+    x0_unmask[:, :cfgd["txt"]] = True
+    xc = torch.where(x0_unmask, x0, torch.full_like(x0, cfgd["mask_index"]))
+    with torch.no_grad():
+        pc_ref = M._ddpm_forward(s5, xc, tt.squeeze(-1), None, x0=x0, x0_unmask=x0_unmask, modality=modality)
+    xu = xc.clone()
+    xu[x0_unmask] = cfgd["mask_index"]
+    lc = R.dit_forward(ocfg, P, xc, modality, mode="fp32")
+    lu = R.dit_forward(ocfg, P, xu, modality, mode="fp32")
+    comb = R.cfg_combine(lc, lu, tt.squeeze(-1), 2.5)
+    pc = R.subs_parameterization(comb, None, modality, cfgd["mask_index"], cfgd["text_vocab_size"]).exp()
+    assert torch.allclose(pc, pc_ref, rtol=2e-4, atol=1e-6), (pc - pc_ref).abs().max()
+    out.update(cfg_x=_np(xc), cfg_unmask=_np(x0_unmask), cfg_p_ref=_np(pc_ref))
+
+    # ---- adap_sche (model_eval.py:2964-3001) and _maskgit_update (model_eval.py:3045-3114)
+    sch_ref = M.adap_sche(xcur, 8, cfgd["mask_index"], mode="arccos")
+    assert torch.equal(R.adap_sche(xcur, 8, cfgd["mask_index"]), sch_ref)
+    s6, _ = make_fake_self(cfgd, ref_dit=dit)
+    s6._ddpm_forward = lambda *a, **k: probs.clone()
+    s6.config.eval["maskgit_r_temp"] = 10
+    torch.manual_seed(20)
+    np.random.seed(20)
+    mg_ref, _ = M._maskgit_update(s6, xcur, tt, dt, schedule=sch_ref, step=2)
+    torch.manual_seed(20)
+    np.random.seed(20)
+    pred = torch.multinomial(probs.view(-1, probs.shape[-1]), 1)[:, 0].view(B, N)
+    gum = torch.from_numpy(np.random.gumbel(size=(B, N)))
+    mg = R.maskgit_update(xcur, tt, probs, pred, gum, sch_ref[:, 2], cfgd["mask_index"], r_temp=10)
+    assert torch.equal(mg, mg_ref)
+    out.update(sche_ref=_np(sch_ref), mg_pred=_np(pred), mg_gumbel=_np(gum), mg_ref=_np(mg_ref))
+
+    np.savez_compressed(os.path.join(OUT, "diffusion_fns.npz"), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    gen_diffusion_fns(*gen_dit())
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

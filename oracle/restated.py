@@ -1,0 +1,459 @@
+"""TEST INFRASTRUCTURE — CPU restatement (pure torch / numpy) of the UniDisc hot path.
+
+This file is the parity ORACLE.  It is imported only by `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py`; the product (`unidisc_b200`) never imports it.
+
+Every function cites the reference file:line it follows (paths relative to the reference repo,
+commit 01b6125c).  Pinning: `oracle/gen_golden.py` runs the *unmodified reference code* in the build
+container (via `oracle/ref_loader.py`) on seeded inputs, asserts that this restatement reproduces it,
+and writes `tests/golden/*.npz`; `tests/test_oracle_golden.py` re-checks the restatement against those
+committed vectors everywhere (no /root/reference needed).  The reference itself ships no tests or
+golden vectors for this path; the one piece whose pin is a restatement-of-a-dependency
+is the 2-D Lumina RoPE table (diffusers 0.32.2, absent here) — "parity unpinned" for that table only.
+
+Two numerics modes for the backbone:
+  mode="fp32" : everything fp32 (reference with `DIT(dtype=torch.float32)`, no outer autocast).
+  mode="bf16" : CUDA-autocast(bf16) semantics restated op by op with the rounding points of
+                SURVEY.md §8(a'): GEMM inputs/outputs bf16 with fp32 accumulate, fp32 residual stream,
+                fp32 norm maths, LayerNorm(q,k)->bf16, RoPE fp32 -> bf16, GELU on the bf16 GEMM output.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+NEG_INF = -1_000_000.0  # `self.neg_infinity`, model_setup.py (used at model.py:626)
+
+
+# --------------------------------------------------------------------------------------
+# configuration of the restated backbone
+# --------------------------------------------------------------------------------------
+@dataclass
+class OracleConfig:
+    hidden_size: int
+    n_heads: int
+    n_blocks: int
+    txt_length: int          # model.txt_length
+    img_length: int          # model.img_length (square)
+    vocab_size: int
+    text_vocab_size: int
+    mask_index: int
+    linear_factor: float = 1.0
+    rms_eps: float = 1e-6    # dit.py:78
+    ln_eps: float = 1e-5     # nn.LayerNorm default, dit.py:569-571
+    time_conditioning: bool = False
+    cond_dim: int = 128
+
+    @property
+    def length(self):
+        return self.txt_length + self.img_length
+
+    @property
+    def head_dim(self):
+        return self.hidden_size // self.n_heads
+
+
+# --------------------------------------------------------------------------------------
+# RoPE tables — dit.py:307-330 (Rotary), dit.py:1046-1061 (get_2d_rope), dit.py:1203-1239
+# --------------------------------------------------------------------------------------
+def rope_table_1d(head_dim: int, seq_len: int):
+    """cos/sin [seq_len, head_dim/2]: angle = pos * 10000^(-2i/head_dim)  (dit.py:310,320-324,1228-1230)."""
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, head_dim, 2).float() / head_dim))
+    t = torch.arange(seq_len).float()
+    freqs = torch.einsum("i,j->ij", t, inv_freq)
+    return freqs.cos(), freqs.sin()
+
+
+def rope_table_2d(head_dim: int, img_len: int, linear_factor: float = 1.0):
+    """cos/sin [img_len, head_dim/2], Lumina 2-D layout [row f0, col f0, row f1, col f1, ...]
+    (dit.py:1046-1061 + diffusers 0.32.2 get_2d_rotary_pos_embed_lumina, restated)."""
+    side = int(math.sqrt(img_len))
+    assert side * side == img_len
+    half = head_dim // 2
+    freqs = 1.0 / (10000.0 ** (torch.arange(0, half, 2, dtype=torch.float32)[: half // 2] / half)) / linear_factor
+    ang = torch.outer(torch.arange(side), freqs).float()        # [side, hd/4]
+    ang_h = ang.view(side, 1, half // 2, 1).repeat(1, side, 1, 1)
+    ang_w = ang.view(1, side, half // 2, 1).repeat(side, 1, 1, 1)
+    a = torch.cat([ang_h, ang_w], dim=-1).flatten(2).flatten(0, 1)  # [img_len, hd/2]
+    # reference takes .real/.imag of polar(1, angle)
+    c = torch.polar(torch.ones_like(a), a)
+    return c.real.contiguous(), c.imag.contiguous()
+
+
+def token_cos_sin(cfg: OracleConfig, modality: torch.Tensor):
+    """Per-token cos/sin [B,N,hd/2] (dit.py:1419-1458, non-sample-ids branch).
+
+    Text tokens use the 1-D table at their absolute position; image tokens use the 2-D table
+    right-aligned to the end of the sequence (NaN padding in the reference is never selected).
+    """
+    B, N = modality.shape
+    hd = cfg.head_dim
+    cos_t, sin_t = rope_table_1d(hd, cfg.length)
+    cos_i, sin_i = rope_table_2d(hd, cfg.img_length, cfg.linear_factor)
+    pos = torch.arange(N)
+    pad = max(N - cfg.img_length, 0)
+    ipos = (pos - pad).clamp(min=0, max=cfg.img_length - 1)
+    is_txt = (modality == 0)[..., None]
+    cos = torch.where(is_txt, cos_t[pos][None], cos_i[ipos][None])
+    sin = torch.where(is_txt, sin_t[pos][None], sin_i[ipos][None])
+    return cos.to(modality.device), sin.to(modality.device)
+
+
+# --------------------------------------------------------------------------------------
+# backbone
+# --------------------------------------------------------------------------------------
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _rms(x32, eps):
+    return x32 * torch.rsqrt(x32.pow(2).mean(-1, keepdim=True) + eps)
+
+
+def _linear(x, w, b, mode):
+    """nn.Linear under autocast: inputs & weight rounded to bf16, fp32 accumulate, bf16 output."""
+    if mode == "fp32":
+        y = x.float() @ w.float().t()
+        return y + b.float() if b is not None else y
+    y = _bf(x).float() @ _bf(w).float().t()
+    if b is not None:
+        y = y + _bf(b).float()
+    return _bf(y)
+
+
+def _rmsnorm(x, w, eps, mode):
+    """RMSNorm.forward dit.py:95-100: `_norm(x.float()).type_as(x) * weight`."""
+    out = _rms(x.float(), eps)
+    if mode == "bf16" and x.dtype == torch.bfloat16:
+        out = _bf(out)            # `.type_as(x)` rounding point for bf16 inputs
+    return out.float() * w.float()
+
+
+def _rope(x, cos, sin):
+    """standalone_rotary.py:14-31 (non-interleaved): x [B,N,H,hd], cos/sin [B,N,hd/2]."""
+    cos2 = torch.cat([cos, cos], dim=-1)[:, :, None, :]
+    sin2 = torch.cat([sin, sin], dim=-1)[:, :, None, :]
+    x1, x2 = x.chunk(2, dim=-1)
+    rot = torch.cat((-x2, x1), dim=-1)
+    return x * cos2 + rot * sin2
+
+
+def attention_core(q, k, v, scale):
+    """softmax(q k^T * scale) v, bidirectional, fp32 math. q,k,v: [B,H,N,hd] (dit.py:826/829)."""
+    s = (q.float() @ k.float().transpose(-1, -2)) * scale
+    p = torch.softmax(s, dim=-1)
+    return p @ v.float()
+
+
+def block_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], i: int, x, cos, sin, mode, sample_ids=None,
+                  taps: Optional[dict] = None):
+    """DDiTBlock.forward dit.py:948-1033 (rms, sandwich, qk_norm, no time-conditioning) with
+    Attention.forward dit.py:616-887 (sdpa branch)."""
+    pre = f"blocks.{i}."
+    B, N, D = x.shape
+    H, hd = cfg.n_heads, cfg.head_dim
+    h = _rmsnorm(x, P[pre + "norm1.weight"], cfg.rms_eps, mode)                       # step 1
+    qkv = _linear(h, P[pre + "attention.attn_qkv.weight"], None, mode)               # step 2  [B,N,3D]
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    ln = lambda t, w, b: torch.nn.functional.layer_norm(t.float(), (D,), w.float(), b.float(), cfg.ln_eps)
+    q = ln(q, P[pre + "attention.q_norm.weight"], P[pre + "attention.q_norm.bias"])   # step 3
+    k = ln(k, P[pre + "attention.k_norm.weight"], P[pre + "attention.k_norm.bias"])
+    if mode == "bf16":
+        q, k = _bf(q), _bf(k)
+    q = _rope(q.reshape(B, N, H, hd).float(), cos, sin)                               # step 4
+    k = _rope(k.reshape(B, N, H, hd).float(), cos, sin)
+    v = v.reshape(B, N, H, hd)
+    if mode == "bf16":
+        q, k = _bf(q), _bf(k)
+    qh, kh, vh = (t.permute(0, 2, 1, 3) for t in (q, k, v))
+    if sample_ids is None:
+        o = attention_core(qh, kh, vh, 1.0 / math.sqrt(hd))                          # step 5
+    else:
+        # document mask (model_utils.py:740-771): (sid[q]==sid[kv]) & (sid[q] != -1)
+        s = (qh.float() @ kh.float().transpose(-1, -2)) / math.sqrt(hd)
+        m = (sample_ids[:, :, None] == sample_ids[:, None, :]) & (sample_ids[:, :, None] != -1)
+        s = s.masked_fill(~m[:, None], float("-inf"))
+        p = torch.softmax(s, dim=-1)
+        p = torch.nan_to_num(p, nan=0.0)
+        o = p @ vh.float()
+    if mode == "bf16":
+        o = _bf(o)
+    o = o.permute(0, 2, 1, 3).reshape(B, N, D)
+    a = _linear(o, P[pre + "attention.attn_out.weight"], None, mode)                  # step 6
+    x1 = x + _rmsnorm(a, P[pre + "pre_residual_norm.weight"], cfg.rms_eps, mode)      # step 7
+    h2 = _rmsnorm(x1, P[pre + "norm2.weight"], cfg.rms_eps, mode)                     # step 8
+    u = _linear(h2, P[pre + "mlp.0.weight"], P[pre + "mlp.0.bias"], mode)             # step 9
+    g = torch.nn.functional.gelu(u.float(), approximate="tanh")
+    if mode == "bf16":
+        g = _bf(g)
+    d = _linear(g, P[pre + "mlp.2.weight"], P[pre + "mlp.2.bias"], mode)
+    x2 = x1 + _rmsnorm(d, P[pre + "post_ff_norm.weight"], cfg.rms_eps, mode)          # step 10 (dropout 0 / eval)
+    if taps is not None:
+        taps[f"b{i}"] = dict(h=h, qkv=qkv, q=q, k=k, o=o, a=a, x1=x1, h2=h2, u=u, g=g, d=d, x2=x2)
+    return x2
+
+
+def dit_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], indices, modality, mode="fp32", sample_ids=None,
+                taps: Optional[dict] = None, return_hidden=False):
+    """DIT.forward dit.py:1324-1500 (discrete, multimodal_batches, modality_embed, rope_2d, no time-cond).
+
+    indices, modality: int64 [B,N].  Returns logits [B,N,V] (bf16 in mode="bf16", fp32 otherwise).
+    """
+    x = P["vocab_embed.embedding"].float()[indices]                                   # dit.py:1375
+    me = P["modality_embed.embedding"].float()
+    x = x + torch.where((modality == 0)[..., None], me[0][None, None], me[1][None, None])  # dit.py:1406
+    cos, sin = token_cos_sin(cfg, modality.cpu())
+    cos, sin = cos.to(x.device), sin.to(x.device)
+    for i in range(cfg.n_blocks):
+        x = block_forward(cfg, P, i, x, cos, sin, mode, sample_ids=sample_ids, taps=taps)
+    if return_hidden:
+        return x
+    hf = _rmsnorm(x, P["output_layer.norm_final.weight"], cfg.rms_eps, mode)          # dit.py:1089
+    return _linear(hf, P["output_layer.linear.weight"], P["output_layer.linear.bias"], mode)  # dit.py:1091
+
+
+# --------------------------------------------------------------------------------------
+# noise schedule / time sampling — noise_schedule.py:128-157, model.py:589-619
+# --------------------------------------------------------------------------------------
+def loglinear_noise(t: torch.Tensor, eps: float = 1e-3):
+    """(total_noise, rate_noise): sigma = -log1p(-(1-eps) t), dsigma = (1-eps)/(1-(1-eps) t)."""
+    return -torch.log1p(-(1 - eps) * t), (1 - eps) / (1 - (1 - eps) * t)
+
+
+def sample_t(u: torch.Tensor, sampling_eps: float = 1e-3, antithetic: bool = True):
+    """model.py:589-619 given the uniform draw `u = torch.rand(n)`."""
+    n = u.shape[0]
+    e = u
+    if antithetic:
+        offset = torch.arange(n, device=u.device) / n
+        e = (e / n + offset) % 1
+    t = (1 - sampling_eps) * e + sampling_eps
+    return t.to(torch.float32)
+
+
+# --------------------------------------------------------------------------------------
+# q_xt — model.py:424-587 (absorbing, multimodal non-interleaved, optional mask_entire_modality)
+# --------------------------------------------------------------------------------------
+def q_xt(x0: torch.Tensor, move_chance: torch.Tensor, rand: torch.Tensor, mask_index: int,
+         modality_mask: Optional[torch.Tensor] = None, mask_entire_modality: Optional[float] = None,
+         rand_txt: Optional[torch.Tensor] = None, rand_img: Optional[torch.Tensor] = None):
+    """`rand` is the tensor the reference draws at model.py:439 (`torch.rand(*x.shape)`); `rand_txt`,
+    `rand_img` [B,1] are the two draws at model.py:479-480.  Returns (xt, move_indices, ignore_mask)."""
+    move = rand < move_chance                                                          # model.py:439
+    ignore = None
+    if mask_entire_modality is not None:
+        smt = rand_txt < mask_entire_modality / 2                                      # model.py:479
+        smi = rand_img < mask_entire_modality / 2                                      # model.py:480
+        both = smt & smi                                                               # model.py:524-526
+        smt = torch.where(both, False, smt)
+        smi = torch.where(both, False, smi)
+        move = torch.where(smt, modality_mask[..., 0], move)                           # model.py:527
+        move = torch.where(smi, modality_mask[..., 1], move)                           # model.py:528
+        ignore = smi | smt                                                             # model.py:529
+    xt = torch.where(move, mask_index, x0)                                             # model.py:579
+    return xt, move, ignore
+
+
+# --------------------------------------------------------------------------------------
+# SUBS parameterization + loss — model.py:621-658, 797-1173
+# --------------------------------------------------------------------------------------
+def subs_parameterization(logits: torch.Tensor, xt: Optional[torch.Tensor], modality: torch.Tensor, mask_index: int,
+                          text_vocab_size: int, force_argmax_valid_indices: bool = True):
+    """model.py:621-658 (multimodal_batches).  Computed in the dtype of `logits` exactly as the reference
+    does (bf16 logits -> bf16 log-softmax); pass fp32 logits for the high-precision variant."""
+    logits = logits.clone()
+    logits[..., mask_index] += NEG_INF                                                 # model.py:626
+    if force_argmax_valid_indices:                                                     # model.py:627-635
+        txt = (modality == 0)[..., None]
+        img = (modality == 1)[..., None]
+        neg = torch.tensor(NEG_INF, dtype=logits.dtype)
+        logits[..., text_vocab_size:] = torch.where(txt, neg, logits[..., text_vocab_size:])
+        logits[..., :text_vocab_size] = torch.where(img, neg, logits[..., :text_vocab_size])
+    logits = logits - torch.logsumexp(logits, dim=-1, keepdim=True)                    # model.py:639
+    if xt is not None:                                                                 # model.py:646-656
+        unmasked = (xt != mask_index)[..., None]
+        logits = torch.where(unmasked, torch.full_like(logits, NEG_INF), logits)
+        onehot = torch.arange(logits.size(-1), device=logits.device) == xt[..., None]
+        logits = torch.where(unmasked & onehot, torch.zeros_like(logits), logits)
+    return logits
+
+
+def diffusion_loss(model_output: torch.Tensor, x0, t, modality, attention_mask, *, text_loss_weight=1.0,
+                   img_loss_weight=0.6, softmin_snr: Optional[float] = None, eps: float = 1e-3):
+    """model.py:924-925, 967-993, 1021-1057 (discrete, subs, T=0).  model_output: log-probs [B,N,V].
+    Returns dict(loss, txt_loss, img_loss, nlls [B,N], std_loss [B,N])."""
+    out = model_output.to(torch.float32)                                               # model.py:924-925
+    sigma, dsigma = loglinear_noise(t, eps)
+    log_p = torch.gather(out, -1, x0[:, :, None]).squeeze(-1)                          # model.py:967
+    std_w = (dsigma / torch.expm1(sigma))[:, None]                                     # model.py:975
+    loss = -log_p * std_w
+    if softmin_snr is not None:                                                        # model.py:990-993
+        w = (dsigma / (torch.expm1(sigma) + (1 / softmin_snr)))[:, None]
+        loss = -log_p * w
+    std_loss = -log_p * std_w
+    modality_mask = torch.stack([modality == 0, modality == 1], dim=-1)
+    am = attention_mask.bool()
+    txt_mask = modality_mask[..., 0] & am                                              # model.py:1021-1022
+    img_mask = modality_mask[..., 1] & am
+    txt_count, img_count = txt_mask.sum(), img_mask.sum()
+    total = txt_count + img_count
+    loss = loss * am
+    txt_loss = (loss[txt_mask].sum() / txt_count) * (txt_count / total) * text_loss_weight   # model.py:1038-1040
+    img_loss = (loss[img_mask].sum() / img_count) * (img_count / total) * img_loss_weight    # model.py:1041-1043
+    txt_loss = torch.nan_to_num(txt_loss, nan=0.0)
+    img_loss = torch.nan_to_num(img_loss, nan=0.0)
+    return dict(loss=txt_loss + img_loss, txt_loss=txt_loss, img_loss=img_loss, nlls=std_loss * am, std_loss=std_loss,
+                log_p=log_p)
+
+
+# --------------------------------------------------------------------------------------
+# samplers — model_utils.py:95-97, model_eval.py:1734-1833, 2042-2104, 2964-3114
+# --------------------------------------------------------------------------------------
+def sample_categorical(probs: torch.Tensor, u: torch.Tensor):
+    """model_utils.py:95-97 given `u = torch.rand_like(probs)`."""
+    gumbel_norm = 1e-10 - (u + 1e-10).log()
+    return (probs / gumbel_norm).argmax(dim=-1)
+
+
+def ddpm_caching_update(x, t, dt, p_x0, u, mask_index):
+    """model_eval.py:2072-2104 (loglinear): x [B,N] int64, t [B] or [B,1], p_x0 [B,N,V], u = rand_like(q_xs)."""
+    if t.ndim > 1:
+        t = t.squeeze(-1)
+    mc_t = t[:, None, None]
+    mc_s = (t - dt)[:, None, None]
+    q_xs = p_x0 * (mc_t - mc_s)                                                        # model_eval.py:2091
+    q_xs[:, :, mask_index] = mc_s[:, :, 0]                                             # model_eval.py:2092
+    _x = sample_categorical(q_xs, u)
+    copy_flag = (x != mask_index).to(x.dtype)
+    return copy_flag * x + (1 - copy_flag) * _x                                        # model_eval.py:2104
+
+
+def ddpm_update(x, t, dt, p_x0, u, mask_index, eps=1e-3):
+    """model_eval.py:2042-2070: move chances from the noise schedule instead of t directly."""
+    if t.ndim > 1:
+        t = t.squeeze(-1)
+    sigma_t, _ = loglinear_noise(t, eps)
+    sigma_s, _ = loglinear_noise(t - dt, eps)
+    mc_t = (1 - torch.exp(-sigma_t))[:, None, None]
+    mc_s = (1 - torch.exp(-sigma_s))[:, None, None]
+    q_xs = p_x0 * (mc_t - mc_s)
+    q_xs[:, :, mask_index] = mc_s[:, :, 0]
+    _x = sample_categorical(q_xs, u)
+    copy_flag = (x != mask_index).to(x.dtype)
+    return copy_flag * x + (1 - copy_flag) * _x
+
+
+def cfg_combine(logit_c, logit_u, t, cfg_scale):
+    """model_eval.py:1746,1812: w = cfg (1 - t); logits = (1+w) c - w u."""
+    w = (cfg_scale * (1 - t))[:, None]
+    if w.ndim == 2 and logit_c.ndim == 3:
+        w = w.unsqueeze(-1)
+    return (1 + w) * logit_c - w * logit_u
+
+
+def adap_sche(x, step, mask_index, mode="arccos"):
+    """model_eval.py:2964-3001: per-sample number of tokens to unmask at each step."""
+    num_masked = (x == mask_index).sum(dim=-1)
+    r = torch.linspace(1, 0, step)
+    if mode == "root":
+        val = 1 - (r ** 0.5)
+    elif mode == "linear":
+        val = 1 - r
+    elif mode == "square":
+        val = 1 - (r ** 2)
+    elif mode == "cosine":
+        val = torch.cos(r * math.pi * 0.5)
+    elif mode == "arccos":
+        val = torch.arccos(r) / (math.pi * 0.5)
+    else:
+        return None
+    out = []
+    for seq_len in num_masked:
+        sche = (val / val.sum()) * seq_len
+        sche = sche.round()
+        sche[sche == 0] = 1
+        sche[-1] += seq_len - sche.sum()
+        sche[-1] = max(sche[-1], 0)
+        out.append(sche.int())
+    return torch.stack(out, dim=0)
+
+
+def maskgit_update(x, t, p_x0, pred_code, gumbel, num_unmask, mask_index, r_temp=10.0):
+    """model_eval.py:3045-3114 given the two random draws the reference makes:
+    `pred_code` = torch.multinomial(p_x0) [B,N] and `gumbel` = np.random.gumbel [B,N].  t: [B,1]."""
+    copy_flag = x != mask_index
+    num_unmask = torch.minimum(num_unmask, (~copy_flag).sum(dim=-1))
+    if torch.all(num_unmask <= 0):
+        return x
+    conf = torch.gather(p_x0, -1, pred_code.unsqueeze(-1)).squeeze(-1)
+    rand = r_temp * gumbel * t
+    conf = torch.log(conf.squeeze()) + rand
+    conf = torch.where(copy_flag, -torch.inf, conf)
+    k = int(num_unmask.max().item())
+    tresh, _ = torch.topk(conf, k=k, dim=-1)
+    gi = torch.clamp(num_unmask - 1, min=0)[:, None]
+    tresh = tresh.gather(-1, gi)
+    tresh = torch.where((num_unmask <= 0)[:, None], torch.inf, tresh)
+    sel = conf >= tresh.expand_as(conf)
+    return torch.where(sel, pred_code, x)
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs and parameter init mirroring the reference module
+# --------------------------------------------------------------------------------------
+def synthetic_batch(B, txt_len, img_len, text_vocab_size, vocab_size, seed=42):
+    g = torch.Generator().manual_seed(seed)
+    txt = torch.randint(0, text_vocab_size - 1, (B, txt_len), generator=g)
+    img = torch.randint(text_vocab_size, vocab_size, (B, img_len), generator=g)
+    ids = torch.cat([txt, img], dim=1)
+    modality = torch.cat([torch.zeros(B, txt_len, dtype=torch.int64), torch.ones(B, img_len, dtype=torch.int64)], dim=1)
+    return ids, modality
+
+
+def init_params(cfg: OracleConfig, seed=0) -> Dict[str, torch.Tensor]:
+    """Random parameters with the reference's state-dict keys/shapes — values are arbitrary
+    (seeded normal/uniform); parity tests copy the SAME tensors into both implementations."""
+    g = torch.Generator().manual_seed(seed)
+    D, V, L = cfg.hidden_size, cfg.vocab_size, cfg.n_blocks
+    u = lambda *s, a: (torch.rand(*s, generator=g) * 2 - 1) * a
+    P = {"vocab_embed.embedding": u(V, D, a=1.0 / math.sqrt(D)),
+         "modality_embed.embedding": u(2, D, a=1.0 / math.sqrt(D))}
+    for i in range(L):
+        p = f"blocks.{i}."
+        P[p + "attention.attn_qkv.weight"] = u(3 * D, D, a=1.0 / math.sqrt(D))
+        P[p + "attention.attn_out.weight"] = u(D, D, a=1.0 / math.sqrt(D))
+        for n in ("q_norm", "k_norm"):
+            P[p + f"attention.{n}.weight"] = 1.0 + u(D, a=0.2)
+            P[p + f"attention.{n}.bias"] = u(D, a=0.1)
+        for n in ("norm1", "norm2", "post_ff_norm", "pre_residual_norm"):
+            P[p + f"{n}.weight"] = 1.0 + u(D, a=0.2)
+        P[p + "mlp.0.weight"] = u(4 * D, D, a=1.0 / math.sqrt(D))
+        P[p + "mlp.0.bias"] = u(4 * D, a=0.1)
+        P[p + "mlp.2.weight"] = u(D, 4 * D, a=1.0 / math.sqrt(4 * D))
+        P[p + "mlp.2.bias"] = u(D, a=0.1)
+    P["output_layer.norm_final.weight"] = 1.0 + u(D, a=0.2)
+    P["output_layer.linear.weight"] = u(V, D, a=1.0 / math.sqrt(D))
+    P["output_layer.linear.bias"] = u(V, a=0.1)
+    return P
+
+
+def training_loss(cfg: OracleConfig, P, x0, modality, attention_mask, u_t, rand_move, mode="fp32", *,
+                  img_loss_weight=0.6, text_loss_weight=1.0, softmin_snr=None, fp32_logsoftmax=True):
+    """q_xt -> DIT -> SUBS -> weighted NLL, i.e. `Diffusion.compute_loss` (model.py:797-1173) for the default
+    large-scale config, driven by explicit random draws (u_t [B], rand_move [B,N])."""
+    t = sample_t(u_t)
+    sigma, _ = loglinear_noise(t)
+    move_chance = 1 - torch.exp(-sigma[:, None])                                       # model.py:858-860
+    xt, move, _ = q_xt(x0, move_chance, rand_move, cfg.mask_index)
+    logits = dit_forward(cfg, P, xt, modality, mode=mode)
+    if fp32_logsoftmax:
+        logits = logits.float()
+    logp = subs_parameterization(logits, xt, modality, cfg.mask_index, cfg.text_vocab_size)
+    out = diffusion_loss(logp, x0, t, modality, attention_mask, text_loss_weight=text_loss_weight,
+                         img_loss_weight=img_loss_weight, softmin_snr=softmin_snr)
+    out.update(xt=xt, t=t, logits=logits)
+    return out

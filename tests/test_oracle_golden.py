@@ -1,0 +1,115 @@
+"""CPU: the restated oracle (oracle/restated.py) against the committed golden vectors that
+oracle/gen_golden.py produced by running the unmodified reference code (tests/golden/*.npz)."""
+import numpy as np
+import torch
+
+from oracle import restated as R
+
+
+def _cfg(g):
+    D, H, L, txt, img, V, tv, mi = [int(v) for v in g["cfg"]]
+    return R.OracleConfig(D, H, L, txt, img, V, tv, mi)
+
+
+def _params(g):
+    return {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("P::")}
+
+
+def test_dit_forward_fp32_matches_reference(golden_dit):
+    g = golden_dit
+    cfg, P = _cfg(g), _params(g)
+    out = R.dit_forward(cfg, P, torch.from_numpy(g["ids"]), torch.from_numpy(g["modality"]), mode="fp32")
+    ref = torch.from_numpy(g["ref_logits_fp32"])
+    assert (out - ref).abs().max().item() < 2e-5
+
+
+def test_dit_forward_bf16_mode_close_to_reference(golden_dit):
+    g = golden_dit
+    cfg, P = _cfg(g), _params(g)
+    out = R.dit_forward(cfg, P, torch.from_numpy(g["ids"]), torch.from_numpy(g["modality"]), mode="bf16").float()
+    # bf16 autocast emulation vs the reference's CPU-autocast run and vs its fp32 run
+    assert (out - torch.from_numpy(g["ref_logits_cpu_bf16"])).abs().max().item() < 0.06
+    assert (out - torch.from_numpy(g["ref_logits_fp32"])).abs().max().item() < 0.06
+
+
+def test_rope_tables(golden_dit):
+    g = golden_dit
+    cfg = _cfg(g)
+    c, s = R.rope_table_2d(cfg.head_dim, cfg.img_length)
+    assert np.array_equal(c.numpy(), g["rope_cos_img"]) and np.array_equal(s.numpy(), g["rope_sin_img"])
+
+
+def test_sample_t_and_noise(golden_fns):
+    g = golden_fns
+    t = R.sample_t(torch.from_numpy(g["sample_t_u"]))
+    assert np.array_equal(t.numpy(), g["sample_t_ref"])
+    s, ds = R.loglinear_noise(t)
+    assert np.array_equal(s.numpy(), g["sigma_ref"]) and np.array_equal(ds.numpy(), g["dsigma_ref"])
+
+
+def test_q_xt_bit_exact(golden_fns, golden_dit):
+    g = golden_fns
+    mi = int(golden_dit["cfg"][7])
+    xt, mv, _ = R.q_xt(torch.from_numpy(g["qxt_x0"]), torch.from_numpy(g["qxt_mc"]), torch.from_numpy(g["qxt_rand"]), mi)
+    assert np.array_equal(xt.numpy(), g["qxt_ref"]) and np.array_equal(mv.numpy(), g["qxt_move_ref"])
+    mod = torch.from_numpy(g["qxtm_mod"])
+    mm = torch.stack([mod == 0, mod == 1], -1)
+    xt, mv, ign = R.q_xt(torch.from_numpy(g["qxtm_x0"]), torch.from_numpy(g["qxtm_mc"]), torch.from_numpy(g["qxtm_rand"]), mi,
+                         modality_mask=mm, mask_entire_modality=0.9, rand_txt=torch.from_numpy(g["qxtm_rt"]),
+                         rand_img=torch.from_numpy(g["qxtm_ri"]))
+    assert np.array_equal(xt.numpy(), g["qxtm_ref"]) and np.array_equal(ign.numpy(), g["qxtm_ignore_ref"])
+
+
+def test_subs_parameterization(golden_fns, golden_dit):
+    g = golden_fns
+    tv, mi = int(golden_dit["cfg"][6]), int(golden_dit["cfg"][7])
+    lg = torch.from_numpy(g["subs_logits"])
+    xt, mod = torch.from_numpy(g["subs_xt"]), torch.from_numpy(g["subs_modality"])
+    assert np.array_equal(R.subs_parameterization(lg, xt, mod, mi, tv).numpy(), g["subs_f32_ref_xt"])
+    assert np.array_equal(R.subs_parameterization(lg, None, mod, mi, tv).numpy(), g["subs_f32_ref_noxt"])
+    assert np.array_equal(R.subs_parameterization(lg.bfloat16(), xt, mod, mi, tv).float().numpy(), g["subs_bf16_ref_xt"])
+
+
+def test_compute_loss(golden_fns, golden_dit):
+    g, gd = golden_fns, golden_dit
+    cfg, P = _cfg(gd), _params(gd)
+    x0, am = torch.from_numpy(g["loss_x0"]), torch.from_numpy(g["loss_am"])
+    mod = torch.from_numpy(gd["modality"])
+    for tag, w, snr in (("loss_w6_snr0", 0.6, None), ("loss_w5_snr5", 0.5, 5.0)):
+        out = R.training_loss(cfg, P, x0, mod, am, torch.from_numpy(g["loss_u_t"]), torch.from_numpy(g["loss_rand_move"]),
+                              mode="fp32", img_loss_weight=w, softmin_snr=snr)
+        ref = g[tag + "_ref"]
+        assert abs(out["loss"].item() - ref[0]) < 1e-4 * max(1, abs(ref[0]))
+        assert abs(out["txt_loss"].item() - ref[1]) < 1e-4 * max(1, abs(ref[1]))
+        assert np.allclose(out["nlls"].numpy(), g[tag + "_nlls_ref"], rtol=1e-4, atol=1e-3)
+
+
+def test_samplers_bit_exact(golden_fns, golden_dit):
+    g = golden_fns
+    mi = int(golden_dit["cfg"][7])
+    probs = torch.from_numpy(g["sc_probs"])
+    assert np.array_equal(R.sample_categorical(probs, torch.from_numpy(g["sc_u"])).numpy(), g["sc_ref"])
+    x, t, dt = torch.from_numpy(g["ddpm_x"]), torch.from_numpy(g["ddpm_t"]), float(g["ddpm_dt"])
+    assert np.array_equal(R.ddpm_caching_update(x, t, dt, probs.clone(), torch.from_numpy(g["ddpm_u"]), mi).numpy(), g["ddpm_cache_ref"])
+    assert np.array_equal(R.ddpm_update(x, t, dt, probs.clone(), torch.from_numpy(g["ddpm_u3"]), mi).numpy(), g["ddpm_ref"])
+    sch = R.adap_sche(x, 8, mi)
+    assert np.array_equal(sch.numpy(), g["sche_ref"])
+    mg = R.maskgit_update(x, t, probs, torch.from_numpy(g["mg_pred"]), torch.from_numpy(g["mg_gumbel"]), sch[:, 2], mi, r_temp=10)
+    assert np.array_equal(mg.numpy(), g["mg_ref"])
+
+
+def test_ddpm_forward_and_cfg(golden_fns, golden_dit):
+    g, gd = golden_fns, golden_dit
+    cfg, P = _cfg(gd), _params(gd)
+    mod = torch.from_numpy(gd["modality"])
+    x = torch.from_numpy(g["ddpm_x"])
+    lg = R.dit_forward(cfg, P, x, mod, mode="fp32")
+    p = R.subs_parameterization(lg, x, mod, cfg.mask_index, cfg.text_vocab_size).exp()
+    assert np.allclose(p.numpy(), g["ddpmfwd_p_ref"], rtol=1e-4, atol=1e-6)
+    xc, um = torch.from_numpy(g["cfg_x"]), torch.from_numpy(g["cfg_unmask"])
+    xu = xc.clone()
+    xu[um] = cfg.mask_index
+    t = torch.from_numpy(g["ddpm_t"]).squeeze(-1)
+    comb = R.cfg_combine(R.dit_forward(cfg, P, xc, mod), R.dit_forward(cfg, P, xu, mod), t, 2.5)
+    pc = R.subs_parameterization(comb, None, mod, cfg.mask_index, cfg.text_vocab_size).exp()
+    assert np.allclose(pc.numpy(), g["cfg_p_ref"], rtol=2e-4, atol=1e-6)
