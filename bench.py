@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — joint-token tokens/sec of one full UniDisc training step (q_xt -> DiT fwd -> SUBS-NLL -> bwd ->
+bf16 gradient all-reduce -> clip + AdamW) on synthetic seq_len=1280 (256 text + 1024 image) batches.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     (reference arm: the CPU restatement of the reference path)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of value / e2e / roofline / cpu_baseline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (preset, per-GPU batch, txt, img)   — BASELINE.json configs[2] / configs[1]
+    "unidisc-1.4B": ("extra_large", 8, 256, 1024),
+    "dit-b": ("small", 32, 256, 1024),
+    "tiny": ("small", 2, 64, 64),     # CI-sized sanity run, never a bench line
+}
+TEXT_VOCAB, IMAGE_VOCAB = 32001, 16384
+
+
+def flops_per_token_fwd(D, L, N, V):
+    return L * (24 * D * D + 4 * N * D) + 2 * D * V
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(source="measured", hbm_gbs=j["hbm_gbs"], bf16_tflops=j["bf16_tflops"],
+                    bf16_tflops_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]))
+    return dict(source="fallback", hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        mx = None
+        for r in self.rows:
+            try:
+                mx = float(r[1])
+                break
+            except Exception:
+                pass
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (q_xt -> DIT -> SUBS -> weighted NLL, fwd+bwd), host cores
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_tokens_per_sec(workload, budget_s=25.0):
+    """Times the oracle restatement (oracle/restated.py, eager torch fp32 on the host cores) of the reference training
+    path on a bounded sample: per-GPU batch 1 at the workload's D/N/V, depth 1 and 3 blocks, fwd+bwd; the per-block and
+    the embed+head+loss costs are separated and extrapolated linearly to the workload's depth."""
+    from oracle import restated as R
+
+    preset, _, txt, img = WORKLOADS[workload]
+    from unidisc_b200.config import MODEL_PRESETS
+    D, L, H = MODEL_PRESETS[preset]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    V, tv, mi = TEXT_VOCAB + IMAGE_VOCAB, TEXT_VOCAB, TEXT_VOCAB - 1
+    N = txt + img
+    ids, modality = R.synthetic_batch(1, txt, img, tv, V, seed=42)
+    am = torch.ones_like(ids, dtype=torch.bool)
+
+    def run(depth):
+        cfg = R.OracleConfig(D, H, depth, txt, img, V, tv, mi)
+        P = {k: v.requires_grad_(True) for k, v in R.init_params(cfg, seed=0).items()}
+        g = torch.Generator().manual_seed(1)
+        best = None
+        for it in range(2):
+            t0 = time.perf_counter()
+            out = R.training_loss(cfg, P, ids, modality, am, torch.rand(1, generator=g), torch.rand(1, N, generator=g), mode="fp32")
+            out["loss"].backward()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            for p in P.values():
+                p.grad = None
+        return best
+
+    t1 = run(1)
+    t3 = run(3)
+    per_block = max((t3 - t1) / 2.0, 1e-6)
+    fixed = max(t1 - per_block, 0.0)
+    t_full = fixed + L * per_block
+    return dict(value=N / t_full, unit="tokens/s", cores=cores, kind="port",
+                sample=f"oracle/restated.py eager-torch fp32 fwd+bwd, B=1 N={N} D={D} V={V}; measured depth 1 ({t1:.2f}s) and 3 ({t3:.2f}s), "
+                       f"extrapolated linearly to depth {L} ({t_full:.1f}s/step); no optimizer step on the CPU arm")
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, min(args.steps, 2))):
+        vals.append(cpu_reference_tokens_per_sec(args.workload))
+    cb = vals[-1]
+    v = max(x["value"] for x in vals)
+    preset, bpg, txt, img = WORKLOADS[args.workload]
+    line = dict(impl="reference", metric="joint_token_tokens_per_sec", value=v, unit="tokens/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
+                data="synthetic", config=dict(workload=args.workload, seq_len=txt + img, per_gpu_batch=1, note="CPU arm, host cores"),
+                cpu_baseline=dict(cb, value=v), e2e=dict(value=v, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="unidisc-1.4B", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    assert args.warmup >= 3 or args.workload == "tiny", "timing rules: W >= 3"
+
+    import torch.distributed as dist
+    from unidisc_b200 import _lib as Lb
+    from unidisc_b200 import ops
+    from unidisc_b200.config import make_config
+    from unidisc_b200.ddp import FusedAdamW, ThinDDP
+    from unidisc_b200.model import Diffusion
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    preset, bpg, txt, img = WORKLOADS[args.workload]
+    small = args.workload == "tiny"
+    cfg = make_config(preset, txt_length=txt, img_length=img, image_vocab_size=IMAGE_VOCAB if not small else 255,
+                      text_vocab_size=TEXT_VOCAB if not small else 257, **(dict(hidden_size=256, n_blocks=2, n_heads=4) if small else {}))
+    torch.manual_seed(0)
+    model = Diffusion(cfg, device=dev)
+    model.train()
+    net = model.backbone
+    ddp = ThinDDP(net) if world > 1 else None
+    opt = FusedAdamW(net, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0)
+    B, N = bpg, txt + img
+    V, tv = model.vocab_size, model.text_vocab_size
+    D, Lyr = cfg.model.hidden_size, cfg.model.n_blocks
+
+    g = torch.Generator().manual_seed(42 + rank)                      # mirrors reference main.py:1062 (seed + rank)
+    ids_h = torch.cat([torch.randint(0, tv - 1, (B, txt), generator=g), torch.randint(tv, V, (B, img), generator=g)], 1).pin_memory()
+    mod_h = torch.cat([torch.zeros(B, txt, dtype=torch.int64), torch.ones(B, img, dtype=torch.int64)], 1).pin_memory()
+    am_h = torch.ones(B, N, dtype=torch.bool).pin_memory()
+    ids_d, mod_d, am_d = ids_h.to(dev), mod_h.to(dev), am_h.to(dev)
+    h2d = ids_h.numel() * 8 + mod_h.numel() * 8 + am_h.numel()
+
+    launches = [0]
+    orig_call = Lb.call
+
+    def counting_call(name, *a):
+        launches[0] += 1
+        return orig_call(name, *a)
+
+    ops.call = counting_call
+    import unidisc_b200.ops as _o
+    _o.call = counting_call
+
+    def step(e2e):
+        if e2e:
+            batch = dict(input_ids=ids_h.to(dev, non_blocking=True), modality=mod_h.to(dev, non_blocking=True),
+                         attention_mask=am_h.to(dev, non_blocking=True))
+        else:
+            batch = dict(input_ids=ids_d, modality=mod_d, attention_mask=am_d)
+        losses = model.compute_loss(batch)
+        losses.loss.backward()
+        opt.step()
+        opt.zero_grad()
+        if e2e:
+            return float(losses.loss)          # device -> host read of the step's result
+        return losses.loss.detach()
+
+    def timed(e2e, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches[0] = 0
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), float(last)
+
+    for _ in range(args.warmup):
+        step(True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, loss_dev = timed(False, args.steps)
+    n_launch = launches[0]
+    ms_e2e, loss_e2e = timed(True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel: the tcgen05 GEMM (MLP up-projection shape of this workload), timed live ----
+    pk = peaks()
+    M = B * N
+    sets = []
+    for i in range(4):                                                # rotate operand sets (> L2) between launches
+        sets.append((torch.randn(M, D, device=dev).to(torch.bfloat16), torch.randn(4 * D, D, device=dev).to(torch.bfloat16),
+                     torch.empty(M, 4 * D, device=dev, dtype=torch.bfloat16)))
+    for a, b_, c in sets:
+        ops.gemm(a, b_, out=c)
+    torch.cuda.synchronize()
+    iters = 24
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(iters):
+        a, b_, c = sets[i % 4]
+        ops.gemm(a, b_, out=c)
+    g1.record()
+    torch.cuda.synchronize()
+    gemm_ms = g0.elapsed_time(g1) / iters
+    gemm_tflops = 2.0 * M * D * 4 * D / (gemm_ms * 1e-3) / 1e12
+    del sets
+
+    tok_step = world * B * N
+    fpt = 3 * flops_per_token_fwd(D, Lyr, N, V)
+    value = tok_step / (ms_dev / args.steps * 1e-3)
+    e2e_v = tok_step / (ms_e2e / args.steps * 1e-3)
+    model_tflops_per_gpu = value / world * fpt / 1e12
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1 and not small:
+            try:
+                cpu = cpu_reference_tokens_per_sec(args.workload)
+            except Exception as e:  # noqa: BLE001
+                cpu = dict(value=None, unit="tokens/s", cores=os.cpu_count(), kind="port", sample=f"failed: {e}")
+        line = dict(
+            metric="joint_token_tokens_per_sec", value=value, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+            config=dict(workload=args.workload, model=f"DiT D={D} L={Lyr} H={cfg.model.n_heads}", seq_len=N, per_gpu_batch=B,
+                        global_batch=world * B, vocab=V, parallelism=f"dp{world}", optimizer="AdamW+clip(1.0)", dropout=0.0,
+                        l2="activations and weights per step >> 126 MB L2 (no flush needed)"),
+            e2e=dict(value=e2e_v, unit="tokens/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                     loss=loss_e2e),
+            gpu_launches=n_launch // max(args.steps, 1),
+            clocks=clocks,
+            roofline=dict(bound="tensor", kernel=f"gemm_kernel<K-major,K-major> M={M} N={4*D} K={D} (MLP up-projection)",
+                          achieved=gemm_tflops, peak=pk["bf16_tflops"], unit="TFLOP/s", frac=gemm_tflops / pk["bf16_tflops"],
+                          peak_source=pk["source"] + " (burst: kernel timed alone)", traffic=None, ms_per_launch=gemm_ms),
+            step_model_tflops_per_gpu=model_tflops_per_gpu,
+            step_frac_of_sustained_peak=model_tflops_per_gpu / pk["bf16_tflops_sustained"],
+            flops_per_token_fwd_bwd=fpt,
+            cpu_baseline=cpu,
+        )
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,130 @@
+"""GPU parity of the tcgen05 attention kernels (forward + backward) against the oracle's fp32 attention core
+(oracle/restated.py::attention_core == reference SDPA semantics, dit.py:826) on bf16 inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def _mk(B, N, H, hd, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    D = H * hd
+    qk = (torch.randn(B * N, 2 * D, generator=g) * scale).to(bf16).to(dev())
+    qkv = (torch.randn(B * N, 3 * D, generator=g) * scale).to(bf16).to(dev())
+    return qk, qkv, D
+
+
+def _ref(q, k, v, B, N, H, hd, sample_ids=None):
+    """fp32 reference on [B,H,N,hd] views (what SDPA computes, with optional document mask)."""
+    qh = q.float().view(B, N, H, hd).permute(0, 2, 1, 3)
+    kh = k.float().view(B, N, H, hd).permute(0, 2, 1, 3)
+    vh = v.float().view(B, N, H, hd).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(hd)
+    if sample_ids is not None:
+        m = (sample_ids[:, :, None] == sample_ids[:, None, :]) & (sample_ids[:, :, None] != -1)
+        s = s.masked_fill(~m[:, None], float("-inf"))
+    p = torch.nan_to_num(torch.softmax(s, -1), nan=0.0)
+    o = p @ vh
+    lse = torch.logsumexp(s, -1)
+    return o.permute(0, 2, 1, 3).reshape(B * N, H * hd), lse
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(1, 128, 1, 64), (2, 256, 2, 64), (1, 128, 1, 128), (2, 384, 3, 128), (1, 200, 2, 64),
+                                      (2, 1280, 2, 128)])
+def test_attn_fwd(B, N, H, hd):
+    from unidisc_b200 import ops
+    qk, qkv, D = _mk(B, N, H, hd, seed=1)
+    q, k, v = qk[:, :D], qk[:, D:], qkv[:, 2 * D:]
+    o, lse = ops.attn_fwd(q, k, v, B, N, H, hd, 1.0 / math.sqrt(hd))
+    torch.cuda.synchronize()
+    o_ref, lse_ref = _ref(q, k, v, B, N, H, hd)
+    err = (o.float() - o_ref).abs().max().item()
+    assert err < 2e-2, f"attention fwd max err {err}"
+    assert torch.allclose(o.float(), o_ref, rtol=2e-2, atol=8e-3)
+    assert torch.allclose(lse, lse_ref, rtol=1e-3, atol=2e-3), (lse - lse_ref).abs().max()
+
+
+def test_attn_fwd_large_scores():
+    """running-max growth and the lazy rescale path: keys ordered so the maximum keeps increasing"""
+    from unidisc_b200 import ops
+    B, N, H, hd = 1, 512, 1, 64
+    qk, qkv, D = _mk(B, N, H, hd, seed=2)
+    ramp = torch.linspace(0.2, 6.0, N, device=dev())[:, None]
+    qk[:, D:] = (qk[:, D:].float() * ramp).to(bf16)
+    q, k, v = qk[:, :D], qk[:, D:], qkv[:, 2 * D:]
+    o, lse = ops.attn_fwd(q, k, v, B, N, H, hd, 1.0 / math.sqrt(hd))
+    torch.cuda.synchronize()
+    o_ref, lse_ref = _ref(q, k, v, B, N, H, hd)
+    assert torch.allclose(o.float(), o_ref, rtol=2e-2, atol=1e-2), (o.float() - o_ref).abs().max()
+    assert torch.allclose(lse, lse_ref, rtol=1e-3, atol=5e-3)
+
+
+def test_attn_fwd_document_mask():
+    from unidisc_b200 import ops
+    B, N, H, hd = 2, 384, 2, 64
+    qk, qkv, D = _mk(B, N, H, hd, seed=3)
+    sid = torch.zeros(B, N, dtype=torch.int64)
+    sid[0, 100:250] = 1
+    sid[0, 250:] = 2
+    sid[1, 50:300] = 1
+    sid[1, 300:] = -1   # padding
+    sid = sid.to(dev())
+    q, k, v = qk[:, :D], qk[:, D:], qkv[:, 2 * D:]
+    o, lse = ops.attn_fwd(q, k, v, B, N, H, hd, 1.0 / math.sqrt(hd), sample_ids=sid)
+    torch.cuda.synchronize()
+    o_ref, _ = _ref(q, k, v, B, N, H, hd, sample_ids=sid)
+    assert torch.allclose(o.float(), o_ref, rtol=2e-2, atol=8e-3), (o.float() - o_ref).abs().max()
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(1, 128, 1, 64), (2, 256, 2, 64), (1, 256, 2, 128), (1, 200, 1, 64), (2, 1280, 1, 128)])
+def test_attn_bwd(B, N, H, hd):
+    from unidisc_b200 import ops
+    qk, qkv, D = _mk(B, N, H, hd, seed=4)
+    q, k, v = qk[:, :D], qk[:, D:], qkv[:, 2 * D:]
+    scale = 1.0 / math.sqrt(hd)
+    o, lse = ops.attn_fwd(q, k, v, B, N, H, hd, scale)
+    g = torch.Generator().manual_seed(9)
+    do = torch.randn(B * N, D, generator=g).to(bf16).to(dev())
+    dqk = torch.zeros(B * N, 2 * D, device=dev(), dtype=bf16)
+    dqkv = torch.zeros(B * N, 3 * D, device=dev(), dtype=bf16)
+    ops.attn_bwd(q, k, v, o, do, lse, dqk[:, :D], dqk[:, D:], dqkv[:, 2 * D:], B, N, H, hd, scale)
+    torch.cuda.synchronize()
+    q32, k32, v32 = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    o_ref, _ = _ref(q32, k32, v32, B, N, H, hd)
+    (o_ref * do.float()).sum().backward()
+    for got, ref, nm in ((dqk[:, :D], q32.grad, "dq"), (dqk[:, D:], k32.grad, "dk"), (dqkv[:, 2 * D:], v32.grad, "dv")):
+        err = (got.float() - ref).abs().max().item()
+        ref_mag = ref.abs().max().item()
+        assert err < 2e-2 * max(1.0, ref_mag), f"{nm}: max err {err} (ref max {ref_mag})"
+        assert torch.allclose(got.float(), ref, rtol=3e-2, atol=2e-2 * max(1.0, ref_mag) * 0.5), nm
+
+
+def test_attn_bwd_document_mask():
+    from unidisc_b200 import ops
+    B, N, H, hd = 1, 384, 1, 64
+    qk, qkv, D = _mk(B, N, H, hd, seed=5)
+    sid = torch.zeros(B, N, dtype=torch.int64)
+    sid[0, 100:250] = 1
+    sid[0, 250:360] = 2
+    sid[0, 360:] = -1
+    sid = sid.to(dev())
+    q, k, v = qk[:, :D], qk[:, D:], qkv[:, 2 * D:]
+    scale = 1.0 / math.sqrt(hd)
+    o, lse = ops.attn_fwd(q, k, v, B, N, H, hd, scale, sample_ids=sid)
+    do = torch.randn(B * N, D, generator=torch.Generator().manual_seed(1)).to(bf16).to(dev())
+    dqk = torch.zeros(B * N, 2 * D, device=dev(), dtype=bf16)
+    dqkv = torch.zeros(B * N, 3 * D, device=dev(), dtype=bf16)
+    ops.attn_bwd(q, k, v, o, do, lse, dqk[:, :D], dqk[:, D:], dqkv[:, 2 * D:], B, N, H, hd, scale, sample_ids=sid)
+    torch.cuda.synchronize()
+    q32, k32, v32 = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    o_ref, _ = _ref(q32, k32, v32, B, N, H, hd, sample_ids=sid)
+    (o_ref * do.float()).sum().backward()
+    for got, ref, nm in ((dqk[:, :D], q32.grad, "dq"), (dqk[:, D:], k32.grad, "dk"), (dqkv[:, 2 * D:], v32.grad, "dv")):
+        assert torch.allclose(got.float(), ref, rtol=3e-2, atol=2e-2), (nm, (got.float() - ref).abs().max())

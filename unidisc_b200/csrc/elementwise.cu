@@ -1,0 +1,597 @@
+// HBM-bound row kernels of the DiT block (sm_100a): embedding, fused RMSNorm/residual, q/k LayerNorm + RoPE,
+// bias-gradient column sums, AdamW, casts, DDP gradient (de)compression.
+//
+// Row kernels use one CTA per token row with blockDim = D/4 threads: every thread owns 4 consecutive hidden columns
+// (one 16-byte fp32 / 8-byte bf16 access), row statistics are block reductions (warp shuffles + one smem exchange),
+// and per-column weight gradients are kept in registers across the rows a CTA visits and flushed with one atomicAdd
+// per column per CTA.  Grid-stride over rows with gridDim a multiple of the SM count.
+#include "common.cuh"
+#include "unidisc_b200.h"
+
+namespace ud {
+
+// ------------------------------------------------------------------------------------------------
+// block reduction of NV running sums (blockDim.x <= 1024).  `scratch` holds 2*32*NV floats; `buf` alternates.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+UD_DEVINL void block_sum(float (&v)[NV], float* scratch, int& buf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    float* s = scratch + buf * 32 * NV;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s[warp * NV + i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float t = 0.f;
+        for (int w = 0; w < nwarps; ++w) t += s[w * NV + i];
+        v[i] = t;
+    }
+    buf ^= 1;
+}
+
+struct F4 { float v[4]; };
+UD_DEVINL F4 ld_f4(const float* p) { float4 t = *reinterpret_cast<const float4*>(p); return {{t.x, t.y, t.z, t.w}}; }
+UD_DEVINL void st_f4(float* p, const F4& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+UD_DEVINL F4 ld_bf4(const __nv_bfloat16* p) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    return {{bf16lo(t.x), bf16hi(t.x), bf16lo(t.y), bf16hi(t.y)}};
+}
+UD_DEVINL void st_bf4(__nv_bfloat16* p, const F4& a) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(a.v[0], a.v[1]), pack_bf16x2(a.v[2], a.v[3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding + modality embedding + RMSNorm   (reference dit.py:1375,1406,95-100)
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_rmsnorm_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ modality,
+                                         const float* __restrict__ E, const float* __restrict__ Emod,
+                                         const float* __restrict__ w, float* __restrict__ x, __nv_bfloat16* __restrict__ h,
+                                         float* __restrict__ rstd, int rows, int D, float eps) {
+    __shared__ float scratch[2 * 32 * 1];
+    int buf = 0;
+    const int c = threadIdx.x * 4;
+    const F4 wv = ld_f4(w + c);
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long id = ids[row];
+        const int md = modality[row] == 0 ? 0 : 1;
+        F4 e = ld_f4(E + id * D + c), m = ld_f4(Emod + (long long)md * D + c), xv;
+        float ss[1] = {0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { xv.v[i] = e.v[i] + m.v[i]; ss[0] += xv.v[i] * xv.v[i]; }
+        block_sum<1>(ss, scratch, buf);
+        const float r = rsqrtf(ss[0] / (float)D + eps);
+        F4 hv;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hv.v[i] = (xv.v[i] * r) * wv.v[i];
+        st_f4(x + (long long)row * D + c, xv);
+        st_bf4(h + (long long)row * D + c, hv);
+        if (threadIdx.x == 0) rstd[row] = r;
+    }
+}
+
+// dE[ids] += g, dEmod[modality] += g.  Modality rows (2 of them) and the `hot_id` row (the mask token, hit by every
+// masked position) are accumulated in registers per CTA instead of per-row atomics.
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ modality,
+                                 const float* __restrict__ g, float* __restrict__ dE, float* __restrict__ dEmod, int rows,
+                                 int D, long long hot_id) {
+    const int c = threadIdx.x * 4;
+    F4 am0 = {{0, 0, 0, 0}}, am1 = {{0, 0, 0, 0}}, ahot = {{0, 0, 0, 0}};
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long id = ids[row];
+        const bool m1 = modality[row] != 0;
+        F4 gv = ld_f4(g + (long long)row * D + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (m1) am1.v[i] += gv.v[i]; else am0.v[i] += gv.v[i];
+        }
+        if (id == hot_id) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ahot.v[i] += gv.v[i];
+        } else {
+            float* d = dE + id * D + c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) atomicAdd(d + i, gv.v[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        atomicAdd(dEmod + c + i, am0.v[i]);
+        atomicAdd(dEmod + D + c + i, am1.v[i]);
+        if (hot_id >= 0) atomicAdd(dE + hot_id * D + c + i, ahot.v[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x_out = x_in + bf16(rms(a)) * w_a ;  h = bf16(rms(x_out) * w_n)       (dit.py:993-994, 1024-1031, 971/1025/1089)
+// ------------------------------------------------------------------------------------------------
+__global__ void norm_residual_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ x_in,
+                                         const float* __restrict__ w_a, const float* __restrict__ w_n,
+                                         float* __restrict__ x_out, __nv_bfloat16* __restrict__ h,
+                                         float* __restrict__ rstd_a, float* __restrict__ rstd_x, int rows, int D, float eps) {
+    __shared__ float scratch[2 * 32 * 1];
+    int buf = 0;
+    const int c = threadIdx.x * 4;
+    const F4 wa = ld_f4(w_a + c), wn = ld_f4(w_n + c);
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long off = (long long)row * D + c;
+        F4 av = ld_bf4(a + off), xi = ld_f4(x_in + off);
+        float s[1] = {0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[0] += av.v[i] * av.v[i];
+        block_sum<1>(s, scratch, buf);
+        const float ra = rsqrtf(s[0] / (float)D + eps);
+        F4 xo;
+        s[0] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xo.v[i] = xi.v[i] + bf16_round(av.v[i] * ra) * wa.v[i];
+            s[0] += xo.v[i] * xo.v[i];
+        }
+        block_sum<1>(s, scratch, buf);
+        const float rx = rsqrtf(s[0] / (float)D + eps);
+        F4 hv;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hv.v[i] = (xo.v[i] * rx) * wn.v[i];
+        st_f4(x_out + off, xo);
+        st_bf4(h + off, hv);
+        if (threadIdx.x == 0) { rstd_a[row] = ra; rstd_x[row] = rx; }
+    }
+}
+
+// backward of the fused kernel (see header).  HAS_BRANCH=false degenerates to a plain RMSNorm backward.
+template <bool HAS_BRANCH>
+__global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const __nv_bfloat16* __restrict__ dh,
+                                         const float* __restrict__ x_out, const float* __restrict__ rstd_x,
+                                         const float* __restrict__ w_n, const __nv_bfloat16* __restrict__ a,
+                                         const float* __restrict__ rstd_a, const float* __restrict__ w_a,
+                                         float* __restrict__ g_in, __nv_bfloat16* __restrict__ da, float* __restrict__ dw_n,
+                                         float* __restrict__ dw_a, int rows, int D) {
+    __shared__ float scratch[2 * 32 * 3];
+    int buf = 0;
+    const int c = threadIdx.x * 4;
+    const F4 wn = ld_f4(w_n + c);
+    F4 wa = {{0, 0, 0, 0}};
+    if (HAS_BRANCH) wa = ld_f4(w_a + c);
+    F4 acc_n = {{0, 0, 0, 0}}, acc_a = {{0, 0, 0, 0}};
+    const float invD = 1.0f / (float)D;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long off = (long long)row * D + c;
+        const float rx = rstd_x[row];
+        F4 dhv = ld_bf4(dh + off), xo = ld_f4(x_out + off);
+        F4 go = {{0, 0, 0, 0}};
+        if (g_out != nullptr) go = ld_f4(g_out + off);
+        F4 av = {{0, 0, 0, 0}};
+        float ra = 0.f;
+        if (HAS_BRANCH) { av = ld_bf4(a + off); ra = rstd_a[row]; }
+        F4 y, base, naf;
+        float s[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            y.v[i] = xo.v[i] * rx;
+            const float dy = dhv.v[i] * wn.v[i];
+            s[0] += dy * y.v[i];
+            base.v[i] = go.v[i] + rx * dy;
+            acc_n.v[i] += dhv.v[i] * y.v[i];
+            if (HAS_BRANCH) {
+                naf.v[i] = av.v[i] * ra;
+                s[1] += base.v[i] * wa.v[i] * naf.v[i];
+                s[2] += y.v[i] * wa.v[i] * naf.v[i];
+            }
+        }
+        block_sum<3>(s, scratch, buf);
+        const float m1 = s[0] * invD;
+        F4 g;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g.v[i] = base.v[i] - rx * y.v[i] * m1;
+        st_f4(g_in + off, g);
+        if (HAS_BRANCH) {
+            const float m2 = (s[1] - rx * m1 * s[2]) * invD;
+            F4 dav;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc_a.v[i] += g.v[i] * bf16_round(naf.v[i]);
+                dav.v[i] = ra * (g.v[i] * wa.v[i] - naf.v[i] * m2);
+            }
+            st_bf4(da + off, dav);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        atomicAdd(dw_n + c + i, acc_n.v[i]);
+        if (HAS_BRANCH) atomicAdd(dw_a + c + i, acc_a.v[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// q/k LayerNorm over the full hidden dim + RoPE   (dit.py:680-682, 724-726; standalone_rotary.py:14-31)
+// ------------------------------------------------------------------------------------------------
+__global__ void qk_ln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ gq,
+                                      const float* __restrict__ bq, const float* __restrict__ gk, const float* __restrict__ bk,
+                                      const float* __restrict__ cosT, const float* __restrict__ sinT,
+                                      __nv_bfloat16* __restrict__ out, float* __restrict__ stats, int rows, int D, int hd,
+                                      float eps) {
+    __shared__ float scratch[2 * 32 * 2];
+    int buf = 0;
+    const int c = threadIdx.x * 4;
+    const int half = hd >> 1;
+    const int j = c % hd;               // position inside the head
+    const bool lo = j < half;
+    const int ti = j % half;            // table index of this thread's first column
+    const int pmask = hd >> 3;          // partner thread = tid ^ (hd/8)  (same warp for hd <= 128)
+    const F4 gqv = ld_f4(gq + c), bqv = ld_f4(bq + c), gkv = ld_f4(gk + c), bkv = ld_f4(bk + c);
+    const float invD = 1.0f / (float)D;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const __nv_bfloat16* src = qkv + (long long)row * 3 * D;
+        F4 q = ld_bf4(src + c), k = ld_bf4(src + D + c);
+        float s[2] = {q.v[0] + q.v[1] + q.v[2] + q.v[3], k.v[0] + k.v[1] + k.v[2] + k.v[3]};
+        block_sum<2>(s, scratch, buf);
+        const float mq = s[0] * invD, mk = s[1] * invD;
+        s[0] = s[1] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            q.v[i] -= mq; k.v[i] -= mk;
+            s[0] += q.v[i] * q.v[i]; s[1] += k.v[i] * k.v[i];
+        }
+        block_sum<2>(s, scratch, buf);
+        const float rq = rsqrtf(s[0] * invD + eps), rk = rsqrtf(s[1] * invD + eps);
+        const F4 cs = ld_f4(cosT + (long long)row * half + ti), sn = ld_f4(sinT + (long long)row * half + ti);
+        F4 oq, ok;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float yq = bf16_round((q.v[i] * rq) * gqv.v[i] + bqv.v[i]);  // LayerNorm output, stored bf16 (dit.py:681)
+            const float yk = bf16_round((k.v[i] * rk) * gkv.v[i] + bkv.v[i]);
+            const float pq = __shfl_xor_sync(0xffffffffu, yq, pmask);
+            const float pk = __shfl_xor_sync(0xffffffffu, yk, pmask);
+            oq.v[i] = yq * cs.v[i] + (lo ? -pq : pq) * sn.v[i];
+            ok.v[i] = yk * cs.v[i] + (lo ? -pk : pk) * sn.v[i];
+        }
+        __nv_bfloat16* dst = out + (long long)row * 2 * D;
+        st_bf4(dst + c, oq);
+        st_bf4(dst + D + c, ok);
+        if (threadIdx.x == 0) {
+            float4 st = make_float4(mq, rq, mk, rk);
+            *reinterpret_cast<float4*>(stats + (long long)row * 4) = st;
+        }
+    }
+}
+
+__global__ void qk_ln_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dqk, const __nv_bfloat16* __restrict__ qkv,
+                                      const float* __restrict__ stats, const float* __restrict__ gq,
+                                      const float* __restrict__ gk, const float* __restrict__ cosT,
+                                      const float* __restrict__ sinT, __nv_bfloat16* __restrict__ dqkv,
+                                      float* __restrict__ dgq, float* __restrict__ dbq, float* __restrict__ dgk,
+                                      float* __restrict__ dbk, int rows, int D, int hd) {
+    __shared__ float scratch[2 * 32 * 4];
+    int buf = 0;
+    const int c = threadIdx.x * 4;
+    const int half = hd >> 1;
+    const int j = c % hd;
+    const bool lo = j < half;
+    const int ti = j % half;
+    const int pmask = hd >> 3;
+    const F4 gqv = ld_f4(gq + c), gkv = ld_f4(gk + c);
+    F4 a_gq = {{0, 0, 0, 0}}, a_bq = {{0, 0, 0, 0}}, a_gk = {{0, 0, 0, 0}}, a_bk = {{0, 0, 0, 0}};
+    const float invD = 1.0f / (float)D;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const float4 st = *reinterpret_cast<const float4*>(stats + (long long)row * 4);
+        const __nv_bfloat16* src = qkv + (long long)row * 3 * D;
+        const __nv_bfloat16* gsrc = dqk + (long long)row * 2 * D;
+        F4 q = ld_bf4(src + c), k = ld_bf4(src + D + c);
+        F4 dq = ld_bf4(gsrc + c), dk = ld_bf4(gsrc + D + c);
+        const F4 cs = ld_f4(cosT + (long long)row * half + ti), sn = ld_f4(sinT + (long long)row * half + ti);
+        F4 xq, xk, eq, ek;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // inverse rotation of the incoming gradients
+            const float pq = __shfl_xor_sync(0xffffffffu, dq.v[i], pmask);
+            const float pk = __shfl_xor_sync(0xffffffffu, dk.v[i], pmask);
+            const float dyq = dq.v[i] * cs.v[i] + (lo ? pq : -pq) * sn.v[i];
+            const float dyk = dk.v[i] * cs.v[i] + (lo ? pk : -pk) * sn.v[i];
+            xq.v[i] = (q.v[i] - st.x) * st.y;
+            xk.v[i] = (k.v[i] - st.z) * st.w;
+            a_gq.v[i] += dyq * xq.v[i]; a_bq.v[i] += dyq;
+            a_gk.v[i] += dyk * xk.v[i]; a_bk.v[i] += dyk;
+            eq.v[i] = dyq * gqv.v[i];
+            ek.v[i] = dyk * gkv.v[i];
+            s[0] += eq.v[i]; s[1] += eq.v[i] * xq.v[i];
+            s[2] += ek.v[i]; s[3] += ek.v[i] * xk.v[i];
+        }
+        block_sum<4>(s, scratch, buf);
+        F4 oq, ok;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            oq.v[i] = st.y * (eq.v[i] - s[0] * invD - xq.v[i] * s[1] * invD);
+            ok.v[i] = st.w * (ek.v[i] - s[2] * invD - xk.v[i] * s[3] * invD);
+        }
+        __nv_bfloat16* dst = dqkv + (long long)row * 3 * D;
+        st_bf4(dst + c, oq);
+        st_bf4(dst + D + c, ok);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        atomicAdd(dgq + c + i, a_gq.v[i]); atomicAdd(dbq + c + i, a_bq.v[i]);
+        atomicAdd(dgk + c + i, a_gk.v[i]); atomicAdd(dbk + c + i, a_bk.v[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bias gradient: db[n] += sum_m dY[m,n]
+// ------------------------------------------------------------------------------------------------
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dY, long long ld, float* __restrict__ db, int M, int N,
+                                   int rows_per_cta) {
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (n >= N) return;
+    const int r0 = blockIdx.y * rows_per_cta;
+    const int r1 = min(M, r0 + rows_per_cta);
+    float a0 = 0.f, a1 = 0.f;
+    if (n + 1 < N) {
+        for (int r = r0; r < r1; ++r) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(dY + (long long)r * ld + n);
+            a0 += bf16lo(v); a1 += bf16hi(v);
+        }
+        atomicAdd(db + n, a0);
+        atomicAdd(db + n + 1, a1);
+    } else {
+        for (int r = r0; r < r1; ++r) a0 += __bfloat162float(dY[(long long)r * ld + n]);
+        atomicAdd(db + n, a0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat-buffer kernels: AdamW (+bf16 shadow), cast, sum of squares, DDP bf16 (de)compression
+// ------------------------------------------------------------------------------------------------
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             __nv_bfloat16* __restrict__ pb, long long n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2_sqrt, const float* __restrict__ grad_scale) {
+    const float gs = grad_scale ? *grad_scale : 1.0f;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            float4 pv = *reinterpret_cast<float4*>(p + i), gv = *reinterpret_cast<const float4*>(g + i);
+            float4 mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+            float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gg = gp[k] * gs;
+                pp[k] *= (1.0f - lr * wd);
+                mp[k] = b1 * mp[k] + (1.0f - b1) * gg;
+                vp[k] = b2 * vp[k] + (1.0f - b2) * gg * gg;
+                const float denom = sqrtf(vp[k]) / bc2_sqrt + eps;
+                pp[k] -= (lr / bc1) * (mp[k] / denom);
+            }
+            *reinterpret_cast<float4*>(p + i) = pv;
+            *reinterpret_cast<float4*>(m + i) = mv;
+            *reinterpret_cast<float4*>(v + i) = vv;
+            if (pb) *reinterpret_cast<uint2*>(pb + i) = make_uint2(pack_bf16x2(pv.x, pv.y), pack_bf16x2(pv.z, pv.w));
+        } else {
+            for (long long k = i; k < n; ++k) {
+                const float gg = g[k] * gs;
+                float pv = p[k] * (1.0f - lr * wd);
+                const float mm = b1 * m[k] + (1.0f - b1) * gg;
+                const float vv = b2 * v[k] + (1.0f - b2) * gg * gg;
+                pv -= (lr / bc1) * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+                p[k] = pv; m[k] = mm; v[k] = vv;
+                if (pb) pb[k] = __float2bfloat16_rn(pv);
+            }
+        }
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            float4 v = *reinterpret_cast<const float4*>(s + i);
+            *reinterpret_cast<uint2*>(d + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        } else {
+            for (long long k = i; k < n; ++k) d[k] = __float2bfloat16_rn(s[k]);
+        }
+    }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+    __shared__ float scratch[2 * 32];
+    int buf = 0;
+    float a[1] = {0.f};
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            float4 v = *reinterpret_cast<const float4*>(g + i);
+            a[0] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        } else {
+            for (long long k = i; k < n; ++k) a[0] += g[k] * g[k];
+        }
+    }
+    block_sum<1>(a, scratch, buf);
+    if (threadIdx.x == 0) atomicAdd(out, a[0]);
+}
+
+__global__ void grad_pack_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ d, long long n, float inv_world) {
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            float4 v = *reinterpret_cast<const float4*>(g + i);
+            // torch's bf16 compress hook: round to bf16 first, then divide in bf16
+            *reinterpret_cast<uint2*>(d + i) =
+                make_uint2(pack_bf16x2(bf16_round(v.x) * inv_world, bf16_round(v.y) * inv_world),
+                           pack_bf16x2(bf16_round(v.z) * inv_world, bf16_round(v.w) * inv_world));
+        } else {
+            for (long long k = i; k < n; ++k) d[k] = __float2bfloat16_rn(bf16_round(g[k]) * inv_world);
+        }
+    }
+}
+
+__global__ void grad_unpack_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ g, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            uint2 v = *reinterpret_cast<const uint2*>(s + i);
+            *reinterpret_cast<float4*>(g + i) = make_float4(bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y));
+        } else {
+            for (long long k = i; k < n; ++k) g[k] = __bfloat162float(s[k]);
+        }
+    }
+}
+
+static int row_grid(int rows, int threads) {
+    int per_sm = 2048 / threads;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    long long g = (long long)sm_count() * per_sm;
+    return (int)(rows < g ? rows : g);
+}
+static int flat_grid(long long n) {
+    long long b = (n / 4 + 255) / 256;
+    long long cap = (long long)sm_count() * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+static bool check_D(int D, const char* what) {
+    if (D % 128 != 0 || D < 128 || D > 4096) {
+        fprintf(stderr, "unidisc_b200: %s needs hidden size D %% 128 == 0 and 128 <= D <= 4096 (got %d)\n", what, D);
+        return false;
+    }
+    return true;
+}
+
+}  // namespace ud
+
+using namespace ud;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int ud_abi_version(void) { return 1; }
+extern "C" int ud_device_sm_count(void) { return sm_count(); }
+
+extern "C" int ud_embed_rmsnorm_fwd(const int64_t* ids, const int64_t* modality, const float* E, const float* Emod,
+                                    const float* w, float* x, void* h, float* rstd, int rows, int D, float eps, void* stream) {
+    if (rows <= 0) return 0;
+    if (!check_D(D, "embed_rmsnorm_fwd")) return -1;
+    embed_rmsnorm_fwd_kernel<<<row_grid(rows, D / 4), D / 4, 0, STREAM(stream)>>>(ids, modality, E, Emod, w, x, BF(h), rstd, rows, D, eps);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_embed_bwd(const int64_t* ids, const int64_t* modality, const float* g, float* dE, float* dEmod, int rows,
+                            int D, long long hot_id, void* stream) {
+    if (rows <= 0) return 0;
+    if (!check_D(D, "embed_bwd")) return -1;
+    int grid = row_grid(rows, D / 4);
+    if (grid > 2 * sm_count()) grid = 2 * sm_count();
+    embed_bwd_kernel<<<grid, D / 4, 0, STREAM(stream)>>>(ids, modality, g, dE, dEmod, rows, D, hot_id);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_norm_residual_fwd(const void* a, const float* x_in, const float* w_a, const float* w_n, float* x_out, void* h,
+                                    float* rstd_a, float* rstd_x, int rows, int D, float eps, void* stream) {
+    if (rows <= 0) return 0;
+    if (!check_D(D, "norm_residual_fwd")) return -1;
+    norm_residual_fwd_kernel<<<row_grid(rows, D / 4), D / 4, 0, STREAM(stream)>>>(CBF(a), x_in, w_a, w_n, x_out, BF(h), rstd_a, rstd_x, rows, D, eps);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_norm_residual_bwd(const float* g_out, const void* dh, const float* x_out, const float* rstd_x,
+                                    const float* w_n, const void* a, const float* rstd_a, const float* w_a, float* g_in,
+                                    void* da, float* dw_n, float* dw_a, int rows, int D, void* stream) {
+    if (rows <= 0) return 0;
+    if (!check_D(D, "norm_residual_bwd")) return -1;
+    int grid = row_grid(rows, D / 4);
+    if (grid > 4 * sm_count()) grid = 4 * sm_count();
+    norm_residual_bwd_kernel<true><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, rows, D);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_rmsnorm_bwd(const float* g_out, const void* dh, const float* x, const float* rstd, const float* w,
+                              float* g_in, float* dw, int rows, int D, void* stream) {
+    if (rows <= 0) return 0;
+    if (!check_D(D, "rmsnorm_bwd")) return -1;
+    int grid = row_grid(rows, D / 4);
+    if (grid > 4 * sm_count()) grid = 4 * sm_count();
+    norm_residual_bwd_kernel<false><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x, rstd, w, nullptr, nullptr, nullptr, g_in, nullptr, dw, nullptr, rows, D);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_qk_ln_rope_fwd(const void* qkv, const float* gq, const float* bq, const float* gk, const float* bk,
+                                 const float* cos, const float* sin, void* qk_out, float* stats, int rows, int D, int head_dim,
+                                 float eps, void* stream) {
+    if (rows <= 0) return 0;
+    if (!check_D(D, "qk_ln_rope_fwd")) return -1;
+    if (head_dim != 32 && head_dim != 64 && head_dim != 128) {
+        fprintf(stderr, "unidisc_b200: qk_ln_rope supports head_dim 32/64/128 (got %d)\n", head_dim);
+        return -1;
+    }
+    qk_ln_rope_fwd_kernel<<<row_grid(rows, D / 4), D / 4, 0, STREAM(stream)>>>(CBF(qkv), gq, bq, gk, bk, cos, sin, BF(qk_out), stats, rows, D, head_dim, eps);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_qk_ln_rope_bwd(const void* dqk, const void* qkv, const float* stats, const float* gq, const float* gk,
+                                 const float* cos, const float* sin, void* dqkv, float* dgq, float* dbq, float* dgk, float* dbk,
+                                 int rows, int D, int head_dim, void* stream) {
+    if (rows <= 0) return 0;
+    if (!check_D(D, "qk_ln_rope_bwd")) return -1;
+    if (head_dim != 32 && head_dim != 64 && head_dim != 128) return -1;
+    int grid = row_grid(rows, D / 4);
+    if (grid > 4 * sm_count()) grid = 4 * sm_count();
+    qk_ln_rope_bwd_kernel<<<grid, D / 4, 0, STREAM(stream)>>>(CBF(dqk), CBF(qkv), stats, gq, gk, cos, sin, BF(dqkv), dgq, dbq, dgk, dbk, rows, D, head_dim);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_colsum_bf16(const void* dY, long long ld, float* db, int M, int N, void* stream) {
+    if (M <= 0 || N <= 0) return 0;
+    const int rows_per_cta = 128;
+    dim3 grid((N / 2 + 1 + 255) / 256, (M + rows_per_cta - 1) / rows_per_cta);
+    colsum_bf16_kernel<<<grid, 256, 0, STREAM(stream)>>>(CBF(dY), ld, db, M, N, rows_per_cta);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream) {
+    if (n <= 0) return 0;
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    adamw_kernel<<<flat_grid(n), 256, 0, STREAM(stream)>>>(p, g, m, v, BF(p_bf16), n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+    if (n <= 0) return 0;
+    cast_f32_bf16_kernel<<<flat_grid(n), 256, 0, STREAM(stream)>>>(src, BF(dst), n);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_sumsq_f32(const float* g, long long n, float* out, void* stream) {
+    if (n <= 0) return 0;
+    sumsq_kernel<<<flat_grid(n), 256, 0, STREAM(stream)>>>(g, n, out);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_grad_pack_bf16(const float* g, void* dst, long long n, float inv_world, void* stream) {
+    if (n <= 0) return 0;
+    grad_pack_kernel<<<flat_grid(n), 256, 0, STREAM(stream)>>>(g, BF(dst), n, inv_world);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_grad_unpack_bf16(const void* src, float* g, long long n, void* stream) {
+    if (n <= 0) return 0;
+    grad_unpack_kernel<<<flat_grid(n), 256, 0, STREAM(stream)>>>(CBF(src), g, n);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,405 @@
+// HBM-bound vocabulary-row kernels (sm_100a): SUBS parameterisation + NLL (forward/backward), absorbing-state masking
+// q_xt, Gumbel-arg-max categorical sampler and the fused absorbing (ddpm / ddpm_cache) update.
+//
+// One CTA per token row, 16-byte coalesced loads over the row's VALID vocabulary range only (text rows never touch the
+// image vocabulary and vice versa: the reference adds -1e6 there, model.py:627-635, which contributes exactly 0 to the
+// fp32 log-sum-exp), warp-shuffle + smem block reductions, one pass over HBM per row.
+#include "common.cuh"
+#include "unidisc_b200.h"
+
+namespace ud {
+
+static constexpr float NEG_INF_SUBS = -1000000.0f;  // self.neg_infinity (model.py:626)
+static constexpr int ROW_THREADS = 256;
+
+struct MaxSum { float m, s; };
+UD_DEVINL void ms_add(MaxSum& a, float x) {
+    if (x > a.m) { a.s = a.s * __expf(a.m - x) + 1.0f; a.m = x; }
+    else a.s += __expf(x - a.m);
+}
+UD_DEVINL MaxSum ms_merge(MaxSum a, MaxSum b) {
+    if (b.m > a.m) { MaxSum t = a; a = b; b = t; }
+    if (b.m == -INFINITY) return a;
+    a.s += b.s * __expf(b.m - a.m);
+    return a;
+}
+UD_DEVINL MaxSum block_ms(MaxSum v, float* sm /*[2*32]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MaxSum t;
+        t.m = __shfl_xor_sync(0xffffffffu, v.m, o);
+        t.s = __shfl_xor_sync(0xffffffffu, v.s, o);
+        v = ms_merge(v, t);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();  // protect sm from the previous use
+    if (lane == 0) { sm[warp] = v.m; sm[32 + warp] = v.s; }
+    __syncthreads();
+    MaxSum r = {sm[0], sm[32]};
+    for (int w = 1; w < nw; ++w) r = ms_merge(r, MaxSum{sm[w], sm[32 + w]});
+    return r;
+}
+
+// valid vocabulary range of a row (model.py:627-635)
+UD_DEVINL void valid_range(long long modality, int V, int text_vocab, int& lo, int& hi) {
+    if (text_vocab <= 0) { lo = 0; hi = V; }
+    else if (modality == 0) { lo = 0; hi = text_vocab; }
+    else { lo = text_vocab; hi = V; }
+}
+
+// log-sum-exp of a bf16 row over [lo,hi) excluding column `skip`
+UD_DEVINL MaxSum row_lse_bf16(const __nv_bfloat16* row, int lo, int hi, int skip) {
+    MaxSum acc = {-INFINITY, 0.f};
+    const int lo_al = min(hi, (lo + 7) & ~7), hi_al = max(lo_al, hi & ~7);
+    for (int v = lo + threadIdx.x; v < lo_al; v += blockDim.x)
+        if (v != skip) ms_add(acc, __bfloat162float(row[v]));
+    for (int v = lo_al + threadIdx.x * 8; v < hi_al; v += blockDim.x * 8) {
+        const uint4 t = ldg_stream(row + v);
+        const float f[8] = {bf16lo(t.x), bf16hi(t.x), bf16lo(t.y), bf16hi(t.y), bf16lo(t.z), bf16hi(t.z), bf16lo(t.w), bf16hi(t.w)};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (v + i != skip) ms_add(acc, f[i]);
+    }
+    for (int v = hi_al + threadIdx.x; v < hi; v += blockDim.x)
+        if (v != skip) ms_add(acc, __bfloat162float(row[v]));
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SUBS NLL forward: logp[r] = log p_theta(x0[r] | xt)   (model.py:621-658 + gather at model.py:967)
+// ------------------------------------------------------------------------------------------------
+__global__ void subs_nll_fwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ldv, const int64_t* __restrict__ xt,
+                                    const int64_t* __restrict__ x0, const int64_t* __restrict__ modality,
+                                    float* __restrict__ logp, float* __restrict__ lse_out, int rows, int V, int text_vocab,
+                                    int mask_index) {
+    __shared__ float sm[64];
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const long long xtr = xt[r], x0r = x0[r];
+        if (xtr != mask_index) {  // carry-over: the row is one-hot at xt (model.py:646-656)
+            if (threadIdx.x == 0) { logp[r] = (x0r == xtr) ? 0.0f : NEG_INF_SUBS; lse_out[r] = 0.0f; }
+            continue;
+        }
+        int lo, hi;
+        valid_range(modality[r], V, text_vocab, lo, hi);
+        const __nv_bfloat16* row = logits + (long long)r * ldv;
+        const MaxSum t = block_ms(row_lse_bf16(row, lo, hi, mask_index), sm);
+        if (threadIdx.x == 0) {
+            const float lse = t.m + logf(t.s);
+            float l = __bfloat162float(row[x0r]);
+            if (x0r < lo || x0r >= hi || x0r == mask_index) l += NEG_INF_SUBS;
+            logp[r] = l - lse;
+            lse_out[r] = lse;
+        }
+    }
+}
+
+// dlogits = dlogp[r] * (onehot(x0) - softmax) on masked rows, 0 elsewhere; in place; every one of the ldv columns written
+__global__ void subs_nll_bwd_kernel(__nv_bfloat16* __restrict__ logits, long long ldv, const int64_t* __restrict__ xt,
+                                    const int64_t* __restrict__ x0, const int64_t* __restrict__ modality,
+                                    const float* __restrict__ lse_in, const float* __restrict__ dlogp, int rows, int V,
+                                    int text_vocab, int mask_index) {
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        __nv_bfloat16* row = logits + (long long)r * ldv;
+        const float g = dlogp[r];
+        const bool active = (xt[r] == mask_index) && (g != 0.0f);
+        int lo = 0, hi = 0;
+        if (active) valid_range(modality[r], V, text_vocab, lo, hi);
+        const float lse = lse_in[r];
+        const int x0r = (int)x0[r];
+        for (int v = threadIdx.x * 8; v < ldv; v += blockDim.x * 8) {
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (active && v + 8 > lo && v < hi) {
+                const uint4 t = *reinterpret_cast<const uint4*>(row + v);
+                const float f[8] = {bf16lo(t.x), bf16hi(t.x), bf16lo(t.y), bf16hi(t.y), bf16lo(t.z), bf16hi(t.z), bf16lo(t.w), bf16hi(t.w)};
+                float d[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = v + i;
+                    const bool valid = c >= lo && c < hi && c != mask_index;
+                    d[i] = valid ? -g * __expf(f[i] - lse) : 0.0f;
+                    if (c == x0r) d[i] += g;
+                }
+                o = make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+            } else if (active && x0r >= v && x0r < v + 8) {
+                float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                d[x0r - v] = g;
+                o = make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+            }
+            *reinterpret_cast<uint4*>(row + v) = o;
+        }
+    }
+}
+
+// full SUBS log-prob rows (API parity with _subs_parameterization)
+template <bool OUT_BF16>
+__global__ void subs_logprobs_kernel(const __nv_bfloat16* __restrict__ logits, long long ldv, const int64_t* __restrict__ xt,
+                                     const int64_t* __restrict__ modality, void* __restrict__ out, long long ldo, int rows,
+                                     int V, int text_vocab, int mask_index) {
+    __shared__ float sm[64];
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const __nv_bfloat16* row = logits + (long long)r * ldv;
+        const bool carry = xt != nullptr && xt[r] != mask_index;
+        const long long xtr = carry ? xt[r] : -1;
+        int lo, hi;
+        valid_range(modality[r], V, text_vocab, lo, hi);
+        float lse = 0.f;
+        if (!carry) {
+            const MaxSum t = block_ms(row_lse_bf16(row, lo, hi, mask_index), sm);
+            lse = t.m + logf(t.s);
+        }
+        for (int v = threadIdx.x; v < V; v += blockDim.x) {
+            float o;
+            if (carry) o = (v == xtr) ? 0.0f : NEG_INF_SUBS;
+            else {
+                float l = __bfloat162float(row[v]);
+                if (v < lo || v >= hi || v == mask_index) l += NEG_INF_SUBS;
+                o = l - lse;
+            }
+            if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[(long long)r * ldo + v] = __float2bfloat16_rn(o);
+            else reinterpret_cast<float*>(out)[(long long)r * ldo + v] = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based RNG for the non-parity "fast" sampling mode)
+// ------------------------------------------------------------------------------------------------
+UD_DEVINL uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+// uniform in [0,1) with 24 random bits for element index `idx`
+UD_DEVINL float philox_uniform(uint64_t seed, uint64_t offset, uint64_t idx) {
+    const uint64_t blk = idx >> 2;
+    uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+    return (float)(w >> 8) * (1.0f / 16777216.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// q_xt   (model.py:439,579)
+// ------------------------------------------------------------------------------------------------
+__global__ void q_xt_kernel(const int64_t* __restrict__ x, const float* __restrict__ move_chance, const float* __restrict__ rnd,
+                            uint64_t seed, uint64_t offset, int64_t mask_index, int64_t* __restrict__ xt,
+                            uint8_t* __restrict__ move, int B, int N) {
+    const long long total = (long long)B * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / N);
+        const float u = rnd ? rnd[i] : philox_uniform(seed, offset, (uint64_t)i);
+        const bool mv = u < move_chance[b];
+        xt[i] = mv ? mask_index : x[i];
+        if (move) move[i] = mv ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gumbel arg-max:  argmax_v  q_v / (1e-10 - log(u_v + 1e-10))     (model_utils.py:95-97)
+// ------------------------------------------------------------------------------------------------
+struct ArgMax { float v; int i; };
+UD_DEVINL void am_upd(ArgMax& a, float v, int i) {
+    if (v > a.v || (v == a.v && i < a.i)) { a.v = v; a.i = i; }
+}
+UD_DEVINL ArgMax block_argmax(ArgMax a, float* smv, int* smi) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, a.v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, a.i, o);
+        am_upd(a, ov, oi);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) { smv[warp] = a.v; smi[warp] = a.i; }
+    __syncthreads();
+    ArgMax r = {smv[0], smi[0]};
+    for (int w = 1; w < nw; ++w) am_upd(r, smv[w], smi[w]);
+    return r;
+}
+UD_DEVINL float gumbel_norm(float u) { return 1e-10f - logf(u + 1e-10f); }
+
+// MODE 0: plain categorical over probs.  MODE 1: absorbing update (q = p*(mc_t-mc_s), q[mask] = mc_s, copy-through).
+template <int MODE>
+__global__ void sample_probs_kernel(const int64_t* __restrict__ x, const float* __restrict__ probs, long long ldp,
+                                    const float* __restrict__ u, uint64_t seed, uint64_t offset, const float* __restrict__ mc_t,
+                                    const float* __restrict__ mc_s, int64_t mask_index, int64_t* __restrict__ out, int R, int N,
+                                    int V) {
+    __shared__ float smv[32];
+    __shared__ int smi[32];
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        float d = 1.0f, ms = 0.0f;
+        if (MODE == 1) {
+            const long long xr = x[r];
+            if (xr != mask_index) {  // copy_flag (model_eval.py:2064,2093)
+                if (threadIdx.x == 0) out[r] = xr;
+                continue;
+            }
+            const int b = r / N;
+            d = mc_t[b] - mc_s[b];
+            ms = mc_s[b];
+        }
+        const float* pr = probs + (long long)r * ldp;
+        const float* ur = u ? u + (long long)r * V : nullptr;
+        ArgMax a = {-INFINITY, 0x7fffffff};
+        for (int v = threadIdx.x; v < V; v += blockDim.x) {
+            float q = pr[v];
+            if (MODE == 1) q = (v == mask_index) ? ms : q * d;
+            const float uu = ur ? ur[v] : philox_uniform(seed, offset, (uint64_t)r * V + v);
+            am_upd(a, __fdiv_rn(q, gumbel_norm(uu)), v);
+        }
+        a = block_argmax(a, smv, smi);
+        if (threadIdx.x == 0) out[r] = a.i;
+    }
+}
+
+// Fused fast path: bf16 logits (+ optional CFG pair) -> SUBS softmax -> absorbing update.  The row's valid range is
+// staged once in shared memory as fp32 (HBM is read exactly once), then reduced for the lse and scanned for the arg-max.
+template <bool CFG>
+__global__ void ddpm_update_logits_kernel(const int64_t* __restrict__ x, const __nv_bfloat16* __restrict__ lc,
+                                          const __nv_bfloat16* __restrict__ lu, long long ldv, const float* __restrict__ cfg_w,
+                                          const int64_t* __restrict__ modality, const float* __restrict__ u, uint64_t seed,
+                                          uint64_t offset, const float* __restrict__ mc_t, const float* __restrict__ mc_s,
+                                          int64_t mask_index, int text_vocab, int64_t* __restrict__ out, int R, int N, int V) {
+    extern __shared__ float srow[];
+    __shared__ float sm[64];
+    __shared__ float smv[32];
+    __shared__ int smi[32];
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        const long long xr = x[r];
+        if (xr != mask_index) {
+            if (threadIdx.x == 0) out[r] = xr;
+            continue;
+        }
+        const int b = r / N;
+        int lo, hi;
+        valid_range(modality[r], V, text_vocab, lo, hi);
+        const __nv_bfloat16* rc = lc + (long long)r * ldv;
+        const __nv_bfloat16* ru = CFG ? lu + (long long)r * ldv : nullptr;
+        const float w = CFG ? cfg_w[b] : 0.f;
+        MaxSum acc = {-INFINITY, 0.f};
+        __syncthreads();  // srow reuse across rows
+        for (int v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+            float l = __bfloat162float(rc[v]);
+            if (CFG) l = (1.0f + w) * l - w * __bfloat162float(ru[v]);   // model_eval.py:1812
+            srow[v - lo] = l;
+            if (v != mask_index) ms_add(acc, l);
+        }
+        const MaxSum t = block_ms(acc, sm);
+        const float lse = t.m + logf(t.s);
+        const float d = mc_t[b] - mc_s[b], ms = mc_s[b];
+        const float* ur = u ? u + (long long)r * V : nullptr;
+        ArgMax a = {-INFINITY, 0x7fffffff};
+        for (int v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+            if (v == mask_index) continue;
+            const float uu = ur ? ur[v] : philox_uniform(seed, offset, (uint64_t)r * V + v);
+            am_upd(a, __fdiv_rn(expf(srow[v - lo] - lse) * d, gumbel_norm(uu)), v);
+        }
+        if (threadIdx.x == 0) {  // the mask column keeps probability mc_s (model_eval.py:2066,2092)
+            const float uu = ur ? ur[mask_index] : philox_uniform(seed, offset, (uint64_t)r * V + mask_index);
+            am_upd(a, __fdiv_rn(ms, gumbel_norm(uu)), (int)mask_index);
+        }
+        a = block_argmax(a, smv, smi);
+        if (threadIdx.x == 0) out[r] = a.i;
+    }
+}
+
+static int rows_grid(int rows) {
+    long long g = (long long)sm_count() * 8;
+    return (int)(rows < g ? rows : g);
+}
+
+}  // namespace ud
+
+using namespace ud;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+extern "C" int ud_subs_nll_fwd(const void* logits, long long ldv, const int64_t* xt, const int64_t* x0, const int64_t* modality,
+                               float* logp, float* lse, int rows, int V, int text_vocab, int mask_index, void* stream) {
+    if (rows <= 0) return 0;
+    if (ldv % 8 != 0) { fprintf(stderr, "unidisc_b200: subs_nll needs ldv %% 8 == 0\n"); return -1; }
+    subs_nll_fwd_kernel<<<rows_grid(rows), ROW_THREADS, 0, STREAM(stream)>>>(CBF(logits), ldv, xt, x0, modality, logp, lse, rows, V, text_vocab, mask_index);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_subs_nll_bwd(void* logits, long long ldv, const int64_t* xt, const int64_t* x0, const int64_t* modality,
+                               const float* lse, const float* dlogp, int rows, int V, int text_vocab, int mask_index,
+                               void* stream) {
+    if (rows <= 0) return 0;
+    if (ldv % 8 != 0) { fprintf(stderr, "unidisc_b200: subs_nll needs ldv %% 8 == 0\n"); return -1; }
+    subs_nll_bwd_kernel<<<rows_grid(rows), ROW_THREADS, 0, STREAM(stream)>>>(BF(logits), ldv, xt, x0, modality, lse, dlogp, rows, V, text_vocab, mask_index);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_subs_logprobs(const void* logits, long long ldv, const int64_t* xt, const int64_t* modality, void* out,
+                                int out_is_bf16, long long ldo, int rows, int V, int text_vocab, int mask_index, void* stream) {
+    if (rows <= 0) return 0;
+    if (ldv % 8 != 0) return -1;
+    if (out_is_bf16)
+        subs_logprobs_kernel<true><<<rows_grid(rows), ROW_THREADS, 0, STREAM(stream)>>>(CBF(logits), ldv, xt, modality, out, ldo, rows, V, text_vocab, mask_index);
+    else
+        subs_logprobs_kernel<false><<<rows_grid(rows), ROW_THREADS, 0, STREAM(stream)>>>(CBF(logits), ldv, xt, modality, out, ldo, rows, V, text_vocab, mask_index);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_q_xt(const int64_t* x, const float* move_chance, const float* rand, uint64_t seed, uint64_t offset,
+                       int64_t mask_index, int64_t* xt, uint8_t* move, int B, int N, void* stream) {
+    const long long total = (long long)B * N;
+    if (total <= 0) return 0;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
+    q_xt_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(x, move_chance, rand, seed, offset, mask_index, xt, move, B, N);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_sample_categorical(const float* probs, long long ldp, const float* u, uint64_t seed, uint64_t offset,
+                                     int64_t* out, int R, int V, void* stream) {
+    if (R <= 0) return 0;
+    sample_probs_kernel<0><<<rows_grid(R), ROW_THREADS, 0, STREAM(stream)>>>(nullptr, probs, ldp, u, seed, offset, nullptr, nullptr, -1, out, R, 1, V);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_ddpm_update_probs(const int64_t* x, const float* p_x0, long long ldp, const float* u, uint64_t seed,
+                                    uint64_t offset, const float* mc_t, const float* mc_s, int64_t mask_index, int64_t* out,
+                                    int B, int N, int V, void* stream) {
+    const int R = B * N;
+    if (R <= 0) return 0;
+    sample_probs_kernel<1><<<rows_grid(R), ROW_THREADS, 0, STREAM(stream)>>>(x, p_x0, ldp, u, seed, offset, mc_t, mc_s, mask_index, out, R, N, V);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_ddpm_update_logits(const int64_t* x, const void* logits, const void* logits_uncond, long long ldv,
+                                     const float* cfg_w, const int64_t* modality, const float* u, uint64_t seed,
+                                     uint64_t offset, const float* mc_t, const float* mc_s, int64_t mask_index, int text_vocab,
+                                     int64_t* out, int B, int N, int V, void* stream) {
+    const int R = B * N;
+    if (R <= 0) return 0;
+    int widest = V;
+    if (text_vocab > 0) widest = text_vocab > V - text_vocab ? text_vocab : V - text_vocab;
+    const size_t smem = (size_t)widest * sizeof(float);
+    if (smem > 200 * 1024) { fprintf(stderr, "unidisc_b200: vocabulary range too wide for the fused sampler (%d)\n", widest); return -1; }
+    const bool cfg = logits_uncond != nullptr;
+    static bool attr[2] = {false, false};
+    if (cfg) {
+        if (!attr[1]) { UD_CUDA_CHECK(cudaFuncSetAttribute(ddpm_update_logits_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[1] = true; }
+        ddpm_update_logits_kernel<true><<<rows_grid(R), 512, smem, STREAM(stream)>>>(x, CBF(logits), CBF(logits_uncond), ldv, cfg_w, modality, u, seed, offset, mc_t, mc_s, mask_index, text_vocab, out, R, N, V);
+    } else {
+        if (!attr[0]) { UD_CUDA_CHECK(cudaFuncSetAttribute(ddpm_update_logits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[0] = true; }
+        ddpm_update_logits_kernel<false><<<rows_grid(R), 512, smem, STREAM(stream)>>>(x, CBF(logits), nullptr, ldv, nullptr, modality, u, seed, offset, mc_t, mc_s, mask_index, text_vocab, out, R, N, V);
+    }
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

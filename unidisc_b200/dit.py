@@ -1,0 +1,441 @@
+"""B200-native drop-in for the reference backbone `models.dit.DIT` (reference models/dit.py:1095-1500).
+
+Same constructor signature, `forward` keyword surface, sub-module / state-dict key names (`vocab_embed.embedding`,
+`blocks.{i}.attention.attn_qkv.weight`, ... SURVEY.md §8b) and class names the launcher keys on (`DDiTBlock`,
+`EmbeddingLayer`).  The sub-modules only HOLD the fp32 master parameters; all maths runs in the CUDA library
+(libunidisc_b200.so) through `unidisc_b200.ops`:
+
+  embed+RMSNorm -> L x [ qkv GEMM -> q/k LayerNorm+RoPE -> tcgen05 attention -> out GEMM -> norm+residual+norm2
+                         -> MLP GEMM(+bias+GELU) -> MLP GEMM(+bias) -> norm+residual+next-norm ] -> head GEMM(+bias)
+
+with the rounding points of the reference's CUDA bf16-autocast execution (SURVEY.md §8a').  Parameters live in one flat
+fp32 buffer (with a bf16 shadow for the tensor cores and a flat fp32 gradient buffer the backward kernels accumulate
+into), so the optimizer and the DDP all-reduce work on contiguous memory.  There is no eager / CPU fallback.
+
+Supported configuration = the shipped large/small-scale training configs: norm_type=rms, sandwich_normalization,
+qk_norm, rope_2d, modality_embed, multimodal_batches, full_attention, no time-conditioning, dropout handled as 0
+(see DESIGN.md for what is not yet covered: adaLN time-conditioning, interleaved per-image RoPE tables, KV caches).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops, rope
+
+bf16 = torch.bfloat16
+
+
+class _AttrDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+def _wrap_cfg(c):
+    if isinstance(c, dict) and not isinstance(c, _AttrDict):
+        return _AttrDict({k: _wrap_cfg(v) for k, v in c.items()})
+    return c
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter containers (names / shapes / init follow the reference so checkpoints load unchanged)
+# ----------------------------------------------------------------------------------------------------------------
+class EmbeddingLayer(nn.Module):                                     # reference dit.py:1036-1043
+    def __init__(self, dim, vocab_dim):
+        super().__init__()
+        self.embedding = nn.Parameter(torch.empty((vocab_dim, dim)))
+        torch.nn.init.kaiming_uniform_(self.embedding, a=math.sqrt(5))
+
+
+class RMSNorm(nn.Module):                                            # reference dit.py:77-100
+    def __init__(self, dim, eps=1e-6):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class Attention(nn.Module):                                          # parameters of reference dit.py:562-571
+    def __init__(self, dim, n_heads):
+        super().__init__()
+        self.n_heads = n_heads
+        self.head_dim = dim // n_heads
+        self.attn_qkv = nn.Linear(dim, 3 * dim, bias=False)
+        self.attn_out = nn.Linear(dim, dim, bias=False)
+        self.q_norm = nn.LayerNorm(dim)
+        self.k_norm = nn.LayerNorm(dim)
+
+
+class DDiTBlock(nn.Module):                                          # parameters of reference dit.py:890-934
+    def __init__(self, dim, n_heads, mlp_ratio=4):
+        super().__init__()
+        self.attention = Attention(dim, n_heads)
+        self.norm1 = RMSNorm(dim)
+        self.norm2 = RMSNorm(dim)
+        self.mlp = nn.Sequential(nn.Linear(dim, mlp_ratio * dim, bias=True), nn.GELU(approximate="tanh"),
+                                 nn.Linear(mlp_ratio * dim, dim, bias=True))
+        self.post_ff_norm = RMSNorm(dim)
+        self.pre_residual_norm = RMSNorm(dim)
+
+
+class DDitFinalLayer(nn.Module):                                     # parameters of reference dit.py:1063-1092
+    def __init__(self, hidden_size, out_channels, zero_linear_init=True):
+        super().__init__()
+        self.norm_final = RMSNorm(hidden_size)
+        self.linear = nn.Linear(hidden_size, out_channels)
+        if zero_linear_init:
+            self.linear.weight.data.zero_()
+        self.linear.bias.data.zero_()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# autograd glue: one Function for the whole backbone.  Parameter gradients are accumulated by the kernels directly
+# into the module's flat gradient buffer (p.grad are views of it); autograd only carries the logits gradient.
+# ----------------------------------------------------------------------------------------------------------------
+class _DiTFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, module, indices, modality, sample_ids, save):
+        logits, saved = module._forward_impl(indices, modality, sample_ids, save=save)
+        ctx.module = module
+        ctx.saved = saved
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        module, saved = ctx.module, ctx.saved
+        if saved is None:
+            raise RuntimeError("unidisc_b200.DIT: backward called on a forward that did not save activations")
+        module._backward_impl(saved, dlogits)
+        ctx.saved = None
+        return torch.zeros_like(module._anchor), None, None, None, None, None
+
+
+class DIT(nn.Module):
+    def __init__(self, config, vocab_size: int, text_vocab_size: int, mask_index: int, dtype=None, device=None,
+                 static_img_sl=None, static_txt_sl=None, **kwargs):
+        super().__init__()
+        config = _wrap_cfg(config)
+        self.config = config
+        self.autocast_dtype = dtype
+        self.vocab_size = vocab_size
+        self.text_vocab_size = text_vocab_size
+        self.mask_index = mask_index
+        self.static_img_sl, self.static_txt_sl = static_img_sl, static_txt_sl
+        m = config.model
+        g = lambda o, k, d=None: getattr(o, k, d) if not isinstance(o, dict) else o.get(k, d)
+        self.time_conditioning = bool(config.time_conditioning or g(m, "force_time_conditioning", False))
+        unsupported = []
+        if self.time_conditioning:
+            unsupported.append("time_conditioning (adaLN)")
+        if g(m, "norm_type", "rms") != "rms":
+            unsupported.append(f"norm_type={g(m, 'norm_type')}")
+        if not g(m, "sandwich_normalization", False):
+            unsupported.append("sandwich_normalization=False")
+        if not g(m, "qk_norm", False):
+            unsupported.append("qk_norm=False")
+        if not g(m, "rope_2d", False) or not g(m, "modality_embed", False) or not g(config.trainer, "multimodal_batches", False):
+            unsupported.append("rope_2d / modality_embed / multimodal_batches must be on")
+        if not g(m, "full_attention", True):
+            unsupported.append("causal attention")
+        if g(config.data, "require_sample_ids", False):
+            unsupported.append("data.require_sample_ids (interleaved per-image RoPE tables)")
+        if g(m, "img_cond", False) or g(m, "use_pretrained_img_emb", False) or g(m, "cond_label", False) \
+                or g(config.trainer, "image_mode", "discrete") == "continuous":
+            unsupported.append("img_cond / pretrained image embedding / label conditioning / continuous image mode")
+        if unsupported:
+            raise NotImplementedError("unidisc_b200.DIT does not implement: " + "; ".join(unsupported))
+
+        D, H, nb = m.hidden_size, m.n_heads, m.n_blocks
+        self.hidden_size, self.n_heads, self.n_blocks = D, H, nb
+        self.head_dim = D // H
+        if self.head_dim not in (64, 128):
+            raise NotImplementedError(f"head_dim {self.head_dim}: the attention kernels are built for 64 and 128")
+        if D % 128 != 0:
+            raise NotImplementedError("hidden_size must be a multiple of 128")
+        self.dropout = float(g(m, "dropout", 0.0))
+        self.txt_length, self.img_length, self.total_length = m.txt_length, m.img_length, m.length
+        self.multimodal_batches = True
+        self.rope_2d = True
+        self.require_sample_ids = False
+        self.use_gradient_checkpointing = bool(g(config.trainer, "use_gradient_checkpointing", False))
+
+        self.vocab_embed = EmbeddingLayer(D, vocab_size)
+        self.modality_embed = EmbeddingLayer(D, 2)
+        self.blocks = nn.ModuleList([DDiTBlock(D, H) for _ in range(nb)])
+        self.output_layer = DDitFinalLayer(D, vocab_size, zero_linear_init=bool(g(m, "zero_linear_init", True)))
+        self.sigma_map = None
+
+        lf = g(m, "linear_factor", 1.0)
+        ci, si = rope.rope_2d(self.head_dim, self.img_length, lf)
+        ct, st = rope.rope_1d(self.head_dim, self.total_length)
+        self.register_buffer("rotary_cos_emb_img", ci, persistent=False)
+        self.register_buffer("rotary_sin_emb_img", si, persistent=False)
+        self.register_buffer("rotary_cos_emb_txt", ct[:, : ci.shape[1]].contiguous(), persistent=False)
+        self.register_buffer("rotary_sin_emb_txt", st[:, : si.shape[1]].contiguous(), persistent=False)
+
+        self.Vp = (vocab_size + 63) // 64 * 64     # logits row pitch (TMA / 16-byte vector stores)
+        self._flat_p = None
+        self._flat_g = None
+        self._flat_bf16 = None
+        self._shadow_dirty = True
+        self._anchor = None
+        self.training_graph_enabled = True
+        self.grad_ready_hook = None                # thin-DDP: called as hook(lo, hi) when flat grads [lo,hi) are final
+        self._grads_attached = False
+        if device is not None:
+            self.to(device)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # reference API stubs
+    # ------------------------------------------------------------------------------------------------------------
+    def reset_kv_cache(self, *a, **k):
+        raise NotImplementedError("unidisc_b200.DIT: KV cache is not implemented (model.use_kv_cache)")
+
+    def set_flex_attention_cache(self, *a, **k):
+        raise NotImplementedError("unidisc_b200.DIT: FlexAttention image-KV cache is not implemented")
+
+    # ------------------------------------------------------------------------------------------------------------
+    # flat parameter / gradient storage
+    # ------------------------------------------------------------------------------------------------------------
+    def _param_order(self):
+        """GEMM weights first (their grads may be overwritten instead of accumulated), then everything else."""
+        named = dict(self.named_parameters())
+        big = [n for n in named if n.endswith(("attn_qkv.weight", "attn_out.weight", "mlp.0.weight", "mlp.2.weight"))
+               or n == "output_layer.linear.weight"]
+        blocks_big = sorted(big, key=lambda n: (0, int(n.split(".")[1])) if n.startswith("blocks.") else (1, 0))
+        rest = [n for n in named if n not in set(big)]
+        return blocks_big, rest, named
+
+    def _flatten(self):
+        big, rest, named = self._param_order()
+        dev = named[big[0]].device
+        if dev.type != "cuda":
+            raise L.UnidiscB200Error("unidisc_b200.DIT runs on CUDA only (no CPU fallback); move the module to a GPU")
+        offs, off = {}, 0
+        for n in big + rest:
+            offs[n] = off
+            off += (named[n].numel() + 63) // 64 * 64      # 256-byte aligned slots
+        total = off
+        self._big_end = offs[rest[0]]
+        flat = torch.empty(total, device=dev, dtype=torch.float32)
+        for n in big + rest:
+            p = named[n]
+            v = flat[offs[n]: offs[n] + p.numel()].view(p.shape)
+            v.copy_(p.data.float())
+            p.data = v
+        self._flat_p = flat
+        self._flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self._flat_bf16 = torch.empty(total, device=dev, dtype=bf16)
+        self._offs = offs
+        self._names = big + rest
+        self._shadow_dirty = True
+        self._anchor = torch.zeros(1, device=dev, requires_grad=True)
+        self._grads_attached = False
+        self._views()
+
+    def _views(self):
+        named = dict(self.named_parameters())
+        o = self._offs
+        f32 = lambda n: named[n].data
+        b16 = lambda n: self._flat_bf16[o[n]: o[n] + named[n].numel()].view(named[n].shape)
+        gr = lambda n: self._flat_g[o[n]: o[n] + named[n].numel()].view(named[n].shape)
+        self._blk = []
+        for i in range(self.n_blocks):
+            p = f"blocks.{i}."
+            self._blk.append(dict(
+                wqkv=b16(p + "attention.attn_qkv.weight"), wout=b16(p + "attention.attn_out.weight"),
+                w1=b16(p + "mlp.0.weight"), b1=b16(p + "mlp.0.bias"), w2=b16(p + "mlp.2.weight"), b2=b16(p + "mlp.2.bias"),
+                gq=f32(p + "attention.q_norm.weight"), bq=f32(p + "attention.q_norm.bias"),
+                gk=f32(p + "attention.k_norm.weight"), bk=f32(p + "attention.k_norm.bias"),
+                n1=f32(p + "norm1.weight"), n2=f32(p + "norm2.weight"), npre=f32(p + "pre_residual_norm.weight"),
+                npost=f32(p + "post_ff_norm.weight"),
+                d_wqkv=gr(p + "attention.attn_qkv.weight"), d_wout=gr(p + "attention.attn_out.weight"),
+                d_w1=gr(p + "mlp.0.weight"), d_b1=gr(p + "mlp.0.bias"), d_w2=gr(p + "mlp.2.weight"), d_b2=gr(p + "mlp.2.bias"),
+                d_gq=gr(p + "attention.q_norm.weight"), d_bq=gr(p + "attention.q_norm.bias"),
+                d_gk=gr(p + "attention.k_norm.weight"), d_bk=gr(p + "attention.k_norm.bias"),
+                d_n1=gr(p + "norm1.weight"), d_n2=gr(p + "norm2.weight"), d_npre=gr(p + "pre_residual_norm.weight"),
+                d_npost=gr(p + "post_ff_norm.weight"),
+            ))
+        self._top = dict(
+            E=f32("vocab_embed.embedding"), Emod=f32("modality_embed.embedding"), nf=f32("output_layer.norm_final.weight"),
+            wh=b16("output_layer.linear.weight"), bh=b16("output_layer.linear.bias"),
+            d_E=gr("vocab_embed.embedding"), d_Emod=gr("modality_embed.embedding"), d_nf=gr("output_layer.norm_final.weight"),
+            d_wh=gr("output_layer.linear.weight"), d_bh=gr("output_layer.linear.bias"),
+        )
+        self._grad_views = {n: gr(n) for n in self._names}
+
+    def _ensure_ready(self):
+        first = self.blocks[0].attention.attn_qkv.weight
+        if self._flat_p is None or first.data_ptr() != self._flat_p.data_ptr() or first.device != self._flat_p.device:
+            self._flatten()
+        if self._shadow_dirty:
+            ops.cast_bf16(self._flat_p, self._flat_bf16)
+            self._shadow_dirty = False
+
+    def mark_weights_updated(self, shadow_is_current: bool = False):
+        """Call after the fp32 parameters changed (optimizer step / load_state_dict)."""
+        self._shadow_dirty = not shadow_is_current
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._shadow_dirty = True
+        return r
+
+    def _attach_grads(self):
+        """Make p.grad a view of the flat gradient buffer.  Returns True if the gradients were (re)created — i.e. the
+        caller zeroed them with set_to_none=True — in which case this backward overwrites instead of accumulating."""
+        named = dict(self.named_parameters())
+        fresh = getattr(self, "_force_fresh_grads", False) or any(
+            named[n].grad is None or named[n].grad.data_ptr() != self._grad_views[n].data_ptr() for n in self._names[:2])
+        self._force_fresh_grads = False
+        if fresh:
+            self._flat_g[self._big_end:].zero_()
+            for n in self._names:
+                named[n].grad = self._grad_views[n]
+        return fresh
+
+    @property
+    def flat_params(self):
+        self._ensure_ready()
+        return self._flat_p
+
+    @property
+    def flat_grads(self):
+        self._ensure_ready()
+        return self._flat_g
+
+    @property
+    def flat_params_bf16(self):
+        self._ensure_ready()
+        return self._flat_bf16
+
+    def block_grad_range(self, i):
+        """[lo, hi) ranges of the flat gradient buffer owned by block i (GEMM weights, then small params)."""
+        p = f"blocks.{i}."
+        names = [n for n in self._names if n.startswith(p)]
+        big = [n for n in names if self._offs[n] < self._big_end]
+        small = [n for n in names if self._offs[n] >= self._big_end]
+        rng = lambda ns: (min(self._offs[n] for n in ns), max(self._offs[n] + (dict(self.named_parameters())[n].numel() + 63) // 64 * 64 for n in ns))
+        return rng(big), rng(small)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # forward / backward
+    # ------------------------------------------------------------------------------------------------------------
+    def forward(self, indices, sigma=None, label=None, x_cond=None, attention_mask=None, continuous_mode=False,
+                x_img_emb=None, modality=None, start_pos=None, block_mask=None, update_cache_slice=None, sample_ids=None):
+        """Returns logits [B,N,V] in bf16 (what the reference returns under its outer bf16 autocast, model.py:693-729).
+        `sigma` is accepted and ignored (no time-conditioning, as in every shipped training config)."""
+        if label is not None or x_cond is not None or continuous_mode or x_img_emb is not None or start_pos is not None \
+                or update_cache_slice is not None:
+            raise NotImplementedError("unidisc_b200.DIT.forward: label/x_cond/continuous/kv-cache arguments are not supported")
+        if attention_mask is not None:
+            raise NotImplementedError("unidisc_b200.DIT.forward: dense attention_mask is not supported (model.use_attention_mask)")
+        if block_mask is not None and sample_ids is None:
+            raise NotImplementedError("unidisc_b200.DIT.forward: FlexAttention block_mask objects are not supported; pass sample_ids")
+        if modality is None:
+            raise ValueError("modality is required (trainer.multimodal_batches)")
+        if not indices.is_cuda:
+            raise L.UnidiscB200Error("unidisc_b200.DIT.forward needs CUDA tensors (no CPU fallback)")
+        self._ensure_ready()
+        save = torch.is_grad_enabled() and self.training_graph_enabled
+        return _DiTFunction.apply(self._anchor, self, indices, modality, sample_ids, save)
+
+    def _forward_impl(self, indices, modality, sample_ids, save):
+        B, N = indices.shape
+        M, D, H, hd, V = B * N, self.hidden_size, self.n_heads, self.head_dim, self.vocab_size
+        T = self._top
+        ids = indices.reshape(-1).contiguous()
+        mod = modality.reshape(-1).contiguous()
+        sid = sample_ids.contiguous() if sample_ids is not None else None
+        cos, sin = rope.token_tables(modality, self.rotary_cos_emb_txt, self.rotary_sin_emb_txt, self.rotary_cos_emb_img,
+                                     self.rotary_sin_emb_img, self.img_length)
+        scale = 1.0 / math.sqrt(hd)
+        x, h, rstd0 = ops.embed_rmsnorm_fwd(ids, mod, T["E"], T["Emod"], self._blk[0]["n1"])
+        saved = dict(ids=ids, mod=mod, sid=sid, cos=cos, sin=sin, B=B, N=N, x0=x, rstd0=rstd0, blocks=[]) if save else None
+        for i, W in enumerate(self._blk):
+            w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
+            qkv = ops.gemm(h, W["wqkv"])
+            qk, stats = ops.qk_ln_rope_fwd(qkv, W["gq"], W["bq"], W["gk"], W["bk"], cos, sin, hd)
+            o, lse = ops.attn_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, N, H, hd, scale, sample_ids=sid)
+            a = ops.gemm(o, W["wout"])
+            x1, h2, ra, rx1 = ops.norm_residual_fwd(a, x, W["npre"], W["n2"])
+            u, gl = ops.gemm(h2, W["w1"], epi=L.EPI_BF16_GELU, bias=W["b1"])
+            d = ops.gemm(gl, W["w2"], bias=W["b2"])
+            x2, h_next, rd, rx2 = ops.norm_residual_fwd(d, x1, W["npost"], w_next)
+            if save:
+                saved["blocks"].append(dict(h=h, qkv=qkv, qk=qk, stats=stats, o=o, lse=lse, a=a, ra=ra, x1=x1, rx1=rx1, h2=h2,
+                                            u=u, g=gl, d=d, rd=rd, x2=x2, rx2=rx2))
+            x, h = x2, h_next
+        buf = torch.empty((M, self.Vp), device=x.device, dtype=bf16)
+        ops.gemm(h, T["wh"], N=V, out=buf[:, :V], bias=T["bh"])
+        if save:
+            saved["hf"] = h
+            saved["logits_buf"] = buf
+        return buf.view(B, N, self.Vp)[:, :, :V], saved
+
+    def _backward_impl(self, S, dlogits):
+        B, N = S["B"], S["N"]
+        M, D, H, hd, V = B * N, self.hidden_size, self.n_heads, self.head_dim, self.vocab_size
+        T = self._top
+        fresh = self._attach_grads()
+        wacc = L.EPI_F32 if fresh else L.EPI_F32_ACC
+        # logits gradient in the padded [M, Vp] layout (produced in place by the fused SUBS-NLL backward when possible)
+        if dlogits.dtype == bf16 and dlogits.dim() == 3 and dlogits.stride() == (N * self.Vp, self.Vp, 1):
+            dl = dlogits.as_strided((M, self.Vp), (self.Vp, 1))[:, :V]
+        else:
+            buf = torch.zeros((M, self.Vp), device=dlogits.device, dtype=bf16)
+            buf[:, :V].copy_(dlogits.reshape(M, V))
+            dl = buf[:, :V]
+        # head
+        ops.gemm(dl, S["hf"], ta=True, tb=True, M=V, N=D, K=M, epi=wacc, out=T["d_wh"])
+        ops.colsum(dl, T["d_bh"], M, V)
+        dh = ops.gemm(dl, T["wh"], tb=True, M=M, N=D, K=V)
+        S["logits_buf"] = None
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(self.n_blocks)      # head weight gradient is final
+        g_res = None       # fp32 gradient flowing down the residual stream
+        scale = 1.0 / math.sqrt(hd)
+        for i in range(self.n_blocks - 1, -1, -1):
+            W, A = self._blk[i], S["blocks"][i]
+            w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
+            d_wnext = self._blk[i + 1]["d_n1"] if i + 1 < self.n_blocks else T["d_nf"]
+            # x2 = x1 + rms(d)*w_post ; h_next = rms(x2)*w_next
+            g_res, dd = ops.norm_residual_bwd(g_res, dh, A["x2"], A["rx2"], w_next, A["d"], A["rd"], W["npost"], d_wnext, W["d_npost"])
+            # MLP
+            ops.gemm(dd, A["g"], ta=True, tb=True, epi=wacc, out=W["d_w2"])
+            ops.colsum(dd, W["d_b2"])
+            du = ops.gemm(dd, W["w2"], tb=True, epi=L.EPI_BF16_DGELU, aux=A["u"])
+            ops.gemm(du, A["h2"], ta=True, tb=True, epi=wacc, out=W["d_w1"])
+            ops.colsum(du, W["d_b1"])
+            dh2 = ops.gemm(du, W["w1"], tb=True)
+            # x1 = x + rms(a)*w_pre ; h2 = rms(x1)*w_n2
+            x_in = S["blocks"][i - 1]["x2"] if i > 0 else S["x0"]
+            g_res, da = ops.norm_residual_bwd(g_res, dh2, A["x1"], A["rx1"], W["n2"], A["a"], A["ra"], W["npre"], W["d_n2"], W["d_npre"])
+            # attention
+            ops.gemm(da, A["o"], ta=True, tb=True, epi=wacc, out=W["d_wout"])
+            do = ops.gemm(da, W["wout"], tb=True)
+            dqk = torch.empty((M, 2 * D), device=do.device, dtype=bf16)
+            dqkv = torch.empty((M, 3 * D), device=do.device, dtype=bf16)
+            qk, qkv = A["qk"], A["qkv"]
+            ops.attn_bwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], A["o"], do, A["lse"], dqk[:, :D], dqk[:, D:], dqkv[:, 2 * D:],
+                         B, N, H, hd, scale, sample_ids=S["sid"])
+            ops.qk_ln_rope_bwd(dqk, qkv, A["stats"], W["gq"], W["gk"], S["cos"], S["sin"], dqkv, W["d_gq"], W["d_bq"], W["d_gk"],
+                               W["d_bk"], hd)
+            ops.gemm(dqkv, A["h"], ta=True, tb=True, epi=wacc, out=W["d_wqkv"])
+            dh = ops.gemm(dqkv, W["wqkv"], tb=True)
+            S["blocks"][i] = None      # release this block's activations
+            if self.grad_ready_hook is not None:
+                self.grad_ready_hook(i)
+            del x_in
+        # first norm + embedding
+        g0 = ops.rmsnorm_bwd(g_res, dh, S["x0"], S["rstd0"], self._blk[0]["n1"], self._blk[0]["d_n1"])
+        ops.embed_bwd(S["ids"], S["mod"], g0, T["d_E"], T["d_Emod"], hot_id=self.mask_index)
+        self._shadow_dirty = True      # an optimizer step is expected to follow
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(-1)

@@ -1,0 +1,478 @@
+"""B200-native mirror of the hot-path methods of the reference trainer class `Diffusion`
+(reference model.py:51 + model_setup.py / model_utils.py / model_eval.py, bound at model.py:54-99).
+
+Method names, argument meaning and return conventions follow the reference so that the parity tests read like the
+reference's own call sites:
+
+  _sample_t (model.py:589)  q_xt (model.py:424)  forward (model.py:674)  _subs_parameterization (model.py:621)
+  compute_loss (model.py:797)  training_step (model.py:420)
+  _sample_prior (model_eval.py:1734)  get_cfg_weight (:1737)  _ddpm_forward (:1761)  _ddpm_update (:2042)
+  _ddpm_caching_update (:2072)  _sample (:2107)  adap_sche (:2964)  _maskgit_update (:3045)
+
+All vocabulary-sized maths (SUBS log-softmax, NLL gather, Gumbel arg-max, absorbing update) runs in the CUDA
+library; only [B,N]-sized bookkeeping stays in torch.  Out of scope: data loading, tokenizers/VAEs,
+evaluation metrics, checkpoint/launcher glue, AR / SEDD / D3PM parameterisations.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import noise_schedule, ops
+from .dit import DIT, _wrap_cfg
+
+bf16 = torch.bfloat16
+
+
+@dataclass
+class Loss:                                                           # reference model_utils.py:110-120
+    loss: torch.Tensor
+    img_loss: torch.Tensor = None
+    txt_loss: torch.Tensor = None
+    nlls: torch.Tensor = None
+    token_mask: torch.Tensor = None
+    txt_nlls: torch.Tensor = None
+    img_nlls: torch.Tensor = None
+    extra_losses: dict = None
+    modality_mask: torch.Tensor = None
+
+
+def _g(o, k, d=None):
+    if o is None:
+        return d
+    if isinstance(o, dict):
+        return o.get(k, d)
+    return getattr(o, k, d)
+
+
+class _SubsNLL(torch.autograd.Function):
+    """log p_theta(x0 | xt) under the SUBS parameterisation, fused: logits are read once, the [B,N,V] log-prob tensor of
+    the reference (model.py:621-658 + gather at :967) is never materialised.  Backward writes dlogits IN PLACE over the
+    logits buffer (it has no other consumer in the training step)."""
+
+    @staticmethod
+    def forward(ctx, logits, xt, x0, modality, V, text_vocab, mask_index):
+        B, N = xt.shape
+        if logits.dtype != bf16 or logits.stride(-1) != 1 or logits.stride(0) != N * logits.stride(1):
+            raise L.UnidiscB200Error("_SubsNLL expects the bf16 logits returned by unidisc_b200.DIT.forward")
+        ldv = logits.stride(1)
+        l2 = logits.as_strided((B * N, ldv), (ldv, 1))
+        xt_f, x0_f, md_f = xt.reshape(-1).contiguous(), x0.reshape(-1).contiguous(), modality.reshape(-1).contiguous()
+        logp, lse = ops.subs_nll_fwd(l2, xt_f, x0_f, md_f, V, text_vocab, mask_index)
+        ctx.save_for_backward(logits, xt_f, x0_f, md_f, lse)
+        ctx.meta = (B, N, V, text_vocab, mask_index, ldv)
+        return logp.view(B, N)
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        logits, xt_f, x0_f, md_f, lse = ctx.saved_tensors
+        B, N, V, text_vocab, mask_index, ldv = ctx.meta
+        l2 = logits.as_strided((B * N, ldv), (ldv, 1))
+        ops.subs_nll_bwd_(l2, xt_f, x0_f, md_f, lse, dlogp.reshape(-1).contiguous().float(), V, text_vocab, mask_index)
+        return logits, None, None, None, None, None, None
+
+
+class Diffusion(nn.Module):
+    def __init__(self, config, tokenizer=None, device=None, vocab_size: Optional[int] = None,
+                 text_vocab_size: Optional[int] = None, mask_index: Optional[int] = None):
+        super().__init__()
+        config = _wrap_cfg(config)
+        self.config = config
+        self.tokenizer = tokenizer
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        prec = str(_g(config.trainer, "precision", "bf16"))
+        self.dtype = torch.float32 if ("fp32" in prec or prec == "no") else bf16
+        if self.dtype != bf16:
+            raise NotImplementedError("unidisc_b200: only trainer.precision=bf16 is built (the reference's CUDA autocast mode)")
+        # ---- vocabulary / mask index: reference model_setup.py:90-115 (unified text+image model) ----
+        if vocab_size is None:
+            tv = _g(config.model, "force_text_vocab_size", None)
+            if tv is None:
+                if tokenizer is None:
+                    raise ValueError("need a tokenizer or explicit vocab sizes")
+                tv = len(tokenizer)
+            if tokenizer is None or getattr(tokenizer, "mask_token", None) is None:
+                mask_index = tv
+                tv += 1
+            else:
+                mask_index = tokenizer.mask_token_id
+            text_vocab_size = tv
+            vocab_size = tv + int(config.model.image_vocab_size)
+        self.vocab_size, self.text_vocab_size, self.mask_index = int(vocab_size), int(text_vocab_size), int(mask_index)
+        self.parameterization = _g(config, "parameterization", "subs")
+        if self.parameterization != "subs" or _g(config, "backbone", "dit") != "dit":
+            raise NotImplementedError("unidisc_b200: only backbone=dit with parameterization=subs is on the hot path")
+        self.T = int(_g(config, "T", 0))
+        self.time_conditioning = bool(_g(config, "time_conditioning", False))
+        self.sampler = _g(_g(config, "sampling"), "predictor", "ddpm_cache")
+        self.antithetic_sampling = bool(_g(config.trainer, "antithetic_sampling", True))
+        self.importance_sampling = bool(_g(config.trainer, "importance_sampling", False))
+        self.change_of_variables = bool(_g(config.trainer, "change_of_variables", False))
+        self.sampling_eps = float(_g(config.trainer, "sampling_eps", 1e-3))
+        self.neg_infinity = -1_000_000.0
+        self.allow_slicing = False
+        self.noise = noise_schedule.get_noise(config)
+        self.static_txt_sl = slice(None, config.model.txt_length)
+        self.static_img_sl = slice(-config.model.img_length, None)
+        self.backbone = DIT(config, vocab_size=self.vocab_size, text_vocab_size=self.text_vocab_size, mask_index=self.mask_index,
+                            static_txt_sl=self.static_txt_sl, static_img_sl=self.static_img_sl)
+        self.backbone.to(self.device)
+        self.global_step = 0
+        self.fast_rng = bool(_g(config.trainer, "b200_philox_rng", False))   # additive key: in-kernel Philox instead of torch.rand
+        self._rng_offset = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    # training side
+    # ------------------------------------------------------------------------------------------------------------
+    def _sample_t(self, n, device):                                   # reference model.py:589-619
+        _eps_t = torch.rand(n, device=device)
+        if self.antithetic_sampling:
+            offset = torch.arange(n, device=device) / n
+            _eps_t = (_eps_t / n + offset) % 1
+        ft = _g(self.config.trainer, "force_timestep", None)
+        if ft is not None:
+            _eps_t[:] = ft
+        t = (1 - self.sampling_eps) * _eps_t + self.sampling_eps
+        return t.to(torch.float32)
+
+    def q_xt(self, x, move_chance, allow_move_mask=None, return_ignore_batch_mask_for_metrics=False, mask_image_square=False,
+             mask_text_region=False, batch=None):
+        """reference model.py:424-587 (absorbing state; multimodal non-interleaved batches)."""
+        if mask_image_square or mask_text_region:
+            raise NotImplementedError("unidisc_b200.q_xt: mask_image_square / mask_text_region are eval-time visualisation paths")
+        mask_prob = _g(self.config.trainer, "mask_entire_modality", None)
+        plain = (mask_prob is None or not self.backbone.training) and allow_move_mask is None \
+            and _g(self.config.trainer, "joint_ar_nar_prob", None) is None and not _g(self.config.trainer, "add_label", False) \
+            and _g(self.config.trainer, "first_token_dropout", None) is None
+        if plain:
+            # one kernel: xt = (rand < move_chance) ? mask : x      (model.py:439,579)
+            if self.fast_rng:
+                self._rng_offset += 1
+                xt, move = ops.q_xt(x, move_chance, self.mask_index, rand=None, seed=int(_g(self.config, "seed", 42)),
+                                    offset=self._rng_offset, return_move=True)
+            else:
+                rnd = torch.rand(*x.shape, device=x.device)
+                xt, move = ops.q_xt(x, move_chance, self.mask_index, rand=rnd, return_move=True)
+            if return_ignore_batch_mask_for_metrics:
+                return xt, None, None, None, None, move
+            return xt
+        # general path: the whole-modality masking logic works on [B,1] / [B,N] booleans (model.py:470-579)
+        move_indices = torch.rand(*x.shape, device=x.device) < move_chance
+        ignore = None
+        should_mask_txt = should_mask_img = None
+        if mask_prob is not None and self.backbone.training:
+            assert batch is not None
+            bsz = x.shape[0]
+            if _g(self.config.trainer, "mask_txt_only", False):
+                should_mask_txt = torch.rand(bsz, 1, device=x.device) < mask_prob
+                should_mask_img = torch.zeros_like(should_mask_txt)
+            else:
+                should_mask_txt = torch.rand(bsz, 1, device=x.device) < mask_prob / 2
+                should_mask_img = torch.rand(bsz, 1, device=x.device) < mask_prob / 2
+            if _g(self.config.trainer, "interleaved", False):
+                raise NotImplementedError("unidisc_b200.q_xt: interleaved per-block modality masking (model.py:483-522)")
+            both = should_mask_txt & should_mask_img
+            should_mask_txt = torch.where(both, False, should_mask_txt)
+            should_mask_img = torch.where(both, False, should_mask_img)
+            move_indices = torch.where(should_mask_txt, batch["modality_mask"][..., 0], move_indices)
+            move_indices = torch.where(should_mask_img, batch["modality_mask"][..., 1], move_indices)
+            ignore = should_mask_img | should_mask_txt
+        if _g(self.config.trainer, "add_label", False):
+            move_indices[:, 0] = False
+        ftd = _g(self.config.trainer, "first_token_dropout", None)
+        if ftd is not None and self.training:
+            init = torch.rand(x.shape[0], device=x.device) < ftd
+            move_indices[:, 0] = torch.where(init, True, move_indices[:, 0])
+            ignore = init if ignore is None else (ignore | init)
+        if allow_move_mask is not None:
+            move_indices = move_indices & allow_move_mask
+        xt = torch.where(move_indices, self.mask_index, x)
+        if return_ignore_batch_mask_for_metrics:
+            return xt, ignore, None, should_mask_txt, should_mask_img, move_indices
+        return xt
+
+    def _process_sigma(self, sigma):                                  # reference model.py:660-672
+        if sigma is None:
+            return sigma
+        if sigma.ndim > 1:
+            sigma = sigma.squeeze(-1)
+        return sigma
+
+    def _modality_of(self, batch, kwargs):
+        md = kwargs.get("modality", None)
+        if md is None and batch is not None:
+            md = batch.get("modality", None)
+        if md is None:
+            raise ValueError("modality is required (trainer.multimodal_batches)")
+        return md
+
+    def _subs_parameterization(self, logits, xt, batch=None, modality=None, **kwargs):
+        """reference model.py:621-658.  `logits` must be the bf16 tensor returned by the backbone; returns fp32
+        log-probs [B,N,V] (the reference keeps bf16 here and upcasts at model.py:924-925; see DESIGN.md numerics)."""
+        if modality is None:
+            modality = batch["modality"]
+        B, N, V = logits.shape
+        ldv = logits.stride(1)
+        l2 = logits.as_strided((B * N, ldv), (ldv, 1))
+        tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", True) else -1
+        out = ops.subs_logprobs(l2, None if xt is None else xt.reshape(-1).contiguous(), modality.reshape(-1).contiguous(), V, tv,
+                                self.mask_index)
+        return out.view(B, N, V)
+
+    def forward(self, x, sigma, batch=None, forward_attention_mask=None, return_additional_loss=False, x_img_emb=None,
+                disable_ar_shift=False, continuous_mode=False, joint_ar_nar_mask=None, return_logits=False, block_mask=None,
+                update_cache_slice=None, **kwargs):
+        """reference model.py:674-795 ("Returns log score")."""
+        sigma = self._process_sigma(sigma)
+        modality = self._modality_of(batch, kwargs)
+        logits = self.backbone(x, sigma, modality=modality, sample_ids=kwargs.get("sample_ids", None))
+        if return_logits:
+            return logits
+        return self._subs_parameterization(logits, xt=x, batch=batch, modality=modality)
+
+    def _log_p_x0(self, logits, xt, x0, modality):
+        tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", True) else -1
+        return _SubsNLL.apply(logits, xt, x0, modality, self.vocab_size, tv, self.mask_index)
+
+    def compute_loss(self, batch, prefix="train", batch_idx=-1):
+        """reference model.py:797-1173 (discrete diffusion, subs, T=0, multimodal loss weighting)."""
+        x0 = batch["input_ids"]
+        attention_mask = batch.get("attention_mask", None)
+        if attention_mask is None:
+            attention_mask = torch.ones_like(x0, dtype=torch.bool)
+        modality = batch["modality"]
+        modality_mask = batch.get("modality_mask", None)
+        if modality_mask is None:
+            modality_mask = torch.stack([modality == 0, modality == 1], dim=-1)
+        t = self._sample_t(x0.shape[0], x0.device)                                   # model.py:844
+        sigma, dsigma = self.noise(t)                                                # model.py:858
+        move_chance = 1 - torch.exp(-sigma[:, None])                                 # model.py:860
+        xt, ignore_batch, _, _, _, _ = self.q_xt(x0, move_chance, return_ignore_batch_mask_for_metrics=True, batch=batch)
+        logits = self.backbone(xt, None if not self.time_conditioning else sigma, modality=modality,
+                               sample_ids=batch.get("sample_ids", None) if _g(self.config.trainer, "interleaved_training_flex_attention", False) else None)
+        log_p_theta = self._log_p_x0(logits, xt, x0, modality)                       # model.py:787 + :967, fused
+        std_weighting = (dsigma / torch.expm1(sigma))[:, None]                       # model.py:975
+        loss = -log_p_theta * std_weighting
+        gamma = _g(self.config.trainer, "softmin_snr", None)
+        if gamma is not None:                                                        # model.py:990-993
+            loss = -log_p_theta * (dsigma / (torch.expm1(sigma) + (1 / gamma)))[:, None]
+        std_loss = (-log_p_theta * std_weighting).detach()
+        am = attention_mask.bool()
+        txt_mask = modality_mask[..., 0] & am                                        # model.py:1021-1022
+        img_mask = modality_mask[..., 1] & am
+        txt_count, img_count = txt_mask.sum(), img_mask.sum()
+        total = txt_count + img_count
+        extra = {"trainer/img_frac": img_count / total, "trainer/txt_frac": txt_count / total,
+                 "trainer/attention_mask_valid_frac": am.sum() / am.numel()}
+        tw, iw = _g(self.config.trainer, "text_loss_weight", None), _g(self.config.trainer, "img_loss_weight", None)
+        loss = loss * am
+        if tw is not None and iw is not None:                                        # model.py:1036-1057
+            txt_loss = ((loss * txt_mask).sum() / txt_count) * (txt_count / total) * tw
+            img_loss = ((loss * img_mask).sum() / img_count) * (img_count / total) * iw
+            ratio = _g(self.config.trainer, "set_max_txt_loss_ratio", None)
+            if ratio is not None:
+                scale = torch.minimum(torch.ones((), device=loss.device), ratio * img_loss.detach() / (txt_loss.detach() + 1e-8))
+                scale = torch.where(torch.isnan(img_loss) | torch.isnan(txt_loss), torch.ones_like(scale), scale)
+                txt_loss = txt_loss * scale
+            txt_loss = torch.nan_to_num(txt_loss, nan=0.0)
+            img_loss = torch.nan_to_num(img_loss, nan=0.0)
+            total_loss = txt_loss + img_loss
+        else:                                                                        # model.py:1070-1073
+            total_loss = torch.nan_to_num(loss.sum() / am.sum(), nan=0.0)
+            txt_loss = img_loss = torch.zeros((), device=loss.device)
+        token_mask = am
+        if ignore_batch is not None:
+            token_mask = torch.where(ignore_batch.reshape(-1, 1), torch.zeros_like(am), am)
+        return Loss(loss=total_loss, img_loss=img_loss.detach(), txt_loss=txt_loss.detach(), nlls=std_loss * am,
+                    txt_nlls=std_loss * modality_mask[..., 0] * am, img_nlls=std_loss * modality_mask[..., 1] * am,
+                    token_mask=token_mask, modality_mask=modality_mask, extra_losses=extra)
+
+    def training_step(self, batch, batch_idx=-1):                                    # reference model.py:420-422
+        return self.compute_loss(batch, prefix="train", batch_idx=batch_idx)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # sampling side
+    # ------------------------------------------------------------------------------------------------------------
+    def _sample_prior(self, *batch_dims):                                            # reference model_eval.py:1734
+        return self.mask_index * torch.ones(*batch_dims, dtype=torch.int64)
+
+    def get_cfg_weight(self, t):                                                     # reference model_eval.py:1737-1759
+        cfg = self.config.eval.cfg
+        return (cfg * (1 - t))[:, None]
+
+    def _ddpm_forward(self, x, t, sigma_t, x0=None, x0_unmask=None, force_cfg=None, **kwargs):
+        """reference model_eval.py:1761-1833: returns p_x0 [B,N,V] (fp32)."""
+        modality = kwargs.get("modality")
+        w = None
+        if _g(_g(self.config, "eval"), "cfg", None) is not None and x0_unmask is not None and x0_unmask.sum() > 0:
+            w = self.get_cfg_weight(t.reshape(-1))
+        if w is not None and (w > 0).any():
+            x_uncond = x.clone()
+            x_uncond[x0_unmask] = self.mask_index
+            lg = self.backbone(torch.cat([x, x_uncond], 0), None, modality=torch.cat([modality, modality], 0)).float()
+            lc, lu = lg.chunk(2, dim=0)
+            out = ((1 + w.unsqueeze(-1)) * lc - w.unsqueeze(-1) * lu).to(bf16)      # model_eval.py:1812 (then SUBS, xt=None)
+            B, N, V = out.shape
+            buf = torch.zeros((B * N, self.backbone.Vp), device=out.device, dtype=bf16)
+            buf[:, :V] = out.reshape(B * N, V)
+            logits = buf.view(B, N, -1)[:, :, :V]
+            return self._subs_parameterization(logits, xt=None, modality=modality).exp()
+        return self.forward(x=x, sigma=sigma_t, modality=modality).exp()
+
+    def _fused_absorbing_update(self, x, t, mc_t, mc_s, x0=None, x0_unmask=None, modality=None, u=None):
+        """backbone -> (CFG) -> SUBS softmax -> q_xs -> Gumbel arg-max -> copy-through in ONE vocabulary pass."""
+        B, N = x.shape
+        V = self.vocab_size
+        cfg = _g(_g(self.config, "eval"), "cfg", None)
+        use_cfg = cfg is not None and x0_unmask is not None and bool(x0_unmask.any())
+        if use_cfg:
+            x_uncond = torch.where(x0_unmask, torch.full_like(x, self.mask_index), x)
+            lg = self.backbone(torch.cat([x, x_uncond], 0), None, modality=torch.cat([modality, modality], 0))
+            ldv = lg.stride(1)
+            l2 = lg.as_strided((2 * B * N, ldv), (ldv, 1))
+            lc, lu = l2[: B * N], l2[B * N:]
+            w = (cfg * (1 - t.reshape(-1))).float().contiguous()
+        else:
+            lg = self.backbone(x, None, modality=modality)
+            ldv = lg.stride(1)
+            lc, lu, w = lg.as_strided((B * N, ldv), (ldv, 1)), None, None
+        self._rng_offset += 1
+        tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", True) else -1
+        return ops.ddpm_update_logits(x, lc, modality.reshape(-1).contiguous(), mc_t.float().contiguous(), mc_s.float().contiguous(),
+                                      self.mask_index, tv, V, logits_uncond=lu, cfg_w=w, u=u,
+                                      seed=int(_g(self.config, "seed", 42)), offset=self._rng_offset)
+
+    @torch.no_grad()
+    def _ddpm_update(self, x, t, dt, **kwargs):                                      # reference model_eval.py:2042-2070
+        tt = t.reshape(-1)
+        sigma_t, _ = self.noise(tt)
+        sigma_s, _ = self.noise(tt - dt)
+        mc_t, mc_s = 1 - torch.exp(-sigma_t), 1 - torch.exp(-sigma_s)
+        if kwargs.pop("parity_noise", False):
+            p_x0 = self._ddpm_forward(x, t, None, **kwargs)
+            u = torch.rand_like(p_x0)
+            return ops.ddpm_update_probs(x, p_x0, mc_t.contiguous(), mc_s.contiguous(), self.mask_index, u=u.view(-1, u.shape[-1])), 1
+        return self._fused_absorbing_update(x, tt, mc_t, mc_s, **{k: kwargs.get(k) for k in ("x0", "x0_unmask", "modality")}), 1
+
+    @torch.no_grad()
+    def _ddpm_caching_update(self, x, t, dt, p_x0=None, x0=None, x0_unmask=None, modality=None, **kwargs):
+        """reference model_eval.py:2072-2104.  With p_x0 given (or parity_noise=True) the update consumes a materialised
+        fp32 p_x0 and torch.rand noise exactly like the reference; otherwise the fused single-pass kernel is used and
+        the returned cache is None (the fused path never materialises p_x0)."""
+        tt = t.reshape(-1)
+        mc_t, mc_s = tt, tt - dt
+        nfe = 0
+        if p_x0 is not None or kwargs.get("parity_noise", False):
+            if p_x0 is None:
+                p_x0 = self._ddpm_forward(x, t, None, x0=x0, x0_unmask=x0_unmask, modality=modality)
+                nfe = 1
+            u = torch.rand_like(p_x0)
+            xn = ops.ddpm_update_probs(x, p_x0, mc_t.float().contiguous(), mc_s.float().contiguous(), self.mask_index,
+                                       u=u.view(-1, u.shape[-1]))
+            return p_x0, xn, nfe
+        return None, self._fused_absorbing_update(x, tt, mc_t, mc_s, x0=x0, x0_unmask=x0_unmask, modality=modality), 1
+
+    @staticmethod
+    def adap_sche(x, step, mask_index, mode="arccos"):                               # reference model_eval.py:2964-3001
+        num_masked = (x == mask_index).sum(dim=-1)
+        r = torch.linspace(1, 0, step)
+        if mode == "root":
+            val = 1 - (r ** 0.5)
+        elif mode == "linear":
+            val = 1 - r
+        elif mode == "square":
+            val = 1 - (r ** 2)
+        elif mode == "cosine":
+            val = torch.cos(r * math.pi * 0.5)
+        elif mode == "arccos":
+            val = torch.arccos(r) / (math.pi * 0.5)
+        else:
+            return None
+        val = val.to(x.device)
+        out = []
+        for seq_len in num_masked:
+            sche = (val / val.sum()) * seq_len
+            sche = sche.round()
+            sche[sche == 0] = 1
+            sche[-1] += seq_len - sche.sum()
+            sche[-1] = max(sche[-1], 0)
+            out.append(sche.int())
+        return torch.stack(out, dim=0)
+
+    @torch.no_grad()
+    def _maskgit_update(self, x, t, dt, schedule=None, step=None, **kwargs):         # reference model_eval.py:3045-3114
+        copy_flag = x != self.mask_index
+        r_temp = _g(_g(self.config, "eval"), "maskgit_r_temp", 10)
+        num_unmask = torch.minimum(schedule[:, step].to(x.device), (~copy_flag).sum(dim=-1))
+        if torch.all(num_unmask <= 0):
+            return x, 0
+        p_x0 = self._ddpm_forward(x, t, None, **{k: kwargs.get(k) for k in ("x0", "x0_unmask", "modality")})
+        pred_code = torch.multinomial(p_x0.view(-1, p_x0.shape[-1]), 1)[:, 0].view(p_x0.shape[:-1])
+        conf = torch.gather(p_x0, -1, pred_code.unsqueeze(-1)).squeeze(-1)
+        rand = r_temp * torch.from_numpy(np.random.gumbel(size=pred_code.shape)).to(x.device) * t
+        conf = torch.log(conf.squeeze()) + rand
+        conf = torch.where(copy_flag, -torch.inf, conf)
+        k = int(num_unmask.max().item())
+        tresh, _ = torch.topk(conf, k=k, dim=-1)
+        tresh = tresh.gather(-1, torch.clamp(num_unmask - 1, min=0)[:, None])
+        tresh = torch.where((num_unmask <= 0)[:, None], torch.inf, tresh)
+        return torch.where(conf >= tresh.expand_as(conf), pred_code, x), 1
+
+    @torch.no_grad()
+    def _sample(self, num_steps=None, eps=1e-5, text_only=True, x0=None, x0_unmask=None, batch_size_per_gpu=None,
+                example_batch=None, sample_batch_idx=None, sample_modality=None, sample_ids=None, return_raw_data=False,
+                return_nfe=False, **kwargs):
+        """reference model_eval.py:2107-2454 (token-space part: returns the sampled token ids [B,N])."""
+        assert (x0 is None) == (x0_unmask is None)
+        B = x0.shape[0] if x0 is not None else (batch_size_per_gpu or _g(_g(self.config, "loader"), "eval_batch_size", 1))
+        N = self.config.model.length
+        modality = sample_modality if sample_modality is not None else kwargs.get("modality")
+        if modality is None:
+            raise ValueError("sample_modality is required")
+        if num_steps is None:
+            num_steps = _g(_g(self.config, "sampling"), "steps", 64)
+        x = self._sample_prior(B, N).to(self.device)
+        if x0_unmask is None:
+            x0_unmask = torch.zeros(B, N, dtype=torch.bool, device=self.device)
+            x0 = x.clone()
+        num_steps = int(min(num_steps, int((~x0_unmask).sum(dim=-1).min())))
+        x = torch.where(x0_unmask, x0, x)
+        schedule = None
+        if self.sampler in ("maskgit",):
+            schedule = self.adap_sche(x, num_steps, self.mask_index, mode="arccos")
+        timesteps = torch.linspace(1, eps, num_steps + 1, device=self.device)
+        dt = (1 - eps) / num_steps
+        p_cache, nfe = None, 0
+        parity = bool(kwargs.get("parity_noise", False))
+        for i in range(num_steps):
+            t = timesteps[i] * torch.ones(B, 1, device=self.device)
+            if self.sampler == "maskgit":
+                x, n = self._maskgit_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, schedule=schedule, step=i, modality=modality)
+            elif self.sampler == "ddpm":
+                x, n = self._ddpm_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, modality=modality, parity_noise=parity)
+            elif self.sampler == "ddpm_cache":
+                p_cache, x_next, n = self._ddpm_caching_update(x, t, dt, p_x0=p_cache, x0=x0, x0_unmask=x0_unmask,
+                                                               modality=modality, parity_noise=parity)
+                if p_cache is not None and (not torch.equal(x_next, x) or self.time_conditioning):
+                    p_cache = None
+                x = x_next
+            else:
+                raise NotImplementedError(f"sampling.predictor={self.sampler}")
+            nfe += n
+            x = torch.where(x0_unmask, x0, x)
+        if _g(_g(self.config, "sampling"), "noise_removal", True):                   # model_eval.py:2440-2446
+            lg = self.backbone(x, None, modality=modality)
+            ldv = lg.stride(1)
+            l2 = lg.as_strided((B * N, ldv), (ldv, 1))
+            # argmax of SUBS log-probs with carry-over == x where unmasked, else argmax over the valid vocabulary
+            lp = self._subs_parameterization(lg, xt=x, modality=modality)
+            x = lp.argmax(dim=-1)
+            del l2
+        x = torch.where(x0_unmask, x0, x)
+        return (x, nfe) if return_nfe else x
