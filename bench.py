@@ -227,7 +227,7 @@ def main():
         opt.step()
         opt.zero_grad()
         if e2e:
-            return float(losses.loss)          # device -> host read of the step's result
+            return float(losses.loss.detach())          # device -> host read of the step's result
         return losses.loss.detach()
 
     def timed(e2e, steps):

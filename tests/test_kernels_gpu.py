@@ -45,7 +45,7 @@ def close_bf16(out, ref, name, frac_bad=1e-3):
 # GEMM family
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (200, 328, 136), (1024, 768, 2048), (130, 48385 // 8 * 8 + 8, 128)])
-@pytest.mark.parametrize("bn", [0, 128, 256])
+@pytest.mark.parametrize("bn", [0, 128, 256, 1024 + 128, 1024 + 256])     # +1024 = force the single-CTA kernel
 def test_gemm_nt(ops, M, N, K, bn):
     a, b = rnd(M, K, seed=1, dtype=bf16), rnd(N, K, seed=2, dtype=bf16)
     ref = a.float() @ b.float().t()
@@ -67,16 +67,17 @@ def test_gemm_odd_n_with_padded_ld(ops):
     assert (buf[:, N:] == 7.0).all(), "padding columns must not be touched"
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (384, 200, 264), (1024, 2048, 768)])
-def test_gemm_dgrad_layout(ops, M, N, K):
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (384, 200, 264), (1024, 2048, 768), (2560, 512, 4096)])
+@pytest.mark.parametrize("bn", [0, 128, 1024])
+def test_gemm_dgrad_layout(ops, M, N, K, bn):
     # dx[M,N] = dy[M,K] @ W[K,N]   (tb=1: B given as [K,N] row-major)
     dy, w = rnd(M, K, seed=3, dtype=bf16), rnd(K, N, seed=4, dtype=bf16)
-    out = ops.gemm(dy, w, tb=True)
+    out = ops.gemm(dy, w, tb=True, bn=bn)
     torch.cuda.synchronize()
     close_bf16(out, (dy.float() @ w.float()).to(bf16), "gemm dgrad")
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (200, 328, 520), (768, 3072, 1024)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (200, 328, 520), (768, 3072, 1024), (1000, 512, 2500)])
 def test_gemm_wgrad_layout(ops, M, N, K):
     # dW[M,N] = dy[K,M]^T @ x[K,N]   (ta=1,tb=1), fp32 output, then accumulate
     dy, x = rnd(K, M, seed=5, dtype=bf16), rnd(K, N, seed=6, dtype=bf16)

@@ -48,6 +48,105 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Epilogue for one 32-column chunk of one accumulator row held in registers (shared by the 1-CTA and 2-CTA kernels).
+template <int EPI>
+UD_DEVINL void epilogue_chunk(const uint32_t (&r)[32], int row, bool row_ok, int col0, const GemmParams& p) {
+    const bool full = (col0 + 32 <= p.N);
+    if constexpr (EPI == UD_EPI_F32 || EPI == UD_EPI_F32_ACC) {
+        float* cp = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+        if (row_ok) {
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    if constexpr (EPI == UD_EPI_F32_ACC) {
+                        float4 o = *reinterpret_cast<float4*>(cp + 4 * j);
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    }
+                    *reinterpret_cast<float4*>(cp + 4 * j) = v;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (col0 + j < p.N) {
+                        float v = __uint_as_float(r[j]);
+                        if constexpr (EPI == UD_EPI_F32_ACC) v += cp[j];
+                        cp[j] = v;
+                    }
+                }
+            }
+        }
+    } else {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + j);
+                    v[8 * j + 0] += bf16lo(b.x); v[8 * j + 1] += bf16hi(b.x);
+                    v[8 * j + 2] += bf16lo(b.y); v[8 * j + 3] += bf16hi(b.y);
+                    v[8 * j + 4] += bf16lo(b.z); v[8 * j + 5] += bf16hi(b.z);
+                    v[8 * j + 6] += bf16lo(b.w); v[8 * j + 7] += bf16hi(b.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
+            }
+        }
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
+        __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ld_aux + col0;
+        if (row_ok) {
+            if constexpr (EPI == UD_EPI_BF16_DGELU) {
+                // C = acc * gelu'(u), u = aux (bf16 pre-activation saved by the forward)
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u = ldg_stream(reinterpret_cast<const uint4*>(xp) + j);
+                        v[8 * j + 0] *= gelu_tanh_grad(bf16lo(u.x)); v[8 * j + 1] *= gelu_tanh_grad(bf16hi(u.x));
+                        v[8 * j + 2] *= gelu_tanh_grad(bf16lo(u.y)); v[8 * j + 3] *= gelu_tanh_grad(bf16hi(u.y));
+                        v[8 * j + 4] *= gelu_tanh_grad(bf16lo(u.z)); v[8 * j + 5] *= gelu_tanh_grad(bf16hi(u.z));
+                        v[8 * j + 6] *= gelu_tanh_grad(bf16lo(u.w)); v[8 * j + 7] *= gelu_tanh_grad(bf16hi(u.w));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) v[j] *= gelu_tanh_grad(__bfloat162float(xp[j]));
+                }
+            }
+            if (full) {
+                uint32_t o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *(reinterpret_cast<uint4*>(cp) + j) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                if constexpr (EPI == UD_EPI_BF16_GELU) {
+                    uint32_t g[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        g[j] = pack_bf16x2(gelu_tanh(bf16lo(o[j])), gelu_tanh(bf16hi(o[j])));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *(reinterpret_cast<uint4*>(xp) + j) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (col0 + j < p.N) {
+                        __nv_bfloat16 ub = __float2bfloat16_rn(v[j]);
+                        cp[j] = ub;
+                        if constexpr (EPI == UD_EPI_BF16_GELU) xp[j] = __float2bfloat16_rn(gelu_tanh(__bfloat162float(ub)));
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <bool A_MN, bool B_MN, int BN, int EPI>
 __global__ void __launch_bounds__(192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
@@ -166,100 +265,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + as * BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
                 tmem_ld_wait();
-                const bool full = (col0 + 32 <= p.N);
-                if constexpr (EPI == UD_EPI_F32 || EPI == UD_EPI_F32_ACC) {
-                    float* cp = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
-                    if (row_ok) {
-                        if (full) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                                if constexpr (EPI == UD_EPI_F32_ACC) {
-                                    float4 o = *reinterpret_cast<float4*>(cp + 4 * j);
-                                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                                }
-                                *reinterpret_cast<float4*>(cp + 4 * j) = v;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (col0 + j < p.N) {
-                                    float v = __uint_as_float(r[j]);
-                                    if constexpr (EPI == UD_EPI_F32_ACC) v += cp[j];
-                                    cp[j] = v;
-                                }
-                            }
-                        }
-                    }
-                } else {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias != nullptr) {
-                        if (full) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + j);
-                                v[8 * j + 0] += bf16lo(b.x); v[8 * j + 1] += bf16hi(b.x);
-                                v[8 * j + 2] += bf16lo(b.y); v[8 * j + 3] += bf16hi(b.y);
-                                v[8 * j + 4] += bf16lo(b.z); v[8 * j + 5] += bf16hi(b.z);
-                                v[8 * j + 6] += bf16lo(b.w); v[8 * j + 7] += bf16hi(b.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
-                        }
-                    }
-                    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
-                    __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ld_aux + col0;
-                    if (row_ok) {
-                        if constexpr (EPI == UD_EPI_BF16_DGELU) {
-                            // C = acc * gelu'(u), u = aux (bf16 pre-activation saved by the forward)
-                            if (full) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    uint4 u = ldg_stream(reinterpret_cast<const uint4*>(xp) + j);
-                                    v[8 * j + 0] *= gelu_tanh_grad(bf16lo(u.x)); v[8 * j + 1] *= gelu_tanh_grad(bf16hi(u.x));
-                                    v[8 * j + 2] *= gelu_tanh_grad(bf16lo(u.y)); v[8 * j + 3] *= gelu_tanh_grad(bf16hi(u.y));
-                                    v[8 * j + 4] *= gelu_tanh_grad(bf16lo(u.z)); v[8 * j + 5] *= gelu_tanh_grad(bf16hi(u.z));
-                                    v[8 * j + 6] *= gelu_tanh_grad(bf16lo(u.w)); v[8 * j + 7] *= gelu_tanh_grad(bf16hi(u.w));
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < p.N) v[j] *= gelu_tanh_grad(__bfloat162float(xp[j]));
-                            }
-                        }
-                        if (full) {
-                            uint32_t o[16];
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                *(reinterpret_cast<uint4*>(cp) + j) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                            if constexpr (EPI == UD_EPI_BF16_GELU) {
-                                uint32_t g[16];
-#pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    g[j] = pack_bf16x2(gelu_tanh(bf16lo(o[j])), gelu_tanh(bf16hi(o[j])));
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    *(reinterpret_cast<uint4*>(xp) + j) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (col0 + j < p.N) {
-                                    __nv_bfloat16 ub = __float2bfloat16_rn(v[j]);
-                                    cp[j] = ub;
-                                    if constexpr (EPI == UD_EPI_BF16_GELU) xp[j] = __float2bfloat16_rn(gelu_tanh(__bfloat162float(ub)));
-                                }
-                            }
-                        }
-                    }
-                }
+                epilogue_chunk<EPI>(r, row, row_ok, col0, p);
             }
             tc_fence_before();
             __syncwarp();
@@ -273,6 +279,161 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BN tile.  Each CTA stages its own 128 rows of A
+// and HALF of the B tile (BN/2 rows), the leader's single thread issues M=256 UMMAs that read both CTAs' shared memory,
+// and each CTA's TMEM receives its 128 accumulator rows.  Per flop this halves the B-operand traffic from L2, which is
+// what bounds the 1-CTA kernel (128x256: 0.0117 B/flop ~ 20 TB/s at peak vs ~12 TB/s of L2).
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct Gemm2Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;            // 128 rows of A per CTA
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;      // half of the B tile per CTA
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 6 : 8;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <bool A_MN, bool B_MN, int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+    using Cfg = Gemm2Cfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;   // tiles of 256 x BN
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 8);     // 4 epilogue warps in each of the two CTAs (used in the leader only)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_ptr_smem);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m0 = (tile % p.num_m_tiles) * 256 + (int)rank * BM;
+                const int n0 = (tile / p.num_m_tiles) * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);   // bytes of BOTH CTAs land on the leader's barrier
+                    const int k0 = kb * BK;
+                    if constexpr (!A_MN) {
+                        tma_load_2d_2sm(sa, &tma_a, &full_bar[s], k0, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &tma_a, &full_bar[s], m0 + 64 * j, k0);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d_2sm(sb, &tma_b, &full_bar[s], k0, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &tma_b, &full_bar[s], n0 + 64 * j, k0);
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== UMMA issuer (leader CTA only) =====================
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
+            int s = 0;
+            uint32_t ph = 0;
+            int as = 0;
+            uint32_t aph = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait_cluster(&tmem_empty[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * (UMMA_K * 128), 8192, 1024)
+                                                 : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
+                        const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), 8192, 1024)
+                                                 : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
+                        umma_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_2sm_mc(&empty_bar[s], 0b11);   // frees the stage in BOTH CTAs
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit_2sm_mc(&tmem_full[as], 0b11);       // accumulator complete -> both epilogues
+                if (++as == 2) { as = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (2..5), both CTAs =====================
+        const int q = warp & 3;
+        int as = 0;
+        uint32_t aph = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m0 = (tile % p.num_m_tiles) * 256 + (int)rank * BM;
+            const int n0 = (tile / p.num_m_tiles) * BN;
+            mbar_wait(&tmem_full[as], aph);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N) break;
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + as * BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
+                tmem_ld_wait();
+                epilogue_chunk<EPI>(r, row, row_ok, col0, p);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[as], 0);
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -385,6 +546,45 @@ static int dispatch_major(int ta_, int tb_, int epi, const CUtensorMap& ta, cons
     return -5;
 }
 
+
+template <bool A_MN, bool B_MN, int BN, int EPI>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<BN>;
+    auto kern = gemm2_kernel<A_MN, B_MN, BN, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    int tiles = p.num_m_tiles * p.num_n_tiles;
+    int clusters = sm_count() / 2;
+    if (tiles < clusters) clusters = tiles;
+    kern<<<2 * clusters, 192, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+template <bool A_MN, bool B_MN, int BN>
+static int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+    switch (epi) {
+        case UD_EPI_BF16: return launch_gemm2<A_MN, B_MN, BN, UD_EPI_BF16>(ta, tb, p, s);
+        case UD_EPI_BF16_GELU: return launch_gemm2<A_MN, B_MN, BN, UD_EPI_BF16_GELU>(ta, tb, p, s);
+        case UD_EPI_BF16_DGELU: return launch_gemm2<A_MN, B_MN, BN, UD_EPI_BF16_DGELU>(ta, tb, p, s);
+        case UD_EPI_F32: return launch_gemm2<A_MN, B_MN, BN, UD_EPI_F32>(ta, tb, p, s);
+        case UD_EPI_F32_ACC: return launch_gemm2<A_MN, B_MN, BN, UD_EPI_F32_ACC>(ta, tb, p, s);
+    }
+    return -4;
+}
+
+template <int BN>
+static int dispatch_major2(int ta_, int tb_, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                           cudaStream_t s) {
+    if (!ta_ && !tb_) return dispatch_epi2<false, false, BN>(epi, ta, tb, p, s);
+    if (!ta_ && tb_) return dispatch_epi2<false, true, BN>(epi, ta, tb, p, s);
+    if (ta_ && tb_) return dispatch_epi2<true, true, BN>(epi, ta, tb, p, s);
+    return -5;
+}
+
 }  // namespace ud
 
 extern "C" int ud_gemm_bf16(int ta, int tb, int M, int N, int K, const void* A, long long lda, const void* B, long long ldb,
@@ -392,32 +592,46 @@ extern "C" int ud_gemm_bf16(int ta, int tb, int M, int N, int K, const void* A, 
                             void* stream) {
     using namespace ud;
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    int BN = bn_hint;
+    // bn_hint: 0 = auto, 128 / 256 = tile width; +1024 forces the single-CTA kernel (A/B testing, tiny problems)
+    const bool force_1cta = (bn_hint & 1024) != 0;
+    int BN = bn_hint & 1023;
+    const bool two_cta = !force_1cta && M > 128;
+    const int TM = two_cta ? 256 : BM;
+    const int units = two_cta ? sm_count() / 2 : sm_count();
     if (BN != 128 && BN != 256) {
-        // pick the tile width that wastes fewer SM-waves
-        auto waves = [&](int bn) {
-            long long t = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn);
-            long long w = (t + sm_count() - 1) / sm_count();
-            return (double)w * bn;  // time ~ waves * tile width
+        // pick the tile width that wastes fewer waves
+        auto cost = [&](int bn) {
+            long long t = (long long)((M + TM - 1) / TM) * ((N + bn - 1) / bn);
+            long long w = (t + units - 1) / units;
+            return (double)w * bn;
         };
-        BN = (waves(256) <= waves(128)) ? 256 : 128;
+        BN = (cost(256) <= cost(128)) ? 256 : 128;
     }
     CUtensorMap tmA, tmB;
     int rc;
     if (!ta) rc = make_tmap_2d_bf16(&tmA, A, M, K, lda, BM, 64);
     else rc = make_tmap_2d_bf16(&tmA, A, K, M, lda, 64, 64);
     if (rc) return rc;
-    if (!tb) rc = make_tmap_2d_bf16(&tmB, B, N, K, ldb, BN, 64);
+    const int b_rows = two_cta ? BN / 2 : BN;
+    if (!tb) rc = make_tmap_2d_bf16(&tmB, B, N, K, ldb, b_rows, 64);
     else rc = make_tmap_2d_bf16(&tmB, B, K, N, ldb, 64, 64);
     if (rc) return rc;
+    if ((reinterpret_cast<uintptr_t>(C) & 15) || (ldc % 4) != 0) {
+        fprintf(stderr, "unidisc_b200: GEMM output needs a 16-byte aligned base and ldc %% 4 == 0\n");
+        return -6;
+    }
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc;
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
     p.aux = aux; p.ld_aux = ld_aux;
-    p.num_m_tiles = (M + BM - 1) / BM;
+    p.num_m_tiles = (M + TM - 1) / TM;
     p.num_n_tiles = (N + BN - 1) / BN;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (two_cta) {
+        if (BN == 256) return dispatch_major2<256>(ta, tb, epi, tmA, tmB, p, s);
+        return dispatch_major2<128>(ta, tb, epi, tmA, tmB, p, s);
+    }
     if (BN == 256) return dispatch_major<256>(ta, tb, epi, tmA, tmB, p, s);
     return dispatch_major<128>(ta, tb, epi, tmA, tmB, p, s);
 }
