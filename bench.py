@@ -282,6 +282,35 @@ def main():
     gemm_tflops = 2.0 * M * D * 4 * D / (gemm_ms * 1e-3) / 1e12
     del sets
 
+    # ---- secondary: the HBM-bound fused absorbing sampler (BASELINE.json configs[3]: B=64, N=1280, all rows masked) ----
+    sampler_info = None
+    if rank == 0 and not small:
+        try:
+            Bs = 64
+            Vp = net.Vp
+            lg = torch.empty(Bs * N, Vp, device=dev, dtype=torch.bfloat16)
+            for c in range(0, Bs * N, 8192):
+                lg[c:c + 8192].normal_(0, 3)
+            xs = torch.full((Bs, N), model.mask_index, dtype=torch.int64, device=dev)
+            mods = mod_d[:1].repeat(Bs, 1).contiguous()
+            tt = torch.full((Bs,), 0.7, device=dev)
+            for _ in range(2):
+                ops.ddpm_update_logits(xs, lg, mods.view(-1), tt, tt - 0.01, model.mask_index, tv, V, seed=1, offset=1)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(5):
+                ops.ddpm_update_logits(xs, lg, mods.view(-1), tt, tt - 0.01, model.mask_index, tv, V, seed=1, offset=2 + i)
+            s1.record()
+            torch.cuda.synchronize()
+            sms = s0.elapsed_time(s1) / 5
+            alg_bytes = Bs * (txt * tv + img * (V - tv)) * 2 + Bs * N * 8 * 2
+            sampler_info = dict(kernel="ddpm_update_logits_kernel<no-cfg> (Philox noise)", workload=f"B={Bs} N={N} V={V} bf16 logits, all masked",
+                                ms_per_launch=sms, algorithmic_bytes=alg_bytes, achieved_gbs=alg_bytes / (sms * 1e-3) / 1e9,
+                                peak_gbs=pk["hbm_gbs"], frac=alg_bytes / (sms * 1e-3) / 1e9 / pk["hbm_gbs"])
+            del lg
+        except Exception as e:  # noqa: BLE001
+            sampler_info = dict(error=str(e))
+
     tok_step = world * B * N
     fpt = 3 * flops_per_token_fwd(D, Lyr, N, V)
     value = tok_step / (ms_dev / args.steps * 1e-3)
@@ -312,6 +341,7 @@ def main():
             step_frac_of_sustained_peak=model_tflops_per_gpu / pk["bf16_tflops_sustained"],
             flops_per_token_fwd_bwd=fpt,
             cpu_baseline=cpu,
+            sampler=sampler_info,
         )
         print(json.dumps(line))
     if world > 1:

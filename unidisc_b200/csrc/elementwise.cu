@@ -108,49 +108,67 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const int64_t*
 // ------------------------------------------------------------------------------------------------
 // x_out = x_in + bf16(rms(a)) * w_a ;  h = bf16(rms(x_out) * w_n)       (dit.py:993-994, 1024-1031, 971/1025/1089)
 // ------------------------------------------------------------------------------------------------
+template <int R>
 __global__ void norm_residual_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ x_in,
                                          const float* __restrict__ w_a, const float* __restrict__ w_n,
                                          float* __restrict__ x_out, __nv_bfloat16* __restrict__ h,
                                          float* __restrict__ rstd_a, float* __restrict__ rstd_x, int rows, int D, float eps) {
-    __shared__ float scratch[2 * 32 * 1];
+    // R rows per iteration: R independent load streams in flight and one block reduction per R rows
+    __shared__ float scratch[2 * 32 * R];
     int buf = 0;
     const int c = threadIdx.x * 4;
     const F4 wa = ld_f4(w_a + c), wn = ld_f4(w_n + c);
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        const long long off = (long long)row * D + c;
-        F4 av = ld_bf4(a + off), xi = ld_f4(x_in + off);
-        float s[1] = {0.f};
+    const float invD = 1.0f / (float)D;
+    for (int r0 = blockIdx.x * R; r0 < rows; r0 += gridDim.x * R) {
+        F4 av[R], xi[R], xo[R];
+        float s[R];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s[0] += av.v[i] * av.v[i];
-        block_sum<1>(s, scratch, buf);
-        const float ra = rsqrtf(s[0] / (float)D + eps);
-        F4 xo;
-        s[0] = 0.f;
+        for (int j = 0; j < R; ++j) {
+            const bool ok = r0 + j < rows;
+            const long long off = (long long)(ok ? r0 + j : r0) * D + c;
+            av[j] = ld_bf4(a + off);
+            xi[j] = ld_f4(x_in + off);
+            s[j] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            xo.v[i] = xi.v[i] + bf16_round(av.v[i] * ra) * wa.v[i];
-            s[0] += xo.v[i] * xo.v[i];
+            for (int i = 0; i < 4; ++i) s[j] += av[j].v[i] * av[j].v[i];
         }
-        block_sum<1>(s, scratch, buf);
-        const float rx = rsqrtf(s[0] / (float)D + eps);
-        F4 hv;
+        block_sum<R>(s, scratch, buf);
+        float ra[R];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) hv.v[i] = (xo.v[i] * rx) * wn.v[i];
-        st_f4(x_out + off, xo);
-        st_bf4(h + off, hv);
-        if (threadIdx.x == 0) { rstd_a[row] = ra; rstd_x[row] = rx; }
+        for (int j = 0; j < R; ++j) {
+            ra[j] = rsqrtf(s[j] * invD + eps);
+            s[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xo[j].v[i] = xi[j].v[i] + bf16_round(av[j].v[i] * ra[j]) * wa.v[i];
+                s[j] += xo[j].v[i] * xo[j].v[i];
+            }
+        }
+        block_sum<R>(s, scratch, buf);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (r0 + j >= rows) break;
+            const float rx = rsqrtf(s[j] * invD + eps);
+            const long long off = (long long)(r0 + j) * D + c;
+            F4 hv;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hv.v[i] = (xo[j].v[i] * rx) * wn.v[i];
+            st_f4(x_out + off, xo[j]);
+            st_bf4(h + off, hv);
+            if (threadIdx.x == 0) { rstd_a[r0 + j] = ra[j]; rstd_x[r0 + j] = rx; }
+        }
     }
 }
 
 // backward of the fused kernel (see header).  HAS_BRANCH=false degenerates to a plain RMSNorm backward.
-template <bool HAS_BRANCH>
+template <bool HAS_BRANCH, int R>
 __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const __nv_bfloat16* __restrict__ dh,
                                          const float* __restrict__ x_out, const float* __restrict__ rstd_x,
                                          const float* __restrict__ w_n, const __nv_bfloat16* __restrict__ a,
                                          const float* __restrict__ rstd_a, const float* __restrict__ w_a,
                                          float* __restrict__ g_in, __nv_bfloat16* __restrict__ da, float* __restrict__ dw_n,
                                          float* __restrict__ dw_a, int rows, int D) {
-    __shared__ float scratch[2 * 32 * 3];
+    __shared__ float scratch[2 * 32 * 3 * R];
     int buf = 0;
     const int c = threadIdx.x * 4;
     const F4 wn = ld_f4(w_n + c);
@@ -158,45 +176,56 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
     if (HAS_BRANCH) wa = ld_f4(w_a + c);
     F4 acc_n = {{0, 0, 0, 0}}, acc_a = {{0, 0, 0, 0}};
     const float invD = 1.0f / (float)D;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        const long long off = (long long)row * D + c;
-        const float rx = rstd_x[row];
-        F4 dhv = ld_bf4(dh + off), xo = ld_f4(x_out + off);
-        F4 go = {{0, 0, 0, 0}};
-        if (g_out != nullptr) go = ld_f4(g_out + off);
-        F4 av = {{0, 0, 0, 0}};
-        float ra = 0.f;
-        if (HAS_BRANCH) { av = ld_bf4(a + off); ra = rstd_a[row]; }
-        F4 y, base, naf;
-        float s[3] = {0.f, 0.f, 0.f};
+    for (int r0 = blockIdx.x * R; r0 < rows; r0 += gridDim.x * R) {
+        F4 y[R], base[R], naf[R];
+        float rx[R], ra[R], s[3 * R];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            y.v[i] = xo.v[i] * rx;
-            const float dy = dhv.v[i] * wn.v[i];
-            s[0] += dy * y.v[i];
-            base.v[i] = go.v[i] + rx * dy;
-            acc_n.v[i] += dhv.v[i] * y.v[i];
-            if (HAS_BRANCH) {
-                naf.v[i] = av.v[i] * ra;
-                s[1] += base.v[i] * wa.v[i] * naf.v[i];
-                s[2] += y.v[i] * wa.v[i] * naf.v[i];
-            }
-        }
-        block_sum<3>(s, scratch, buf);
-        const float m1 = s[0] * invD;
-        F4 g;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) g.v[i] = base.v[i] - rx * y.v[i] * m1;
-        st_f4(g_in + off, g);
-        if (HAS_BRANCH) {
-            const float m2 = (s[1] - rx * m1 * s[2]) * invD;
-            F4 dav;
+        for (int j = 0; j < R; ++j) {
+            const bool ok = r0 + j < rows;
+            const int row = ok ? r0 + j : r0;
+            const long long off = (long long)row * D + c;
+            rx[j] = rstd_x[row];
+            F4 dhv = ld_bf4(dh + off), xo = ld_f4(x_out + off);
+            F4 go = {{0, 0, 0, 0}};
+            if (g_out != nullptr) go = ld_f4(g_out + off);
+            F4 av = {{0, 0, 0, 0}};
+            ra[j] = 0.f;
+            if (HAS_BRANCH) { av = ld_bf4(a + off); ra[j] = rstd_a[row]; }
+            s[3 * j] = s[3 * j + 1] = s[3 * j + 2] = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                acc_a.v[i] += g.v[i] * bf16_round(naf.v[i]);
-                dav.v[i] = ra * (g.v[i] * wa.v[i] - naf.v[i] * m2);
+                y[j].v[i] = xo.v[i] * rx[j];
+                const float dy = dhv.v[i] * wn.v[i];
+                s[3 * j] += dy * y[j].v[i];
+                base[j].v[i] = go.v[i] + rx[j] * dy;
+                if (ok) acc_n.v[i] += dhv.v[i] * y[j].v[i];
+                if (HAS_BRANCH) {
+                    naf[j].v[i] = av.v[i] * ra[j];
+                    s[3 * j + 1] += base[j].v[i] * wa.v[i] * naf[j].v[i];
+                    s[3 * j + 2] += y[j].v[i] * wa.v[i] * naf[j].v[i];
+                }
             }
-            st_bf4(da + off, dav);
+        }
+        block_sum<3 * R>(s, scratch, buf);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (r0 + j >= rows) break;
+            const long long off = (long long)(r0 + j) * D + c;
+            const float m1 = s[3 * j] * invD;
+            F4 g;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g.v[i] = base[j].v[i] - rx[j] * y[j].v[i] * m1;
+            st_f4(g_in + off, g);
+            if (HAS_BRANCH) {
+                const float m2 = (s[3 * j + 1] - rx[j] * m1 * s[3 * j + 2]) * invD;
+                F4 dav;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc_a.v[i] += g.v[i] * bf16_round(naf[j].v[i]);
+                    dav.v[i] = ra[j] * (g.v[i] * wa.v[i] - naf[j].v[i] * m2);
+                }
+                st_bf4(da + off, dav);
+            }
         }
     }
 #pragma unroll
@@ -209,108 +238,138 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
 // ------------------------------------------------------------------------------------------------
 // q/k LayerNorm over the full hidden dim + RoPE   (dit.py:680-682, 724-726; standalone_rotary.py:14-31)
 // ------------------------------------------------------------------------------------------------
+template <int R>
 __global__ void qk_ln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ gq,
                                       const float* __restrict__ bq, const float* __restrict__ gk, const float* __restrict__ bk,
                                       const float* __restrict__ cosT, const float* __restrict__ sinT,
                                       __nv_bfloat16* __restrict__ out, float* __restrict__ stats, int rows, int D, int hd,
                                       float eps) {
-    __shared__ float scratch[2 * 32 * 2];
+    __shared__ float scratch[2 * 32 * 2 * R];
     int buf = 0;
     const int c = threadIdx.x * 4;
     const int half = hd >> 1;
-    const int j = c % hd;               // position inside the head
-    const bool lo = j < half;
-    const int ti = j % half;            // table index of this thread's first column
+    const int j0 = c % hd;              // position inside the head
+    const bool lo = j0 < half;
+    const int ti = j0 % half;           // table index of this thread's first column
     const int pmask = hd >> 3;          // partner thread = tid ^ (hd/8)  (same warp for hd <= 128)
     const F4 gqv = ld_f4(gq + c), bqv = ld_f4(bq + c), gkv = ld_f4(gk + c), bkv = ld_f4(bk + c);
     const float invD = 1.0f / (float)D;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        const __nv_bfloat16* src = qkv + (long long)row * 3 * D;
-        F4 q = ld_bf4(src + c), k = ld_bf4(src + D + c);
-        float s[2] = {q.v[0] + q.v[1] + q.v[2] + q.v[3], k.v[0] + k.v[1] + k.v[2] + k.v[3]};
-        block_sum<2>(s, scratch, buf);
-        const float mq = s[0] * invD, mk = s[1] * invD;
-        s[0] = s[1] = 0.f;
+    for (int r0 = blockIdx.x * R; r0 < rows; r0 += gridDim.x * R) {
+        F4 q[R], k[R], cs[R], sn[R];
+        float s[2 * R];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            q.v[i] -= mq; k.v[i] -= mk;
-            s[0] += q.v[i] * q.v[i]; s[1] += k.v[i] * k.v[i];
+        for (int j = 0; j < R; ++j) {
+            const int row = (r0 + j < rows) ? r0 + j : r0;
+            const __nv_bfloat16* src = qkv + (long long)row * 3 * D;
+            q[j] = ld_bf4(src + c);
+            k[j] = ld_bf4(src + D + c);
+            cs[j] = ld_f4(cosT + (long long)row * half + ti);
+            sn[j] = ld_f4(sinT + (long long)row * half + ti);
+            s[2 * j] = q[j].v[0] + q[j].v[1] + q[j].v[2] + q[j].v[3];
+            s[2 * j + 1] = k[j].v[0] + k[j].v[1] + k[j].v[2] + k[j].v[3];
         }
-        block_sum<2>(s, scratch, buf);
-        const float rq = rsqrtf(s[0] * invD + eps), rk = rsqrtf(s[1] * invD + eps);
-        const F4 cs = ld_f4(cosT + (long long)row * half + ti), sn = ld_f4(sinT + (long long)row * half + ti);
-        F4 oq, ok;
+        block_sum<2 * R>(s, scratch, buf);
+        float mq[R], mk[R];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float yq = bf16_round((q.v[i] * rq) * gqv.v[i] + bqv.v[i]);  // LayerNorm output, stored bf16 (dit.py:681)
-            const float yk = bf16_round((k.v[i] * rk) * gkv.v[i] + bkv.v[i]);
-            const float pq = __shfl_xor_sync(0xffffffffu, yq, pmask);
-            const float pk = __shfl_xor_sync(0xffffffffu, yk, pmask);
-            oq.v[i] = yq * cs.v[i] + (lo ? -pq : pq) * sn.v[i];
-            ok.v[i] = yk * cs.v[i] + (lo ? -pk : pk) * sn.v[i];
+        for (int j = 0; j < R; ++j) {
+            mq[j] = s[2 * j] * invD; mk[j] = s[2 * j + 1] * invD;
+            s[2 * j] = s[2 * j + 1] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                q[j].v[i] -= mq[j]; k[j].v[i] -= mk[j];
+                s[2 * j] += q[j].v[i] * q[j].v[i]; s[2 * j + 1] += k[j].v[i] * k[j].v[i];
+            }
         }
-        __nv_bfloat16* dst = out + (long long)row * 2 * D;
-        st_bf4(dst + c, oq);
-        st_bf4(dst + D + c, ok);
-        if (threadIdx.x == 0) {
-            float4 st = make_float4(mq, rq, mk, rk);
-            *reinterpret_cast<float4*>(stats + (long long)row * 4) = st;
+        block_sum<2 * R>(s, scratch, buf);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const float rq = rsqrtf(s[2 * j] * invD + eps), rk = rsqrtf(s[2 * j + 1] * invD + eps);
+            F4 oq, ok;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float yq = bf16_round((q[j].v[i] * rq) * gqv.v[i] + bqv.v[i]);  // LayerNorm output, stored bf16 (dit.py:681)
+                const float yk = bf16_round((k[j].v[i] * rk) * gkv.v[i] + bkv.v[i]);
+                const float pq = __shfl_xor_sync(0xffffffffu, yq, pmask);
+                const float pk = __shfl_xor_sync(0xffffffffu, yk, pmask);
+                oq.v[i] = yq * cs[j].v[i] + (lo ? -pq : pq) * sn[j].v[i];
+                ok.v[i] = yk * cs[j].v[i] + (lo ? -pk : pk) * sn[j].v[i];
+            }
+            if (r0 + j < rows) {
+                __nv_bfloat16* dst = out + (long long)(r0 + j) * 2 * D;
+                st_bf4(dst + c, oq);
+                st_bf4(dst + D + c, ok);
+                if (threadIdx.x == 0) *reinterpret_cast<float4*>(stats + (long long)(r0 + j) * 4) = make_float4(mq[j], rq, mk[j], rk);
+            }
         }
     }
 }
 
+template <int R>
 __global__ void qk_ln_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dqk, const __nv_bfloat16* __restrict__ qkv,
                                       const float* __restrict__ stats, const float* __restrict__ gq,
                                       const float* __restrict__ gk, const float* __restrict__ cosT,
                                       const float* __restrict__ sinT, __nv_bfloat16* __restrict__ dqkv,
                                       float* __restrict__ dgq, float* __restrict__ dbq, float* __restrict__ dgk,
                                       float* __restrict__ dbk, int rows, int D, int hd) {
-    __shared__ float scratch[2 * 32 * 4];
+    __shared__ float scratch[2 * 32 * 4 * R];
     int buf = 0;
     const int c = threadIdx.x * 4;
     const int half = hd >> 1;
-    const int j = c % hd;
-    const bool lo = j < half;
-    const int ti = j % half;
+    const int j0 = c % hd;
+    const bool lo = j0 < half;
+    const int ti = j0 % half;
     const int pmask = hd >> 3;
     const F4 gqv = ld_f4(gq + c), gkv = ld_f4(gk + c);
     F4 a_gq = {{0, 0, 0, 0}}, a_bq = {{0, 0, 0, 0}}, a_gk = {{0, 0, 0, 0}}, a_bk = {{0, 0, 0, 0}};
     const float invD = 1.0f / (float)D;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        const float4 st = *reinterpret_cast<const float4*>(stats + (long long)row * 4);
-        const __nv_bfloat16* src = qkv + (long long)row * 3 * D;
-        const __nv_bfloat16* gsrc = dqk + (long long)row * 2 * D;
-        F4 q = ld_bf4(src + c), k = ld_bf4(src + D + c);
-        F4 dq = ld_bf4(gsrc + c), dk = ld_bf4(gsrc + D + c);
-        const F4 cs = ld_f4(cosT + (long long)row * half + ti), sn = ld_f4(sinT + (long long)row * half + ti);
-        F4 xq, xk, eq, ek;
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r0 = blockIdx.x * R; r0 < rows; r0 += gridDim.x * R) {
+        F4 xq[R], xk[R], eq[R], ek[R];
+        float4 st[R];
+        float s[4 * R];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            // inverse rotation of the incoming gradients
-            const float pq = __shfl_xor_sync(0xffffffffu, dq.v[i], pmask);
-            const float pk = __shfl_xor_sync(0xffffffffu, dk.v[i], pmask);
-            const float dyq = dq.v[i] * cs.v[i] + (lo ? pq : -pq) * sn.v[i];
-            const float dyk = dk.v[i] * cs.v[i] + (lo ? pk : -pk) * sn.v[i];
-            xq.v[i] = (q.v[i] - st.x) * st.y;
-            xk.v[i] = (k.v[i] - st.z) * st.w;
-            a_gq.v[i] += dyq * xq.v[i]; a_bq.v[i] += dyq;
-            a_gk.v[i] += dyk * xk.v[i]; a_bk.v[i] += dyk;
-            eq.v[i] = dyq * gqv.v[i];
-            ek.v[i] = dyk * gkv.v[i];
-            s[0] += eq.v[i]; s[1] += eq.v[i] * xq.v[i];
-            s[2] += ek.v[i]; s[3] += ek.v[i] * xk.v[i];
-        }
-        block_sum<4>(s, scratch, buf);
-        F4 oq, ok;
+        for (int j = 0; j < R; ++j) {
+            const bool okr = r0 + j < rows;
+            const int row = okr ? r0 + j : r0;
+            st[j] = *reinterpret_cast<const float4*>(stats + (long long)row * 4);
+            const __nv_bfloat16* src = qkv + (long long)row * 3 * D;
+            const __nv_bfloat16* gsrc = dqk + (long long)row * 2 * D;
+            F4 q = ld_bf4(src + c), k = ld_bf4(src + D + c);
+            F4 dq = ld_bf4(gsrc + c), dk = ld_bf4(gsrc + D + c);
+            const F4 cs = ld_f4(cosT + (long long)row * half + ti), sn = ld_f4(sinT + (long long)row * half + ti);
+            s[4 * j] = s[4 * j + 1] = s[4 * j + 2] = s[4 * j + 3] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            oq.v[i] = st.y * (eq.v[i] - s[0] * invD - xq.v[i] * s[1] * invD);
-            ok.v[i] = st.w * (ek.v[i] - s[2] * invD - xk.v[i] * s[3] * invD);
+            for (int i = 0; i < 4; ++i) {
+                // inverse rotation of the incoming gradients
+                const float pq = __shfl_xor_sync(0xffffffffu, dq.v[i], pmask);
+                const float pk = __shfl_xor_sync(0xffffffffu, dk.v[i], pmask);
+                const float dyq = dq.v[i] * cs.v[i] + (lo ? pq : -pq) * sn.v[i];
+                const float dyk = dk.v[i] * cs.v[i] + (lo ? pk : -pk) * sn.v[i];
+                xq[j].v[i] = (q.v[i] - st[j].x) * st[j].y;
+                xk[j].v[i] = (k.v[i] - st[j].z) * st[j].w;
+                if (okr) {
+                    a_gq.v[i] += dyq * xq[j].v[i]; a_bq.v[i] += dyq;
+                    a_gk.v[i] += dyk * xk[j].v[i]; a_bk.v[i] += dyk;
+                }
+                eq[j].v[i] = dyq * gqv.v[i];
+                ek[j].v[i] = dyk * gkv.v[i];
+                s[4 * j] += eq[j].v[i]; s[4 * j + 1] += eq[j].v[i] * xq[j].v[i];
+                s[4 * j + 2] += ek[j].v[i]; s[4 * j + 3] += ek[j].v[i] * xk[j].v[i];
+            }
         }
-        __nv_bfloat16* dst = dqkv + (long long)row * 3 * D;
-        st_bf4(dst + c, oq);
-        st_bf4(dst + D + c, ok);
+        block_sum<4 * R>(s, scratch, buf);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (r0 + j >= rows) break;
+            F4 oq, ok;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                oq.v[i] = st[j].y * (eq[j].v[i] - s[4 * j] * invD - xq[j].v[i] * s[4 * j + 1] * invD);
+                ok.v[i] = st[j].w * (ek[j].v[i] - s[4 * j + 2] * invD - xk[j].v[i] * s[4 * j + 3] * invD);
+            }
+            __nv_bfloat16* dst = dqkv + (long long)(r0 + j) * 3 * D;
+            st_bf4(dst + c, oq);
+            st_bf4(dst + D + c, ok);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -494,7 +553,7 @@ extern "C" int ud_norm_residual_fwd(const void* a, const float* x_in, const floa
                                     float* rstd_a, float* rstd_x, int rows, int D, float eps, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "norm_residual_fwd")) return -1;
-    norm_residual_fwd_kernel<<<row_grid(rows, D / 4), D / 4, 0, STREAM(stream)>>>(CBF(a), x_in, w_a, w_n, x_out, BF(h), rstd_a, rstd_x, rows, D, eps);
+    norm_residual_fwd_kernel<4><<<row_grid((rows + 3) / 4, D / 4), D / 4, 0, STREAM(stream)>>>(CBF(a), x_in, w_a, w_n, x_out, BF(h), rstd_a, rstd_x, rows, D, eps);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -504,9 +563,9 @@ extern "C" int ud_norm_residual_bwd(const float* g_out, const void* dh, const fl
                                     void* da, float* dw_n, float* dw_a, int rows, int D, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "norm_residual_bwd")) return -1;
-    int grid = row_grid(rows, D / 4);
+    int grid = row_grid((rows + 1) / 2, D / 4);
     if (grid > 4 * sm_count()) grid = 4 * sm_count();
-    norm_residual_bwd_kernel<true><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, rows, D);
+    norm_residual_bwd_kernel<true, 2><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, rows, D);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -515,9 +574,9 @@ extern "C" int ud_rmsnorm_bwd(const float* g_out, const void* dh, const float* x
                               float* g_in, float* dw, int rows, int D, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "rmsnorm_bwd")) return -1;
-    int grid = row_grid(rows, D / 4);
+    int grid = row_grid((rows + 1) / 2, D / 4);
     if (grid > 4 * sm_count()) grid = 4 * sm_count();
-    norm_residual_bwd_kernel<false><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x, rstd, w, nullptr, nullptr, nullptr, g_in, nullptr, dw, nullptr, rows, D);
+    norm_residual_bwd_kernel<false, 2><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x, rstd, w, nullptr, nullptr, nullptr, g_in, nullptr, dw, nullptr, rows, D);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -531,7 +590,7 @@ extern "C" int ud_qk_ln_rope_fwd(const void* qkv, const float* gq, const float* 
         fprintf(stderr, "unidisc_b200: qk_ln_rope supports head_dim 32/64/128 (got %d)\n", head_dim);
         return -1;
     }
-    qk_ln_rope_fwd_kernel<<<row_grid(rows, D / 4), D / 4, 0, STREAM(stream)>>>(CBF(qkv), gq, bq, gk, bk, cos, sin, BF(qk_out), stats, rows, D, head_dim, eps);
+    qk_ln_rope_fwd_kernel<4><<<row_grid((rows + 3) / 4, D / 4), D / 4, 0, STREAM(stream)>>>(CBF(qkv), gq, bq, gk, bk, cos, sin, BF(qk_out), stats, rows, D, head_dim, eps);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -542,9 +601,9 @@ extern "C" int ud_qk_ln_rope_bwd(const void* dqk, const void* qkv, const float* 
     if (rows <= 0) return 0;
     if (!check_D(D, "qk_ln_rope_bwd")) return -1;
     if (head_dim != 32 && head_dim != 64 && head_dim != 128) return -1;
-    int grid = row_grid(rows, D / 4);
+    int grid = row_grid((rows + 1) / 2, D / 4);
     if (grid > 4 * sm_count()) grid = 4 * sm_count();
-    qk_ln_rope_bwd_kernel<<<grid, D / 4, 0, STREAM(stream)>>>(CBF(dqk), CBF(qkv), stats, gq, gk, cos, sin, BF(dqkv), dgq, dbq, dgk, dbk, rows, D, head_dim);
+    qk_ln_rope_bwd_kernel<2><<<grid, D / 4, 0, STREAM(stream)>>>(CBF(dqk), CBF(qkv), stats, gq, gk, cos, sin, BF(dqkv), dgq, dbq, dgk, dbk, rows, D, head_dim);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

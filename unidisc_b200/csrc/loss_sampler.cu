@@ -284,11 +284,27 @@ __global__ void ddpm_update_logits_kernel(const int64_t* __restrict__ x, const _
         const float w = CFG ? cfg_w[b] : 0.f;
         MaxSum acc = {-INFINITY, 0.f};
         __syncthreads();  // srow reuse across rows
-        for (int v = lo + threadIdx.x; v < hi; v += blockDim.x) {
-            float l = __bfloat162float(rc[v]);
-            if (CFG) l = (1.0f + w) * l - w * __bfloat162float(ru[v]);   // model_eval.py:1812
+        auto put = [&](int v, float lcv, float luv) {
+            float l = lcv;
+            if (CFG) l = (1.0f + w) * lcv - w * luv;                     // model_eval.py:1812
             srow[v - lo] = l;
             if (v != mask_index) ms_add(acc, l);
+        };
+        {
+            const int lo_al = min(hi, (lo + 7) & ~7), hi_al = max(lo_al, hi & ~7);
+            for (int v = lo + threadIdx.x; v < lo_al; v += blockDim.x)
+                put(v, __bfloat162float(rc[v]), CFG ? __bfloat162float(ru[v]) : 0.f);
+            for (int v = lo_al + threadIdx.x * 8; v < hi_al; v += blockDim.x * 8) {
+                const uint4 a = ldg_stream(rc + v);
+                uint4 bq = make_uint4(0, 0, 0, 0);
+                if (CFG) bq = ldg_stream(ru + v);
+                put(v + 0, bf16lo(a.x), bf16lo(bq.x)); put(v + 1, bf16hi(a.x), bf16hi(bq.x));
+                put(v + 2, bf16lo(a.y), bf16lo(bq.y)); put(v + 3, bf16hi(a.y), bf16hi(bq.y));
+                put(v + 4, bf16lo(a.z), bf16lo(bq.z)); put(v + 5, bf16hi(a.z), bf16hi(bq.z));
+                put(v + 6, bf16lo(a.w), bf16lo(bq.w)); put(v + 7, bf16hi(a.w), bf16hi(bq.w));
+            }
+            for (int v = hi_al + threadIdx.x; v < hi; v += blockDim.x)
+                put(v, __bfloat162float(rc[v]), CFG ? __bfloat162float(ru[v]) : 0.f);
         }
         const MaxSum t = block_ms(acc, sm);
         const float lse = t.m + logf(t.s);

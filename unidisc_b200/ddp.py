@@ -135,7 +135,7 @@ class FusedAdamW:
     @torch.no_grad()
     def step(self):
         m = self.module
-        p, g = m.flat_params, m.flat_grads
+        p, g = m._flat_p, m._flat_g              # (not the properties: they would refresh the bf16 shadow we are about to rewrite)
         self.step_count += 1
         scale = None
         if self.max_grad_norm is not None:
@@ -145,7 +145,7 @@ class FusedAdamW:
             self.last_grad_norm = norm
             torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0, out=self._scale)    # torch clip_grad_norm_ coefficient
             scale = self._scale
-        ops.adamw_step(p, g, self.exp_avg, self.exp_avg_sq, m.flat_params_bf16, self.lr, self.betas[0], self.betas[1], self.eps,
+        ops.adamw_step(p, g, self.exp_avg, self.exp_avg_sq, m._flat_bf16, self.lr, self.betas[0], self.betas[1], self.eps,
                        self.weight_decay, self.step_count, grad_scale=scale)
         m.mark_weights_updated(shadow_is_current=True)
 
