@@ -398,3 +398,31 @@ def test_flat_helpers(ops):
     assert torch.allclose(out, (g * g).sum(), rtol=1e-4)
     assert torch.equal(dst, (g.to(bf16) / 8))
     assert torch.equal(back, dst.float())
+
+
+def test_ddpm_update_from_logits_philox_distribution(ops):
+    """fast (in-kernel Philox, log-domain Gumbel-max) mode: empirical distribution == the absorbing posterior
+    P(v) = (mc_t-mc_s) p_v / mc_t, P(stay masked) = mc_s / mc_t   (model_eval.py:2064-2067)."""
+    V, tv, mi, ldv = 24, 9, 8, 24
+    R_, N = 40000, 2
+    g = torch.Generator().manual_seed(0)
+    row_t = (torch.randn(V, generator=g) * 1.5).to(bf16)
+    logits = row_t[None].repeat(R_ * N, 1).contiguous().to(dev())
+    modality = torch.tensor([[0, 1]]).repeat(R_, 1).to(dev())
+    x = torch.full((R_, N), mi, dtype=torch.int64, device=dev())
+    mc_t = torch.full((R_,), 0.8, device=dev())
+    mc_s = torch.full((R_,), 0.6, device=dev())
+    out = ops.ddpm_update_logits(x, logits, modality.view(-1), mc_t, mc_s, mi, tv, V, seed=123, offset=7)
+    out2 = ops.ddpm_update_logits(x, logits, modality.view(-1), mc_t, mc_s, mi, tv, V, seed=123, offset=7)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    lf = row_t.float()
+    for pos, (lo, hi) in enumerate([(0, tv - 1), (tv, V)]):       # text row: cols 0..7 (mask col 8 excluded); image row: 9..23
+        p = torch.zeros(V + 1)
+        p[lo:hi] = torch.softmax(lf[lo:hi], 0) * (0.2 / 0.8)
+        p[V] = 0.6 / 0.8                                            # slot V counts "stay masked"
+        o = out[:, pos].cpu()
+        o = torch.where(o == mi, torch.full_like(o, V), o)
+        freq = torch.bincount(o, minlength=V + 1).float() / R_
+        assert (freq[:lo].sum() + freq[hi:V].sum()) == 0, "sampled outside the valid vocabulary range"
+        assert torch.allclose(freq, p, atol=0.012), (freq - p).abs().max()

@@ -325,6 +325,139 @@ __global__ void ddpm_update_logits_kernel(const int64_t* __restrict__ x, const _
     }
 }
 
+
+// Philox ("fast") variant of the fused absorbing update: ONE pass over the row, ~10 instructions per logit, HBM-bound.
+// The Gumbel arg-max of model_utils.py:95-97 is evaluated hierarchically and in the log domain (both exact in
+// distribution): P(8-column group) ~ sum of its q_v, then P(v | group) ~ q_v, so the row pass needs ONE uniform per 8 logits:
+//     group score = log2( sum_{v in group} exp(l_v) ) - log2(E),   E = -ln(u) ~ Exp(1)     (Gumbel-max over groups)
+// computed in the same pass as the online log-sum-exp; the winning group is re-read once (16 bytes) and a token drawn
+// inside it; the mask column (probability mc_s, model_eval.py:2066/2092) is compared at the end.
+UD_DEVINL float u01_from_bits(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0,1)
+UD_DEVINL float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+UD_DEVINL float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <bool CFG>
+__global__ void __launch_bounds__(256)
+ddpm_update_logits_fast_kernel(const int64_t* __restrict__ x, const __nv_bfloat16* __restrict__ lc,
+                               const __nv_bfloat16* __restrict__ lu, long long ldv, const float* __restrict__ cfg_w,
+                               const int64_t* __restrict__ modality, uint64_t seed, uint64_t offset,
+                               const float* __restrict__ mc_t, const float* __restrict__ mc_s, int64_t mask_index,
+                               int text_vocab, int64_t* __restrict__ out, int R, int N, int V) {
+    // ONE WARP PER ROW: no shared memory, no block barriers; 64 independent rows in flight per SM hide the HBM latency and
+    // the short serial tail (final draw by lane 0).
+    constexpr float L2E = 1.4426950408889634f, LN2_ = 0.6931471805599453f;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32));
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int r = gw; r < R; r += nw) {
+        const long long xr = x[r];
+        if (xr != mask_index) {
+            if (lane == 0) out[r] = xr;
+            continue;
+        }
+        const int b = r / N;
+        int lo, hi;
+        valid_range(modality[r], V, text_vocab, lo, hi);
+        const __nv_bfloat16* rc = lc + (long long)r * ldv;
+        const __nv_bfloat16* ru = CFG ? lu + (long long)r * ldv : nullptr;
+        const float w = CFG ? cfg_w[b] : 0.f;
+        float m2 = -INFINITY, ssum = 0.f;        // running max (log2 units) and sum of 2^(l2 - m2)
+        float best = -INFINITY;                  // best group score (log2 units)
+        int best_v = 0x7fffffff;
+        const int g0 = lo & ~7;
+        int it = 0;
+        for (int base = g0; base < hi; base += 1024, ++it) {
+            uint4 a[4], bq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {        // 4 fully coalesced 16-byte loads in flight per lane
+                const int v = base + k * 256 + lane * 8;
+                a[k] = make_uint4(0, 0, 0, 0);
+                bq[k] = make_uint4(0, 0, 0, 0);
+                if (v < hi) {
+                    a[k] = ldg_stream(rc + v);
+                    if (CFG) bq[k] = ldg_stream(ru + v);
+                }
+            }
+            const uint4 rn = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)it, (uint32_t)lane, (uint32_t)offset), key);
+            const uint32_t rnd[4] = {rn.x, rn.y, rn.z, rn.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int v = base + k * 256 + lane * 8;
+                if (v >= hi) continue;
+                float l2[8] = {bf16lo(a[k].x), bf16hi(a[k].x), bf16lo(a[k].y), bf16hi(a[k].y),
+                               bf16lo(a[k].z), bf16hi(a[k].z), bf16lo(a[k].w), bf16hi(a[k].w)};
+                if (CFG) {
+                    const float f[8] = {bf16lo(bq[k].x), bf16hi(bq[k].x), bf16lo(bq[k].y), bf16hi(bq[k].y),
+                                        bf16lo(bq[k].z), bf16hi(bq[k].z), bf16lo(bq[k].w), bf16hi(bq[k].w)};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) l2[i] = (1.0f + w) * l2[i] - w * f[i];     // model_eval.py:1812
+                }
+                float gm = -INFINITY;
+                const bool edge = (v < lo) || (v + 8 > hi) || (mask_index >= v && mask_index < v + 8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    l2[i] *= L2E;
+                    if (edge) { const int c = v + i; if (c < lo || c >= hi || c == mask_index) l2[i] = -INFINITY; }
+                    gm = fmaxf(gm, l2[i]);
+                }
+                if (gm == -INFINITY) continue;
+                if (gm > m2) { ssum *= (m2 == -INFINITY) ? 0.f : ex2f(m2 - gm); m2 = gm; }
+                float gsum = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gsum += ex2f(l2[i] - m2);
+                ssum += gsum;
+                const float E = -LN2_ * lg2f(u01_from_bits(rnd[k]));
+                const float sc = m2 + lg2f(gsum) - lg2f(E);
+                if (sc > best) { best = sc; best_v = v; }
+            }
+        }
+        // warp merge: log-sum-exp (log2 units) and arg-max over group scores
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m2, o), os = __shfl_xor_sync(0xffffffffu, ssum, o);
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+            const float nm = fmaxf(m2, om);
+            if (nm != -INFINITY) ssum = ssum * ex2f(m2 - nm) + os * ex2f(om - nm);
+            m2 = nm;
+            if (ob > best || (ob == best && ov < best_v)) { best = ob; best_v = ov; }
+        }
+        if (lane == 0) {
+            const float lse2 = m2 + lg2f(ssum);                                   // log2 of the row's sum of exp(l)
+            const float d = mc_t[b] - mc_s[b], msk = mc_s[b];
+            const uint4 fin = philox4x32_10(make_uint4((uint32_t)r, 0xffffffffu, 0u, (uint32_t)offset), key);
+            const float gscore = best + lg2f(fmaxf(d, 0.f)) - lse2;               // log2(q_group) + Gumbel (log2 units)
+            const float stay = lg2f(fmaxf(msk, 0.f)) - lg2f(-LN2_ * lg2f(u01_from_bits(fin.x)));
+            int64_t res = mask_index;
+            if (best_v != 0x7fffffff && !(stay > gscore)) {
+                // draw the token inside the winning group: Gumbel-max over its (up to 8) valid columns
+                const uint4 fin2 = philox4x32_10(make_uint4((uint32_t)r, 0xfffffffeu, 0u, (uint32_t)offset), key);
+                const uint4 fin3 = philox4x32_10(make_uint4((uint32_t)r, 0xfffffffdu, 0u, (uint32_t)offset), key);
+                const int v = best_v;
+                const uint4 a4 = *reinterpret_cast<const uint4*>(rc + v);
+                float l2[8] = {bf16lo(a4.x), bf16hi(a4.x), bf16lo(a4.y), bf16hi(a4.y), bf16lo(a4.z), bf16hi(a4.z), bf16lo(a4.w), bf16hi(a4.w)};
+                if (CFG) {
+                    const uint4 b4 = *reinterpret_cast<const uint4*>(ru + v);
+                    const float f[8] = {bf16lo(b4.x), bf16hi(b4.x), bf16lo(b4.y), bf16hi(b4.y), bf16lo(b4.z), bf16hi(b4.z), bf16lo(b4.w), bf16hi(b4.w)};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) l2[i] = (1.0f + w) * l2[i] - w * f[i];
+                }
+                const uint32_t rr[8] = {fin2.x, fin2.y, fin2.z, fin2.w, fin3.x, fin3.y, fin3.z, fin3.w};
+                float bs = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = v + i;
+                    if (c < lo || c >= hi || c == mask_index) continue;
+                    const float sc = l2[i] * L2E - lg2f(-LN2_ * lg2f(u01_from_bits(rr[i])));
+                    if (sc > bs) { bs = sc; res = c; }
+                }
+            }
+            out[r] = res;
+        }
+    }
+}
+
 static int rows_grid(int rows) {
     long long g = (long long)sm_count() * 8;
     return (int)(rows < g ? rows : g);
@@ -408,6 +541,17 @@ extern "C" int ud_ddpm_update_logits(const int64_t* x, const void* logits, const
     const size_t smem = (size_t)widest * sizeof(float);
     if (smem > 200 * 1024) { fprintf(stderr, "unidisc_b200: vocabulary range too wide for the fused sampler (%d)\n", widest); return -1; }
     const bool cfg = logits_uncond != nullptr;
+    if (u == nullptr) {   // Philox noise: single-pass log-domain kernel, no shared-memory staging
+        if (ldv % 8 != 0) { fprintf(stderr, "unidisc_b200: fused sampler needs ldv %% 8 == 0\n"); return -1; }
+        long long want = ((long long)R * 32 + 255) / 256;          // one warp per row, 8 warps per CTA
+        const int grid = (int)(want < (long long)sm_count() * 8 ? want : (long long)sm_count() * 8);
+        if (cfg)
+            ddpm_update_logits_fast_kernel<true><<<grid, 256, 0, STREAM(stream)>>>(x, CBF(logits), CBF(logits_uncond), ldv, cfg_w, modality, seed, offset, mc_t, mc_s, mask_index, text_vocab, out, R, N, V);
+        else
+            ddpm_update_logits_fast_kernel<false><<<grid, 256, 0, STREAM(stream)>>>(x, CBF(logits), nullptr, ldv, nullptr, modality, seed, offset, mc_t, mc_s, mask_index, text_vocab, out, R, N, V);
+        UD_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     static bool attr[2] = {false, false};
     if (cfg) {
         if (!attr[1]) { UD_CUDA_CHECK(cudaFuncSetAttribute(ddpm_update_logits_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[1] = true; }
