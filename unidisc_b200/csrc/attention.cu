@@ -11,6 +11,8 @@
 //   warp2-5 softmax: thread r owns query row r: tcgen05.ld S row -> running max / exp2 / row sum -> bf16 P -> tcgen05.st
 //           lazy O rescaling (only when the running max grows by > 2^8), final O/l and lse.
 // TMEM: S0[128] S1[128] O[hd] P0[64] P1[64] columns.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "unidisc_b200.h"
 
@@ -226,6 +228,248 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         // ---- epilogue: O / l, lse ----
         mbar_wait(pv_done, (T - 1) & 1);
+        tc_fence_after();
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        __nv_bfloat16* orow = p.o + ((long long)b * p.N + row) * p.ldo + h * HD;
+#pragma unroll
+        for (int c = 0; c < HD / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tO + c * 32 + lane_off, r);
+            tmem_ld_wait();
+            if (row < p.N) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 o4;
+                    o4.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
+                    o4.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
+                    o4.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
+                    o4.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = o4;
+                }
+            }
+        }
+        if (row < p.N) p.lse[((long long)b * p.H + h) * p.N + row] = l > 0.f ? (m_used + log2f(l)) * LN2 : INFINITY;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Forward v2: one CTA owns TWO 128-query tiles (A, B) and two softmax warpgroups, so the tensor core works on one tile
+// (S = QK^T, O += PV) while the other tile's warpgroup does the exp / row-sum arithmetic, and every SM sub-partition
+// has two softmax warps.  P (bf16) is written over the first 64 columns of its own S buffer (read back by the TS MMA).
+//   TMEM: S_A[128] S_B[128] O_A[HD] O_B[HD]          smem: Q_A Q_B | 2 stages of (K, V)
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(320, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+    using S = AttnSmem<HD>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                           // [2] tiles
+    uint8_t* sK = sQ + 2 * S::TILE_BYTES;         // [2] stages
+    uint8_t* sV = sK + 2 * S::TILE_BYTES;         // [2] stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * S::TILE_BYTES);
+    uint64_t* q_full = bars;           // 1
+    uint64_t* k_full = bars + 1;       // 2
+    uint64_t* v_full = bars + 3;       // 2
+    uint64_t* kv_empty = bars + 5;     // 2
+    uint64_t* s_full = bars + 7;       // 2 (per tile)
+    uint64_t* p_full = bars + 9;       // 2 (per tile)
+    uint64_t* pv_done = bars + 11;     // 2 (per tile)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+    __shared__ int sid_k[2 * 2 * 128];   // [warpgroup][stage][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+    const int T = (p.N + ATT_BKV - 1) / ATT_BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1); mbar_init(&v_full[s], 1); mbar_init(&kv_empty[s], 1);
+            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&pv_done[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, 2 * S::TILE_BYTES);
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int bx = 0; bx < S::NBOX; ++bx)
+                    tma_load_3d(sQ + t * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_q, q_full, h * HD + bx * 64, q0 + t * 128, b);
+            for (int j = 0; j < T; ++j) {
+                const int s = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(&kv_empty[s], ph ^ 1);
+                mbar_expect_tx(&k_full[s], S::TILE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < S::NBOX; ++bx)
+                    tma_load_3d(sK + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_k, &k_full[s], h * HD + bx * 64, j * ATT_BKV, b);
+                mbar_expect_tx(&v_full[s], S::TILE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < S::NBOX; ++bx)
+                    tma_load_3d(sV + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_v, &v_full[s], h * HD + bx * 64, j * ATT_BKV, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
+            auto issue_s = [&](int t, int j) {
+                const uint32_t aQ = smem_u32(sQ + t * S::TILE_BYTES), aK = smem_u32(sK + (j & 1) * S::TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < HD / 16; ++ks)
+                    umma_ss(tmem + t * 128, desc_kmajor(aQ, ks), desc_kmajor(aK, ks), idesc_s, ks != 0);
+                umma_commit(&s_full[t]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            for (int j = 0; j < T; ++j) {
+                const int s = j & 1;
+                mbar_wait(&v_full[s], (j >> 1) & 1);
+                const uint32_t aV = smem_u32(sV + s * S::TILE_BYTES);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    mbar_wait(&p_full[t], j & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                        umma_ts(tmem + 256 + t * HD, tmem + t * 128 + ks * 8, desc_mnmajor(aV, ks), idesc_pv, (j | ks) != 0);
+                    umma_commit(&pv_done[t]);
+                }
+                umma_commit(&kv_empty[s]);
+                if (j + 1 < T) {
+                    mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        mbar_wait(&pv_done[t], j & 1);      // P_t(j) (aliased on S_t) fully consumed
+                        tc_fence_after();
+                        issue_s(t, j + 1);
+                    }
+                }
+            }
+        }
+    } else {
+        const int wg = (warp - 2) >> 2;              // tile index
+        const int qd = warp & 3;
+        const int rloc = qd * 32 + lane;
+        const int row = q0 + wg * 128 + rloc;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const uint32_t tS = tmem + wg * 128, tO = tmem + 256 + wg * HD;
+        const bool use_ids = p.sample_ids != nullptr;
+        int sid_q = 0;
+        if (use_ids) sid_q = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
+        const int tid128 = (threadIdx.x - 64) & 127;
+        const float scl = p.scale_log2;
+        const int Ntok = p.N;
+        float m_used = -INFINITY, l = 0.f;
+        for (int j = 0; j < T; ++j) {
+            const int s = j & 1;
+            int* sk = sid_k + (wg * 2 + s) * 128;
+            if (use_ids) {
+                const int kk = j * ATT_BKV + tid128;
+                sk[tid128] = kk < Ntok ? (int)p.sample_ids[(long long)b * Ntok + kk] : -2;
+                named_bar_sync(1 + wg, 128);
+            }
+            mbar_wait(&s_full[wg], j & 1);
+            tc_fence_after();
+            const int kbase = j * ATT_BKV;
+            const bool slow = use_ids || (kbase + ATT_BKV > Ntok);
+            // the whole S row (128 fp32) is fetched with four back-to-back tcgen05.ld and ONE wait: TMEM load latency is
+            // paid once per tile instead of once per chunk
+            uint32_t r0[32], r1[32], r2[32], r3[32];
+            tmem_ld_32x32b_x32(tS + 0 + lane_off, r0);
+            tmem_ld_32x32b_x32(tS + 32 + lane_off, r1);
+            tmem_ld_32x32b_x32(tS + 64 + lane_off, r2);
+            tmem_ld_32x32b_x32(tS + 96 + lane_off, r3);
+            tmem_ld_wait();
+            if (slow) {
+                auto maskchunk = [&](uint32_t (&r)[32], int cb) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        bool ok = kbase + cb + i < Ntok;
+                        if (use_ids) ok = ok && sk[cb + i] == sid_q && sid_q != -1;
+                        if (!ok) r[i] = 0xff800000u;   // -inf
+                    }
+                };
+                maskchunk(r0, 0); maskchunk(r1, 32); maskchunk(r2, 64); maskchunk(r3, 96);
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r1[i]));
+                mx2 = fmaxf(mx2, __uint_as_float(r2[i])); mx3 = fmaxf(mx3, __uint_as_float(r3[i]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scl;
+            const float m_new = fmaxf(m_used, mx);
+            const bool grow = m_new > m_used + 8.0f;   // also true for -inf -> finite
+            if (__any_sync(0xffffffffu, grow)) {
+                const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_new);
+                if (j > 0) {
+                    mbar_wait(&pv_done[wg], (j - 1) & 1);   // O must be quiescent before it is rescaled
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < HD / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tO + c * 32 + lane_off, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tmem_st_32x32b_x32(tO + c * 32 + lane_off, r);
+                    }
+                    tmem_st_wait();
+                }
+                l *= alpha;
+                m_used = m_new;
+            }
+            const float mref = (m_used == -INFINITY) ? 0.f : m_used;
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+            // probabilities are packed IN PLACE (r0/r2 become the two 32-column P stores) to keep the live set at 128 registers
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float a0 = ex2(fmaf(__uint_as_float(r0[2 * i]), scl, -mref)), a1 = ex2(fmaf(__uint_as_float(r0[2 * i + 1]), scl, -mref));
+                const float c0 = ex2(fmaf(__uint_as_float(r2[2 * i]), scl, -mref)), c1 = ex2(fmaf(__uint_as_float(r2[2 * i + 1]), scl, -mref));
+                l0 += a0 + a1; l2 += c0 + c1;
+                r0[i] = pack_bf16x2(a0, a1);
+                r2[i] = pack_bf16x2(c0, c1);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float b0 = ex2(fmaf(__uint_as_float(r1[2 * i]), scl, -mref)), b1 = ex2(fmaf(__uint_as_float(r1[2 * i + 1]), scl, -mref));
+                const float d0 = ex2(fmaf(__uint_as_float(r3[2 * i]), scl, -mref)), d1 = ex2(fmaf(__uint_as_float(r3[2 * i + 1]), scl, -mref));
+                l1 += b0 + b1; l3 += d0 + d1;
+                r0[16 + i] = pack_bf16x2(b0, b1);
+                r2[16 + i] = pack_bf16x2(d0, d1);
+            }
+            tmem_st_32x32b_x32(tS + lane_off, r0);          // P columns [0,32)  = keys 0..63
+            tmem_st_32x32b_x32(tS + 32 + lane_off, r2);     // P columns [32,64) = keys 64..127
+            l += (l0 + l1) + (l2 + l3);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_full[wg]);
+        }
+        // ---- epilogue: O / l, lse ----
+        mbar_wait(&pv_done[wg], (T - 1) & 1);
         tc_fence_after();
         const float inv = l > 0.f ? 1.0f / l : 0.f;
         __nv_bfloat16* orow = p.o + ((long long)b * p.N + row) * p.ldo + h * HD;
@@ -503,28 +747,288 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constant
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Backward v2: same maths as attn_bwd_kernel, but the streamed operand is cut into 64-row sub-tiles and the score
+// accumulators are double-buffered in TMEM, so the tensor core (scores of sub-tile i+2, accumulation of sub-tile i)
+// runs concurrently with the exp / dS arithmetic of sub-tile i+1 instead of strictly alternating with it.
+//   TMEM: ScA[64] DpA[64] ScB[64] DpB[64] | Acc0[HD] Acc1[HD]          smem: 2 fixed 128-row tiles + 4-stage ring of 64-row tiles
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+struct AttnBwd2Smem {
+    static constexpr int FIX_BYTES = 128 * HD * 2;
+    static constexpr int SUB_BYTES = 64 * HD * 2;       // one streamed 64-row tile
+    static constexpr int SUB_BOX = 64 * 128;            // 64 rows x 64 bf16
+    static constexpr int NST = 4;
+    static constexpr int NBOX = HD / 64;
+    static constexpr int BYTES = 2 * FIX_BYTES + NST * 2 * SUB_BYTES + 1024 + 4096;
+};
+UD_DEVINL uint64_t desc_kmajor64(uint32_t tile_base, int ks) {   // [64 rows][HD] as HD/64 boxes of [64][64]
+    return make_smem_desc_sw128(tile_base + (ks >> 2) * (64 * 128) + (ks & 3) * 32, 16, 1024);
+}
+UD_DEVINL uint64_t desc_mnmajor64(uint32_t tile_base, int ks) {  // MN-major view: k-step = 16 rows, MN chunks 8 KB apart
+    return make_smem_desc_sw128(tile_base + ks * 2048, 64 * 128, 1024);
+}
+
+template <int HD, int MODE>
+__global__ void __launch_bounds__(320, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fb,
+                 const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const AttnBwdParams p) {
+    using S = AttnBwd2Smem<HD>;
+    constexpr int NST = S::NST;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sFA = smem;
+    uint8_t* sFB = sFA + S::FIX_BYTES;
+    uint8_t* sST = sFB + S::FIX_BYTES;                   // stage s: [SA | SB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sST + NST * 2 * S::SUB_BYTES);
+    uint64_t* f_full = bars;                 // 1
+    uint64_t* st_full = bars + 1;            // NST
+    uint64_t* st_empty = bars + 1 + NST;     // NST
+    uint64_t* sc_full = bars + 1 + 2 * NST;  // 2
+    uint64_t* pr_full = sc_full + 2;         // 2
+    uint64_t* acc_done = pr_full + 2;        // 2
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_done + 2);
+    __shared__ __align__(16) float s_lse[2 * 64];   // per-column metadata of the streamed sub-tile, one slot per warpgroup
+    __shared__ __align__(16) float s_dlt[2 * 64];
+    __shared__ __align__(16) int s_sid[2 * 64];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int T2 = (p.N + 63) / 64;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_fa); tma_prefetch_desc(&tm_fb); tma_prefetch_desc(&tm_sa); tma_prefetch_desc(&tm_sb);
+        mbar_init(f_full, 1);
+        for (int s = 0; s < NST; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sc_full[s], 1); mbar_init(&pr_full[s], 128); mbar_init(&acc_done[s], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+    const uint32_t tAcc0 = tmem + 256, tAcc1 = tmem + 256 + HD;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(f_full, 2 * S::FIX_BYTES);
+#pragma unroll
+            for (int bx = 0; bx < S::NBOX; ++bx) {
+                tma_load_3d(sFA + bx * (128 * 128), &tm_fa, f_full, h * HD + bx * 64, t0, b);
+                tma_load_3d(sFB + bx * (128 * 128), &tm_fb, f_full, h * HD + bx * 64, t0, b);
+            }
+            for (int i = 0; i < T2; ++i) {
+                const int s = i % NST;
+                mbar_wait(&st_empty[s], ((i / NST) & 1) ^ 1);
+                mbar_expect_tx(&st_full[s], 2 * S::SUB_BYTES);
+                uint8_t* sa = sST + s * 2 * S::SUB_BYTES;
+                uint8_t* sb = sa + S::SUB_BYTES;
+#pragma unroll
+                for (int bx = 0; bx < S::NBOX; ++bx) {
+                    tma_load_3d(sa + bx * S::SUB_BOX, &tm_sa, &st_full[s], h * HD + bx * 64, i * 64, b);
+                    tma_load_3d(sb + bx * S::SUB_BOX, &tm_sb, &st_full[s], h * HD + bx * 64, i * 64, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_sc = make_idesc_bf16(128, 64, false, false);
+            constexpr uint32_t idesc_acc = make_idesc_bf16(128, HD, false, true);
+            const uint32_t aFA = smem_u32(sFA), aFB = smem_u32(sFB);
+            auto issue_scores = [&](int i) {
+                const int s = i % NST, bf = i & 1;
+                mbar_wait(&st_full[s], (i / NST) & 1);
+                tc_fence_after();
+                const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
+                const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
+#pragma unroll
+                for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tSc, desc_kmajor(aFA, ks), desc_kmajor64(aSA, ks), idesc_sc, ks != 0);
+#pragma unroll
+                for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tDp, desc_kmajor(aFB, ks), desc_kmajor64(aSB, ks), idesc_sc, ks != 0);
+                umma_commit(&sc_full[bf]);
+            };
+            mbar_wait(f_full, 0);
+            issue_scores(0);
+            if (T2 > 1) issue_scores(1);
+            for (int i = 0; i < T2; ++i) {
+                const int s = i % NST, bf = i & 1;
+                const uint32_t ph = (i >> 1) & 1;
+                mbar_wait(&pr_full[bf], ph);
+                tc_fence_after();
+                const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
+                const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
+                if (MODE == 0) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc1, tSc + ks * 8, desc_mnmajor64(aSB, ks), idesc_acc, (i | ks) != 0);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, (i | ks) != 0);
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, (i | ks) != 0);
+                }
+                umma_commit(&st_empty[s]);
+                umma_commit(&acc_done[bf]);
+                if (i + 2 < T2) {
+                    mbar_wait(&acc_done[bf], ph);     // probabilities of sub-tile i consumed -> its score columns are free
+                    issue_scores(i + 2);
+                }
+            }
+        }
+    } else {
+        // two softmax warpgroups (warps 2-5 and 6-9): warpgroup g owns the sub-tiles i == g (mod 2), i.e. score buffer g,
+        // so two sub-tiles are in flight and every SM sub-partition has two warps to hide ALU / MUFU latency
+        const int wg = (warp - 2) >> 2;
+        const int qd = warp & 3;
+        const int rloc = qd * 32 + lane;
+        const int row = t0 + rloc;   // MODE0: key index ; MODE1: query index
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const int tid128 = (threadIdx.x - 64) & 127;
+        const bool use_ids = p.sample_ids != nullptr;
+        const long long bh = (long long)b * p.H + h;
+        int sid_row = 0;
+        if (use_ids) sid_row = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
+        float lse_row = 0.f, dlt_row = 0.f;
+        if (MODE == 1 && row < p.N) { lse_row = p.lse[bh * p.N + row] * LOG2E; dlt_row = p.delta[bh * p.N + row]; }
+        const bool row_ok = row < p.N;
+        const int bf = wg;
+        const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
+        const float scl = p.scale_log2;
+        const int Ntok = p.N;
+        for (int i = wg; i < T2; i += 2) {
+            if (MODE == 0 || use_ids) {
+                if (tid128 < 64) {
+                    const int cidx = i * 64 + tid128;
+                    if (MODE == 0) {
+                        s_lse[bf * 64 + tid128] = cidx < Ntok ? p.lse[bh * Ntok + cidx] * LOG2E : INFINITY;
+                        s_dlt[bf * 64 + tid128] = cidx < Ntok ? p.delta[bh * Ntok + cidx] : 0.f;
+                    }
+                    if (use_ids) s_sid[bf * 64 + tid128] = cidx < Ntok ? (int)p.sample_ids[(long long)b * Ntok + cidx] : -2;
+                }
+                named_bar_sync(1 + wg, 128);
+            }
+            mbar_wait(&sc_full[bf], (i >> 1) & 1);
+            tc_fence_after();
+            const bool slow = use_ids || (i * 64 + 64 > Ntok) || !row_ok;   // masks needed only on edge tiles / document masks
+            uint32_t rsA[32], rsB[32], rdA[32], rdB[32];
+            tmem_ld_32x32b_x32(tSc + lane_off, rsA);
+            tmem_ld_32x32b_x32(tDp + lane_off, rdA);
+            tmem_ld_32x32b_x32(tSc + 32 + lane_off, rsB);
+            tmem_ld_32x32b_x32(tDp + 32 + lane_off, rdB);
+            tmem_ld_wait();                                   // one exposed TMEM latency per sub-tile
+            // P / dS are packed in place into rsA / rdA (chunk 0 -> entries 0..15, chunk 1 -> 16..31)
+            auto chunk = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c) {
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    float l4[4], d4[4];
+                    if (MODE == 0) {
+                        const float4 lv = *reinterpret_cast<const float4*>(&s_lse[bf * 64 + c * 32 + e4 * 4]);
+                        const float4 dv = *reinterpret_cast<const float4*>(&s_dlt[bf * 64 + c * 32 + e4 * 4]);
+                        l4[0] = lv.x; l4[1] = lv.y; l4[2] = lv.z; l4[3] = lv.w;
+                        d4[0] = dv.x; d4[1] = dv.y; d4[2] = dv.z; d4[3] = dv.w;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { l4[u] = lse_row; d4[u] = dlt_row; }
+                    }
+                    float pv[4], dvv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int col = c * 32 + e4 * 4 + u;
+                        float pr = ex2(fmaf(__uint_as_float(rs[e4 * 4 + u]), scl, -l4[u]));
+                        if (slow) {
+                            bool ok = row_ok && (i * 64 + col < Ntok);
+                            if (use_ids) {
+                                const int sq = s_sid[bf * 64 + col];
+                                ok = ok && sq == sid_row && sid_row != -1;
+                            }
+                            if (!ok) pr = 0.f;
+                        }
+                        pv[u] = pr;
+                        dvv[u] = pr * (__uint_as_float(rd[e4 * 4 + u]) - d4[u]);
+                    }
+                    rsA[c * 16 + e4 * 2] = pack_bf16x2(pv[0], pv[1]); rsA[c * 16 + e4 * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+                    rdA[c * 16 + e4 * 2] = pack_bf16x2(dvv[0], dvv[1]); rdA[c * 16 + e4 * 2 + 1] = pack_bf16x2(dvv[2], dvv[3]);
+                }
+            };
+            chunk(rsA, rdA, 0);
+            chunk(rsB, rdB, 1);
+            if (MODE == 0) tmem_st_32x32b_x32(tSc + lane_off, rsA);
+            tmem_st_32x32b_x32(tDp + lane_off, rdA);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&pr_full[bf]);
+        }
+        // ---- write the accumulators (the two warpgroups split the work) ----
+        mbar_wait(&acc_done[(T2 - 1) & 1], ((T2 - 1) >> 1) & 1);
+        tc_fence_after();
+        {
+            // MODE0: warpgroup 0 stores dK (Acc0), warpgroup 1 stores dV (Acc1).  MODE1: each stores half of dQ's columns.
+            const int a = (MODE == 0) ? wg : 0;
+            const uint32_t tA = a == 0 ? tAcc0 : tAcc1;
+            __nv_bfloat16* dst = (a == 0 ? p.out0 : p.out1) + ((long long)b * p.N + row) * (a == 0 ? p.ld0 : p.ld1) + h * HD;
+            const float sc = a == 0 ? p.scale : 1.0f;
+            const int c_lo = (MODE == 0) ? 0 : wg * (HD / 64), c_hi = (MODE == 0) ? HD / 32 : (wg + 1) * (HD / 64);
+#pragma unroll 1
+            for (int c = c_lo; c < c_hi; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tA + c * 32 + lane_off, r);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        uint4 o4;
+                        o4.x = pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) * sc, __uint_as_float(r[8 * q4 + 1]) * sc);
+                        o4.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * sc, __uint_as_float(r[8 * q4 + 3]) * sc);
+                        o4.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * sc, __uint_as_float(r[8 * q4 + 5]) * sc);
+                        o4.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * sc, __uint_as_float(r[8 * q4 + 7]) * sc);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = o4;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
 template <int HD>
 static int attn_smem_bytes(int ntiles) { return ntiles * AttnSmem<HD>::TILE_BYTES + 1024 + 4096; }
 
-static int make_head_tmap(CUtensorMap* tm, const void* base, long long ld, int B, int N, int D) {
-    // dims: (column, token, batch); box = 64 columns x 128 tokens x 1 batch
-    return make_tmap_3d_bf16(tm, base, (uint64_t)D, (uint64_t)N, (uint64_t)B, (uint64_t)ld, (uint64_t)ld * N, 64, 128, 1);
+static int make_head_tmap(CUtensorMap* tm, const void* base, long long ld, int B, int N, int D, int box_rows = 128) {
+    // dims: (column, token, batch); box = 64 columns x box_rows tokens x 1 batch
+    return make_tmap_3d_bf16(tm, base, (uint64_t)D, (uint64_t)N, (uint64_t)B, (uint64_t)ld, (uint64_t)ld * N, 64, box_rows, 1);
 }
 
 template <int HD>
 static int launch_attn_fwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const AttnParams& p,
                            cudaStream_t stream) {
+    static const bool use_v1 = getenv("UD_ATTN_FWD_V2") == nullptr;     // default: one query tile per CTA; UD_ATTN_FWD_V2=1 selects the two-tile kernel (A/B testing)
     CUtensorMap tq, tk, tv;
     const int D = p.H * HD;
     int rc = make_head_tmap(&tq, q, ldqk, p.B, p.N, D);
     if (rc) return rc;
     if ((rc = make_head_tmap(&tk, k, ldqk, p.B, p.N, D))) return rc;
     if ((rc = make_head_tmap(&tv, v, ldv, p.B, p.N, D))) return rc;
-    const int smem = attn_smem_bytes<HD>(5);
-    static bool attr = false;
-    if (!attr) { UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-    dim3 grid((p.N + ATT_BQ - 1) / ATT_BQ, p.H, p.B);
-    attn_fwd_kernel<HD><<<grid, 192, smem, stream>>>(tq, tk, tv, p);
+    if (use_v1) {
+        const int smem = attn_smem_bytes<HD>(5);
+        static bool attr = false;
+        if (!attr) { UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+        dim3 grid((p.N + ATT_BQ - 1) / ATT_BQ, p.H, p.B);
+        attn_fwd_kernel<HD><<<grid, 192, smem, stream>>>(tq, tk, tv, p);
+        UD_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
+    const int smem = attn_smem_bytes<HD>(6);
+    static bool attr2 = false;
+    if (!attr2) { UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr2 = true; }
+    dim3 grid((p.N + 255) / 256, p.H, p.B);
+    attn_fwd2_kernel<HD><<<grid, 320, smem, stream>>>(tq, tk, tv, p);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -533,28 +1037,47 @@ template <int HD>
 static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const void* d_o,
                            long long ldo, AttnBwdParams p, __nv_bfloat16* dq, __nv_bfloat16* dk, long long lddqk,
                            __nv_bfloat16* dv, long long lddv, cudaStream_t stream) {
-    CUtensorMap tq, tk, tv, tdo;
+    static const bool use_v1 = getenv("UD_ATTN_BWD_V1") != nullptr;     // A/B switch: strictly alternating v1 kernel
+    CUtensorMap tq, tk, tv, tdo, tq64, tk64, tv64, tdo64;
     const int D = p.H * HD;
     int rc;
     if ((rc = make_head_tmap(&tq, q, ldqk, p.B, p.N, D))) return rc;
     if ((rc = make_head_tmap(&tk, k, ldqk, p.B, p.N, D))) return rc;
     if ((rc = make_head_tmap(&tv, v, ldv, p.B, p.N, D))) return rc;
     if ((rc = make_head_tmap(&tdo, d_o, ldo, p.B, p.N, D))) return rc;
-    const int smem = attn_smem_bytes<HD>(6);
-    static bool attr = false;
-    if (!attr) {
-        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<HD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<HD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
     dim3 grid((p.N + 127) / 128, p.H, p.B);
     AttnBwdParams p0 = p;
     p0.out0 = dk; p0.ld0 = lddqk; p0.out1 = dv; p0.ld1 = lddv;
-    attn_bwd_kernel<HD, 0><<<grid, 192, smem, stream>>>(tk, tv, tq, tdo, p0);
-    UD_CUDA_CHECK(cudaGetLastError());
     AttnBwdParams p1 = p;
     p1.out0 = dq; p1.ld0 = lddqk; p1.out1 = nullptr; p1.ld1 = 0;
-    attn_bwd_kernel<HD, 1><<<grid, 192, smem, stream>>>(tq, tdo, tk, tv, p1);
+    if (use_v1) {
+        const int smem = attn_smem_bytes<HD>(6);
+        static bool attr = false;
+        if (!attr) {
+            UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<HD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<HD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr = true;
+        }
+        attn_bwd_kernel<HD, 0><<<grid, 192, smem, stream>>>(tk, tv, tq, tdo, p0);
+        UD_CUDA_CHECK(cudaGetLastError());
+        attn_bwd_kernel<HD, 1><<<grid, 192, smem, stream>>>(tq, tdo, tk, tv, p1);
+        UD_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
+    if ((rc = make_head_tmap(&tq64, q, ldqk, p.B, p.N, D, 64))) return rc;
+    if ((rc = make_head_tmap(&tk64, k, ldqk, p.B, p.N, D, 64))) return rc;
+    if ((rc = make_head_tmap(&tv64, v, ldv, p.B, p.N, D, 64))) return rc;
+    if ((rc = make_head_tmap(&tdo64, d_o, ldo, p.B, p.N, D, 64))) return rc;
+    const int smem = AttnBwd2Smem<HD>::BYTES;
+    static bool attr2 = false;
+    if (!attr2) {
+        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2_kernel<HD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2_kernel<HD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr2 = true;
+    }
+    attn_bwd2_kernel<HD, 0><<<grid, 320, smem, stream>>>(tk, tv, tq64, tdo64, p0);
+    UD_CUDA_CHECK(cudaGetLastError());
+    attn_bwd2_kernel<HD, 1><<<grid, 320, smem, stream>>>(tq, tdo, tk64, tv64, p1);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -15,22 +15,29 @@ namespace ud {
 // ------------------------------------------------------------------------------------------------
 template <int NV>
 UD_DEVINL void block_sum(float (&v)[NV], float* scratch, int& buf) {
+    // warp shuffles -> one partial per warp -> the first NV lanes of warp 0 finish the sums -> NV broadcast reads.
+    // (Two barriers, but NV shared loads per thread instead of nwarps*NV: the row kernels were LDS/issue bound.)
+    static_assert(NV <= 32, "block_sum handles at most 32 running sums");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
-    float* s = scratch + buf * 32 * NV;
+    if (nwarps == 1) return;
+    float* part = scratch;               // [32][NV]
+    float* tot = scratch + 32 * NV;      // [NV]
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) s[warp * NV + i] = v[i];
+        for (int i = 0; i < NV; ++i) part[warp * NV + i] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0 && lane < NV) {
+        float t = 0.f;
+        for (int w = 0; w < nwarps; ++w) t += part[w * NV + lane];
+        tot[lane] = t;
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        float t = 0.f;
-        for (int w = 0; w < nwarps; ++w) t += s[w * NV + i];
-        v[i] = t;
-    }
-    buf ^= 1;
+    for (int i = 0; i < NV; ++i) v[i] = tot[i];
+    (void)buf;
 }
 
 struct F4 { float v[4]; };
