@@ -51,10 +51,11 @@ int ud_norm_residual_fwd(const void* a_bf16, const float* x_in, const float* w_a
                          void* h_bf16, float* rstd_a, float* rstd_x, int rows, int D, float eps, void* stream);
 /* backward of the above.  g_out: fp32 grad wrt x_out from the residual stream (may be NULL = 0); dh: bf16 grad wrt h.
  * Writes g_in (fp32 total grad wrt x_out == grad wrt x_in), da (bf16 grad wrt a), and atomically accumulates
- * dw_n += sum_rows dh * xhat,  dw_a += sum_rows g * bf16(rms(a)). */
+ * dw_n += sum_rows dh * xhat,  dw_a += sum_rows g * bf16(rms(a)),  and (if db_a != NULL) db_a += sum_rows da — the bias
+ * gradient of the Linear that produced `a` (mlp.2.bias, dit.py:919), saving a separate column-sum pass. */
 int ud_norm_residual_bwd(const float* g_out, const void* dh_bf16, const float* x_out, const float* rstd_x, const float* w_n,
                          const void* a_bf16, const float* rstd_a, const float* w_a, float* g_in, void* da_bf16,
-                         float* dw_n, float* dw_a, int rows, int D, void* stream);
+                         float* dw_n, float* dw_a, float* db_a, int rows, int D, void* stream);
 /* backward of the first norm only: g_in = g_out + rms_bwd(dh) ; dw += ... */
 int ud_rmsnorm_bwd(const float* g_out, const void* dh_bf16, const float* x, const float* rstd, const float* w, float* g_in,
                    float* dw, int rows, int D, void* stream);

@@ -162,7 +162,8 @@ def test_norm_residual_fwd_bwd(ops, D):
     g_out = rnd(rows, D, seed=5)
     dh = rnd(rows, D, seed=6, dtype=bf16)
     dw_n, dw_a = torch.zeros(D, device=dev()), torch.zeros(D, device=dev())
-    g_in, da = ops.norm_residual_bwd(g_out, dh, x_out, rx, w_n, a, ra, w_a, dw_n, dw_a)
+    db = torch.zeros(D, device=dev())
+    g_in, da = ops.norm_residual_bwd(g_out, dh, x_out, rx, w_n, a, ra, w_a, dw_n, dw_a, db_a=db)
     torch.cuda.synchronize()
     a32 = a.float().requires_grad_(True)
     xi = x_in.clone().requires_grad_(True)
@@ -174,6 +175,7 @@ def test_norm_residual_fwd_bwd(ops, D):
     close_bf16(da, a32.grad.to(bf16), "da", frac_bad=5e-3)
     assert torch.allclose(dw_n, wn_.grad, rtol=2e-3, atol=2e-3), (dw_n - wn_.grad).abs().max()
     assert torch.allclose(dw_a, wa_.grad, rtol=2e-3, atol=2e-3), (dw_a - wa_.grad).abs().max()
+    assert torch.allclose(db, a32.grad.sum(0), rtol=2e-3, atol=2e-3), (db - a32.grad.sum(0)).abs().max()
     # plain rmsnorm backward
     dw = torch.zeros(D, device=dev())
     g2 = ops.rmsnorm_bwd(g_out, dh, x_out, rx, w_n, dw)

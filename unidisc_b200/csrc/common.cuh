@@ -41,17 +41,26 @@ UD_DEVINL float fast_tanh(float x) {
     float e = __expf(2.0f * x);
     return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
+// single-MUFU tanh (max rel. error 2^-11, well below the bf16 rounding that follows every use in the GEMM epilogues)
+UD_DEVINL float tanh_mufu(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // GELU(tanh) and derivative — nn.GELU(approximate="tanh") (reference models/dit.py:918)
 UD_DEVINL float gelu_tanh(float x) {
-    const float k = 0.7978845608028654f, c = 0.044715f;
-    float t = fast_tanh(k * (x + c * x * x * x));
-    return 0.5f * x * (1.0f + t);
+    const float k = 0.7978845608028654f, kc = 0.7978845608028654f * 0.044715f;
+    const float x2 = x * x;
+    const float t = tanh_mufu(x * fmaf(kc, x2, k));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
 }
 UD_DEVINL float gelu_tanh_grad(float x) {
-    const float k = 0.7978845608028654f, c = 0.044715f;
-    float x2 = x * x;
-    float t = fast_tanh(k * (x + c * x * x2));
-    return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k * (1.0f + 3.0f * c * x2);
+    const float k = 0.7978845608028654f, kc = 0.7978845608028654f * 0.044715f;
+    const float x2 = x * x;
+    const float t = tanh_mufu(x * fmaf(kc, x2, k));
+    const float dt = fmaf(-t, t, 1.0f) * fmaf(3.0f * kc, x2, k);     // (1 - t^2) * k (1 + 3c x^2)
+    return fmaf(0.5f * x, dt, fmaf(0.5f, t, 0.5f));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -174,14 +174,14 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
                                          const float* __restrict__ w_n, const __nv_bfloat16* __restrict__ a,
                                          const float* __restrict__ rstd_a, const float* __restrict__ w_a,
                                          float* __restrict__ g_in, __nv_bfloat16* __restrict__ da, float* __restrict__ dw_n,
-                                         float* __restrict__ dw_a, int rows, int D) {
+                                         float* __restrict__ dw_a, float* __restrict__ db_a, int rows, int D) {
     __shared__ float scratch[2 * 32 * 3 * R];
     int buf = 0;
     const int c = threadIdx.x * 4;
     const F4 wn = ld_f4(w_n + c);
     F4 wa = {{0, 0, 0, 0}};
     if (HAS_BRANCH) wa = ld_f4(w_a + c);
-    F4 acc_n = {{0, 0, 0, 0}}, acc_a = {{0, 0, 0, 0}};
+    F4 acc_n = {{0, 0, 0, 0}}, acc_a = {{0, 0, 0, 0}}, acc_b = {{0, 0, 0, 0}};
     const float invD = 1.0f / (float)D;
     for (int r0 = blockIdx.x * R; r0 < rows; r0 += gridDim.x * R) {
         F4 y[R], base[R], naf[R];
@@ -230,6 +230,7 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
                 for (int i = 0; i < 4; ++i) {
                     acc_a.v[i] += g.v[i] * bf16_round(naf[j].v[i]);
                     dav.v[i] = ra[j] * (g.v[i] * wa.v[i] - naf[j].v[i] * m2);
+                    acc_b.v[i] += dav.v[i];          // bias gradient of the Linear that produced `a` (column sum of da)
                 }
                 st_bf4(da + off, dav);
             }
@@ -238,13 +239,18 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         atomicAdd(dw_n + c + i, acc_n.v[i]);
-        if (HAS_BRANCH) atomicAdd(dw_a + c + i, acc_a.v[i]);
+        if (HAS_BRANCH) {
+            atomicAdd(dw_a + c + i, acc_a.v[i]);
+            if (db_a != nullptr) atomicAdd(db_a + c + i, acc_b.v[i]);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // q/k LayerNorm over the full hidden dim + RoPE   (dit.py:680-682, 724-726; standalone_rotary.py:14-31)
 // ------------------------------------------------------------------------------------------------
+struct QkRaw { uint2 q, k; float4 cs, sn; };
+
 template <int R>
 __global__ void qk_ln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ gq,
                                       const float* __restrict__ bq, const float* __restrict__ gk, const float* __restrict__ bk,
@@ -261,17 +267,34 @@ __global__ void qk_ln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, con
     const int pmask = hd >> 3;          // partner thread = tid ^ (hd/8)  (same warp for hd <= 128)
     const F4 gqv = ld_f4(gq + c), bqv = ld_f4(bq + c), gkv = ld_f4(gk + c), bkv = ld_f4(bk + c);
     const float invD = 1.0f / (float)D;
+    auto fetch = [&](int row) {
+        QkRaw t;
+        const __nv_bfloat16* src = qkv + (long long)row * 3 * D;
+        t.q = *reinterpret_cast<const uint2*>(src + c);
+        t.k = *reinterpret_cast<const uint2*>(src + D + c);
+        t.cs = *reinterpret_cast<const float4*>(cosT + (long long)row * half + ti);
+        t.sn = *reinterpret_cast<const float4*>(sinT + (long long)row * half + ti);
+        return t;
+    };
+    // software prefetch: the next iteration's rows are in flight while this iteration reduces / rotates / stores
+    QkRaw nxt[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) nxt[j] = fetch(min(blockIdx.x * R + j, rows - 1));
     for (int r0 = blockIdx.x * R; r0 < rows; r0 += gridDim.x * R) {
-        F4 q[R], k[R], cs[R], sn[R];
+        QkRaw cur[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) cur[j] = nxt[j];
+        const int rn = r0 + gridDim.x * R;
+        if (rn < rows) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) nxt[j] = fetch(min(rn + j, rows - 1));
+        }
+        F4 q[R], k[R];
         float s[2 * R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            const int row = (r0 + j < rows) ? r0 + j : r0;
-            const __nv_bfloat16* src = qkv + (long long)row * 3 * D;
-            q[j] = ld_bf4(src + c);
-            k[j] = ld_bf4(src + D + c);
-            cs[j] = ld_f4(cosT + (long long)row * half + ti);
-            sn[j] = ld_f4(sinT + (long long)row * half + ti);
+            q[j] = {{bf16lo(cur[j].q.x), bf16hi(cur[j].q.x), bf16lo(cur[j].q.y), bf16hi(cur[j].q.y)}};
+            k[j] = {{bf16lo(cur[j].k.x), bf16hi(cur[j].k.x), bf16lo(cur[j].k.y), bf16hi(cur[j].k.y)}};
             s[2 * j] = q[j].v[0] + q[j].v[1] + q[j].v[2] + q[j].v[3];
             s[2 * j + 1] = k[j].v[0] + k[j].v[1] + k[j].v[2] + k[j].v[3];
         }
@@ -291,6 +314,8 @@ __global__ void qk_ln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, con
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const float rq = rsqrtf(s[2 * j] * invD + eps), rk = rsqrtf(s[2 * j + 1] * invD + eps);
+            const float csv[4] = {cur[j].cs.x, cur[j].cs.y, cur[j].cs.z, cur[j].cs.w};
+            const float snv[4] = {cur[j].sn.x, cur[j].sn.y, cur[j].sn.z, cur[j].sn.w};
             F4 oq, ok;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -298,8 +323,8 @@ __global__ void qk_ln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, con
                 const float yk = bf16_round((k[j].v[i] * rk) * gkv.v[i] + bkv.v[i]);
                 const float pq = __shfl_xor_sync(0xffffffffu, yq, pmask);
                 const float pk = __shfl_xor_sync(0xffffffffu, yk, pmask);
-                oq.v[i] = yq * cs[j].v[i] + (lo ? -pq : pq) * sn[j].v[i];
-                ok.v[i] = yk * cs[j].v[i] + (lo ? -pk : pk) * sn[j].v[i];
+                oq.v[i] = yq * csv[i] + (lo ? -pq : pq) * snv[i];
+                ok.v[i] = yk * csv[i] + (lo ? -pk : pk) * snv[i];
             }
             if (r0 + j < rows) {
                 __nv_bfloat16* dst = out + (long long)(r0 + j) * 2 * D;
@@ -310,6 +335,8 @@ __global__ void qk_ln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, con
         }
     }
 }
+
+struct QkRawB { uint2 q, k, dq, dk; float4 cs, sn, st; };
 
 template <int R>
 __global__ void qk_ln_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dqk, const __nv_bfloat16* __restrict__ qkv,
@@ -329,30 +356,53 @@ __global__ void qk_ln_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dqk, con
     const F4 gqv = ld_f4(gq + c), gkv = ld_f4(gk + c);
     F4 a_gq = {{0, 0, 0, 0}}, a_bq = {{0, 0, 0, 0}}, a_gk = {{0, 0, 0, 0}}, a_bk = {{0, 0, 0, 0}};
     const float invD = 1.0f / (float)D;
+    auto fetch = [&](int row) {
+        QkRawB t;
+        const __nv_bfloat16* src = qkv + (long long)row * 3 * D;
+        const __nv_bfloat16* gsrc = dqk + (long long)row * 2 * D;
+        t.q = *reinterpret_cast<const uint2*>(src + c);
+        t.k = *reinterpret_cast<const uint2*>(src + D + c);
+        t.dq = *reinterpret_cast<const uint2*>(gsrc + c);
+        t.dk = *reinterpret_cast<const uint2*>(gsrc + D + c);
+        t.cs = *reinterpret_cast<const float4*>(cosT + (long long)row * half + ti);
+        t.sn = *reinterpret_cast<const float4*>(sinT + (long long)row * half + ti);
+        t.st = *reinterpret_cast<const float4*>(stats + (long long)row * 4);
+        return t;
+    };
+    QkRawB nxt[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) nxt[j] = fetch(min(blockIdx.x * R + j, rows - 1));
     for (int r0 = blockIdx.x * R; r0 < rows; r0 += gridDim.x * R) {
+        QkRawB cur[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) cur[j] = nxt[j];
+        const int rn = r0 + gridDim.x * R;
+        if (rn < rows) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) nxt[j] = fetch(min(rn + j, rows - 1));
+        }
         F4 xq[R], xk[R], eq[R], ek[R];
-        float4 st[R];
         float s[4 * R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const bool okr = r0 + j < rows;
-            const int row = okr ? r0 + j : r0;
-            st[j] = *reinterpret_cast<const float4*>(stats + (long long)row * 4);
-            const __nv_bfloat16* src = qkv + (long long)row * 3 * D;
-            const __nv_bfloat16* gsrc = dqk + (long long)row * 2 * D;
-            F4 q = ld_bf4(src + c), k = ld_bf4(src + D + c);
-            F4 dq = ld_bf4(gsrc + c), dk = ld_bf4(gsrc + D + c);
-            const F4 cs = ld_f4(cosT + (long long)row * half + ti), sn = ld_f4(sinT + (long long)row * half + ti);
+            const float4 st = cur[j].st;
+            const float qv[4] = {bf16lo(cur[j].q.x), bf16hi(cur[j].q.x), bf16lo(cur[j].q.y), bf16hi(cur[j].q.y)};
+            const float kv[4] = {bf16lo(cur[j].k.x), bf16hi(cur[j].k.x), bf16lo(cur[j].k.y), bf16hi(cur[j].k.y)};
+            const float dqv[4] = {bf16lo(cur[j].dq.x), bf16hi(cur[j].dq.x), bf16lo(cur[j].dq.y), bf16hi(cur[j].dq.y)};
+            const float dkv[4] = {bf16lo(cur[j].dk.x), bf16hi(cur[j].dk.x), bf16lo(cur[j].dk.y), bf16hi(cur[j].dk.y)};
+            const float csv[4] = {cur[j].cs.x, cur[j].cs.y, cur[j].cs.z, cur[j].cs.w};
+            const float snv[4] = {cur[j].sn.x, cur[j].sn.y, cur[j].sn.z, cur[j].sn.w};
             s[4 * j] = s[4 * j + 1] = s[4 * j + 2] = s[4 * j + 3] = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 // inverse rotation of the incoming gradients
-                const float pq = __shfl_xor_sync(0xffffffffu, dq.v[i], pmask);
-                const float pk = __shfl_xor_sync(0xffffffffu, dk.v[i], pmask);
-                const float dyq = dq.v[i] * cs.v[i] + (lo ? pq : -pq) * sn.v[i];
-                const float dyk = dk.v[i] * cs.v[i] + (lo ? pk : -pk) * sn.v[i];
-                xq[j].v[i] = (q.v[i] - st[j].x) * st[j].y;
-                xk[j].v[i] = (k.v[i] - st[j].z) * st[j].w;
+                const float pq = __shfl_xor_sync(0xffffffffu, dqv[i], pmask);
+                const float pk = __shfl_xor_sync(0xffffffffu, dkv[i], pmask);
+                const float dyq = dqv[i] * csv[i] + (lo ? pq : -pq) * snv[i];
+                const float dyk = dkv[i] * csv[i] + (lo ? pk : -pk) * snv[i];
+                xq[j].v[i] = (qv[i] - st.x) * st.y;
+                xk[j].v[i] = (kv[i] - st.z) * st.w;
                 if (okr) {
                     a_gq.v[i] += dyq * xq[j].v[i]; a_bq.v[i] += dyq;
                     a_gk.v[i] += dyk * xk[j].v[i]; a_bk.v[i] += dyk;
@@ -367,11 +417,12 @@ __global__ void qk_ln_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dqk, con
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             if (r0 + j >= rows) break;
+            const float4 st = cur[j].st;
             F4 oq, ok;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                oq.v[i] = st[j].y * (eq[j].v[i] - s[4 * j] * invD - xq[j].v[i] * s[4 * j + 1] * invD);
-                ok.v[i] = st[j].w * (ek[j].v[i] - s[4 * j + 2] * invD - xk[j].v[i] * s[4 * j + 3] * invD);
+                oq.v[i] = st.y * (eq[j].v[i] - s[4 * j] * invD - xq[j].v[i] * s[4 * j + 1] * invD);
+                ok.v[i] = st.w * (ek[j].v[i] - s[4 * j + 2] * invD - xk[j].v[i] * s[4 * j + 3] * invD);
             }
             __nv_bfloat16* dst = dqkv + (long long)(r0 + j) * 3 * D;
             st_bf4(dst + c, oq);
@@ -567,12 +618,12 @@ extern "C" int ud_norm_residual_fwd(const void* a, const float* x_in, const floa
 
 extern "C" int ud_norm_residual_bwd(const float* g_out, const void* dh, const float* x_out, const float* rstd_x,
                                     const float* w_n, const void* a, const float* rstd_a, const float* w_a, float* g_in,
-                                    void* da, float* dw_n, float* dw_a, int rows, int D, void* stream) {
+                                    void* da, float* dw_n, float* dw_a, float* db_a, int rows, int D, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "norm_residual_bwd")) return -1;
     int grid = row_grid((rows + 1) / 2, D / 4);
     if (grid > 4 * sm_count()) grid = 4 * sm_count();
-    norm_residual_bwd_kernel<true, 2><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, rows, D);
+    norm_residual_bwd_kernel<true, 2><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, db_a, rows, D);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -583,7 +634,7 @@ extern "C" int ud_rmsnorm_bwd(const float* g_out, const void* dh, const float* x
     if (!check_D(D, "rmsnorm_bwd")) return -1;
     int grid = row_grid((rows + 1) / 2, D / 4);
     if (grid > 4 * sm_count()) grid = 4 * sm_count();
-    norm_residual_bwd_kernel<false, 2><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x, rstd, w, nullptr, nullptr, nullptr, g_in, nullptr, dw, nullptr, rows, D);
+    norm_residual_bwd_kernel<false, 2><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x, rstd, w, nullptr, nullptr, nullptr, g_in, nullptr, dw, nullptr, nullptr, rows, D);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -597,7 +648,7 @@ extern "C" int ud_qk_ln_rope_fwd(const void* qkv, const float* gq, const float* 
         fprintf(stderr, "unidisc_b200: qk_ln_rope supports head_dim 32/64/128 (got %d)\n", head_dim);
         return -1;
     }
-    qk_ln_rope_fwd_kernel<4><<<row_grid((rows + 3) / 4, D / 4), D / 4, 0, STREAM(stream)>>>(CBF(qkv), gq, bq, gk, bk, cos, sin, BF(qk_out), stats, rows, D, head_dim, eps);
+    qk_ln_rope_fwd_kernel<2><<<row_grid((rows + 1) / 2, D / 4), D / 4, 0, STREAM(stream)>>>(CBF(qkv), gq, bq, gk, bk, cos, sin, BF(qk_out), stats, rows, D, head_dim, eps);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -28,6 +28,18 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int UMMA_K = 16;
 
+// Tile order: groups of RASTER_GM row-tiles are swept across all column-tiles before moving on, so the operand panels a
+// wave of CTAs touches (GM row panels + ~wave/GM column panels) stay L2-resident instead of streaming all of A per column.
+static constexpr int RASTER_GM = 8;
+UD_DEVINL void tile_coords(int tile, int num_m, int num_n, int& tm, int& tn) {
+    const int per_group = RASTER_GM * num_n;
+    const int g = tile / per_group, local = tile - g * per_group;
+    const int m_base = g * RASTER_GM;
+    const int gm = min(RASTER_GM, num_m - m_base);
+    tm = m_base + local % gm;
+    tn = local / gm;
+}
+
 struct GemmParams {
     int M, N, K;
     void* C;
@@ -190,8 +202,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile % p.num_m_tiles) * BM;
-                const int n0 = (tile / p.num_m_tiles) * BN;
+                int tm, tn;
+                tile_coords(tile, p.num_m_tiles, p.num_n_tiles, tm, tn);
+                const int m0 = tm * BM;
+                const int n0 = tn * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
@@ -252,8 +266,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         int as = 0;
         uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile % p.num_m_tiles) * BM;
-            const int n0 = (tile / p.num_m_tiles) * BN;
+            int tm, tn;
+            tile_coords(tile, p.num_m_tiles, p.num_n_tiles, tm, tn);
+            const int m0 = tm * BM;
+            const int n0 = tn * BN;
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
             const int row = m0 + q * 32 + lane;
@@ -345,8 +361,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             int s = 0;
             uint32_t ph = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m0 = (tile % p.num_m_tiles) * 256 + (int)rank * BM;
-                const int n0 = (tile / p.num_m_tiles) * BN + (int)rank * (BN / 2);
+                int tm, tn;
+                tile_coords(tile, p.num_m_tiles, p.num_n_tiles, tm, tn);
+                const int m0 = tm * 256 + (int)rank * BM;
+                const int n0 = tn * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
@@ -407,8 +425,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         int as = 0;
         uint32_t aph = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            const int m0 = (tile % p.num_m_tiles) * 256 + (int)rank * BM;
-            const int n0 = (tile / p.num_m_tiles) * BN;
+            int tm, tn;
+            tile_coords(tile, p.num_m_tiles, p.num_n_tiles, tm, tn);
+            const int m0 = tm * 256 + (int)rank * BM;
+            const int n0 = tn * BN;
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
             const int row = m0 + q * 32 + lane;

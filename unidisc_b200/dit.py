@@ -406,10 +406,10 @@ class DIT(nn.Module):
             w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
             d_wnext = self._blk[i + 1]["d_n1"] if i + 1 < self.n_blocks else T["d_nf"]
             # x2 = x1 + rms(d)*w_post ; h_next = rms(x2)*w_next
-            g_res, dd = ops.norm_residual_bwd(g_res, dh, A["x2"], A["rx2"], w_next, A["d"], A["rd"], W["npost"], d_wnext, W["d_npost"])
+            g_res, dd = ops.norm_residual_bwd(g_res, dh, A["x2"], A["rx2"], w_next, A["d"], A["rd"], W["npost"], d_wnext, W["d_npost"],
+                                              db_a=W["d_b2"])           # also accumulates mlp.2.bias.grad = colsum(dd)
             # MLP
             ops.gemm(dd, A["g"], ta=True, tb=True, epi=wacc, out=W["d_w2"])
-            ops.colsum(dd, W["d_b2"])
             du = ops.gemm(dd, W["w2"], tb=True, epi=L.EPI_BF16_DGELU, aux=A["u"])
             ops.gemm(du, A["h2"], ta=True, tb=True, epi=wacc, out=W["d_w1"])
             ops.colsum(du, W["d_b1"])

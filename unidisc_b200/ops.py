@@ -65,14 +65,14 @@ def norm_residual_fwd(a, x_in, w_a, w_n, eps=1e-6, x_out=None, h=None):
     return x_out, h, ra, rx
 
 
-def norm_residual_bwd(g_out, dh, x_out, rstd_x, w_n, a, rstd_a, w_a, dw_n, dw_a, g_in=None, da=None):
+def norm_residual_bwd(g_out, dh, x_out, rstd_x, w_n, a, rstd_a, w_a, dw_n, dw_a, g_in=None, da=None, db_a=None):
     rows, D = x_out.shape
     if g_in is None:
         g_in = torch.empty_like(x_out)
     if da is None:
         da = torch.empty((rows, D), device=x_out.device, dtype=bf16)
     call("ud_norm_residual_bwd", P(g_out), P(dh), P(x_out), P(rstd_x), P(w_n), P(a), P(rstd_a), P(w_a), P(g_in), P(da),
-         P(dw_n), P(dw_a), rows, D, stream())
+         P(dw_n), P(dw_a), P(db_a), rows, D, stream())
     return g_in, da
 
 
