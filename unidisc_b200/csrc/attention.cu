@@ -12,6 +12,7 @@
 //           lazy O rescaling (only when the running max grows by > 2^8), final O/l and lse.
 // TMEM: S0[128] S1[128] O[hd] P0[64] P1[64] columns.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "unidisc_b200.h"
@@ -501,6 +502,249 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Forward v3: the v1 dataflow (one 128-query tile per CTA, double-buffered S and P in TMEM so QK^T of tile j+1 runs under
+// the softmax of tile j) with EIGHT softmax warps: warpgroup g owns key columns [64g, 64g+64) of every S tile, i.e. each
+// thread handles 64 scores (two tcgen05.ld in flight, one wait), the two halves exchange their row maxima / sums through
+// shared memory, and every SM sub-partition has two softmax warps to overlap MUFU, ALU and TMEM latency.
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(320, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+    using S = AttnSmem<HD>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + S::TILE_BYTES;            // [2] stages
+    uint8_t* sV = sK + 2 * S::TILE_BYTES;        // [2] stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * S::TILE_BYTES);
+    uint64_t* q_full = bars;           // 1
+    uint64_t* k_full = bars + 1;       // 2
+    uint64_t* v_full = bars + 3;       // 2
+    uint64_t* v_empty = bars + 5;      // 2   V stage free once P.V of that tile retired
+    uint64_t* s_full = bars + 7;       // 2
+    uint64_t* p_full = bars + 9;       // 2
+    uint64_t* pv_done = bars + 11;     // 1
+    uint64_t* k_empty = bars + 12;     // 2   K stage free as soon as Q.K^T of that tile retired (long before P.V):
+                                       //     the next K tile is prefetched under the softmax instead of after it
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+    __shared__ int sid_k[2 * 128];            // [stage][128]
+    __shared__ float xch[2 * 2 * 128];        // [stage][warpgroup][row]: partial row maxima (and final row sums)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
+    const int T = (p.N + ATT_BKV - 1) / ATT_BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); mbar_init(&k_empty[s], 1);
+            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256);
+        }
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+    const uint32_t tS0 = tmem, tO = tmem + 256, tP0 = tmem + 256 + HD;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, S::TILE_BYTES);
+#pragma unroll
+            for (int bx = 0; bx < S::NBOX; ++bx) tma_load_3d(sQ + bx * S::BOX_BYTES, &tm_q, q_full, h * HD + bx * 64, q0, b);
+            for (int j = 0; j < T; ++j) {
+                const int s = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(&k_empty[s], ph ^ 1);
+                mbar_expect_tx(&k_full[s], S::TILE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < S::NBOX; ++bx)
+                    tma_load_3d(sK + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_k, &k_full[s], h * HD + bx * 64, j * ATT_BKV, b);
+                mbar_wait(&v_empty[s], ph ^ 1);
+                mbar_expect_tx(&v_full[s], S::TILE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < S::NBOX; ++bx)
+                    tma_load_3d(sV + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_v, &v_full[s], h * HD + bx * 64, j * ATT_BKV, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
+            const uint32_t aQ = smem_u32(sQ);
+            auto issue_s = [&](int j) {
+                const int s = j & 1;
+                mbar_wait(&k_full[s], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t aK = smem_u32(sK + s * S::TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < HD / 16; ++ks)
+                    umma_ss(tS0 + s * 128, desc_kmajor(aQ, ks), desc_kmajor(aK, ks), idesc_s, ks != 0);
+                umma_commit(&s_full[s]);
+                umma_commit(&k_empty[s]);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < T; ++j) {
+                if (j + 1 < T) issue_s(j + 1);
+                const int s = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(&v_full[s], ph);
+                mbar_wait(&p_full[s], ph);
+                tc_fence_after();
+                const uint32_t aV = smem_u32(sV + s * S::TILE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                    umma_ts(tO, tP0 + s * 64 + ks * 8, desc_mnmajor(aV, ks), idesc_pv, (j | ks) != 0);
+                umma_commit(&v_empty[s]);
+                umma_commit(pv_done);
+            }
+        }
+    } else {
+        const int wg = (warp - 2) >> 2;           // which half of the key columns
+        const int qd = warp & 3;
+        const int rloc = qd * 32 + lane;          // row inside the tile == TMEM lane
+        const int row = q0 + rloc;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const bool use_ids = p.sample_ids != nullptr;
+        int sid_q = 0;
+        if (use_ids) sid_q = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
+        const int tid256 = threadIdx.x - 64;
+        const float scl = p.scale_log2;
+        const int Ntok = p.N;
+        float m_used = -INFINITY, l = 0.f;
+        for (int j = 0; j < T; ++j) {
+            const int s = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
+            if (use_ids && tid256 < 128) {
+                const int kk = j * ATT_BKV + tid256;
+                sid_k[s * 128 + tid256] = kk < Ntok ? (int)p.sample_ids[(long long)b * Ntok + kk] : -2;
+            }
+            mbar_wait(&s_full[s], ph);
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(tS0 + s * 128 + wg * 64 + lane_off, r0);
+            tmem_ld_32x32b_x32(tS0 + s * 128 + wg * 64 + 32 + lane_off, r1);
+            tmem_ld_wait();
+            const int kbase = j * ATT_BKV + wg * 64;
+            const bool tail = kbase + 64 > Ntok;
+            if (tail && !use_ids) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (kbase + i >= Ntok) r0[i] = 0xff800000u;
+                    if (kbase + 32 + i >= Ntok) r1[i] = 0xff800000u;
+                }
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            if (!use_ids) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(r1[i])); mx3 = fmaxf(mx3, __uint_as_float(r1[i + 1]));
+                }
+            }
+            float* xs = xch + s * 256;
+            if (!use_ids) xs[wg * 128 + rloc] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            named_bar_sync(1, 256);                       // also publishes sid_k for this tile
+            if (use_ids) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const bool ok0 = kbase + i < Ntok && sid_k[s * 128 + wg * 64 + i] == sid_q && sid_q != -1;
+                    const bool ok1 = kbase + 32 + i < Ntok && sid_k[s * 128 + wg * 64 + 32 + i] == sid_q && sid_q != -1;
+                    if (!ok0) r0[i] = 0xff800000u;
+                    if (!ok1) r1[i] = 0xff800000u;
+                    mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx2 = fmaxf(mx2, __uint_as_float(r1[i]));
+                }
+                xs[wg * 128 + rloc] = fmaxf(mx0, mx2);
+                named_bar_sync(2, 256);
+            }
+            const float mx = fmaxf(xs[rloc], xs[128 + rloc]) * scl;
+            const float m_new = fmaxf(m_used, mx);
+            const bool grow = m_new > m_used + 8.0f;      // identical decision in both warpgroups (same inputs)
+            if (__any_sync(0xffffffffu, grow)) {
+                const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_new);
+                if (j > 0) {
+                    mbar_wait(pv_done, (j - 1) & 1);       // O must be quiescent before it is rescaled
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < HD / 64; ++c) {   // each warpgroup rescales its half of O's columns
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tO + wg * (HD / 2) + c * 32 + lane_off, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tmem_st_32x32b_x32(tO + wg * (HD / 2) + c * 32 + lane_off, r);
+                    }
+                    tmem_st_wait();
+                }
+                l *= alpha;
+                m_used = m_new;
+            }
+            const float mref = (m_used == -INFINITY) ? 0.f : m_used;
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float a0 = ex2(fmaf(__uint_as_float(r0[2 * i]), scl, -mref)), a1 = ex2(fmaf(__uint_as_float(r0[2 * i + 1]), scl, -mref));
+                l0 += a0 + a1;
+                r0[i] = pack_bf16x2(a0, a1);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float b0 = ex2(fmaf(__uint_as_float(r1[2 * i]), scl, -mref)), b1 = ex2(fmaf(__uint_as_float(r1[2 * i + 1]), scl, -mref));
+                l1 += b0 + b1;
+                r0[16 + i] = pack_bf16x2(b0, b1);
+            }
+            l += l0 + l1;
+            tmem_st_32x32b_x32(tP0 + s * 64 + wg * 32 + lane_off, r0);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_full[s]);
+        }
+        // ---- epilogue: combine the two half-row sums, O / l, lse ----
+        float* xs = xch;                                   // last tile used xch[(T-1)&1]; use the other slot for the sums
+        xs += ((T & 1) ? 256 : 0);
+        xs[wg * 128 + rloc] = l;
+        named_bar_sync(1, 256);
+        const float lt = xs[rloc] + xs[128 + rloc];
+        mbar_wait(pv_done, (T - 1) & 1);
+        tc_fence_after();
+        const float inv = lt > 0.f ? 1.0f / lt : 0.f;
+        __nv_bfloat16* orow = p.o + ((long long)b * p.N + row) * p.ldo + h * HD + wg * (HD / 2);
+#pragma unroll
+        for (int c = 0; c < HD / 64; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tO + wg * (HD / 2) + c * 32 + lane_off, r);
+            tmem_ld_wait();
+            if (row < p.N) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 o4;
+                    o4.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
+                    o4.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
+                    o4.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
+                    o4.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = o4;
+                }
+            }
+        }
+        if (wg == 0 && row < p.N) p.lse[((long long)b * p.H + h) * p.N + row] = lt > 0.f ? (m_used + log2f(lt)) * LN2 : INFINITY;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // delta[b,h,n] = sum_d o[n,d] * do[n,d]   (softmax backward row term)
 // ------------------------------------------------------------------------------------------------
@@ -547,6 +791,7 @@ struct AttnBwdParams {
     __nv_bfloat16* out1;  // MODE0: dV
     long long ld0, ld1;
     const int64_t* sample_ids;
+    int safe_order;
 };
 
 template <int HD, int MODE>
@@ -789,9 +1034,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
     uint64_t* pr_full = sc_full + 2;         // 2
     uint64_t* acc_done = pr_full + 2;        // 2
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_done + 2);
-    __shared__ __align__(16) float s_lse[2 * 64];   // per-column metadata of the streamed sub-tile, one slot per warpgroup
-    __shared__ __align__(16) float s_dlt[2 * 64];
-    __shared__ __align__(16) int s_sid[2 * 64];
+    __shared__ __align__(16) float s_lse[4 * 64];   // per-column metadata of the streamed sub-tile: [warpgroup][2 slots][64]
+    __shared__ __align__(16) float s_dlt[4 * 64];   // (two alternating slots per warpgroup: a fast thread may already publish
+    __shared__ __align__(16) int s_sid[4 * 64];     //  sub-tile i+2 while a slow one still reads sub-tile i)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -871,7 +1116,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 umma_commit(&st_empty[s]);
                 umma_commit(&acc_done[bf]);
                 if (i + 2 < T2) {
-                    mbar_wait(&acc_done[bf], ph);     // probabilities of sub-tile i consumed -> its score columns are free
+                    // scores(i+2) overwrite the columns the accumulation MMAs above read P / dS from.  tcgen05.mma issued by
+                    // one thread execute in issue order, so no completion wait is needed here (UD_ATTN_BWD_SAFE=1 re-enables it)
+                    if (p.safe_order) mbar_wait(&acc_done[bf], ph);
                     issue_scores(i + 2);
                 }
             }
@@ -896,17 +1143,29 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
         const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
         const float scl = p.scale_log2;
         const int Ntok = p.N;
+        // metadata of this warpgroup's next sub-tile is fetched one iteration ahead (global latency off the critical path)
+        float pf_lse = INFINITY, pf_dlt = 0.f;
+        int pf_sid = -2;
+        auto fetch_meta = [&](int i) {
+            if ((MODE == 0 || use_ids) && tid128 < 64 && i < T2) {
+                const int cidx = i * 64 + tid128;
+                if (MODE == 0) {
+                    pf_lse = cidx < Ntok ? p.lse[bh * Ntok + cidx] * LOG2E : INFINITY;
+                    pf_dlt = cidx < Ntok ? p.delta[bh * Ntok + cidx] : 0.f;
+                }
+                if (use_ids) pf_sid = cidx < Ntok ? (int)p.sample_ids[(long long)b * Ntok + cidx] : -2;
+            }
+        };
+        fetch_meta(wg);
         for (int i = wg; i < T2; i += 2) {
+            const int ms = (wg * 2 + ((i >> 1) & 1)) * 64;    // metadata slot of this sub-tile
             if (MODE == 0 || use_ids) {
                 if (tid128 < 64) {
-                    const int cidx = i * 64 + tid128;
-                    if (MODE == 0) {
-                        s_lse[bf * 64 + tid128] = cidx < Ntok ? p.lse[bh * Ntok + cidx] * LOG2E : INFINITY;
-                        s_dlt[bf * 64 + tid128] = cidx < Ntok ? p.delta[bh * Ntok + cidx] : 0.f;
-                    }
-                    if (use_ids) s_sid[bf * 64 + tid128] = cidx < Ntok ? (int)p.sample_ids[(long long)b * Ntok + cidx] : -2;
+                    if (MODE == 0) { s_lse[ms + tid128] = pf_lse; s_dlt[ms + tid128] = pf_dlt; }
+                    if (use_ids) s_sid[ms + tid128] = pf_sid;
                 }
                 named_bar_sync(1 + wg, 128);
+                fetch_meta(i + 2);
             }
             mbar_wait(&sc_full[bf], (i >> 1) & 1);
             tc_fence_after();
@@ -917,14 +1176,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             tmem_ld_32x32b_x32(tSc + 32 + lane_off, rsB);
             tmem_ld_32x32b_x32(tDp + 32 + lane_off, rdB);
             tmem_ld_wait();                                   // one exposed TMEM latency per sub-tile
-            // P / dS are packed in place into rsA / rdA (chunk 0 -> entries 0..15, chunk 1 -> 16..31)
-            auto chunk = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c) {
+            // P / dS are packed in place into rsA / rdA (chunk 0 -> entries 0..15, chunk 1 -> 16..31).  Interior tiles take the
+            // mask-free instantiation (no per-element compare / select instructions).
+            auto chunk = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c, auto slow_tag) {
+                constexpr bool SLOW = decltype(slow_tag)::value;
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
                     float l4[4], d4[4];
                     if (MODE == 0) {
-                        const float4 lv = *reinterpret_cast<const float4*>(&s_lse[bf * 64 + c * 32 + e4 * 4]);
-                        const float4 dv = *reinterpret_cast<const float4*>(&s_dlt[bf * 64 + c * 32 + e4 * 4]);
+                        const float4 lv = *reinterpret_cast<const float4*>(&s_lse[ms + c * 32 + e4 * 4]);
+                        const float4 dv = *reinterpret_cast<const float4*>(&s_dlt[ms + c * 32 + e4 * 4]);
                         l4[0] = lv.x; l4[1] = lv.y; l4[2] = lv.z; l4[3] = lv.w;
                         d4[0] = dv.x; d4[1] = dv.y; d4[2] = dv.z; d4[3] = dv.w;
                     } else {
@@ -934,12 +1195,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                     float pv[4], dvv[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int col = c * 32 + e4 * 4 + u;
                         float pr = ex2(fmaf(__uint_as_float(rs[e4 * 4 + u]), scl, -l4[u]));
-                        if (slow) {
+                        if (SLOW) {
+                            const int col = c * 32 + e4 * 4 + u;
                             bool ok = row_ok && (i * 64 + col < Ntok);
                             if (use_ids) {
-                                const int sq = s_sid[bf * 64 + col];
+                                const int sq = s_sid[ms + col];
                                 ok = ok && sq == sid_row && sid_row != -1;
                             }
                             if (!ok) pr = 0.f;
@@ -951,8 +1212,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                     rdA[c * 16 + e4 * 2] = pack_bf16x2(dvv[0], dvv[1]); rdA[c * 16 + e4 * 2 + 1] = pack_bf16x2(dvv[2], dvv[3]);
                 }
             };
-            chunk(rsA, rdA, 0);
-            chunk(rsB, rdB, 1);
+            if (slow) {
+                chunk(rsA, rdA, 0, std::true_type{});
+                chunk(rsB, rdB, 1, std::true_type{});
+            } else {
+                chunk(rsA, rdA, 0, std::false_type{});
+                chunk(rsB, rdB, 1, std::false_type{});
+            }
             if (MODE == 0) tmem_st_32x32b_x32(tSc + lane_off, rsA);
             tmem_st_32x32b_x32(tDp + lane_off, rdA);
             tmem_st_wait();
@@ -1008,7 +1274,8 @@ static int make_head_tmap(CUtensorMap* tm, const void* base, long long ld, int B
 template <int HD>
 static int launch_attn_fwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const AttnParams& p,
                            cudaStream_t stream) {
-    static const bool use_v1 = getenv("UD_ATTN_FWD_V2") == nullptr;     // default: one query tile per CTA; UD_ATTN_FWD_V2=1 selects the two-tile kernel (A/B testing)
+    static const int variant = getenv("UD_ATTN_FWD") ? atoi(getenv("UD_ATTN_FWD")) : 3;   // 3 = eight softmax warps (default); 1, 2 = A/B variants
+    const bool use_v1 = variant == 1;
     CUtensorMap tq, tk, tv;
     const int D = p.H * HD;
     int rc = make_head_tmap(&tq, q, ldqk, p.B, p.N, D);
@@ -1021,6 +1288,15 @@ static int launch_attn_fwd(const void* q, const void* k, long long ldqk, const v
         if (!attr) { UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
         dim3 grid((p.N + ATT_BQ - 1) / ATT_BQ, p.H, p.B);
         attn_fwd_kernel<HD><<<grid, 192, smem, stream>>>(tq, tk, tv, p);
+        UD_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
+    if (variant == 3) {
+        const int smem3 = attn_smem_bytes<HD>(5);
+        static bool attr3 = false;
+        if (!attr3) { UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); attr3 = true; }
+        dim3 grid3((p.N + ATT_BQ - 1) / ATT_BQ, p.H, p.B);
+        attn_fwd3_kernel<HD><<<grid3, 320, smem3, stream>>>(tq, tk, tv, p);
         UD_CUDA_CHECK(cudaGetLastError());
         return 0;
     }
@@ -1126,6 +1402,7 @@ extern "C" int ud_attn_bwd(const void* q, const void* k, long long ldqk, const v
     p.sample_ids = sample_ids;
     p.out0 = p.out1 = nullptr;
     p.ld0 = p.ld1 = 0;
+    p.safe_order = getenv("UD_ATTN_BWD_SAFE") != nullptr;
     auto* dqp = reinterpret_cast<__nv_bfloat16*>(dq);
     auto* dkp = reinterpret_cast<__nv_bfloat16*>(dk);
     auto* dvp = reinterpret_cast<__nv_bfloat16*>(dv);

@@ -5,6 +5,8 @@
 // (one 16-byte fp32 / 8-byte bf16 access), row statistics are block reductions (warp shuffles + one smem exchange),
 // and per-column weight gradients are kept in registers across the rows a CTA visits and flushed with one atomicAdd
 // per column per CTA.  Grid-stride over rows with gridDim a multiple of the SM count.
+#include <algorithm>
+
 #include "common.cuh"
 #include "unidisc_b200.h"
 
@@ -437,6 +439,88 @@ __global__ void qk_ln_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dqk, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-per-row variant of the q/k LayerNorm + RoPE forward kernel (D = 128*NI).  Lane l owns columns 128*i + 4l .. +3 for
+// i < NI, so every load/store instruction of the warp is one contiguous 256-byte segment, the LayerNorm statistics are
+// pure warp-shuffle reductions (no shared memory, no block barriers), RoPE partners sit in the same warp (lane ^ hd/8)
+// and all of a row's loads are issued back to back.  The affine parameters are staged once per CTA in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int NI>
+__global__ void __launch_bounds__(256)
+qk_ln_rope_fwd_warp_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ gq, const float* __restrict__ bq,
+                           const float* __restrict__ gk, const float* __restrict__ bk, const float* __restrict__ cosT,
+                           const float* __restrict__ sinT, __nv_bfloat16* __restrict__ out, float* __restrict__ stats, int rows,
+                           int hd, float eps) {
+    constexpr int D = 128 * NI;
+    extern __shared__ __align__(16) float aff[];      // [4][D]: gq, bq, gk, bk
+    for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+        *reinterpret_cast<float4*>(aff + i) = *reinterpret_cast<const float4*>(gq + i);
+        *reinterpret_cast<float4*>(aff + D + i) = *reinterpret_cast<const float4*>(bq + i);
+        *reinterpret_cast<float4*>(aff + 2 * D + i) = *reinterpret_cast<const float4*>(gk + i);
+        *reinterpret_cast<float4*>(aff + 3 * D + i) = *reinterpret_cast<const float4*>(bk + i);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int half = hd >> 1, pmask = hd >> 3;
+    const int j0 = (4 * lane) % hd;
+    const bool lo = j0 < half;
+    const int ti = j0 % half;
+    const float invD = 1.0f / (float)D;
+    for (int row = gw; row < rows; row += nw) {
+        const __nv_bfloat16* src = qkv + (long long)row * 3 * D + 4 * lane;
+        uint2 qr[NI], kr[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            qr[i] = *reinterpret_cast<const uint2*>(src + 128 * i);
+            kr[i] = *reinterpret_cast<const uint2*>(src + D + 128 * i);
+        }
+        const float4 cs4 = *reinterpret_cast<const float4*>(cosT + (long long)row * half + ti);
+        const float4 sn4 = *reinterpret_cast<const float4*>(sinT + (long long)row * half + ti);
+        const float cs[4] = {cs4.x, cs4.y, cs4.z, cs4.w}, sn[4] = {sn4.x, sn4.y, sn4.z, sn4.w};
+        float sq = 0.f, sk = 0.f;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            sq += (bf16lo(qr[i].x) + bf16hi(qr[i].x)) + (bf16lo(qr[i].y) + bf16hi(qr[i].y));
+            sk += (bf16lo(kr[i].x) + bf16hi(kr[i].x)) + (bf16lo(kr[i].y) + bf16hi(kr[i].y));
+        }
+        const float mq = warp_sum(sq) * invD, mk = warp_sum(sk) * invD;
+        float vq = 0.f, vk = 0.f;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const float q4[4] = {bf16lo(qr[i].x) - mq, bf16hi(qr[i].x) - mq, bf16lo(qr[i].y) - mq, bf16hi(qr[i].y) - mq};
+            const float k4[4] = {bf16lo(kr[i].x) - mk, bf16hi(kr[i].x) - mk, bf16lo(kr[i].y) - mk, bf16hi(kr[i].y) - mk};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { vq += q4[e] * q4[e]; vk += k4[e] * k4[e]; }
+        }
+        const float rq = rsqrtf(warp_sum(vq) * invD + eps), rk = rsqrtf(warp_sum(vk) * invD + eps);
+        __nv_bfloat16* dst = out + (long long)row * 2 * D + 4 * lane;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int c = 128 * i + 4 * lane;
+            const float4 g1 = *reinterpret_cast<const float4*>(aff + c), b1 = *reinterpret_cast<const float4*>(aff + D + c);
+            const float4 g2 = *reinterpret_cast<const float4*>(aff + 2 * D + c), b2 = *reinterpret_cast<const float4*>(aff + 3 * D + c);
+            const float gqv[4] = {g1.x, g1.y, g1.z, g1.w}, bqv[4] = {b1.x, b1.y, b1.z, b1.w};
+            const float gkv[4] = {g2.x, g2.y, g2.z, g2.w}, bkv[4] = {b2.x, b2.y, b2.z, b2.w};
+            const float q4[4] = {bf16lo(qr[i].x) - mq, bf16hi(qr[i].x) - mq, bf16lo(qr[i].y) - mq, bf16hi(qr[i].y) - mq};
+            const float k4[4] = {bf16lo(kr[i].x) - mk, bf16hi(kr[i].x) - mk, bf16lo(kr[i].y) - mk, bf16hi(kr[i].y) - mk};
+            F4 oq, ok;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float yq = bf16_round((q4[e] * rq) * gqv[e] + bqv[e]);   // LayerNorm output, stored bf16 (dit.py:681)
+                const float yk = bf16_round((k4[e] * rk) * gkv[e] + bkv[e]);
+                const float pq = __shfl_xor_sync(0xffffffffu, yq, pmask);
+                const float pk = __shfl_xor_sync(0xffffffffu, yk, pmask);
+                oq.v[e] = yq * cs[e] + (lo ? -pq : pq) * sn[e];
+                ok.v[e] = yk * cs[e] + (lo ? -pk : pk) * sn[e];
+            }
+            st_bf4(dst + 128 * i, oq);
+            st_bf4(dst + D + 128 * i, ok);
+        }
+        if (lane == 0) *reinterpret_cast<float4*>(stats + (long long)row * 4) = make_float4(mq, rq, mk, rk);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // bias gradient: db[n] += sum_m dY[m,n]
 // ------------------------------------------------------------------------------------------------
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dY, long long ld, float* __restrict__ db, int M, int N,
@@ -647,6 +731,22 @@ extern "C" int ud_qk_ln_rope_fwd(const void* qkv, const float* gq, const float* 
     if (head_dim != 32 && head_dim != 64 && head_dim != 128) {
         fprintf(stderr, "unidisc_b200: qk_ln_rope supports head_dim 32/64/128 (got %d)\n", head_dim);
         return -1;
+    }
+    {   // warp-per-row kernel for the common hidden sizes; block-per-row kernel otherwise
+        const int wgrid = (int)std::min<long long>(((long long)rows * 32 + 255) / 256, (long long)sm_count() * 4);
+        bool done = true;
+        switch (D / 128) {
+#define UD_QKF(NI)                                                                                                              \
+    case NI: {                                                                                                                  \
+        static bool attr = false;                                                                                               \
+        if (!attr) { UD_CUDA_CHECK(cudaFuncSetAttribute(qk_ln_rope_fwd_warp_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 128 * NI * 4)); attr = true; } \
+        qk_ln_rope_fwd_warp_kernel<NI><<<wgrid, 256, 4 * 128 * NI * 4, STREAM(stream)>>>(CBF(qkv), gq, bq, gk, bk, cos, sin, BF(qk_out), stats, rows, head_dim, eps); \
+    } break;
+            UD_QKF(1) UD_QKF(2) UD_QKF(3) UD_QKF(4) UD_QKF(6) UD_QKF(8) UD_QKF(10) UD_QKF(16)
+#undef UD_QKF
+            default: done = false;
+        }
+        if (done && D % 128 == 0) { UD_CUDA_CHECK(cudaGetLastError()); return 0; }
     }
     qk_ln_rope_fwd_kernel<2><<<row_grid((rows + 1) / 2, D / 4), D / 4, 0, STREAM(stream)>>>(CBF(qkv), gq, bq, gk, bk, cos, sin, BF(qk_out), stats, rows, D, head_dim, eps);
     UD_CUDA_CHECK(cudaGetLastError());
