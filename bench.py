@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="unidisc-1.4B", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1, help="model.dropout (reference configs/model/extra_large.yaml:9 = 0.1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,7 +187,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     preset, bpg, txt, img = WORKLOADS[args.workload]
     small = args.workload == "tiny"
-    cfg = make_config(preset, txt_length=txt, img_length=img, image_vocab_size=IMAGE_VOCAB if not small else 255,
+    cfg = make_config(preset, txt_length=txt, img_length=img, dropout=args.dropout, image_vocab_size=IMAGE_VOCAB if not small else 255,
                       text_vocab_size=TEXT_VOCAB if not small else 257, **(dict(hidden_size=256, n_blocks=2, n_heads=4) if small else {}))
     torch.manual_seed(0)
     model = Diffusion(cfg, device=dev)
@@ -328,7 +329,7 @@ def main():
             metric="joint_token_tokens_per_sec", value=value, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
             config=dict(workload=args.workload, model=f"DiT D={D} L={Lyr} H={cfg.model.n_heads}", seq_len=N, per_gpu_batch=B,
-                        global_batch=world * B, vocab=V, parallelism=f"dp{world}", optimizer="AdamW+clip(1.0)", dropout=0.0,
+                        global_batch=world * B, vocab=V, parallelism=f"dp{world}", optimizer="AdamW+clip(1.0)", dropout=args.dropout,
                         l2="activations and weights per step >> 126 MB L2 (no flush needed)"),
             e2e=dict(value=e2e_v, unit="tokens/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                      loss=loss_e2e),

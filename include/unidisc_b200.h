@@ -44,18 +44,24 @@ int ud_embed_bwd(const int64_t* ids, const int64_t* modality, const float* g, fl
                  long long hot_id /* id accumulated per CTA (the mask token), -1 = none */, void* stream);
 
 /* ---- fused "sandwich" norm + residual + next pre-norm -------------------------------------------------------
- * x_out = x_in + bf16(rms(a)) * w_a ;  h = bf16(rms(x_out) * w_n)
+ * x_out = x_in + dropout_p(bf16(rms(a)) * w_a) ;  h = bf16(rms(x_out) * w_n)
  * = pre_residual_norm/post_ff_norm + residual (dit.py:993-994,1024-1031) fused with the following norm2 / next block's
- * norm1 / norm_final (dit.py:971,1025,1089).  a: bf16 [rows,D] branch output; x_in/x_out fp32; w_* fp32 [D]. */
+ * norm1 / norm_final (dit.py:971,1025,1089).  a: bf16 [rows,D] branch output; x_in/x_out fp32; w_* fp32 [D].
+ * p_drop > 0: training-mode dropout of the branch (bias_dropout_add_scale, dit.py:229-253; model.dropout) with an in-kernel
+ * Philox4x32-10 mask keyed by (seed, offset, row, column group); backward regenerates the mask from the same triple. */
 int ud_norm_residual_fwd(const void* a_bf16, const float* x_in, const float* w_a, const float* w_n, float* x_out,
-                         void* h_bf16, float* rstd_a, float* rstd_x, int rows, int D, float eps, void* stream);
+                         void* h_bf16, float* rstd_a, float* rstd_x, int rows, int D, float eps, float p_drop, uint64_t seed,
+                         uint64_t offset, void* stream);
+/* the keep-scales (0 or 1/(1-p), fp32 [rows,D]) the two kernels above/below use for (p_drop, seed, offset) — test hook */
+int ud_dropout_scales(float* out, int rows, int D, float p_drop, uint64_t seed, uint64_t offset, void* stream);
 /* backward of the above.  g_out: fp32 grad wrt x_out from the residual stream (may be NULL = 0); dh: bf16 grad wrt h.
  * Writes g_in (fp32 total grad wrt x_out == grad wrt x_in), da (bf16 grad wrt a), and atomically accumulates
  * dw_n += sum_rows dh * xhat,  dw_a += sum_rows g * bf16(rms(a)),  and (if db_a != NULL) db_a += sum_rows da — the bias
  * gradient of the Linear that produced `a` (mlp.2.bias, dit.py:919), saving a separate column-sum pass. */
 int ud_norm_residual_bwd(const float* g_out, const void* dh_bf16, const float* x_out, const float* rstd_x, const float* w_n,
                          const void* a_bf16, const float* rstd_a, const float* w_a, float* g_in, void* da_bf16,
-                         float* dw_n, float* dw_a, float* db_a, int rows, int D, void* stream);
+                         float* dw_n, float* dw_a, float* db_a, int rows, int D, float p_drop, uint64_t seed, uint64_t offset,
+                         void* stream);
 /* backward of the first norm only: g_in = g_out + rms_bwd(dh) ; dw += ... */
 int ud_rmsnorm_bwd(const float* g_out, const void* dh_bf16, const float* x, const float* rstd, const float* w, float* g_in,
                    float* dw, int rows, int D, void* stream);

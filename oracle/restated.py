@@ -150,7 +150,7 @@ def attention_core(q, k, v, scale):
 
 
 def block_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], i: int, x, cos, sin, mode, sample_ids=None,
-                  taps: Optional[dict] = None):
+                  taps: Optional[dict] = None, drop_scale: Optional[torch.Tensor] = None):
     """DDiTBlock.forward dit.py:948-1033 (rms, sandwich, qk_norm, no time-conditioning) with
     Attention.forward dit.py:616-887 (sdpa branch)."""
     pre = f"blocks.{i}."
@@ -191,14 +191,19 @@ def block_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], i: int, x, cos,
     if mode == "bf16":
         g = _bf(g)
     d = _linear(g, P[pre + "mlp.2.weight"], P[pre + "mlp.2.bias"], mode)
-    x2 = x1 + _rmsnorm(d, P[pre + "post_ff_norm.weight"], cfg.rms_eps, mode)          # step 10 (dropout 0 / eval)
+    br = _rmsnorm(d, P[pre + "post_ff_norm.weight"], cfg.rms_eps, mode)
+    if drop_scale is not None:
+        # F.dropout(training=True) of the branch (dit.py:218-222,239,1024-1031) with an explicit keep-scale tensor
+        # (0 or 1/(1-p)) standing in for the Bernoulli draw
+        br = br * drop_scale
+    x2 = x1 + br                                                                       # step 10
     if taps is not None:
         taps[f"b{i}"] = dict(h=h, qkv=qkv, q=q, k=k, o=o, a=a, x1=x1, h2=h2, u=u, g=g, d=d, x2=x2)
     return x2
 
 
 def dit_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], indices, modality, mode="fp32", sample_ids=None,
-                taps: Optional[dict] = None, return_hidden=False):
+                taps: Optional[dict] = None, return_hidden=False, drop_scales=None):
     """DIT.forward dit.py:1324-1500 (discrete, multimodal_batches, modality_embed, rope_2d, no time-cond).
 
     indices, modality: int64 [B,N].  Returns logits [B,N,V] (bf16 in mode="bf16", fp32 otherwise).
@@ -209,7 +214,8 @@ def dit_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], indices, modality
     cos, sin = token_cos_sin(cfg, modality.cpu())
     cos, sin = cos.to(x.device), sin.to(x.device)
     for i in range(cfg.n_blocks):
-        x = block_forward(cfg, P, i, x, cos, sin, mode, sample_ids=sample_ids, taps=taps)
+        x = block_forward(cfg, P, i, x, cos, sin, mode, sample_ids=sample_ids, taps=taps,
+                          drop_scale=None if drop_scales is None else drop_scales[i])
     if return_hidden:
         return x
     hf = _rmsnorm(x, P["output_layer.norm_final.weight"], cfg.rms_eps, mode)          # dit.py:1089
@@ -442,14 +448,14 @@ def init_params(cfg: OracleConfig, seed=0) -> Dict[str, torch.Tensor]:
 
 
 def training_loss(cfg: OracleConfig, P, x0, modality, attention_mask, u_t, rand_move, mode="fp32", *,
-                  img_loss_weight=0.6, text_loss_weight=1.0, softmin_snr=None, fp32_logsoftmax=True):
+                  img_loss_weight=0.6, text_loss_weight=1.0, softmin_snr=None, fp32_logsoftmax=True, drop_scales=None):
     """q_xt -> DIT -> SUBS -> weighted NLL, i.e. `Diffusion.compute_loss` (model.py:797-1173) for the default
     large-scale config, driven by explicit random draws (u_t [B], rand_move [B,N])."""
     t = sample_t(u_t)
     sigma, _ = loglinear_noise(t)
     move_chance = 1 - torch.exp(-sigma[:, None])                                       # model.py:858-860
     xt, move, _ = q_xt(x0, move_chance, rand_move, cfg.mask_index)
-    logits = dit_forward(cfg, P, xt, modality, mode=mode)
+    logits = dit_forward(cfg, P, xt, modality, mode=mode, drop_scales=drop_scales)
     if fp32_logsoftmax:
         logits = logits.float()
     logp = subs_parameterization(logits, xt, modality, cfg.mask_index, cfg.text_vocab_size)

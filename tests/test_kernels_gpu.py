@@ -187,6 +187,51 @@ def test_norm_residual_fwd_bwd(ops, D):
     assert torch.allclose(dw, w2.grad, rtol=2e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("D,p", [(256, 0.1), (2048, 0.1), (768, 0.5)])
+def test_norm_residual_dropout_fwd_bwd(ops, D, p):
+    """training-mode dropout of the branch (reference dit.py:229-253,1024-1031): the in-kernel Philox keep-scales are
+    materialised with ud_dropout_scales and fed to the torch reference."""
+    rows, seed, off = 515, 1234, 77
+    a = rnd(rows, D, seed=1, scale=2.0, dtype=bf16)
+    x_in = rnd(rows, D, seed=2)
+    w_a, w_n = 1 + 0.2 * rnd(D, seed=3), 1 + 0.2 * rnd(D, seed=4)
+    ks = ops.dropout_scales(rows, D, p, seed, off, dev())
+    torch.cuda.synchronize()
+    vals = torch.unique(ks)
+    assert vals.numel() == 2 and vals[0] == 0 and abs(float(vals[1]) - 1 / (1 - p)) < 1e-6
+    assert abs(float((ks == 0).float().mean()) - p) < 0.01
+    # different offsets / seeds give different masks; same triple is reproducible
+    assert not torch.equal(ks, ops.dropout_scales(rows, D, p, seed, off + 1, dev()))
+    assert torch.equal(ks, ops.dropout_scales(rows, D, p, seed, off, dev()))
+    x_out, h, ra, rx = ops.norm_residual_fwd(a, x_in, w_a, w_n, p_drop=p, seed=seed, offset=off)
+
+    def ref_fwd(a_, x_, wa_, wn_):
+        n = _rms(a_.float())
+        n = n + (n.to(bf16).float() - n).detach()
+        xo = x_ + (n * wa_) * ks
+        return xo, _rms(xo) * wn_
+
+    xo_ref, h_ref = ref_fwd(a, x_in, w_a, w_n)
+    assert torch.allclose(x_out, xo_ref, rtol=1e-5, atol=1e-5)
+    close_bf16(h, h_ref.to(bf16), "h")
+    g_out = rnd(rows, D, seed=5)
+    dh = rnd(rows, D, seed=6, dtype=bf16)
+    dw_n, dw_a, db = (torch.zeros(D, device=dev()) for _ in range(3))
+    g_in, da = ops.norm_residual_bwd(g_out, dh, x_out, rx, w_n, a, ra, w_a, dw_n, dw_a, db_a=db, p_drop=p, seed=seed, offset=off)
+    torch.cuda.synchronize()
+    a32 = a.float().requires_grad_(True)
+    xi = x_in.clone().requires_grad_(True)
+    wa_, wn_ = w_a.clone().requires_grad_(True), w_n.clone().requires_grad_(True)
+    xo, hh = ref_fwd(a32, xi, wa_, wn_)
+    (xo * g_out).sum().backward(retain_graph=True)
+    (hh * dh.float()).sum().backward()
+    assert torch.allclose(g_in, xi.grad, rtol=1e-3, atol=1e-4), (g_in - xi.grad).abs().max()
+    close_bf16(da, a32.grad.to(bf16), "da", frac_bad=5e-3)
+    assert torch.allclose(dw_n, wn_.grad, rtol=2e-3, atol=2e-3), (dw_n - wn_.grad).abs().max()
+    assert torch.allclose(dw_a, wa_.grad, rtol=2e-3, atol=2e-3), (dw_a - wa_.grad).abs().max()
+    assert torch.allclose(db, a32.grad.sum(0), rtol=2e-3, atol=3e-3), (db - a32.grad.sum(0)).abs().max()
+
+
 @pytest.mark.parametrize("D,hd", [(128, 64), (768, 64), (2048, 128), (128, 32)])
 def test_qk_ln_rope_fwd_bwd(ops, D, hd):
     from oracle import restated as R

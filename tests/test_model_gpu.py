@@ -113,6 +113,61 @@ def test_training_step_loss_and_grads_vs_oracle():
     print("worst grad rel err:", worst)
 
 
+def test_training_step_with_dropout_vs_oracle():
+    """model.dropout=0.1 (the reference's training default, config.yaml model.dropout): the CUDA path's Philox keep-scales
+    for each block are materialised and handed to the oracle, then loss and gradients must agree as in the p=0 test."""
+    from oracle import restated as R
+    from unidisc_b200 import ops
+    from unidisc_b200.config import make_config
+    from unidisc_b200.model import Diffusion
+    D, H, L, txt, img, tv, iv = 256, 4, 2, 64, 64, 257, 255
+    cfg = make_config("small", hidden_size=D, n_blocks=L, n_heads=H, txt_length=txt, img_length=img, image_vocab_size=iv,
+                      text_vocab_size=tv, img_loss_weight=0.6, dropout=0.1)
+    torch.manual_seed(0)
+    model = Diffusion(cfg, device=dev())
+    model.train()
+    net = model.backbone
+    assert net.dropout == 0.1
+    V, mi = model.vocab_size, model.mask_index
+    B, N = 4, txt + img
+    ids, modality = R.synthetic_batch(B, txt, img, tv, V, seed=3)
+    am = torch.ones(B, N, dtype=torch.bool)
+    batch = dict(input_ids=ids.to(dev()), modality=modality.to(dev()), attention_mask=am.to(dev()))
+    torch.manual_seed(11)
+    out = model.compute_loss(batch)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    base = net._dropout_calls * L
+    ks = [ops.dropout_scales(B * N, D, 0.1, net.dropout_seed, base + i, dev()).view(B, N, D).cpu() for i in range(L)]
+    assert all(0.05 < float((k == 0).float().mean()) < 0.15 for k in ks)
+    torch.manual_seed(11)
+    u_t = torch.rand(B, device=dev()).cpu()
+    rand_move = torch.rand(B, N, device=dev()).cpu()
+    P = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    ocfg = R.OracleConfig(D, H, L, txt, img, V, tv, mi)
+    ref_bf = R.training_loss(ocfg, {k: v.detach() for k, v in P.items()}, ids, modality, am, u_t, rand_move, mode="bf16", drop_scales=ks)
+    ref_nodrop = R.training_loss(ocfg, {k: v.detach() for k, v in P.items()}, ids, modality, am, u_t, rand_move, mode="bf16")
+    ref32 = R.training_loss(ocfg, P, ids, modality, am, u_t, rand_move, mode="fp32", drop_scales=ks)
+    ref32["loss"].backward()
+    got = float(out.loss.detach())
+    print(f"loss cuda={got:.6f} oracle_bf16={float(ref_bf['loss']):.6f} (no-dropout oracle {float(ref_nodrop['loss']):.6f})")
+    assert abs(got - float(ref_bf["loss"])) < 1e-3 * max(1.0, abs(float(ref_bf["loss"]))) + 2e-3
+    assert abs(float(ref_bf["loss"]) - float(ref_nodrop["loss"])) > 1e-4       # the mask really changes the result
+    for name, p in net.named_parameters():
+        gref = P[name].grad
+        gg = p.grad.detach().float().cpu()
+        den = gref.norm().item()
+        rel = (gg - gref).norm().item() / max(den, 1e-8)
+        lim = 1e-1 if ("q_norm" in name or "k_norm" in name) else 3e-2
+        assert rel < lim or den < 1e-6, f"grad {name}: rel L2 err {rel:.4f} (|ref|={den:.3e})"
+    # eval mode: dropout off, forward deterministic
+    model.eval()
+    with torch.no_grad():
+        l1 = net(batch["input_ids"], None, modality=batch["modality"]).float()
+        l2 = net(batch["input_ids"], None, modality=batch["modality"]).float()
+    assert torch.equal(l1, l2)
+
+
 def test_grad_accumulation_and_fresh_overwrite():
     from oracle import restated as R
     from unidisc_b200.config import make_config

@@ -115,13 +115,15 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const int64_t*
 }
 
 // ------------------------------------------------------------------------------------------------
-// x_out = x_in + bf16(rms(a)) * w_a ;  h = bf16(rms(x_out) * w_n)       (dit.py:993-994, 1024-1031, 971/1025/1089)
+// x_out = x_in + dropout(bf16(rms(a)) * w_a) ;  h = bf16(rms(x_out) * w_n)       (dit.py:993-994, 1024-1031, 971/1025/1089)
+// DROP: training-mode dropout of the branch (bias_dropout_add_scale, dit.py:229-253), Philox mask regenerated in backward.
 // ------------------------------------------------------------------------------------------------
-template <int R>
+template <int R, bool DROP>
 __global__ void norm_residual_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ x_in,
                                          const float* __restrict__ w_a, const float* __restrict__ w_n,
                                          float* __restrict__ x_out, __nv_bfloat16* __restrict__ h,
-                                         float* __restrict__ rstd_a, float* __restrict__ rstd_x, int rows, int D, float eps) {
+                                         float* __restrict__ rstd_a, float* __restrict__ rstd_x, int rows, int D, float eps,
+                                         uint32_t drop_thresh, float inv_keep, uint64_t seed, uint64_t offset) {
     // R rows per iteration: R independent load streams in flight and one block reduction per R rows
     __shared__ float scratch[2 * 32 * R];
     int buf = 0;
@@ -147,9 +149,13 @@ __global__ void norm_residual_fwd_kernel(const __nv_bfloat16* __restrict__ a, co
         for (int j = 0; j < R; ++j) {
             ra[j] = rsqrtf(s[j] * invD + eps);
             s[j] = 0.f;
+            float ks[4] = {1.f, 1.f, 1.f, 1.f};
+            if (DROP) dropout_scales4(seed, offset, (uint32_t)(r0 + j), threadIdx.x, drop_thresh, inv_keep, ks);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                xo[j].v[i] = xi[j].v[i] + bf16_round(av[j].v[i] * ra[j]) * wa.v[i];
+                float t = bf16_round(av[j].v[i] * ra[j]) * wa.v[i];
+                if (DROP) t *= ks[i];
+                xo[j].v[i] = xi[j].v[i] + t;
                 s[j] += xo[j].v[i] * xo[j].v[i];
             }
         }
@@ -170,13 +176,14 @@ __global__ void norm_residual_fwd_kernel(const __nv_bfloat16* __restrict__ a, co
 }
 
 // backward of the fused kernel (see header).  HAS_BRANCH=false degenerates to a plain RMSNorm backward.
-template <bool HAS_BRANCH, int R>
+template <bool HAS_BRANCH, int R, bool DROP>
 __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const __nv_bfloat16* __restrict__ dh,
                                          const float* __restrict__ x_out, const float* __restrict__ rstd_x,
                                          const float* __restrict__ w_n, const __nv_bfloat16* __restrict__ a,
                                          const float* __restrict__ rstd_a, const float* __restrict__ w_a,
                                          float* __restrict__ g_in, __nv_bfloat16* __restrict__ da, float* __restrict__ dw_n,
-                                         float* __restrict__ dw_a, float* __restrict__ db_a, int rows, int D) {
+                                         float* __restrict__ dw_a, float* __restrict__ db_a, int rows, int D,
+                                         uint32_t drop_thresh, float inv_keep, uint64_t seed, uint64_t offset) {
     __shared__ float scratch[2 * 32 * 3 * R];
     int buf = 0;
     const int c = threadIdx.x * 4;
@@ -186,7 +193,7 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
     F4 acc_n = {{0, 0, 0, 0}}, acc_a = {{0, 0, 0, 0}}, acc_b = {{0, 0, 0, 0}};
     const float invD = 1.0f / (float)D;
     for (int r0 = blockIdx.x * R; r0 < rows; r0 += gridDim.x * R) {
-        F4 y[R], base[R], naf[R];
+        F4 y[R], base[R], naf[R], wae[R];     // wae = w_a * dropout keep-scale: the branch's effective per-element weight
         float rx[R], ra[R], s[3 * R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
@@ -200,6 +207,13 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
             F4 av = {{0, 0, 0, 0}};
             ra[j] = 0.f;
             if (HAS_BRANCH) { av = ld_bf4(a + off); ra[j] = rstd_a[row]; }
+            wae[j] = wa;
+            if (HAS_BRANCH && DROP) {
+                float ks[4];
+                dropout_scales4(seed, offset, (uint32_t)row, threadIdx.x, drop_thresh, inv_keep, ks);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) wae[j].v[i] *= ks[i];
+            }
             s[3 * j] = s[3 * j + 1] = s[3 * j + 2] = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -210,8 +224,8 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
                 if (ok) acc_n.v[i] += dhv.v[i] * y[j].v[i];
                 if (HAS_BRANCH) {
                     naf[j].v[i] = av.v[i] * ra[j];
-                    s[3 * j + 1] += base[j].v[i] * wa.v[i] * naf[j].v[i];
-                    s[3 * j + 2] += y[j].v[i] * wa.v[i] * naf[j].v[i];
+                    s[3 * j + 1] += base[j].v[i] * wae[j].v[i] * naf[j].v[i];
+                    s[3 * j + 2] += y[j].v[i] * wae[j].v[i] * naf[j].v[i];
                 }
             }
         }
@@ -230,8 +244,9 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
                 F4 dav;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    acc_a.v[i] += g.v[i] * bf16_round(naf[j].v[i]);
-                    dav.v[i] = ra[j] * (g.v[i] * wa.v[i] - naf[j].v[i] * m2);
+                    if (DROP) acc_a.v[i] += g.v[i] * bf16_round(naf[j].v[i]) * (wae[j].v[i] != 0.f ? inv_keep : 0.f);
+                    else acc_a.v[i] += g.v[i] * bf16_round(naf[j].v[i]);
+                    dav.v[i] = ra[j] * (g.v[i] * wae[j].v[i] - naf[j].v[i] * m2);
                     acc_b.v[i] += dav.v[i];          // bias gradient of the Linear that produced `a` (column sum of da)
                 }
                 st_bf4(da + off, dav);
@@ -639,6 +654,16 @@ __global__ void grad_unpack_kernel(const __nv_bfloat16* __restrict__ s, float* _
     }
 }
 
+// materialises the dropout keep-scales the fused norm kernels regenerate on the fly (for parity tests / debugging)
+__global__ void dropout_scale_kernel(float* __restrict__ out, int rows, int D, uint32_t thresh, float inv_keep, uint64_t seed,
+                                     uint64_t offset) {
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        float ks[4];
+        dropout_scales4(seed, offset, (uint32_t)row, threadIdx.x, thresh, inv_keep, ks);
+        *reinterpret_cast<float4*>(out + (long long)row * D + threadIdx.x * 4) = make_float4(ks[0], ks[1], ks[2], ks[3]);
+    }
+}
+
 static int row_grid(int rows, int threads) {
     int per_sm = 2048 / threads;
     if (per_sm < 1) per_sm = 1;
@@ -668,7 +693,7 @@ using namespace ud;
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
-extern "C" int ud_abi_version(void) { return 1; }
+extern "C" int ud_abi_version(void) { return 2; }
 extern "C" int ud_device_sm_count(void) { return sm_count(); }
 
 extern "C" int ud_embed_rmsnorm_fwd(const int64_t* ids, const int64_t* modality, const float* E, const float* Emod,
@@ -692,22 +717,43 @@ extern "C" int ud_embed_bwd(const int64_t* ids, const int64_t* modality, const f
 }
 
 extern "C" int ud_norm_residual_fwd(const void* a, const float* x_in, const float* w_a, const float* w_n, float* x_out, void* h,
-                                    float* rstd_a, float* rstd_x, int rows, int D, float eps, void* stream) {
+                                    float* rstd_a, float* rstd_x, int rows, int D, float eps, float p_drop, uint64_t seed,
+                                    uint64_t offset, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "norm_residual_fwd")) return -1;
-    norm_residual_fwd_kernel<4><<<row_grid((rows + 3) / 4, D / 4), D / 4, 0, STREAM(stream)>>>(CBF(a), x_in, w_a, w_n, x_out, BF(h), rstd_a, rstd_x, rows, D, eps);
+    if (p_drop < 0.f || p_drop >= 1.f) { fprintf(stderr, "unidisc_b200: dropout p must be in [0,1)\n"); return -1; }
+    const int grid = row_grid((rows + 3) / 4, D / 4);
+    if (p_drop > 0.f)
+        norm_residual_fwd_kernel<4, true><<<grid, D / 4, 0, STREAM(stream)>>>(CBF(a), x_in, w_a, w_n, x_out, BF(h), rstd_a, rstd_x, rows, D, eps,
+                                                                             dropout_thresh(p_drop), 1.0f / (1.0f - p_drop), seed, offset);
+    else
+        norm_residual_fwd_kernel<4, false><<<grid, D / 4, 0, STREAM(stream)>>>(CBF(a), x_in, w_a, w_n, x_out, BF(h), rstd_a, rstd_x, rows, D, eps, 0u, 1.f, 0, 0);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
 extern "C" int ud_norm_residual_bwd(const float* g_out, const void* dh, const float* x_out, const float* rstd_x,
                                     const float* w_n, const void* a, const float* rstd_a, const float* w_a, float* g_in,
-                                    void* da, float* dw_n, float* dw_a, float* db_a, int rows, int D, void* stream) {
+                                    void* da, float* dw_n, float* dw_a, float* db_a, int rows, int D, float p_drop,
+                                    uint64_t seed, uint64_t offset, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "norm_residual_bwd")) return -1;
+    if (p_drop < 0.f || p_drop >= 1.f) { fprintf(stderr, "unidisc_b200: dropout p must be in [0,1)\n"); return -1; }
     int grid = row_grid((rows + 1) / 2, D / 4);
     if (grid > 4 * sm_count()) grid = 4 * sm_count();
-    norm_residual_bwd_kernel<true, 2><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, db_a, rows, D);
+    if (p_drop > 0.f)
+        norm_residual_bwd_kernel<true, 2, true><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, db_a, rows, D,
+                                                                                   dropout_thresh(p_drop), 1.0f / (1.0f - p_drop), seed, offset);
+    else
+        norm_residual_bwd_kernel<true, 2, false><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, db_a, rows, D, 0u, 1.f, 0, 0);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_dropout_scales(float* out, int rows, int D, float p_drop, uint64_t seed, uint64_t offset, void* stream) {
+    if (rows <= 0) return 0;
+    if (!check_D(D, "dropout_scales")) return -1;
+    dropout_scale_kernel<<<row_grid(rows, D / 4), D / 4, 0, STREAM(stream)>>>(out, rows, D, dropout_thresh(p_drop), 1.0f / (1.0f - p_drop), seed, offset);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -718,7 +764,7 @@ extern "C" int ud_rmsnorm_bwd(const float* g_out, const void* dh, const float* x
     if (!check_D(D, "rmsnorm_bwd")) return -1;
     int grid = row_grid((rows + 1) / 2, D / 4);
     if (grid > 4 * sm_count()) grid = 4 * sm_count();
-    norm_residual_bwd_kernel<false, 2><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x, rstd, w, nullptr, nullptr, nullptr, g_in, nullptr, dw, nullptr, nullptr, rows, D);
+    norm_residual_bwd_kernel<false, 2, false><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x, rstd, w, nullptr, nullptr, nullptr, g_in, nullptr, dw, nullptr, nullptr, rows, D, 0u, 1.f, 0, 0);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

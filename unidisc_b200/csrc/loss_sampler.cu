@@ -162,29 +162,6 @@ __global__ void subs_logprobs_kernel(const __nv_bfloat16* __restrict__ logits, l
 }
 
 // ------------------------------------------------------------------------------------------------
-// Philox4x32-10 (counter-based RNG for the non-parity "fast" sampling mode)
-// ------------------------------------------------------------------------------------------------
-UD_DEVINL uint4 philox4x32_10(uint4 ctr, uint2 key) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += W0; key.y += W1;
-    }
-    return ctr;
-}
-// uniform in [0,1) with 24 random bits for element index `idx`
-UD_DEVINL float philox_uniform(uint64_t seed, uint64_t offset, uint64_t idx) {
-    const uint64_t blk = idx >> 2;
-    uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
-                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    const uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
-    return (float)(w >> 8) * (1.0f / 16777216.0f);
-}
-
-// ------------------------------------------------------------------------------------------------
 // q_xt   (model.py:439,579)
 // ------------------------------------------------------------------------------------------------
 __global__ void q_xt_kernel(const int64_t* __restrict__ x, const float* __restrict__ move_chance, const float* __restrict__ rnd,

@@ -13,7 +13,8 @@ fp32 buffer (with a bf16 shadow for the tensor cores and a flat fp32 gradient bu
 into), so the optimizer and the DDP all-reduce work on contiguous memory.  There is no eager / CPU fallback.
 
 Supported configuration = the shipped large/small-scale training configs: norm_type=rms, sandwich_normalization,
-qk_norm, rope_2d, modality_embed, multimodal_batches, full_attention, no time-conditioning, dropout handled as 0
+qk_norm, rope_2d, modality_embed, multimodal_batches, full_attention, no time-conditioning; `model.dropout` is applied
+to the MLP branch in training mode exactly where the reference does (in-kernel Philox mask, regenerated in backward)
 (see DESIGN.md for what is not yet covered: adaLN time-conditioning, interleaved per-image RoPE tables, KV caches).
 """
 from __future__ import annotations
@@ -159,6 +160,8 @@ class DIT(nn.Module):
         if D % 128 != 0:
             raise NotImplementedError("hidden_size must be a multiple of 128")
         self.dropout = float(g(m, "dropout", 0.0))
+        self.dropout_seed = int(g(config, "seed", 42))
+        self._dropout_calls = 0
         self.txt_length, self.img_length, self.total_length = m.txt_length, m.img_length, m.length
         self.multimodal_batches = True
         self.rope_2d = True
@@ -357,7 +360,12 @@ class DIT(nn.Module):
                                      self.rotary_sin_emb_img, self.img_length)
         scale = 1.0 / math.sqrt(hd)
         x, h, rstd0 = ops.embed_rmsnorm_fwd(ids, mod, T["E"], T["Emod"], self._blk[0]["n1"])
-        saved = dict(ids=ids, mod=mod, sid=sid, cos=cos, sin=sin, B=B, N=N, x0=x, rstd0=rstd0, blocks=[]) if save else None
+        # training-mode dropout of the MLP branch (dit.py:1024-1031): Philox mask keyed by (seed, call counter * L + block)
+        p_drop = self.dropout if self.training else 0.0
+        self._dropout_calls += 1
+        drop_base = self._dropout_calls * self.n_blocks
+        saved = dict(ids=ids, mod=mod, sid=sid, cos=cos, sin=sin, B=B, N=N, x0=x, rstd0=rstd0, blocks=[], p_drop=p_drop,
+                     drop_base=drop_base) if save else None
         for i, W in enumerate(self._blk):
             w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
             qkv = ops.gemm(h, W["wqkv"])
@@ -367,7 +375,8 @@ class DIT(nn.Module):
             x1, h2, ra, rx1 = ops.norm_residual_fwd(a, x, W["npre"], W["n2"])
             u, gl = ops.gemm(h2, W["w1"], epi=L.EPI_BF16_GELU, bias=W["b1"])
             d = ops.gemm(gl, W["w2"], bias=W["b2"])
-            x2, h_next, rd, rx2 = ops.norm_residual_fwd(d, x1, W["npost"], w_next)
+            x2, h_next, rd, rx2 = ops.norm_residual_fwd(d, x1, W["npost"], w_next, p_drop=p_drop, seed=self.dropout_seed,
+                                                        offset=drop_base + i)
             if save:
                 saved["blocks"].append(dict(h=h, qkv=qkv, qk=qk, stats=stats, o=o, lse=lse, a=a, ra=ra, x1=x1, rx1=rx1, h2=h2,
                                             u=u, g=gl, d=d, rd=rd, x2=x2, rx2=rx2))
@@ -407,7 +416,8 @@ class DIT(nn.Module):
             d_wnext = self._blk[i + 1]["d_n1"] if i + 1 < self.n_blocks else T["d_nf"]
             # x2 = x1 + rms(d)*w_post ; h_next = rms(x2)*w_next
             g_res, dd = ops.norm_residual_bwd(g_res, dh, A["x2"], A["rx2"], w_next, A["d"], A["rd"], W["npost"], d_wnext, W["d_npost"],
-                                              db_a=W["d_b2"])           # also accumulates mlp.2.bias.grad = colsum(dd)
+                                              db_a=W["d_b2"],           # also accumulates mlp.2.bias.grad = colsum(dd)
+                                              p_drop=S["p_drop"], seed=self.dropout_seed, offset=S["drop_base"] + i)
             # MLP
             ops.gemm(dd, A["g"], ta=True, tb=True, epi=wacc, out=W["d_w2"])
             du = ops.gemm(dd, W["w2"], tb=True, epi=L.EPI_BF16_DGELU, aux=A["u"])

@@ -53,7 +53,7 @@ def embed_bwd(ids, modality, g, dE, dEmod, hot_id=-1):
     call("ud_embed_bwd", P(ids), P(modality), P(g), P(dE), P(dEmod), rows, D, hot_id, stream())
 
 
-def norm_residual_fwd(a, x_in, w_a, w_n, eps=1e-6, x_out=None, h=None):
+def norm_residual_fwd(a, x_in, w_a, w_n, eps=1e-6, x_out=None, h=None, p_drop=0.0, seed=0, offset=0):
     rows, D = x_in.shape
     if x_out is None:
         x_out = torch.empty_like(x_in)
@@ -61,18 +61,27 @@ def norm_residual_fwd(a, x_in, w_a, w_n, eps=1e-6, x_out=None, h=None):
         h = torch.empty((rows, D), device=x_in.device, dtype=bf16)
     ra = torch.empty((rows,), device=x_in.device, dtype=torch.float32)
     rx = torch.empty((rows,), device=x_in.device, dtype=torch.float32)
-    call("ud_norm_residual_fwd", P(a), P(x_in), P(w_a), P(w_n), P(x_out), P(h), P(ra), P(rx), rows, D, eps, stream())
+    call("ud_norm_residual_fwd", P(a), P(x_in), P(w_a), P(w_n), P(x_out), P(h), P(ra), P(rx), rows, D, eps, float(p_drop),
+         seed, offset, stream())
     return x_out, h, ra, rx
 
 
-def norm_residual_bwd(g_out, dh, x_out, rstd_x, w_n, a, rstd_a, w_a, dw_n, dw_a, g_in=None, da=None, db_a=None):
+def dropout_scales(rows, D, p_drop, seed, offset, device):
+    """The keep-scales (0 or 1/(1-p)) the fused norm kernels apply for (p_drop, seed, offset) — used by parity tests."""
+    out = torch.empty((rows, D), device=device, dtype=torch.float32)
+    call("ud_dropout_scales", P(out), rows, D, float(p_drop), seed, offset, stream())
+    return out
+
+
+def norm_residual_bwd(g_out, dh, x_out, rstd_x, w_n, a, rstd_a, w_a, dw_n, dw_a, g_in=None, da=None, db_a=None, p_drop=0.0,
+                      seed=0, offset=0):
     rows, D = x_out.shape
     if g_in is None:
         g_in = torch.empty_like(x_out)
     if da is None:
         da = torch.empty((rows, D), device=x_out.device, dtype=bf16)
     call("ud_norm_residual_bwd", P(g_out), P(dh), P(x_out), P(rstd_x), P(w_n), P(a), P(rstd_a), P(w_a), P(g_in), P(da),
-         P(dw_n), P(dw_a), P(db_a), rows, D, stream())
+         P(dw_n), P(dw_a), P(db_a), rows, D, float(p_drop), seed, offset, stream())
     return g_in, da
 
 
