@@ -135,6 +135,93 @@ def cpu_reference_tokens_per_sec(workload, budget_s=25.0):
                        f"extrapolated linearly to depth {L} ({t_full:.1f}s/step); no optimizer step on the CPU arm")
 
 
+def run_reference_gpu_arm(args, rank, world, local):
+    """`--impl reference --ref-device cuda`: the reference's own torch path on the GPU — oracle/torch_eager.py, the library-op
+    restatement of models/dit.py + model.py::compute_loss (nn.Linear / F.layer_norm / F.scaled_dot_product_attention under
+    torch.autocast(bf16), materialised SUBS log-probs, torch.optim.AdamW(fused) + clip_grad_norm_, torch DDP with the BF16
+    compress hook for N>1: reference main.py:641-656, model_setup.py:385-424,703) on the same workload, same timing rules.
+    This is the denominator of BASELINE.json's ">= 1.5x the reference's torch-sdpa GPU path" target; the driver's
+    reference arm stays the CPU one."""
+    import torch.distributed as dist
+    from oracle import restated as R
+    from oracle import torch_eager as TE
+    from unidisc_b200.config import MODEL_PRESETS
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    preset, bpg, txt, img = WORKLOADS[args.workload]
+    D, L, H = MODEL_PRESETS[preset]
+    V, tv, mi = TEXT_VOCAB + IMAGE_VOCAB, TEXT_VOCAB, TEXT_VOCAB - 1
+    N, B = txt + img, bpg
+    torch.manual_seed(0)
+    ocfg = R.OracleConfig(D, H, L, txt, img, V, tv, mi)
+    model = TE.EagerDIT(ocfg, dropout=args.dropout).to(dev)
+    model.train()
+    net = model
+    if world > 1:
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+        net.register_comm_hook(None, default_hooks.bf16_compress_hook)
+    fwd = net
+    if args.ref_compile:
+        fwd = torch.compile(net, mode="max-autotune-no-cudagraphs")                   # reference config.yaml:227
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, fused=True)
+    g = torch.Generator().manual_seed(42 + rank)
+    ids_h = torch.cat([torch.randint(0, tv - 1, (B, txt), generator=g), torch.randint(tv, V, (B, img), generator=g)], 1).pin_memory()
+    mod_h = torch.cat([torch.zeros(B, txt, dtype=torch.int64), torch.ones(B, img, dtype=torch.int64)], 1).pin_memory()
+    am_h = torch.ones(B, N, dtype=torch.bool).pin_memory()
+
+    class _W(torch.nn.Module):                     # lets DDP / compile wrap the backbone while the loss code calls model(xt, modality)
+        def forward(self, xt, modality):
+            return fwd(xt, modality)
+
+    def step():
+        ids, mod, am = ids_h.to(dev, non_blocking=True), mod_h.to(dev, non_blocking=True), am_h.to(dev, non_blocking=True)
+        loss = TE.reference_style_loss(_W(), ids, mod, am, mi, tv)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return float(loss.detach())
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        last = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        v = world * B * N / (ms.item() / args.steps * 1e-3)
+        kind = "torch eager" + (" + torch.compile(max-autotune-no-cudagraphs)" if args.ref_compile else "")
+        print(json.dumps(dict(
+            impl="reference", device="cuda", metric="joint_token_tokens_per_sec", value=v, unit="tokens/s", n_gpus=world, steps=args.steps,
+            warmup=args.warmup, ms_per_step=ms.item() / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+            data="synthetic", config=dict(workload=args.workload, seq_len=N, per_gpu_batch=B, global_batch=world * B, vocab=V,
+                                          parallelism=f"dp{world}", optimizer="torch AdamW(fused)+clip_grad_norm_(1.0)", dropout=args.dropout,
+                                          note=f"oracle/torch_eager.py ({kind}, SDPA, autocast bf16) — the reference's torch path restated, on the GPU"),
+            e2e=dict(value=v, unit="tokens/s", h2d_bytes_per_step=ids_h.numel() * 16 + am_h.numel(), d2h_bytes_per_step=4, loss=last),
+            gpu_launches=0, clocks=clocks, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -162,6 +249,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="unidisc-1.4B", choices=list(WORKLOADS))
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="reference arm: host cores (driver contract) or the "
+                    "torch-eager restatement on the GPU (the >=1.5x target's denominator)")
+    ap.add_argument("--ref-compile", action="store_true", help="with --ref-device cuda: torch.compile the backbone like the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1, help="model.dropout (reference configs/model/extra_large.yaml:9 = 0.1)")
     args = ap.parse_args()
@@ -169,7 +259,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        if args.ref_device == "cuda":
+            run_reference_gpu_arm(args, rank, world, local)
+        else:
+            run_reference_arm(args, rank, world)
         return
     assert args.warmup >= 3 or args.workload == "tiny", "timing rules: W >= 3"
 

@@ -113,3 +113,25 @@ def test_ddpm_forward_and_cfg(golden_fns, golden_dit):
     comb = R.cfg_combine(R.dit_forward(cfg, P, xc, mod), R.dit_forward(cfg, P, xu, mod), t, 2.5)
     pc = R.subs_parameterization(comb, None, mod, cfg.mask_index, cfg.text_vocab_size).exp()
     assert np.allclose(pc.numpy(), g["cfg_p_ref"], rtol=2e-4, atol=1e-6)
+
+
+def test_torch_eager_module_matches_restated_oracle():
+    """oracle/torch_eager.py (the library-op restatement timed as "the reference's torch-SDPA path" by bench.py) computes
+    the same function as oracle/restated.py (pinned against the unmodified reference above)."""
+    from oracle import restated as R
+    from oracle import torch_eager as TE
+    cfg = R.OracleConfig(128, 4, 2, 16, 16, 64 + 33, 33, 32)
+    P = R.init_params(cfg, seed=1)
+    m = TE.EagerDIT(cfg, dropout=0.0)
+    missing, unexpected = m.load_state_dict(P, strict=True)
+    assert not missing and not unexpected
+    ids, modality = R.synthetic_batch(3, 16, 16, cfg.text_vocab_size, cfg.vocab_size, seed=5)
+    want = R.dit_forward(cfg, P, ids, modality, mode="fp32")
+    got = m(ids, modality)
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+    # training-step restatement runs and back-propagates in eager mode
+    m.train()
+    loss = TE.reference_style_loss(m, ids, modality, torch.ones_like(ids, dtype=torch.bool), cfg.mask_index, cfg.text_vocab_size,
+                                   autocast=False, generator=torch.Generator().manual_seed(0))
+    loss.backward()
+    assert torch.isfinite(loss) and m.blocks[0].mlp[0].weight.grad.abs().sum() > 0
