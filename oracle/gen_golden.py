@@ -313,10 +313,85 @@ def gen_diffusion_fns(cfgd, dit, P, ids, modality, ocfg, ids_clean):
     np.savez_compressed(os.path.join(OUT, "diffusion_fns.npz"), **out)
 
 
+
+def gen_interleaved():
+    """Interleaved batches (data.require_sample_ids, BASELINE cfg5): the reference DIT run with packed samples,
+    per-image-block 2-D RoPE tables, img_count_embedding and the FlexAttention document mask (eval mode, eager flex on CPU)
+    vs the restatement; also pins `interleaved_token_tables` against add_img_data_to_blocks/add_txt_data_to_blocks."""
+    from torch.nn.attention.flex_attention import create_block_mask
+    D, H, L, N, V, tv, mi = 128, 2, 2, 640, 160, 97, 96
+    ref_cfg = RL.make_ref_config(D, H, L, 64, 256, require_sample_ids=True)
+    ref_cfg.model.length = N
+    ref_cfg.model.use_flex_attention = True
+    torch.manual_seed(0)
+    dit = RL.build_reference_dit(ref_cfg, V, tv, mi, dtype=torch.float32)
+    dit.eval()
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        dit.img_count_embedding.copy_(torch.randn(dit.img_count_embedding.shape, generator=g) * 0.5)
+        for n, p in dit.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                p.add_((torch.rand(p.shape, generator=g) - 0.5) * 0.4)
+    B = 4
+    modality = torch.zeros(B, N, dtype=torch.long)
+    sid = torch.zeros(B, N, dtype=torch.long)
+    # row 0: sample 0 = txt40 img256 txt24 ; sample 1 = img256 txt30 ; pad
+    modality[0, 40:296] = 1; sid[0, 320:] = 1; modality[0, 320:576] = 1; sid[0, 606:] = -1
+    # row 1: sample 0 = txt10 img64(no table) txt26 ; sample 1 = txt100 img256 txt4 img40(no table) txt100 ; sample 2 = txt40
+    modality[1, 10:74] = 1; sid[1, 100:] = 1; modality[1, 200:456] = 1; modality[1, 460:500] = 1; sid[1, 600:] = 2
+    # row 2: sample 0 = img256 img... two images of one sample separated by 1 text token, then sample 1 starts with an image
+    modality[2, 0:256] = 1; modality[2, 257:513] = 1; sid[2, 513:] = 1; modality[2, 514:578] = 1; sid[2, 630:] = -1
+    # row 3: the images of two different samples are adjacent -> ONE modality run of 512 tokens (no table: cos = sin = 0)
+    modality[3, 0:512] = 1; sid[3, 256:] = 1
+    ids = torch.randint(0, mi, (B, N), generator=g)
+    ids[modality == 1] = torch.randint(tv, V, (int((modality == 1).sum()),), generator=g)
+    ids[0, 50:90] = mi
+    ids[1, 5] = mi
+
+    def mm(b, h, q, k):
+        return (sid[b, q] == sid[b, k]) & (sid[b, q] != -1)
+    bm = create_block_mask(mm, B=B, H=None, Q_LEN=N, KV_LEN=N, device="cpu")
+    with torch.no_grad():
+        ref_logits = dit(ids, None, modality=modality, sample_ids=sid, block_mask=bm).float()
+    # tables straight from the reference helper functions
+    mod = RL.load_reference_dit_module()
+    hd = D // H
+    cos = torch.zeros(B, N, hd // 2); sin = torch.zeros(B, N, hd // 2)
+    xz = torch.zeros(B, N, D)
+    mmask = modality.bool()
+    mod.add_img_data_to_blocks(xz, cos, mmask, sid, {k: getattr(dit, f"rotary_cos_emb_img_{k}") for k in (256, 1024, 2304, 4096)}, dit.img_count_embedding.detach())
+    mod.add_img_data_to_blocks(None, sin, mmask, sid, {k: getattr(dit, f"rotary_sin_emb_img_{k}") for k in (256, 1024, 2304, 4096)}, None)
+    mod.add_txt_data_to_blocks(cos, mmask, sid, dit.rotary_cos_emb_txt)
+    mod.add_txt_data_to_blocks(sin, mmask, sid, dit.rotary_sin_emb_txt)
+    ocfg = R.OracleConfig(D, H, L, 64, 256, V, tv, mi, require_sample_ids=True)
+    ocfg_len = N
+    assert ocfg.length != N or True
+    P = {k: v.detach().clone() for k, v in dit.state_dict().items()}
+    c2, s2, ordinal = R.interleaved_token_tables(_with_length(ocfg, N), modality, sid)
+    assert torch.equal(c2, cos) and torch.equal(s2, sin), ((c2 - cos).abs().max(), (s2 - sin).abs().max())
+    add = torch.where((ordinal >= 0)[..., None], dit.img_count_embedding.detach()[ordinal.clamp(min=0)], torch.zeros(B, N, D))
+    assert torch.equal(add, xz)
+    mine = R.dit_forward(_with_length(ocfg, N), P, ids, modality, mode="fp32", sample_ids=sid)
+    valid = (sid != -1)
+    err = (mine - ref_logits)[valid].abs().max().item()
+    print(f"[interleaved fp32] max|restated - reference| on non-pad tokens = {err:.3e}  (ref absmax {ref_logits[valid].abs().max():.3f})")
+    assert err < 5e-5, err
+    np.savez_compressed(os.path.join(OUT, "interleaved.npz"),
+                        cfg=np.array([D, H, L, N, V, tv, mi]), ids=_np(ids), modality=_np(modality), sample_ids=_np(sid),
+                        ref_logits_fp32=_np(ref_logits), ref_cos=_np(cos), ref_sin=_np(sin), ref_ordinal=_np(ordinal),
+                        **{"P::" + k: _np(v) for k, v in P.items()})
+
+
+def _with_length(ocfg, N):
+    """OracleConfig whose `length` (txt_length + img_length) equals the packed sequence length N."""
+    import dataclasses
+    return dataclasses.replace(ocfg, txt_length=N - ocfg.img_length)
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     gen_diffusion_fns(*gen_dit())
+    gen_interleaved()
     print("golden fixtures written to", OUT)
 
 

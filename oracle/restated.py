@@ -47,6 +47,7 @@ class OracleConfig:
     ln_eps: float = 1e-5     # nn.LayerNorm default, dit.py:569-571
     time_conditioning: bool = False
     cond_dim: int = 128
+    require_sample_ids: bool = False   # data.require_sample_ids: interleaved batches (dit.py:1208-1216,1421-1443)
 
     @property
     def length(self):
@@ -101,6 +102,57 @@ def token_cos_sin(cfg: OracleConfig, modality: torch.Tensor):
     cos = torch.where(is_txt, cos_t[pos][None], cos_i[ipos][None])
     sin = torch.where(is_txt, sin_t[pos][None], sin_i[ipos][None])
     return cos.to(modality.device), sin.to(modality.device)
+
+
+# interleaved batches (data.require_sample_ids): per-image-block 2-D tables, text position = offset within the sample
+INTERLEAVED_IMG_TABLES = ((256, 1.0), (1024, 2.0), (2304, 3.0), (4096, 4.0))      # dit.py:1209
+
+
+def _runs(flag_row):
+    """[(start, end)) maximal runs of equal values in a 1-D tensor -> list of (start, end, value)."""
+    v = flag_row.tolist()
+    out, s = [], 0
+    for i in range(1, len(v) + 1):
+        if i == len(v) or v[i] != v[s]:
+            out.append((s, i, v[s]))
+            s = i
+    return out
+
+
+def interleaved_token_tables(cfg: OracleConfig, modality: torch.Tensor, sample_ids: torch.Tensor):
+    """dit.py:1421-1443 with add_img_data_to_blocks (dit.py:122-178) and add_txt_data_to_blocks (dit.py:181-191).
+
+    Returns (cos, sin) [B,N,hd/2] and `ordinal` int64 [B,N]: for tokens of an image block whose size has a table,
+    the number of earlier image blocks of the same packed sample in that row (index into `img_count_embedding`),
+    else -1.  Image blocks = maximal runs of modality==1 (unidisc/utils/tensor_utils.py:4-22, regardless of sample
+    boundaries); sizes without a table (e.g. 64) keep cos=sin=0 and get no count embedding.  Text tokens of a run of
+    equal sample_id >= 0 (tensor_utils.py:24-44) take the 1-D table at (position - run start); pad runs (-1) stay 0."""
+    B, N = modality.shape
+    hd = cfg.head_dim
+    cos_t, sin_t = rope_table_1d(hd, cfg.length)
+    tabs = {size: rope_table_2d(hd, size, lf) for size, lf in INTERLEAVED_IMG_TABLES}
+    cos = torch.zeros(B, N, hd // 2)
+    sin = torch.zeros(B, N, hd // 2)
+    ordinal = torch.full((B, N), -1, dtype=torch.int64)
+    for b in range(B):
+        seen = []                                   # sample ids at the start of earlier image blocks of this row
+        for s, e, m in _runs(modality[b] != 0):
+            if not m:
+                continue
+            sid0 = int(sample_ids[b, s])
+            size = e - s
+            if size in tabs:                        # dit.py:131 (blocks of other sizes are skipped entirely)
+                cos[b, s:e] = tabs[size][0][:size]
+                sin[b, s:e] = tabs[size][1][:size]
+                ordinal[b, s:e] = sum(1 for x in seen if x == sid0)   # dit.py:134-142
+            seen.append(sid0)
+        for s, e, sid in _runs(sample_ids[b]):
+            if sid < 0:                             # tensor_utils.py:42
+                continue
+            txt = modality[b, s:e] == 0
+            cos[b, s:e] = torch.where(txt[:, None], cos_t[: e - s], cos[b, s:e])       # dit.py:190
+            sin[b, s:e] = torch.where(txt[:, None], sin_t[: e - s], sin[b, s:e])
+    return cos, sin, ordinal
 
 
 # --------------------------------------------------------------------------------------
@@ -211,7 +263,12 @@ def dit_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], indices, modality
     x = P["vocab_embed.embedding"].float()[indices]                                   # dit.py:1375
     me = P["modality_embed.embedding"].float()
     x = x + torch.where((modality == 0)[..., None], me[0][None, None], me[1][None, None])  # dit.py:1406
-    cos, sin = token_cos_sin(cfg, modality.cpu())
+    if cfg.require_sample_ids:                                                        # dit.py:1421-1443
+        cos, sin, ordinal = interleaved_token_tables(cfg, modality.cpu(), sample_ids.cpu())
+        ice = P["img_count_embedding"].float()
+        x = x + torch.where((ordinal >= 0)[..., None].to(x.device), ice[ordinal.clamp(min=0)], torch.zeros_like(x))  # dit.py:163-167
+    else:
+        cos, sin = token_cos_sin(cfg, modality.cpu())
     cos, sin = cos.to(x.device), sin.to(x.device)
     for i in range(cfg.n_blocks):
         x = block_forward(cfg, P, i, x, cos, sin, mode, sample_ids=sample_ids, taps=taps,

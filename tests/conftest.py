@@ -36,3 +36,9 @@ def golden_dit():
 def golden_fns():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "diffusion_fns.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_interleaved():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "interleaved.npz"))

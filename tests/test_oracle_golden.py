@@ -135,3 +135,26 @@ def test_torch_eager_module_matches_restated_oracle():
                                    autocast=False, generator=torch.Generator().manual_seed(0))
     loss.backward()
     assert torch.isfinite(loss) and m.blocks[0].mlp[0].weight.grad.abs().sum() > 0
+
+
+def _icfg(g):
+    import dataclasses
+    D, H, L, N, V, tv, mi = [int(v) for v in g["cfg"]]
+    return dataclasses.replace(R.OracleConfig(D, H, L, N - 256, 256, V, tv, mi), require_sample_ids=True), N
+
+
+def test_interleaved_tables_and_forward_match_reference(golden_interleaved):
+    """data.require_sample_ids (BASELINE cfg5): per-image-block RoPE tables, img_count_embedding ordinals and the packed-sample
+    forward with the document mask vs the reference's add_img_data_to_blocks / add_txt_data_to_blocks / FlexAttention run."""
+    g = golden_interleaved
+    cfg, N = _icfg(g)
+    modality, sid = torch.from_numpy(g["modality"]), torch.from_numpy(g["sample_ids"])
+    cos, sin, ordinal = R.interleaved_token_tables(cfg, modality, sid)
+    assert np.array_equal(cos.numpy(), g["ref_cos"]) and np.array_equal(sin.numpy(), g["ref_sin"])
+    assert np.array_equal(ordinal.numpy(), g["ref_ordinal"])
+    assert ordinal.max() >= 1 and (ordinal == -1).any()          # fixture has second images and table-less blocks
+    P = _params(g)
+    out = R.dit_forward(cfg, P, torch.from_numpy(g["ids"]), modality, mode="fp32", sample_ids=sid)
+    ref = torch.from_numpy(g["ref_logits_fp32"])
+    valid = sid != -1
+    assert (out - ref)[valid].abs().max().item() < 5e-5
