@@ -36,12 +36,27 @@ int ud_gemm_bf16(int ta, int tb, int M, int N, int K, const void* A, long long l
                  long long ldc, int epi, const void* bias, void* aux, long long ld_aux, int bn_hint, void* stream);
 
 /* ---- embedding + first RMSNorm ------------------------------------------------------------------------------
- * x = E[ids] + Emod[modality]  (dit.py:1375,1406);  h = bf16(rms(x) * w)  (dit.py:95-100,971).  rows = B*N. */
+ * x = E[ids] + Emod[modality] (+ Ecount[ordinal] where ordinal >= 0)  (dit.py:1375,1406,163-167);
+ * h = bf16(rms(x) * w)  (dit.py:95-100,971).  rows = B*N.  ordinal (int32 [rows], from ud_interleaved_prep) / Ecount
+ * (`img_count_embedding`, fp32 [16,D]) are NULL outside interleaved batches. */
 int ud_embed_rmsnorm_fwd(const int64_t* ids, const int64_t* modality, const float* E, const float* Emod, const float* w,
-                         float* x, void* h_bf16, float* rstd, int rows, int D, float eps, void* stream);
-/* dE[ids] += g ; dEmod[modality] += g   (g = gradient wrt x, fp32 [rows,D]) */
+                         float* x, void* h_bf16, float* rstd, int rows, int D, float eps, const int* ordinal,
+                         const float* Ecount, void* stream);
+/* dE[ids] += g ; dEmod[modality] += g ; dEcount[ordinal] += g   (g = gradient wrt x, fp32 [rows,D]) */
 int ud_embed_bwd(const int64_t* ids, const int64_t* modality, const float* g, float* dE, float* dEmod, int rows, int D,
-                 long long hot_id /* id accumulated per CTA (the mask token), -1 = none */, void* stream);
+                 long long hot_id /* id accumulated per CTA (the mask token), -1 = none */, const int* ordinal,
+                 float* dEcount, void* stream);
+
+/* ---- interleaved-batch preparation (data.require_sample_ids; dit.py:122-191,1421-1443, tensor_utils.py:4-44) ----------
+ * One launch replaces the reference's Python loops over image / sample blocks.  modality, sample_ids: int64 [B,N].
+ * cos_tab/sin_tab: fp32 [rows_total, hd2] = the 1-D text table at row txt_off and the 2-D tables of the 256/1024/2304/4096
+ * -token image blocks at off256..off4096 (dit.py:1208-1212).  Outputs per token: cos/sin [B*N, hd2] and the image ordinal
+ * (index into img_count_embedding, -1 = none).  Image block = maximal run of modality != 0; blocks whose size has no
+ * table keep cos = sin = 0 and ordinal -1 (as in the reference); text tokens use (pos - start of their sample_id run);
+ * pad runs (sample_id < 0) stay 0.  scratch: int32 [B, 4N]. */
+int ud_interleaved_prep(const int64_t* modality, const int64_t* sample_ids, int B, int N, const float* cos_tab,
+                        const float* sin_tab, int hd2, int txt_off, int off256, int off1024, int off2304, int off4096,
+                        float* cos_out, float* sin_out, int* ordinal_out, int* scratch, void* stream);
 
 /* ---- fused "sandwich" norm + residual + next pre-norm -------------------------------------------------------
  * x_out = x_in + dropout_p(bf16(rms(a)) * w_a) ;  h = bf16(rms(x_out) * w_n)

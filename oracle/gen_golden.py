@@ -376,7 +376,27 @@ def gen_interleaved():
     err = (mine - ref_logits)[valid].abs().max().item()
     print(f"[interleaved fp32] max|restated - reference| on non-pad tokens = {err:.3e}  (ref absmax {ref_logits[valid].abs().max():.3f})")
     assert err < 5e-5, err
+    # ---- q_xt, interleaved whole-block masking (model.py:483-522), reference code on a fake self
+    cfgd = dict(txt=N - 256, img=256, mask_index=mi, text_vocab_size=tv, vocab_size=V)
+    s2, _ = make_fake_self(cfgd, ref_dit=SimpleNamespace(training=True), mask_entire_modality=0.2)
+    s2.config.trainer.interleaved = True
+    x0 = torch.where(ids == mi, torch.zeros_like(ids), ids)
+    mc = torch.full((B, 1), 0.3)
+    torch.manual_seed(21)
+    xt_ref, ign_ref, _, _, _, mv_ref = s2.q_xt(x0, mc, return_ignore_batch_mask_for_metrics=True, batch=dict(modality=modality, sample_ids=sid))
+    torch.manual_seed(21)
+    rand = torch.rand(B, N); _rt, _ri = torch.rand(B, 1), torch.rand(B, 1)
+    from unidisc.utils.tensor_utils import get_contiguous_blocks_per_sample
+    bi, sp, ep = get_contiguous_blocks_per_sample(modality, sid)
+    Mb = int(((ep - sp) > 4).sum())
+    rand_blocks = torch.rand(Mb, 1)
+    xt_o, mv_o, ign_o = R.q_xt_interleaved(x0, mc, rand, mi, modality, sid, 0.2, rand_blocks)
+    assert torch.equal(xt_o, xt_ref) and torch.equal(mv_o, mv_ref) and torch.equal(ign_o, ign_ref.bool())
+    assert ign_ref.any() and not ign_ref.all(), ign_ref
+    print(f"[interleaved q_xt] {Mb} blocks, rows force-masked: {ign_ref.tolist()}")
     np.savez_compressed(os.path.join(OUT, "interleaved.npz"),
+                        qxt_x0=_np(x0), qxt_mc=_np(mc), qxt_rand=_np(rand), qxt_rand_blocks=_np(rand_blocks), qxt_seed=np.array(21),
+                        qxt_ref=_np(xt_ref), qxt_move_ref=_np(mv_ref), qxt_ignore_ref=_np(ign_ref.bool()),
                         cfg=np.array([D, H, L, N, V, tv, mi]), ids=_np(ids), modality=_np(modality), sample_ids=_np(sid),
                         ref_logits_fp32=_np(ref_logits), ref_cos=_np(cos), ref_sin=_np(sin), ref_ordinal=_np(ordinal),
                         **{"P::" + k: _np(v) for k, v in P.items()})

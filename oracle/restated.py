@@ -321,6 +321,30 @@ def q_xt(x0: torch.Tensor, move_chance: torch.Tensor, rand: torch.Tensor, mask_i
     return xt, move, ignore
 
 
+def q_xt_interleaved(x0, move_chance, rand, mask_index, modality, sample_ids, mask_entire_modality, rand_blocks):
+    """model.py:439 + 483-522 + 579 (trainer.interleaved with mask_entire_modality).  `rand` [B,N] is the draw at :439,
+    `rand_blocks` [M,1] the per-block draw at :510 (M = number of (modality, sample) blocks longer than 4 tokens, in
+    row-major order; the two [B,1] draws at :479-480 are consumed by the reference but unused on this branch).
+    Returns (xt, move_indices, ignore [B])."""
+    B, N = x0.shape
+    move = (rand < move_chance).clone()
+    blocks = []                                          # tensor_utils.py:46-68 + model.py:486-488
+    for b in range(B):
+        key = modality[b] * (int(sample_ids.max()) + 3) + (sample_ids[b] + 1)
+        for s, e, _ in _runs(key):
+            if int(sample_ids[b, s]) >= 0 and e - s > 4:
+                blocks.append((b, s, e, int(sample_ids[b, s])))
+    assert rand_blocks.shape[0] == len(blocks)
+    ignore = torch.zeros(B, dtype=torch.bool)
+    for i, (b, s, e, sid) in enumerate(blocks):
+        k = sum(1 for (b2, _, _, sid2) in blocks[:i] if b2 == b and sid2 == sid)
+        K = sum(1 for (b2, _, _, sid2) in blocks if b2 == b and sid2 == sid)
+        if float(rand_blocks[i, 0]) < float(torch.tensor(mask_entire_modality, dtype=torch.float32) * torch.tensor((k + 1) / K, dtype=torch.float32) * 2):
+            move[b, s:e] = True
+            ignore[b] = True
+    return torch.where(move, mask_index, x0), move, ignore
+
+
 # --------------------------------------------------------------------------------------
 # SUBS parameterization + loss — model.py:621-658, 797-1173
 # --------------------------------------------------------------------------------------

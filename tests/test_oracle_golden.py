@@ -158,3 +158,24 @@ def test_interleaved_tables_and_forward_match_reference(golden_interleaved):
     ref = torch.from_numpy(g["ref_logits_fp32"])
     valid = sid != -1
     assert (out - ref)[valid].abs().max().item() < 5e-5
+
+
+def test_interleaved_q_xt_oracle_and_host_logic_bit_exact(golden_interleaved):
+    """model.py:483-522 — whole-block masking of packed batches.  (1) the oracle restatement fed the recorded draws and
+    (2) the product's torch host function `unidisc_b200.model.q_xt_general` replaying the recorded CPU seed must both
+    reproduce the reference's xt / move / ignore masks bit for bit."""
+    g = golden_interleaved
+    mi = int(g["cfg"][6])
+    x0, mc = torch.from_numpy(g["qxt_x0"]), torch.from_numpy(g["qxt_mc"])
+    modality, sid = torch.from_numpy(g["modality"]), torch.from_numpy(g["sample_ids"])
+    xt, mv, ign = R.q_xt_interleaved(x0, mc, torch.from_numpy(g["qxt_rand"]), mi, modality, sid, 0.2,
+                                     torch.from_numpy(g["qxt_rand_blocks"]))
+    assert np.array_equal(xt.numpy(), g["qxt_ref"]) and np.array_equal(mv.numpy(), g["qxt_move_ref"])
+    assert np.array_equal(ign.numpy(), g["qxt_ignore_ref"])
+    from unidisc_b200.model import q_xt_general
+    trainer = dict(mask_entire_modality=0.2, interleaved=True)
+    torch.manual_seed(int(g["qxt_seed"]))
+    xt2, ign2, _, _, mv2 = q_xt_general(x0, mc, mi, trainer, backbone_training=True, training=True,
+                                        batch=dict(modality=modality, sample_ids=sid))
+    assert np.array_equal(xt2.numpy(), g["qxt_ref"]) and np.array_equal(mv2.numpy(), g["qxt_move_ref"])
+    assert np.array_equal(ign2.numpy(), g["qxt_ignore_ref"])

@@ -20,8 +20,9 @@ _SIGS = {
     "ud_abi_version": [],
     "ud_device_sm_count": [],
     "ud_gemm_bf16": [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp],
-    "ud_embed_rmsnorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
-    "ud_embed_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
+    "ud_embed_rmsnorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp],
+    "ud_embed_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp],
+    "ud_interleaved_prep": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ud_norm_residual_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _u64, _u64, _vp],
     "ud_norm_residual_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _u64, _u64, _vp],
     "ud_dropout_scales": [_vp, _i, _i, _f, _u64, _u64, _vp],

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libunidisc_b200.so")
-SOURCES = ["gemm.cu", "elementwise.cu", "loss_sampler.cu", "attention.cu"]
+SOURCES = ["gemm.cu", "elementwise.cu", "loss_sampler.cu", "attention.cu", "interleaved.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-I", os.path.join(ROOT, "include"), "-I", CSRC, "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

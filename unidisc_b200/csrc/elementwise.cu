@@ -59,7 +59,8 @@ UD_DEVINL void st_bf4(__nv_bfloat16* p, const F4& a) {
 __global__ void embed_rmsnorm_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ modality,
                                          const float* __restrict__ E, const float* __restrict__ Emod,
                                          const float* __restrict__ w, float* __restrict__ x, __nv_bfloat16* __restrict__ h,
-                                         float* __restrict__ rstd, int rows, int D, float eps) {
+                                         float* __restrict__ rstd, int rows, int D, float eps,
+                                         const int* __restrict__ ordinal, const float* __restrict__ Ecount) {
     __shared__ float scratch[2 * 32 * 1];
     int buf = 0;
     const int c = threadIdx.x * 4;
@@ -70,7 +71,17 @@ __global__ void embed_rmsnorm_fwd_kernel(const int64_t* __restrict__ ids, const 
         F4 e = ld_f4(E + id * D + c), m = ld_f4(Emod + (long long)md * D + c), xv;
         float ss[1] = {0.f};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { xv.v[i] = e.v[i] + m.v[i]; ss[0] += xv.v[i] * xv.v[i]; }
+        for (int i = 0; i < 4; ++i) xv.v[i] = e.v[i] + m.v[i];
+        if (ordinal != nullptr) {            // interleaved batches: + img_count_embedding[k] on the k-th image of a sample (dit.py:163-167)
+            const int od = ordinal[row];
+            if (od >= 0) {
+                const F4 ce = ld_f4(Ecount + (long long)od * D + c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xv.v[i] += ce.v[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ss[0] += xv.v[i] * xv.v[i];
         block_sum<1>(ss, scratch, buf);
         const float r = rsqrtf(ss[0] / (float)D + eps);
         F4 hv;
@@ -82,14 +93,18 @@ __global__ void embed_rmsnorm_fwd_kernel(const int64_t* __restrict__ ids, const 
     }
 }
 
-// dE[ids] += g, dEmod[modality] += g.  Modality rows (2 of them) and the `hot_id` row (the mask token, hit by every
-// masked position) are accumulated in registers per CTA instead of per-row atomics.
+// dE[ids] += g, dEmod[modality] += g, dEcount[ordinal] += g.  Each CTA owns a CONTIGUOUS chunk of rows; the modality rows
+// (2 of them), the `hot_id` row (the mask token, hit by every masked position) and the current image ordinal (constant
+// over an image block) are accumulated in registers and flushed with one atomic per column instead of per-row atomics.
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ modality,
                                  const float* __restrict__ g, float* __restrict__ dE, float* __restrict__ dEmod, int rows,
-                                 int D, long long hot_id) {
+                                 int D, long long hot_id, const int* __restrict__ ordinal, float* __restrict__ dEcount) {
     const int c = threadIdx.x * 4;
-    F4 am0 = {{0, 0, 0, 0}}, am1 = {{0, 0, 0, 0}}, ahot = {{0, 0, 0, 0}};
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    F4 am0 = {{0, 0, 0, 0}}, am1 = {{0, 0, 0, 0}}, ahot = {{0, 0, 0, 0}}, aord = {{0, 0, 0, 0}};
+    int cur_ord = -1;
+    const int per = (rows + gridDim.x - 1) / gridDim.x;
+    const int r_lo = blockIdx.x * per, r_hi = min(rows, r_lo + per);
+    for (int row = r_lo; row < r_hi; ++row) {
         const long long id = ids[row];
         const bool m1 = modality[row] != 0;
         F4 gv = ld_f4(g + (long long)row * D + c);
@@ -105,12 +120,27 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const int64_t*
 #pragma unroll
             for (int i = 0; i < 4; ++i) atomicAdd(d + i, gv.v[i]);
         }
+        if (ordinal != nullptr) {
+            const int od = ordinal[row];
+            if (od != cur_ord) {
+                if (cur_ord >= 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { atomicAdd(dEcount + (long long)cur_ord * D + c + i, aord.v[i]); aord.v[i] = 0.f; }
+                }
+                cur_ord = od;
+            }
+            if (od >= 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) aord.v[i] += gv.v[i];
+            }
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         atomicAdd(dEmod + c + i, am0.v[i]);
         atomicAdd(dEmod + D + c + i, am1.v[i]);
         if (hot_id >= 0) atomicAdd(dE + hot_id * D + c + i, ahot.v[i]);
+        if (cur_ord >= 0) atomicAdd(dEcount + (long long)cur_ord * D + c + i, aord.v[i]);
     }
 }
 
@@ -693,25 +723,28 @@ using namespace ud;
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
-extern "C" int ud_abi_version(void) { return 2; }
+extern "C" int ud_abi_version(void) { return 3; }
 extern "C" int ud_device_sm_count(void) { return sm_count(); }
 
 extern "C" int ud_embed_rmsnorm_fwd(const int64_t* ids, const int64_t* modality, const float* E, const float* Emod,
-                                    const float* w, float* x, void* h, float* rstd, int rows, int D, float eps, void* stream) {
+                                    const float* w, float* x, void* h, float* rstd, int rows, int D, float eps,
+                                    const int* ordinal, const float* Ecount, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "embed_rmsnorm_fwd")) return -1;
-    embed_rmsnorm_fwd_kernel<<<row_grid(rows, D / 4), D / 4, 0, STREAM(stream)>>>(ids, modality, E, Emod, w, x, BF(h), rstd, rows, D, eps);
+    if (ordinal != nullptr && Ecount == nullptr) return -1;
+    embed_rmsnorm_fwd_kernel<<<row_grid(rows, D / 4), D / 4, 0, STREAM(stream)>>>(ids, modality, E, Emod, w, x, BF(h), rstd, rows, D, eps, ordinal, Ecount);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
 extern "C" int ud_embed_bwd(const int64_t* ids, const int64_t* modality, const float* g, float* dE, float* dEmod, int rows,
-                            int D, long long hot_id, void* stream) {
+                            int D, long long hot_id, const int* ordinal, float* dEcount, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "embed_bwd")) return -1;
+    if (ordinal != nullptr && dEcount == nullptr) return -1;
     int grid = row_grid(rows, D / 4);
     if (grid > 2 * sm_count()) grid = 2 * sm_count();
-    embed_bwd_kernel<<<grid, D / 4, 0, STREAM(stream)>>>(ids, modality, g, dE, dEmod, rows, D, hot_id);
+    embed_bwd_kernel<<<grid, D / 4, 0, STREAM(stream)>>>(ids, modality, g, dE, dEmod, rows, D, hot_id, ordinal, dEcount);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -15,7 +15,9 @@ into), so the optimizer and the DDP all-reduce work on contiguous memory.  There
 Supported configuration = the shipped large/small-scale training configs: norm_type=rms, sandwich_normalization,
 qk_norm, rope_2d, modality_embed, multimodal_batches, full_attention, no time-conditioning; `model.dropout` is applied
 to the MLP branch in training mode exactly where the reference does (in-kernel Philox mask, regenerated in backward)
-(see DESIGN.md for what is not yet covered: adaLN time-conditioning, interleaved per-image RoPE tables, KV caches).
+`data.require_sample_ids` (interleaved / packed batches): per-image-block RoPE tables, `img_count_embedding` and the
+document mask are derived on the device from `modality` / `sample_ids` (csrc/interleaved.cu).
+(see DESIGN.md for what is not yet covered: adaLN time-conditioning, KV caches).
 """
 from __future__ import annotations
 
@@ -101,8 +103,8 @@ class DDitFinalLayer(nn.Module):                                     # parameter
 # ----------------------------------------------------------------------------------------------------------------
 class _DiTFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, module, indices, modality, sample_ids, save):
-        logits, saved = module._forward_impl(indices, modality, sample_ids, save=save)
+    def forward(ctx, anchor, module, indices, modality, sample_ids, save, doc_mask):
+        logits, saved = module._forward_impl(indices, modality, sample_ids, save=save, doc_mask=doc_mask)
         ctx.module = module
         ctx.saved = saved
         return logits
@@ -114,7 +116,7 @@ class _DiTFunction(torch.autograd.Function):
             raise RuntimeError("unidisc_b200.DIT: backward called on a forward that did not save activations")
         module._backward_impl(saved, dlogits)
         ctx.saved = None
-        return torch.zeros_like(module._anchor), None, None, None, None, None
+        return torch.zeros_like(module._anchor), None, None, None, None, None, None
 
 
 class DIT(nn.Module):
@@ -144,8 +146,6 @@ class DIT(nn.Module):
             unsupported.append("rope_2d / modality_embed / multimodal_batches must be on")
         if not g(m, "full_attention", True):
             unsupported.append("causal attention")
-        if g(config.data, "require_sample_ids", False):
-            unsupported.append("data.require_sample_ids (interleaved per-image RoPE tables)")
         if g(m, "img_cond", False) or g(m, "use_pretrained_img_emb", False) or g(m, "cond_label", False) \
                 or g(config.trainer, "image_mode", "discrete") == "continuous":
             unsupported.append("img_cond / pretrained image embedding / label conditioning / continuous image mode")
@@ -165,7 +165,7 @@ class DIT(nn.Module):
         self.txt_length, self.img_length, self.total_length = m.txt_length, m.img_length, m.length
         self.multimodal_batches = True
         self.rope_2d = True
-        self.require_sample_ids = False
+        self.require_sample_ids = bool(g(config.data, "require_sample_ids", False))
         self.use_gradient_checkpointing = bool(g(config.trainer, "use_gradient_checkpointing", False))
 
         self.vocab_embed = EmbeddingLayer(D, vocab_size)
@@ -175,12 +175,29 @@ class DIT(nn.Module):
         self.sigma_map = None
 
         lf = g(m, "linear_factor", 1.0)
-        ci, si = rope.rope_2d(self.head_dim, self.img_length, lf)
         ct, st = rope.rope_1d(self.head_dim, self.total_length)
-        self.register_buffer("rotary_cos_emb_img", ci, persistent=False)
-        self.register_buffer("rotary_sin_emb_img", si, persistent=False)
-        self.register_buffer("rotary_cos_emb_txt", ct[:, : ci.shape[1]].contiguous(), persistent=False)
-        self.register_buffer("rotary_sin_emb_txt", st[:, : si.shape[1]].contiguous(), persistent=False)
+        if self.require_sample_ids:
+            # interleaved batches: one 2-D table per supported image-block size, count embedding (dit.py:1208-1216)
+            cat_c, cat_s, off = [ct], [st], {"txt": 0}
+            rows = ct.shape[0]
+            for size, factor in rope.INTERLEAVED_IMG_TABLES:
+                ci, si = rope.rope_2d(self.head_dim, size, factor)
+                self.register_buffer(f"rotary_cos_emb_img_{size}", ci, persistent=False)
+                self.register_buffer(f"rotary_sin_emb_img_{size}", si, persistent=False)
+                off[f"s{size}"] = rows
+                rows += size
+                cat_c.append(ci)
+                cat_s.append(si)
+            self._rope_offsets = off
+            self.register_buffer("_rope_cat_cos", torch.cat(cat_c, 0).contiguous(), persistent=False)
+            self.register_buffer("_rope_cat_sin", torch.cat(cat_s, 0).contiguous(), persistent=False)
+            self.img_count_embedding = nn.Parameter(torch.zeros((16, D)))
+        else:
+            ci, si = rope.rope_2d(self.head_dim, self.img_length, lf)
+            self.register_buffer("rotary_cos_emb_img", ci, persistent=False)
+            self.register_buffer("rotary_sin_emb_img", si, persistent=False)
+        self.register_buffer("rotary_cos_emb_txt", ct.contiguous(), persistent=False)
+        self.register_buffer("rotary_sin_emb_txt", st.contiguous(), persistent=False)
 
         self.Vp = (vocab_size + 63) // 64 * 64     # logits row pitch (TMA / 16-byte vector stores)
         self._flat_p = None
@@ -271,6 +288,8 @@ class DIT(nn.Module):
             d_E=gr("vocab_embed.embedding"), d_Emod=gr("modality_embed.embedding"), d_nf=gr("output_layer.norm_final.weight"),
             d_wh=gr("output_layer.linear.weight"), d_bh=gr("output_layer.linear.bias"),
         )
+        if self.require_sample_ids:
+            self._top["Ecount"], self._top["d_Ecount"] = f32("img_count_embedding"), gr("img_count_embedding")
         self._grad_views = {n: gr(n) for n in self._names}
 
     def _ensure_ready(self):
@@ -341,31 +360,46 @@ class DIT(nn.Module):
             raise NotImplementedError("unidisc_b200.DIT.forward: dense attention_mask is not supported (model.use_attention_mask)")
         if block_mask is not None and sample_ids is None:
             raise NotImplementedError("unidisc_b200.DIT.forward: FlexAttention block_mask objects are not supported; pass sample_ids")
+        if self.require_sample_ids and sample_ids is None:
+            raise ValueError("data.require_sample_ids: sample_ids is required")
         if modality is None:
             raise ValueError("modality is required (trainer.multimodal_batches)")
         if not indices.is_cuda:
             raise L.UnidiscB200Error("unidisc_b200.DIT.forward needs CUDA tensors (no CPU fallback)")
         self._ensure_ready()
         save = torch.is_grad_enabled() and self.training_graph_enabled
-        return _DiTFunction.apply(self._anchor, self, indices, modality, sample_ids, save)
+        # The reference hands FlexAttention a BlockMask built from sample_ids (model.py:876-878, model_utils.py:740-771);
+        # here a non-None `block_mask` switches the attention kernels' document mask on and the mask itself is derived
+        # from `sample_ids` on the fly.  Without require_sample_ids, passing sample_ids alone also enables it.
+        doc_mask = sample_ids is not None and (block_mask is not None or not self.require_sample_ids)
+        return _DiTFunction.apply(self._anchor, self, indices, modality, sample_ids, save, doc_mask)
 
-    def _forward_impl(self, indices, modality, sample_ids, save):
+    def _forward_impl(self, indices, modality, sample_ids, save, doc_mask=True):
         B, N = indices.shape
         M, D, H, hd, V = B * N, self.hidden_size, self.n_heads, self.head_dim, self.vocab_size
         T = self._top
         ids = indices.reshape(-1).contiguous()
         mod = modality.reshape(-1).contiguous()
-        sid = sample_ids.contiguous() if sample_ids is not None else None
-        cos, sin = rope.token_tables(modality, self.rotary_cos_emb_txt, self.rotary_sin_emb_txt, self.rotary_cos_emb_img,
-                                     self.rotary_sin_emb_img, self.img_length)
+        sid = sample_ids.contiguous() if (sample_ids is not None and doc_mask) else None
+        ordinal = None
+        if self.require_sample_ids:
+            cos, sin, ordinal = ops.interleaved_prep(modality, sample_ids, self._rope_cat_cos, self._rope_cat_sin, self._rope_offsets)
+            if sid is not None:
+                # model_utils.py:764-767: a row that is all padding gets one token re-labelled so no query row is empty
+                allpad = (sid == -1).all(dim=-1)
+                sid = torch.where(allpad[:, None] & (torch.arange(N, device=sid.device) == 0)[None], torch.zeros_like(sid), sid)
+        else:
+            cos, sin = rope.token_tables(modality, self.rotary_cos_emb_txt, self.rotary_sin_emb_txt, self.rotary_cos_emb_img,
+                                         self.rotary_sin_emb_img, self.img_length)
         scale = 1.0 / math.sqrt(hd)
-        x, h, rstd0 = ops.embed_rmsnorm_fwd(ids, mod, T["E"], T["Emod"], self._blk[0]["n1"])
+        x, h, rstd0 = ops.embed_rmsnorm_fwd(ids, mod, T["E"], T["Emod"], self._blk[0]["n1"], ordinal=ordinal,
+                                            Ecount=T.get("Ecount"))
         # training-mode dropout of the MLP branch (dit.py:1024-1031): Philox mask keyed by (seed, call counter * L + block)
         p_drop = self.dropout if self.training else 0.0
         self._dropout_calls += 1
         drop_base = self._dropout_calls * self.n_blocks
         saved = dict(ids=ids, mod=mod, sid=sid, cos=cos, sin=sin, B=B, N=N, x0=x, rstd0=rstd0, blocks=[], p_drop=p_drop,
-                     drop_base=drop_base) if save else None
+                     drop_base=drop_base, ordinal=ordinal) if save else None
         for i, W in enumerate(self._blk):
             w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
             qkv = ops.gemm(h, W["wqkv"])
@@ -445,7 +479,8 @@ class DIT(nn.Module):
             del x_in
         # first norm + embedding
         g0 = ops.rmsnorm_bwd(g_res, dh, S["x0"], S["rstd0"], self._blk[0]["n1"], self._blk[0]["d_n1"])
-        ops.embed_bwd(S["ids"], S["mod"], g0, T["d_E"], T["d_Emod"], hot_id=self.mask_index)
+        ops.embed_bwd(S["ids"], S["mod"], g0, T["d_E"], T["d_Emod"], hot_id=self.mask_index, ordinal=S["ordinal"],
+                      dEcount=T.get("d_Ecount"))
         self._shadow_dirty = True      # an optimizer step is expected to follow
         if self.grad_ready_hook is not None:
             self.grad_ready_hook(-1)

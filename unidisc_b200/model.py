@@ -51,6 +51,78 @@ def _g(o, k, d=None):
     return getattr(o, k, d)
 
 
+def interleaved_block_masking(move_indices, modality, sample_ids, mask_prob):
+    """reference model.py:483-522 (trainer.interleaved + mask_entire_modality): every (modality, sample) block longer than 4
+    tokens is force-masked with probability mask_prob * 2 * (k+1)/K, k = its index among the K blocks of its packed sample.
+    Draws `torch.rand(M, 1)` (M = number of blocks) exactly like the reference.  Returns (move_indices, ignore [B])."""
+    B, N = modality.shape
+    dev = modality.device
+    diff = (modality[:, 1:] != modality[:, :-1]) | (sample_ids[:, 1:] != sample_ids[:, :-1])    # tensor_utils.py:46-68
+    diff = torch.nn.functional.pad(diff, (1, 0), mode="constant", value=True)
+    starts = diff.nonzero(as_tuple=False)
+    ends = torch.nn.functional.pad(diff[:, 1:], (0, 1), mode="constant", value=True).nonzero(as_tuple=False)
+    bi, sp, ep = starts[:, 0], starts[:, 1], ends[:, 1] + 1
+    keep = (sample_ids[bi, sp] >= 0) & ((ep - sp) > 4)                                            # model.py:486-488
+    bi, sp, ep = bi[keep], sp[keep], ep[keep]
+    M = bi.shape[0]
+    sids = sample_ids[bi, sp]
+    same = (bi[:, None] == bi[None, :]) & (sids[:, None] == sids[None, :])
+    order = torch.arange(M, device=dev)
+    block_counts = (same & (order[None, :] < order[:, None])).sum(dim=1)                          # model.py:494-505
+    max_num = same.sum(dim=1)
+    block_prob = (block_counts + 1) / max_num
+    positions = torch.arange(N, device=dev).unsqueeze(0)
+    mask = (positions >= sp.unsqueeze(1)) & (positions < ep.unsqueeze(1))
+    mask = mask & (torch.rand(M, 1, device=dev) < (mask_prob * block_prob * 2)[..., None])
+    accum = torch.zeros((B, N), dtype=torch.int32, device=dev)
+    accum.scatter_add_(0, bi.unsqueeze(1).expand(-1, N), mask.int())
+    move_indices = move_indices | accum.to(torch.bool)
+    ignore = torch.zeros((B,), dtype=torch.int32, device=dev)
+    ignore.scatter_add_(0, bi, mask.any(dim=-1).int())
+    return move_indices, ignore.to(torch.bool)
+
+
+def q_xt_general(x, move_chance, mask_index, trainer_cfg, *, backbone_training, training, batch=None, allow_move_mask=None):
+    """reference model.py:439-579 for absorbing diffusion on multimodal batches, in torch on [B,N] / [B,1] booleans, with
+    the reference's order of torch.rand draws.  Returns (xt, ignore_batch_mask, should_mask_txt, should_mask_img, move)."""
+    move_indices = torch.rand(*x.shape, device=x.device) < move_chance
+    ignore = None
+    should_mask_txt = should_mask_img = None
+    mask_prob = _g(trainer_cfg, "mask_entire_modality", None)
+    if mask_prob is not None and backbone_training:
+        assert batch is not None
+        bsz = x.shape[0]
+        if _g(trainer_cfg, "mask_txt_only", False):
+            should_mask_txt = torch.rand(bsz, 1, device=x.device) < mask_prob
+            should_mask_img = torch.zeros_like(should_mask_txt)
+        else:
+            should_mask_txt = torch.rand(bsz, 1, device=x.device) < mask_prob / 2
+            should_mask_img = torch.rand(bsz, 1, device=x.device) < mask_prob / 2
+        if _g(trainer_cfg, "interleaved", False):
+            move_indices, ignore = interleaved_block_masking(move_indices, batch["modality"], batch["sample_ids"], mask_prob)
+        else:
+            modality_mask = batch.get("modality_mask", None)
+            if modality_mask is None:
+                modality_mask = torch.stack([batch["modality"] == 0, batch["modality"] == 1], dim=-1)
+            both = should_mask_txt & should_mask_img
+            should_mask_txt = torch.where(both, False, should_mask_txt)
+            should_mask_img = torch.where(both, False, should_mask_img)
+            move_indices = torch.where(should_mask_txt, modality_mask[..., 0], move_indices)
+            move_indices = torch.where(should_mask_img, modality_mask[..., 1], move_indices)
+            ignore = should_mask_img | should_mask_txt
+    if _g(trainer_cfg, "add_label", False):
+        move_indices[:, 0] = False
+    ftd = _g(trainer_cfg, "first_token_dropout", None)
+    if ftd is not None and training:
+        init = torch.rand(x.shape[0], device=x.device) < ftd
+        move_indices[:, 0] = torch.where(init, True, move_indices[:, 0])
+        ignore = init if ignore is None else (ignore | init)
+    if allow_move_mask is not None:
+        move_indices = move_indices & allow_move_mask
+    xt = torch.where(move_indices, mask_index, x)
+    return xt, ignore, should_mask_txt, should_mask_img, move_indices
+
+
 class _SubsNLL(torch.autograd.Function):
     """log p_theta(x0 | xt) under the SUBS parameterisation, fused: logits are read once, the [B,N,V] log-prob tensor of
     the reference (model.py:621-658 + gather at :967) is never materialised.  Backward writes dlogits IN PLACE over the
@@ -163,38 +235,11 @@ class Diffusion(nn.Module):
                 return xt, None, None, None, None, move
             return xt
         # general path: the whole-modality masking logic works on [B,1] / [B,N] booleans (model.py:470-579)
-        move_indices = torch.rand(*x.shape, device=x.device) < move_chance
-        ignore = None
-        should_mask_txt = should_mask_img = None
-        if mask_prob is not None and self.backbone.training:
-            assert batch is not None
-            bsz = x.shape[0]
-            if _g(self.config.trainer, "mask_txt_only", False):
-                should_mask_txt = torch.rand(bsz, 1, device=x.device) < mask_prob
-                should_mask_img = torch.zeros_like(should_mask_txt)
-            else:
-                should_mask_txt = torch.rand(bsz, 1, device=x.device) < mask_prob / 2
-                should_mask_img = torch.rand(bsz, 1, device=x.device) < mask_prob / 2
-            if _g(self.config.trainer, "interleaved", False):
-                raise NotImplementedError("unidisc_b200.q_xt: interleaved per-block modality masking (model.py:483-522)")
-            both = should_mask_txt & should_mask_img
-            should_mask_txt = torch.where(both, False, should_mask_txt)
-            should_mask_img = torch.where(both, False, should_mask_img)
-            move_indices = torch.where(should_mask_txt, batch["modality_mask"][..., 0], move_indices)
-            move_indices = torch.where(should_mask_img, batch["modality_mask"][..., 1], move_indices)
-            ignore = should_mask_img | should_mask_txt
-        if _g(self.config.trainer, "add_label", False):
-            move_indices[:, 0] = False
-        ftd = _g(self.config.trainer, "first_token_dropout", None)
-        if ftd is not None and self.training:
-            init = torch.rand(x.shape[0], device=x.device) < ftd
-            move_indices[:, 0] = torch.where(init, True, move_indices[:, 0])
-            ignore = init if ignore is None else (ignore | init)
-        if allow_move_mask is not None:
-            move_indices = move_indices & allow_move_mask
-        xt = torch.where(move_indices, self.mask_index, x)
+        xt, ignore, smt, smi, move_indices = q_xt_general(x, move_chance, self.mask_index, self.config.trainer,
+                                                          backbone_training=self.backbone.training, training=self.training,
+                                                          batch=batch, allow_move_mask=allow_move_mask)
         if return_ignore_batch_mask_for_metrics:
-            return xt, ignore, None, should_mask_txt, should_mask_img, move_indices
+            return xt, ignore, None, smt, smi, move_indices
         return xt
 
     def _process_sigma(self, sigma):                                  # reference model.py:660-672
@@ -231,7 +276,7 @@ class Diffusion(nn.Module):
         """reference model.py:674-795 ("Returns log score")."""
         sigma = self._process_sigma(sigma)
         modality = self._modality_of(batch, kwargs)
-        logits = self.backbone(x, sigma, modality=modality, sample_ids=kwargs.get("sample_ids", None))
+        logits = self.backbone(x, sigma, modality=modality, sample_ids=kwargs.get("sample_ids", None), block_mask=block_mask)
         if return_logits:
             return logits
         return self._subs_parameterization(logits, xt=x, batch=batch, modality=modality)
@@ -254,8 +299,12 @@ class Diffusion(nn.Module):
         sigma, dsigma = self.noise(t)                                                # model.py:858
         move_chance = 1 - torch.exp(-sigma[:, None])                                 # model.py:860
         xt, ignore_batch, _, _, _, _ = self.q_xt(x0, move_chance, return_ignore_batch_mask_for_metrics=True, batch=batch)
+        # model.py:876-878: packed batches hand the backbone sample_ids + the document BlockMask (here: a flag, the mask is
+        # evaluated inside the attention kernels from sample_ids)
+        flex = bool(_g(self.config.trainer, "interleaved_training_flex_attention", False))
         logits = self.backbone(xt, None if not self.time_conditioning else sigma, modality=modality,
-                               sample_ids=batch.get("sample_ids", None) if _g(self.config.trainer, "interleaved_training_flex_attention", False) else None)
+                               sample_ids=batch.get("sample_ids", None) if (flex or self.backbone.require_sample_ids) else None,
+                               block_mask=True if flex else None)
         log_p_theta = self._log_p_x0(logits, xt, x0, modality)                       # model.py:787 + :967, fused
         std_weighting = (dsigma / torch.expm1(sigma))[:, None]                       # model.py:975
         loss = -log_p_theta * std_weighting

@@ -39,18 +39,35 @@ def gemm(a, b, *, ta=False, tb=False, M=None, N=None, K=None, out=None, epi=L.EP
     return out
 
 
-def embed_rmsnorm_fwd(ids, modality, E, Emod, w, eps=1e-6):
+def embed_rmsnorm_fwd(ids, modality, E, Emod, w, eps=1e-6, ordinal=None, Ecount=None):
     rows, D = ids.numel(), E.shape[1]
     x = torch.empty((rows, D), device=E.device, dtype=torch.float32)
     h = torch.empty((rows, D), device=E.device, dtype=bf16)
     rstd = torch.empty((rows,), device=E.device, dtype=torch.float32)
-    call("ud_embed_rmsnorm_fwd", P(ids), P(modality), P(E), P(Emod), P(w), P(x), P(h), P(rstd), rows, D, eps, stream())
+    call("ud_embed_rmsnorm_fwd", P(ids), P(modality), P(E), P(Emod), P(w), P(x), P(h), P(rstd), rows, D, eps, P(ordinal),
+         P(Ecount), stream())
     return x, h, rstd
 
 
-def embed_bwd(ids, modality, g, dE, dEmod, hot_id=-1):
+def embed_bwd(ids, modality, g, dE, dEmod, hot_id=-1, ordinal=None, dEcount=None):
     rows, D = g.shape
-    call("ud_embed_bwd", P(ids), P(modality), P(g), P(dE), P(dEmod), rows, D, hot_id, stream())
+    call("ud_embed_bwd", P(ids), P(modality), P(g), P(dE), P(dEmod), rows, D, hot_id, P(ordinal), P(dEcount), stream())
+
+
+def interleaved_prep(modality, sample_ids, cos_tab, sin_tab, offsets):
+    """modality, sample_ids: int64 [B,N]; cos_tab/sin_tab fp32 [rows,hd2]; offsets = dict(txt=, s256=, s1024=, s2304=, s4096=)
+    (row offsets of the tables inside cos_tab, -1 = table absent).  Returns cos, sin [B*N,hd2] fp32 and ordinal int32 [B*N]."""
+    B, N = modality.shape
+    hd2 = cos_tab.shape[1]
+    dev = modality.device
+    cos = torch.empty((B * N, hd2), device=dev, dtype=torch.float32)
+    sin = torch.empty((B * N, hd2), device=dev, dtype=torch.float32)
+    ordinal = torch.empty((B * N,), device=dev, dtype=torch.int32)
+    scratch = torch.empty((B, 4 * N), device=dev, dtype=torch.int32)
+    call("ud_interleaved_prep", P(modality.contiguous()), P(sample_ids.contiguous()), B, N, P(cos_tab), P(sin_tab), hd2,
+         offsets["txt"], offsets["s256"], offsets["s1024"], offsets["s2304"], offsets["s4096"], P(cos), P(sin), P(ordinal),
+         P(scratch), stream())
+    return cos, sin, ordinal
 
 
 def norm_residual_fwd(a, x_in, w_a, w_n, eps=1e-6, x_out=None, h=None, p_drop=0.0, seed=0, offset=0):

@@ -12,6 +12,10 @@ import math
 import torch
 
 
+# data.require_sample_ids: (image-block size, linear_factor) of the per-size 2-D tables (reference models/dit.py:1209)
+INTERLEAVED_IMG_TABLES = ((256, 1.0), (1024, 2.0), (2304, 3.0), (4096, 4.0))
+
+
 def rope_1d(head_dim: int, seq_len: int):
     inv_freq = 1.0 / (10000 ** (torch.arange(0, head_dim, 2).float() / head_dim))
     ang = torch.einsum("i,j->ij", torch.arange(seq_len).float(), inv_freq)
