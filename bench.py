@@ -276,8 +276,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from unidisc_b200.ddp import nccl_options
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, pg_options=nccl_options())
     preset, bpg, txt, img = WORKLOADS[args.workload]
     small = args.workload == "tiny"
     cfg = make_config(preset, txt_length=txt, img_length=img, dropout=args.dropout, image_vocab_size=IMAGE_VOCAB if not small else 255,
@@ -286,7 +287,7 @@ def main():
     model = Diffusion(cfg, device=dev)
     model.train()
     net = model.backbone
-    ddp = ThinDDP(net) if world > 1 else None
+    ddp = ThinDDP(net, bf16_compress=bool(int(os.environ.get('UD_DDP_COMPRESS', '1')))) if world > 1 else None
     opt = FusedAdamW(net, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0)
     B, N = bpg, txt + img
     V, tv = model.vocab_size, model.text_vocab_size
@@ -353,6 +354,31 @@ def main():
     n_launch = launches[0]
     ms_e2e, loss_e2e = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("UD_PHASE_TIMING"):
+        # debug: CUDA-event split of one step into forward+loss / backward / optimizer (rank 0, stderr)
+        for _ in range(3):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            batch = dict(input_ids=ids_d, modality=mod_d, attention_mask=am_d)
+            evs[0].record()
+            losses = model.compute_loss(batch)
+            evs[1].record()
+            losses.loss.backward()
+            evs[2].record()
+            opt.step()
+            opt.zero_grad()
+            evs[3].record()
+            torch.cuda.synchronize()
+            if rank == 0:
+                print(f"[phase] fwd+loss {evs[0].elapsed_time(evs[1]):.2f} ms  bwd {evs[1].elapsed_time(evs[2]):.2f} ms  "
+                      f"opt(+allreduce tail) {evs[2].elapsed_time(evs[3]):.2f} ms", file=sys.stderr)
+    if ddp is not None and ddp.debug_timing:
+        ddp._dbg_events = []
+        step(False)
+        rows = ddp.debug_report()
+        if rank == 0:
+            print("[ddp timeline] bucket ready_ms start_ms end_ms chain_ms", file=sys.stderr)
+            for b_, r_, s_, e_ in rows:
+                print(f"[ddp timeline] {b_:3d} {r_:8.2f} {s_:8.2f} {e_:8.2f} {e_ - s_:7.2f}", file=sys.stderr)
 
     # ---- roofline of the dominant kernel: the tcgen05 GEMM (MLP up-projection shape of this workload), timed live ----
     pk = peaks()

@@ -148,9 +148,10 @@ int ud_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, lo
 int ud_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 /* sum of squares of a flat fp32 buffer, accumulated into out[0] (out must be zeroed by the caller) */
 int ud_sumsq_f32(const float* g, long long n, float* out, void* stream);
-/* DDP bf16 compress hook (torch default_hooks._compress_hook): dst = bf16(bf16(g) / world) ; and decompress */
-int ud_grad_pack_bf16(const float* g, void* dst_bf16, long long n, float inv_world, void* stream);
-int ud_grad_unpack_bf16(const void* src_bf16, float* g, long long n, void* stream);
+/* DDP bf16 compress hook (torch default_hooks._compress_hook): dst = bf16(bf16(g) / world) ; and decompress.
+ * max_ctas > 0 caps the grid so the side-stream copies leave the SMs to the backward GEMMs they overlap with. */
+int ud_grad_pack_bf16(const float* g, void* dst_bf16, long long n, float inv_world, int max_ctas, void* stream);
+int ud_grad_unpack_bf16(const void* src_bf16, float* g, long long n, int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

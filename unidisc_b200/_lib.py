@@ -42,8 +42,8 @@ _SIGS = {
     "ud_adamw_step": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp, _vp],
     "ud_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],
     "ud_sumsq_f32": [_vp, _ll, _vp, _vp],
-    "ud_grad_pack_bf16": [_vp, _vp, _ll, _f, _vp],
-    "ud_grad_unpack_bf16": [_vp, _vp, _ll, _vp],
+    "ud_grad_pack_bf16": [_vp, _vp, _ll, _f, _i, _vp],
+    "ud_grad_unpack_bf16": [_vp, _vp, _ll, _i, _vp],
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS.keys())

@@ -657,29 +657,51 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
     if (threadIdx.x == 0) atomicAdd(out, a[0]);
 }
 
+// 4 independent 16-byte loads per thread per iteration: with the grid capped to a few dozen CTAs (side stream), memory-level
+// parallelism has to come from each thread.
 __global__ void grad_pack_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ d, long long n, float inv_world) {
-    const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-        if (i + 4 <= n) {
-            float4 v = *reinterpret_cast<const float4*>(g + i);
-            // torch's bf16 compress hook: round to bf16 first, then divide in bf16
-            *reinterpret_cast<uint2*>(d + i) =
-                make_uint2(pack_bf16x2(bf16_round(v.x) * inv_world, bf16_round(v.y) * inv_world),
-                           pack_bf16x2(bf16_round(v.z) * inv_world, bf16_round(v.w) * inv_world));
-        } else {
-            for (long long k = i; k < n; ++k) d[k] = __float2bfloat16_rn(bf16_round(g[k]) * inv_world);
+    const long long tile = (long long)blockDim.x * 16;                       // elements per CTA per iteration
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        float4 v[4];
+        long long idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            idx[u] = base + ((long long)u * blockDim.x + threadIdx.x) * 4;
+            if (idx[u] + 4 <= n) v[u] = *reinterpret_cast<const float4*>(g + idx[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = idx[u];
+            if (i + 4 <= n) {
+                // torch's bf16 compress hook: round to bf16 first, then divide in bf16
+                *reinterpret_cast<uint2*>(d + i) =
+                    make_uint2(pack_bf16x2(bf16_round(v[u].x) * inv_world, bf16_round(v[u].y) * inv_world),
+                               pack_bf16x2(bf16_round(v[u].z) * inv_world, bf16_round(v[u].w) * inv_world));
+            } else {
+                for (long long k = i; k < n; ++k) d[k] = __float2bfloat16_rn(bf16_round(g[k]) * inv_world);
+            }
         }
     }
 }
 
 __global__ void grad_unpack_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ g, long long n) {
-    const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-        if (i + 4 <= n) {
-            uint2 v = *reinterpret_cast<const uint2*>(s + i);
-            *reinterpret_cast<float4*>(g + i) = make_float4(bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y));
-        } else {
-            for (long long k = i; k < n; ++k) g[k] = __bfloat162float(s[k]);
+    const long long tile = (long long)blockDim.x * 16;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        uint2 v[4];
+        long long idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            idx[u] = base + ((long long)u * blockDim.x + threadIdx.x) * 4;
+            if (idx[u] + 4 <= n) v[u] = *reinterpret_cast<const uint2*>(s + idx[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = idx[u];
+            if (i + 4 <= n) {
+                *reinterpret_cast<float4*>(g + i) = make_float4(bf16lo(v[u].x), bf16hi(v[u].x), bf16lo(v[u].y), bf16hi(v[u].y));
+            } else {
+                for (long long k = i; k < n; ++k) g[k] = __bfloat162float(s[k]);
+            }
         }
     }
 }
@@ -878,16 +900,19 @@ extern "C" int ud_sumsq_f32(const float* g, long long n, float* out, void* strea
     return 0;
 }
 
-extern "C" int ud_grad_pack_bf16(const float* g, void* dst, long long n, float inv_world, void* stream) {
+// max_ctas > 0 caps the grid: the DDP side stream runs these next to the backward GEMMs and should take few SM slots
+static int capped(int grid, int max_ctas) { return (max_ctas > 0 && grid > max_ctas) ? max_ctas : grid; }
+
+extern "C" int ud_grad_pack_bf16(const float* g, void* dst, long long n, float inv_world, int max_ctas, void* stream) {
     if (n <= 0) return 0;
-    grad_pack_kernel<<<flat_grid(n), 256, 0, STREAM(stream)>>>(g, BF(dst), n, inv_world);
+    grad_pack_kernel<<<capped(flat_grid(n / 4 + 1), max_ctas), 256, 0, STREAM(stream)>>>(g, BF(dst), n, inv_world);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
-extern "C" int ud_grad_unpack_bf16(const void* src, float* g, long long n, void* stream) {
+extern "C" int ud_grad_unpack_bf16(const void* src, float* g, long long n, int max_ctas, void* stream) {
     if (n <= 0) return 0;
-    grad_unpack_kernel<<<flat_grid(n), 256, 0, STREAM(stream)>>>(CBF(src), g, n);
+    grad_unpack_kernel<<<capped(flat_grid(n / 4 + 1), max_ctas), 256, 0, STREAM(stream)>>>(CBF(src), g, n);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

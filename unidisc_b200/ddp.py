@@ -11,6 +11,7 @@ model.py:1518-1537): one pass over the flat buffers that also emits the bf16 sha
 from __future__ import annotations
 
 import contextlib
+import os
 
 import torch
 import torch.distributed as dist
@@ -21,15 +22,33 @@ from . import ops
 bf16 = torch.bfloat16
 
 
+def nccl_options(max_ctas=None):
+    """ProcessGroupNCCL options that cap the SMs NCCL takes (`ncclConfig_t.maxCTAs`); 0 = NCCL's default (what bench.py uses).
+    Measured on 2xB200 (profiles/r01_ddp_overlap.md): capping NCCL to 2/4/8/16 CTAs makes the step SLOWER (175.9 / 128.9 /
+    121.8 / 118.5 ms vs 116.0 ms uncapped) — a longer-running all-reduce keeps a few SMs slow for longer and the persistent
+    GEMMs' statically assigned tiles wait for them — so the knob stays off by default."""
+    if max_ctas is None:
+        max_ctas = int(os.environ.get("UD_NCCL_MAX_CTAS", 0))
+    if max_ctas <= 0:
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = max_ctas
+    opts.config.min_ctas = min(max_ctas, 4)
+    return opts
+
+
 class ThinDDP(nn.Module):
-    def __init__(self, module, process_group=None, bf16_compress: bool = True, _pack=None, _unpack=None):
+    def __init__(self, module, process_group=None, bf16_compress: bool = True, _pack=None, _unpack=None, side_ctas=None):
         super().__init__()
         self.module = module
         self.pg = process_group
         # (de)compression kernels; injectable so the bucket planning / collective sequencing can be exercised with a
         # gloo process group on CPU in tests (the product path always uses the CUDA kernels)
-        self._pack = _pack or ops.grad_pack
-        self._unpack = _unpack or ops.grad_unpack
+        # optional grid cap of the (de)compression kernels on the side stream (0 = uncapped, the measured optimum: a short
+        # wide kernel disturbs the overlapped backward less than a long narrow one, see nccl_options)
+        self.side_ctas = int(os.environ.get("UD_DDP_SIDE_CTAS", 0)) if side_ctas is None else int(side_ctas)
+        self._pack = _pack or (lambda g, d, w: ops.grad_pack(g, d, w, self.side_ctas))
+        self._unpack = _unpack or (lambda s, g: ops.grad_unpack(s, g, self.side_ctas))
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.bf16_compress = bf16_compress
         self._sync = True
@@ -65,6 +84,19 @@ class ThinDDP(nn.Module):
         self._done_event = None
         module.grad_ready_hook = self._on_grads_ready
         self.bytes_on_wire_per_step = 0
+        self.debug_timing = bool(int(os.environ.get("UD_DDP_DEBUG", "0")))
+        self._dbg_events = []
+
+    def debug_report(self):
+        """(UD_DDP_DEBUG=1) per-bucket timeline of the last step, in ms relative to the first gradient-ready event:
+        ready = when backward produced the bucket, start/end = the pack -> all-reduce -> unpack chain on the comm stream."""
+        torch.cuda.synchronize()
+        if not self._dbg_events:
+            return []
+        t0 = self._dbg_events[0][1]
+        rows = [(b, t0.elapsed_time(ev), t0.elapsed_time(c0), t0.elapsed_time(c1)) for b, ev, c0, c1 in self._dbg_events]
+        self._dbg_events = []
+        return rows
 
     def forward(self, *a, **k):
         return self.module(*a, **k)
@@ -86,8 +118,9 @@ class ThinDDP(nn.Module):
             self._stage = torch.empty(self._max_range, device=g.device, dtype=bf16 if self.bf16_compress else torch.float32)
             if cuda:
                 self._comm_stream = torch.cuda.Stream(priority=-1)
+        dbg = cuda and self.debug_timing
         if cuda:
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=dbg)
             ev.record(torch.cuda.current_stream())
             ctx = torch.cuda.stream(self._comm_stream)
         else:
@@ -95,6 +128,9 @@ class ThinDDP(nn.Module):
         with ctx:
             if cuda:
                 self._comm_stream.wait_event(ev)
+            if dbg:
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(self._comm_stream)
             for lo, hi in self._ranges_by_block.get(block_idx, []):
                 seg = g[lo:hi]
                 if self.bf16_compress:
@@ -107,8 +143,11 @@ class ThinDDP(nn.Module):
                     seg.div_(self.world)
                     dist.all_reduce(seg, group=self.pg)
                     self.bytes_on_wire_per_step += 4 * (hi - lo)
+            if dbg:
+                c1.record(self._comm_stream)
+                self._dbg_events.append((block_idx, ev, c0, c1))
             if block_idx == -1 and cuda:
-                self._done_event = torch.cuda.Event()
+                self._done_event = torch.cuda.Event(enable_timing=dbg)
                 self._done_event.record(self._comm_stream)
         if block_idx == -1 and cuda and self._done_event is not None:
             torch.cuda.current_stream().wait_event(self._done_event)   # optimizer waits on ONE event

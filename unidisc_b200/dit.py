@@ -440,8 +440,17 @@ class DIT(nn.Module):
         ops.colsum(dl, T["d_bh"], M, V)
         dh = ops.gemm(dl, T["wh"], tb=True, M=M, N=D, K=V)
         S["logits_buf"] = None
-        if self.grad_ready_hook is not None:
-            self.grad_ready_hook(self.n_blocks)      # head weight gradient is final
+        # Gradient buckets that are final are handed to the DDP hook right BEFORE the next attention backward: the
+        # all-reduce chain (pack -> NCCL -> unpack, ~0.4 ms) then runs next to the attention / row kernels, whose many
+        # small CTAs are load-balanced by the hardware scheduler, instead of next to a persistent GEMM whose statically
+        # assigned tiles wait for the SMs the NCCL CTAs slow down (measured: 7.7 ms -> see DESIGN.md §5).
+        pending = [self.n_blocks]                    # head weight gradient is final
+
+        def flush_pending():
+            if self.grad_ready_hook is not None:
+                for b in pending:
+                    self.grad_ready_hook(b)
+            pending.clear()
         g_res = None       # fp32 gradient flowing down the residual stream
         scale = 1.0 / math.sqrt(hd)
         for i in range(self.n_blocks - 1, -1, -1):
@@ -467,6 +476,7 @@ class DIT(nn.Module):
             dqk = torch.empty((M, 2 * D), device=do.device, dtype=bf16)
             dqkv = torch.empty((M, 3 * D), device=do.device, dtype=bf16)
             qk, qkv = A["qk"], A["qkv"]
+            flush_pending()
             ops.attn_bwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], A["o"], do, A["lse"], dqk[:, :D], dqk[:, D:], dqkv[:, 2 * D:],
                          B, N, H, hd, scale, sample_ids=S["sid"])
             ops.qk_ln_rope_bwd(dqk, qkv, A["stats"], W["gq"], W["gk"], S["cos"], S["sin"], dqkv, W["d_gq"], W["d_bq"], W["d_gk"],
@@ -474,13 +484,12 @@ class DIT(nn.Module):
             ops.gemm(dqkv, A["h"], ta=True, tb=True, epi=wacc, out=W["d_wqkv"])
             dh = ops.gemm(dqkv, W["wqkv"], tb=True)
             S["blocks"][i] = None      # release this block's activations
-            if self.grad_ready_hook is not None:
-                self.grad_ready_hook(i)
+            pending.append(i)
             del x_in
         # first norm + embedding
         g0 = ops.rmsnorm_bwd(g_res, dh, S["x0"], S["rstd0"], self._blk[0]["n1"], self._blk[0]["d_n1"])
         ops.embed_bwd(S["ids"], S["mod"], g0, T["d_E"], T["d_Emod"], hot_id=self.mask_index, ordinal=S["ordinal"],
                       dEcount=T.get("d_Ecount"))
         self._shadow_dirty = True      # an optimizer step is expected to follow
-        if self.grad_ready_hook is not None:
-            self.grad_ready_hook(-1)
+        pending.append(-1)
+        flush_pending()

@@ -232,9 +232,9 @@ def sumsq(g, out):
     return out
 
 
-def grad_pack(g, dst, inv_world):
-    call("ud_grad_pack_bf16", P(g), P(dst), g.numel(), inv_world, stream())
+def grad_pack(g, dst, inv_world, max_ctas=0):
+    call("ud_grad_pack_bf16", P(g), P(dst), g.numel(), inv_world, max_ctas, stream())
 
 
-def grad_unpack(src, g):
-    call("ud_grad_unpack_bf16", P(src), P(g), g.numel(), stream())
+def grad_unpack(src, g, max_ctas=0):
+    call("ud_grad_unpack_bf16", P(src), P(g), g.numel(), max_ctas, stream())
