@@ -91,6 +91,56 @@ def test_gemm_wgrad_layout(ops, M, N, K):
     assert torch.allclose(out, 2 * ref, rtol=1e-3, atol=2e-3 * math.sqrt(K))
 
 
+@pytest.mark.parametrize("case", ["fwd_n2048", "dgrad_n2048", "wgrad_64tiles", "wgrad_192tiles", "gelu_tail", "ragged"])
+def test_gemm_streamk_tail(ops, case):
+    """Shapes whose last wave of 256x256 tiles is partial: the tail tiles' k-blocks are shared between all clusters
+    (stream-K) through fp32 partials in a workspace.  Launched several times back to back (the arrival counters re-arm
+    themselves) and compared with fp32 torch matmuls."""
+    from unidisc_b200._lib import EPI_BF16_GELU, EPI_F32, EPI_F32_ACC
+    if case == "fwd_n2048":            # attn_out / mlp.2 forward of the 1.4B model: 320 tiles on 74 clusters
+        M, N, K = 10240, 2048, 2048
+        a, b = rnd(M, K, seed=1, dtype=bf16), rnd(N, K, seed=2, scale=0.05, dtype=bf16)
+        ref = (a.float() @ b.float().t()).to(bf16)
+        for _ in range(3):
+            out = ops.gemm(a, b)
+        torch.cuda.synchronize()
+        close_bf16(out, ref, case)
+    elif case == "dgrad_n2048":
+        M, N, K = 10240, 2048, 6144
+        dy, w = rnd(M, K, seed=3, dtype=bf16), rnd(K, N, seed=4, scale=0.05, dtype=bf16)
+        ref = (dy.float() @ w.float()).to(bf16)
+        for _ in range(2):
+            out = ops.gemm(dy, w, tb=True)
+        torch.cuda.synchronize()
+        close_bf16(out, ref, case)
+    elif case in ("wgrad_64tiles", "wgrad_192tiles"):
+        M, N, K = (2048, 2048, 10240) if case == "wgrad_64tiles" else (6144, 2048, 10240)
+        dy, x = rnd(K, M, seed=5, scale=0.1, dtype=bf16), rnd(K, N, seed=6, scale=0.1, dtype=bf16)
+        ref = dy.float().t() @ x.float()
+        out = ops.gemm(dy, x, ta=True, tb=True, epi=EPI_F32)
+        torch.cuda.synchronize()
+        assert torch.allclose(out, ref, rtol=1e-3, atol=2e-3), (out - ref).abs().max()
+        ops.gemm(dy, x, ta=True, tb=True, epi=EPI_F32_ACC, out=out)
+        ops.gemm(dy, x, ta=True, tb=True, epi=EPI_F32_ACC, out=out)
+        torch.cuda.synchronize()
+        assert torch.allclose(out, 3 * ref, rtol=1e-3, atol=6e-3), (out - 3 * ref).abs().max()
+    elif case == "gelu_tail":          # fused epilogue on the owner of a split tile
+        M, N, K = 2560, 2304, 1024
+        a, b = rnd(M, K, seed=1, dtype=bf16), rnd(N, K, seed=2, scale=0.05, dtype=bf16)
+        bias = rnd(N, seed=3, dtype=bf16)
+        u, g = ops.gemm(a, b, epi=EPI_BF16_GELU, bias=bias)
+        torch.cuda.synchronize()
+        close_bf16(u, (a.float() @ b.float().t() + bias.float()).to(bf16), "u")
+        close_bf16(g, torch.nn.functional.gelu(u.float(), approximate="tanh").to(bf16), "g")
+    else:                              # ragged M / N / K edges together with split tiles
+        M, N, K = 1000, 1336, 1992
+        a, b = rnd(M, K, seed=1, dtype=bf16), rnd(N, K, seed=2, scale=0.05, dtype=bf16)
+        for _ in range(2):
+            out = ops.gemm(a, b)
+        torch.cuda.synchronize()
+        close_bf16(out, (a.float() @ b.float().t()).to(bf16), case)
+
+
 def test_gemm_bias_gelu_and_dgelu(ops):
     from unidisc_b200._lib import EPI_BF16_DGELU, EPI_BF16_GELU
     M, N, K = 256, 512, 128

@@ -219,6 +219,14 @@ UD_DEVINL void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// same, relaxed: no memory ordering of the caller's prior global stores is needed (and none is paid for: the .release form
+// compiles to MEMBAR.ALL + ERRBAR, which waits for every outstanding epilogue store).  Used for TMEM hand-offs, where the
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync pair already orders the TMEM reads.
+UD_DEVINL void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 UD_DEVINL bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
