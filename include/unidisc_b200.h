@@ -35,13 +35,32 @@ enum {
 int ud_gemm_bf16(int ta, int tb, int M, int N, int K, const void* A, long long lda, const void* B, long long ldb, void* C,
                  long long ldc, int epi, const void* bias, void* aux, long long ld_aux, int bn_hint, void* stream);
 
+/* ---- time conditioning (config.time_conditioning; dit.py:966-967 adaLN chunks, 258-268/301-304 modulate_fused, 229-253
+ * bias_dropout_add_scale with modality).  Passed as NULL by every shipped training config.  The adaLN Linear's bf16 output
+ * [B, ld] is consumed in place: shift/scale modulate the h output of the fused norm kernels on rows with sel = 1
+ * (image tokens; every token when the batch holds no image token), gate multiplies the dropped branch on img rows (text rows get
+ * the plain branch).  Backward accumulates the per-sample gradients with atomics into fp32 [B, ld_d] buffers. */
+typedef struct ud_adaln {
+    const uint8_t* sel;        /* [rows] */
+    const uint8_t* img;        /* [rows] */
+    const void* shift;         /* bf16, element (b, j) at [b * ld + j]; NULL = no modulation of h */
+    const void* scale;
+    const void* gate;          /* bf16; NULL = branch is not gated (pre_residual_norm under sandwich normalisation) */
+    long long ld;
+    int tokens_per_sample;     /* sample of row r = r / tokens_per_sample */
+    float* d_shift;            /* backward only */
+    float* d_scale;
+    float* d_gate;
+    long long ld_d;
+} ud_adaln;
+
 /* ---- embedding + first RMSNorm ------------------------------------------------------------------------------
  * x = E[ids] + Emod[modality] (+ Ecount[ordinal] where ordinal >= 0)  (dit.py:1375,1406,163-167);
  * h = bf16(rms(x) * w)  (dit.py:95-100,971).  rows = B*N.  ordinal (int32 [rows], from ud_interleaved_prep) / Ecount
  * (`img_count_embedding`, fp32 [16,D]) are NULL outside interleaved batches. */
 int ud_embed_rmsnorm_fwd(const int64_t* ids, const int64_t* modality, const float* E, const float* Emod, const float* w,
                          float* x, void* h_bf16, float* rstd, int rows, int D, float eps, const int* ordinal,
-                         const float* Ecount, void* stream);
+                         const float* Ecount, const ud_adaln* tc /* NULL = no time conditioning */, void* stream);
 /* dE[ids] += g ; dEmod[modality] += g ; dEcount[ordinal] += g   (g = gradient wrt x, fp32 [rows,D]) */
 int ud_embed_bwd(const int64_t* ids, const int64_t* modality, const float* g, float* dE, float* dEmod, int rows, int D,
                  long long hot_id /* id accumulated per CTA (the mask token), -1 = none */, const int* ordinal,
@@ -66,7 +85,7 @@ int ud_interleaved_prep(const int64_t* modality, const int64_t* sample_ids, int 
  * Philox4x32-10 mask keyed by (seed, offset, row, column group); backward regenerates the mask from the same triple. */
 int ud_norm_residual_fwd(const void* a_bf16, const float* x_in, const float* w_a, const float* w_n, float* x_out,
                          void* h_bf16, float* rstd_a, float* rstd_x, int rows, int D, float eps, float p_drop, uint64_t seed,
-                         uint64_t offset, void* stream);
+                         uint64_t offset, const ud_adaln* tc, void* stream);
 /* the keep-scales (0 or 1/(1-p), fp32 [rows,D]) the two kernels above/below use for (p_drop, seed, offset) — test hook */
 int ud_dropout_scales(float* out, int rows, int D, float p_drop, uint64_t seed, uint64_t offset, void* stream);
 /* backward of the above.  g_out: fp32 grad wrt x_out from the residual stream (may be NULL = 0); dh: bf16 grad wrt h.
@@ -76,10 +95,10 @@ int ud_dropout_scales(float* out, int rows, int D, float p_drop, uint64_t seed, 
 int ud_norm_residual_bwd(const float* g_out, const void* dh_bf16, const float* x_out, const float* rstd_x, const float* w_n,
                          const void* a_bf16, const float* rstd_a, const float* w_a, float* g_in, void* da_bf16,
                          float* dw_n, float* dw_a, float* db_a, int rows, int D, float p_drop, uint64_t seed, uint64_t offset,
-                         void* stream);
+                         const ud_adaln* tc, void* stream);
 /* backward of the first norm only: g_in = g_out + rms_bwd(dh) ; dw += ... */
 int ud_rmsnorm_bwd(const float* g_out, const void* dh_bf16, const float* x, const float* rstd, const float* w, float* g_in,
-                   float* dw, int rows, int D, void* stream);
+                   float* dw, int rows, int D, const ud_adaln* tc, void* stream);
 
 /* ---- q/k LayerNorm (over the full hidden dim) + RoPE ---------------------------------------------------------
  * qk_out[:, 0:D] = rope(bf16(LN(q))), qk_out[:, D:2D] = rope(bf16(LN(k)))   (dit.py:680-682, 724-726,

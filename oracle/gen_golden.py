@@ -402,6 +402,51 @@ def gen_interleaved():
                         **{"P::" + k: _np(v) for k, v in P.items()})
 
 
+def gen_timecond():
+    """config.time_conditioning=True (adaLN shift/scale/gate from sigma; off in every shipped config): reference DIT vs the
+    restatement, including the all-text batch quirk of modulate_fused (dit.py:301-304)."""
+    import dataclasses
+    D, H, L, txt, img, V, tv, mi = 128, 2, 2, 64, 64, 160, 97, 96
+    ref_cfg = RL.make_ref_config(D, H, L, txt, img, time_conditioning=True)
+    torch.manual_seed(0)
+    dit = RL.build_reference_dit(ref_cfg, V, tv, mi, dtype=torch.float32)
+    dit.eval()
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in dit.named_parameters():
+            if "adaLN_modulation" in n:                       # zero-initialised in the reference: make them matter
+                p.copy_((torch.rand(p.shape, generator=g) - 0.5) * (0.4 if n.endswith("weight") else 0.2))
+            elif "norm" in n and n.endswith("weight"):
+                p.add_((torch.rand(p.shape, generator=g) - 0.5) * 0.4)
+    P = {k: v.detach().clone() for k, v in dit.state_dict().items()}
+    ids, modality = R.synthetic_batch(3, txt, img, tv, V, seed=43)
+    ids[0, 3] = mi
+    ids[1, 70:90] = mi
+    sigma = torch.tensor([0.15, 1.3, 4.0])
+    with torch.no_grad():
+        ref_logits = dit(ids, sigma, modality=modality)
+    ocfg = dataclasses.replace(R.OracleConfig(D, H, L, txt, img, V, tv, mi), time_conditioning=True)
+    mine = R.dit_forward(ocfg, P, ids, modality, mode="fp32", sigma=sigma)
+    err = (mine - ref_logits).abs().max().item()
+    print(f"[timecond fp32] max|restated - reference| = {err:.3e} (ref absmax {ref_logits.abs().max():.3f})")
+    assert err < 3e-5, err
+    # all-text batch: modulate_fused modulates every token
+    ids_t = torch.randint(0, mi, (2, txt + img), generator=g)
+    mod_t = torch.zeros_like(ids_t)
+    with torch.no_grad():
+        ref_t = dit(ids_t, sigma[:2], modality=mod_t)
+    mine_t = R.dit_forward(ocfg, P, ids_t, mod_t, mode="fp32", sigma=sigma[:2])
+    err_t = (mine_t - ref_t).abs().max().item()
+    print(f"[timecond fp32, all-text batch] max|restated - reference| = {err_t:.3e}")
+    assert err_t < 3e-5, err_t
+    # without conditioning the logits differ: the fixture really exercises adaLN
+    plain = R.dit_forward(R.OracleConfig(D, H, L, txt, img, V, tv, mi), P, ids, modality, mode="fp32")
+    assert (plain - ref_logits).abs().max() > 1e-2
+    np.savez_compressed(os.path.join(OUT, "timecond.npz"), cfg=np.array([D, H, L, txt, img, V, tv, mi]), ids=_np(ids),
+                        modality=_np(modality), sigma=_np(sigma), ref_logits_fp32=_np(ref_logits), ids_txt=_np(ids_t),
+                        modality_txt=_np(mod_t), ref_logits_txt_fp32=_np(ref_t), **{"P::" + k: _np(v) for k, v in P.items()})
+
+
 def _with_length(ocfg, N):
     """OracleConfig whose `length` (txt_length + img_length) equals the packed sequence length N."""
     import dataclasses
@@ -412,6 +457,7 @@ def main():
     torch.set_num_threads(8)
     gen_diffusion_fns(*gen_dit())
     gen_interleaved()
+    gen_timecond()
     print("golden fixtures written to", OUT)
 
 

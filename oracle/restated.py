@@ -156,6 +156,42 @@ def interleaved_token_tables(cfg: OracleConfig, modality: torch.Tensor, sample_i
 
 
 # --------------------------------------------------------------------------------------
+# time conditioning (config.time_conditioning, off in every shipped config) — dit.py:415-449, 266-268, 301-304, 229-253
+# --------------------------------------------------------------------------------------
+def timestep_embedding(t, dim=256, max_period=10000):
+    """TimestepEmbedder.timestep_embedding dit.py:426-444 (t: [B])."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(t.device)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def conditioning_vector(P, sigma, mode):
+    """c = silu(sigma_map(sigma)) (dit.py:446-449, 1378-1379); under autocast every Linear / SiLU output is bf16."""
+    e = timestep_embedding(sigma)
+    h = _linear(e, P["sigma_map.mlp.0.weight"], P["sigma_map.mlp.0.bias"], mode)
+    h = torch.nn.functional.silu(h.float())
+    if mode == "bf16":
+        h = _bf(h)
+    h = _linear(h, P["sigma_map.mlp.2.weight"], P["sigma_map.mlp.2.bias"], mode)
+    c = torch.nn.functional.silu(h.float())
+    return _bf(c) if mode == "bf16" else c
+
+
+def modulate_fused(x, shift, scale, modality, mode):
+    """dit.py:258-268, 301-304: image tokens only — unless the batch holds no image token at all, in which case the
+    reference modulates EVERY token (`modality.any()` false -> plain `modulate`).  `1 + scale` is evaluated in the dtype of
+    `scale` (bf16 under autocast), the product / sum promote to fp32."""
+    one_plus = (1 + scale)
+    if mode == "bf16":
+        one_plus = _bf(one_plus)
+    y = x.float() * one_plus.float() + shift.float()
+    if modality is not None and bool(modality.any()):
+        return torch.where((modality == 1)[..., None], y, x.float())
+    return y
+
+
+# --------------------------------------------------------------------------------------
 # backbone
 # --------------------------------------------------------------------------------------
 def _bf(x):
@@ -202,13 +238,17 @@ def attention_core(q, k, v, scale):
 
 
 def block_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], i: int, x, cos, sin, mode, sample_ids=None,
-                  taps: Optional[dict] = None, drop_scale: Optional[torch.Tensor] = None):
+                  taps: Optional[dict] = None, drop_scale: Optional[torch.Tensor] = None, c=None, modality=None):
     """DDiTBlock.forward dit.py:948-1033 (rms, sandwich, qk_norm, no time-conditioning) with
     Attention.forward dit.py:616-887 (sdpa branch)."""
     pre = f"blocks.{i}."
     B, N, D = x.shape
     H, hd = cfg.n_heads, cfg.head_dim
     h = _rmsnorm(x, P[pre + "norm1.weight"], cfg.rms_eps, mode)                       # step 1
+    if c is not None:                                                                 # dit.py:966-967, 973-974
+        cond = _linear(c, P[pre + "adaLN_modulation.weight"], P[pre + "adaLN_modulation.bias"], mode)[:, None, :]
+        shift_msa, scale_msa, _gate_msa, shift_mlp, scale_mlp, gate_mlp = cond.chunk(6, dim=2)
+        h = modulate_fused(h, shift_msa, scale_msa, modality, mode)
     qkv = _linear(h, P[pre + "attention.attn_qkv.weight"], None, mode)               # step 2  [B,N,3D]
     q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
     ln = lambda t, w, b: torch.nn.functional.layer_norm(t.float(), (D,), w.float(), b.float(), cfg.ln_eps)
@@ -238,16 +278,23 @@ def block_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], i: int, x, cos,
     a = _linear(o, P[pre + "attention.attn_out.weight"], None, mode)                  # step 6
     x1 = x + _rmsnorm(a, P[pre + "pre_residual_norm.weight"], cfg.rms_eps, mode)      # step 7
     h2 = _rmsnorm(x1, P[pre + "norm2.weight"], cfg.rms_eps, mode)                     # step 8
+    if c is not None:
+        h2 = modulate_fused(h2, shift_mlp, scale_mlp, modality, mode)                 # dit.py:1017
     u = _linear(h2, P[pre + "mlp.0.weight"], P[pre + "mlp.0.bias"], mode)             # step 9
     g = torch.nn.functional.gelu(u.float(), approximate="tanh")
     if mode == "bf16":
         g = _bf(g)
     d = _linear(g, P[pre + "mlp.2.weight"], P[pre + "mlp.2.bias"], mode)
     br = _rmsnorm(d, P[pre + "post_ff_norm.weight"], cfg.rms_eps, mode)
+    plain = br
     if drop_scale is not None:
         # F.dropout(training=True) of the branch (dit.py:218-222,239,1024-1031) with an explicit keep-scale tensor
         # (0 or 1/(1-p)) standing in for the Bernoulli draw
         br = br * drop_scale
+    if c is not None:
+        # bias_dropout_add_scale with modality (dit.py:239-249): image tokens get gate * dropout(branch), text tokens the
+        # plain branch (no gate, no dropout)
+        br = torch.where((modality == 1)[..., None], gate_mlp.float() * br, plain)
     x2 = x1 + br                                                                       # step 10
     if taps is not None:
         taps[f"b{i}"] = dict(h=h, qkv=qkv, q=q, k=k, o=o, a=a, x1=x1, h2=h2, u=u, g=g, d=d, x2=x2)
@@ -255,7 +302,7 @@ def block_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], i: int, x, cos,
 
 
 def dit_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], indices, modality, mode="fp32", sample_ids=None,
-                taps: Optional[dict] = None, return_hidden=False, drop_scales=None):
+                taps: Optional[dict] = None, return_hidden=False, drop_scales=None, sigma=None):
     """DIT.forward dit.py:1324-1500 (discrete, multimodal_batches, modality_embed, rope_2d, no time-cond).
 
     indices, modality: int64 [B,N].  Returns logits [B,N,V] (bf16 in mode="bf16", fp32 otherwise).
@@ -270,12 +317,17 @@ def dit_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], indices, modality
     else:
         cos, sin = token_cos_sin(cfg, modality.cpu())
     cos, sin = cos.to(x.device), sin.to(x.device)
+    c = conditioning_vector(P, sigma, mode) if cfg.time_conditioning else None       # dit.py:1378-1379
     for i in range(cfg.n_blocks):
         x = block_forward(cfg, P, i, x, cos, sin, mode, sample_ids=sample_ids, taps=taps,
-                          drop_scale=None if drop_scales is None else drop_scales[i])
+                          drop_scale=None if drop_scales is None else drop_scales[i], c=c, modality=modality)
     if return_hidden:
         return x
     hf = _rmsnorm(x, P["output_layer.norm_final.weight"], cfg.rms_eps, mode)          # dit.py:1089
+    if c is not None:                                                                 # dit.py:1083-1087
+        cond = _linear(c, P["output_layer.adaLN_modulation.weight"], P["output_layer.adaLN_modulation.bias"], mode)[:, None, :]
+        shift, scale = cond.chunk(2, dim=2)
+        hf = modulate_fused(hf, shift, scale, modality, mode)
     return _linear(hf, P["output_layer.linear.weight"], P["output_layer.linear.bias"], mode)  # dit.py:1091
 
 
@@ -531,12 +583,13 @@ def init_params(cfg: OracleConfig, seed=0) -> Dict[str, torch.Tensor]:
 def training_loss(cfg: OracleConfig, P, x0, modality, attention_mask, u_t, rand_move, mode="fp32", *,
                   img_loss_weight=0.6, text_loss_weight=1.0, softmin_snr=None, fp32_logsoftmax=True, drop_scales=None):
     """q_xt -> DIT -> SUBS -> weighted NLL, i.e. `Diffusion.compute_loss` (model.py:797-1173) for the default
-    large-scale config, driven by explicit random draws (u_t [B], rand_move [B,N])."""
+    large-scale config, driven by explicit random draws (u_t [B], rand_move [B,N]).  With time conditioning sigma is handed
+    to the backbone exactly as compute_loss does (model.py:858-859)."""
     t = sample_t(u_t)
     sigma, _ = loglinear_noise(t)
     move_chance = 1 - torch.exp(-sigma[:, None])                                       # model.py:858-860
     xt, move, _ = q_xt(x0, move_chance, rand_move, cfg.mask_index)
-    logits = dit_forward(cfg, P, xt, modality, mode=mode, drop_scales=drop_scales)
+    logits = dit_forward(cfg, P, xt, modality, mode=mode, drop_scales=drop_scales, sigma=sigma if cfg.time_conditioning else None)
     if fp32_logsoftmax:
         logits = logits.float()
     logp = subs_parameterization(logits, xt, modality, cfg.mask_index, cfg.text_vocab_size)

@@ -42,3 +42,9 @@ def golden_fns():
 def golden_interleaved():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "interleaved.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_timecond():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "timecond.npz"))

@@ -179,3 +179,19 @@ def test_interleaved_q_xt_oracle_and_host_logic_bit_exact(golden_interleaved):
                                         batch=dict(modality=modality, sample_ids=sid))
     assert np.array_equal(xt2.numpy(), g["qxt_ref"]) and np.array_equal(mv2.numpy(), g["qxt_move_ref"])
     assert np.array_equal(ign2.numpy(), g["qxt_ignore_ref"])
+
+
+def test_time_conditioning_matches_reference(golden_timecond):
+    """config.time_conditioning (adaLN shift / scale / gate from sigma, dit.py:966-1031, 1083-1091) incl. the all-text quirk."""
+    import dataclasses
+    g = golden_timecond
+    cfg = dataclasses.replace(_cfg(g), time_conditioning=True)
+    P = _params(g)
+    sigma = torch.from_numpy(g["sigma"])
+    out = R.dit_forward(cfg, P, torch.from_numpy(g["ids"]), torch.from_numpy(g["modality"]), mode="fp32", sigma=sigma)
+    assert (out - torch.from_numpy(g["ref_logits_fp32"])).abs().max().item() < 3e-5
+    out_t = R.dit_forward(cfg, P, torch.from_numpy(g["ids_txt"]), torch.from_numpy(g["modality_txt"]), mode="fp32", sigma=sigma[:2])
+    assert (out_t - torch.from_numpy(g["ref_logits_txt_fp32"])).abs().max().item() < 3e-5
+    # bf16-emulating mode stays close to the fp32 reference
+    out_bf = R.dit_forward(cfg, P, torch.from_numpy(g["ids"]), torch.from_numpy(g["modality"]), mode="bf16", sigma=sigma).float()
+    assert (out_bf - torch.from_numpy(g["ref_logits_fp32"])).abs().max().item() < 0.08

@@ -20,13 +20,13 @@ _SIGS = {
     "ud_abi_version": [],
     "ud_device_sm_count": [],
     "ud_gemm_bf16": [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp],
-    "ud_embed_rmsnorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp],
+    "ud_embed_rmsnorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp],
     "ud_embed_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp],
     "ud_interleaved_prep": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
-    "ud_norm_residual_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _u64, _u64, _vp],
-    "ud_norm_residual_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _u64, _u64, _vp],
+    "ud_norm_residual_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _u64, _u64, _vp, _vp],
+    "ud_norm_residual_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _u64, _u64, _vp, _vp],
     "ud_dropout_scales": [_vp, _i, _i, _f, _u64, _u64, _vp],
-    "ud_rmsnorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "ud_rmsnorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp],
     "ud_qk_ln_rope_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     "ud_qk_ln_rope_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "ud_attn_fwd": [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp],
@@ -47,6 +47,18 @@ _SIGS = {
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS.keys())
+
+
+class AdaLN(C.Structure):
+    """`ud_adaln` of include/unidisc_b200.h (time conditioning; NULL in the default configuration)."""
+    _fields_ = [("sel", _vp), ("img", _vp), ("shift", _vp), ("scale", _vp), ("gate", _vp), ("ld", _ll), ("tokens_per_sample", _i),
+                ("d_shift", _vp), ("d_scale", _vp), ("d_gate", _vp), ("ld_d", _ll)]
+
+
+def adaln(sel, img, shift=None, scale=None, gate=None, ld=0, tokens_per_sample=1, d_shift=None, d_scale=None, d_gate=None, ld_d=0):
+    """Builds the struct from tensors (views into the adaLN output / its fp32 gradient buffer); returns (byref pointer, keepalive)."""
+    s = AdaLN(P(sel), P(img), P(shift), P(scale), P(gate), ld, tokens_per_sample, P(d_shift), P(d_scale), P(d_gate), ld_d)
+    return C.cast(C.pointer(s), _vp), s
 
 EPI_BF16, EPI_BF16_GELU, EPI_BF16_DGELU, EPI_F32, EPI_F32_ACC = 0, 1, 2, 3, 4
 

@@ -16,11 +16,11 @@ MODEL_PRESETS = {
 def make_config(preset="extra_large", *, txt_length=256, img_length=1024, image_vocab_size=16384, text_vocab_size=32001,
                 hidden_size=None, n_blocks=None, n_heads=None, dropout=0.0, img_loss_weight=0.6, text_loss_weight=1.0,
                 softmin_snr=None, mask_entire_modality=None, predictor="ddpm_cache", sampling_steps=64, cfg=None, seed=42,
-                zero_linear_init=False, **extra):
+                zero_linear_init=False, time_conditioning=False, **extra):
     d, l, h = MODEL_PRESETS[preset]
     d, l, h = hidden_size or d, n_blocks or l, n_heads or h
     cfgd = dict(
-        mode="train", backbone="dit", parameterization="subs", time_conditioning=False, T=0, seed=seed,
+        mode="train", backbone="dit", parameterization="subs", time_conditioning=bool(time_conditioning), T=0, seed=seed,
         noise=dict(type="loglinear"),
         data=dict(require_sample_ids=False),
         model=dict(hidden_size=d, n_blocks=l, n_heads=h, cond_dim=128, dropout=dropout, length=txt_length + img_length,

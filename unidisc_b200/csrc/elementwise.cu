@@ -294,6 +294,235 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Time-conditioned (adaLN) variants of the fused norm kernels (config.time_conditioning; dit.py:266-268, 301-304,
+// 229-253, 966-1031, 1083-1091).  Separate, simpler kernels (one row per CTA iteration) so the default path above keeps
+// its register budget; the variant is off in every shipped training config.
+//   h      = sel ? (rms(x) * w_n) * bf16(1 + scale[b]) + shift[b] : rms(x) * w_n          (modulate_fused)
+//   branch = img ? gate[b] * dropout(t) : t            with t = bf16(rms(a)) * w_a         (bias_dropout_add_scale w/ modality)
+// shift / scale / gate are bf16 [B, ld] rows of the adaLN Linear's output, sample b = row / tokens_per_sample.
+// ------------------------------------------------------------------------------------------------
+struct AdaLN {
+    const uint8_t* sel;
+    const uint8_t* img;
+    const __nv_bfloat16* shift;
+    const __nv_bfloat16* scale;
+    const __nv_bfloat16* gate;
+    long long ld;
+    int tokens_per_sample;
+    float* d_shift;
+    float* d_scale;
+    float* d_gate;
+    long long ld_d;
+};
+
+UD_DEVINL F4 modulate4(const F4& hn, const AdaLN& t, long long boff, int c) {
+    const F4 sc = ld_bf4(t.scale + boff + c), sh = ld_bf4(t.shift + boff + c);
+    F4 o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.v[i] = hn.v[i] * bf16_round(1.0f + sc.v[i]) + sh.v[i];
+    return o;
+}
+
+__global__ void embed_rmsnorm_fwd_tc_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ modality,
+                                            const float* __restrict__ E, const float* __restrict__ Emod,
+                                            const float* __restrict__ w, float* __restrict__ x, __nv_bfloat16* __restrict__ h,
+                                            float* __restrict__ rstd, int rows, int D, float eps,
+                                            const int* __restrict__ ordinal, const float* __restrict__ Ecount, AdaLN tc) {
+    __shared__ float scratch[2 * 32 * 1];
+    int buf = 0;
+    const int c = threadIdx.x * 4;
+    const F4 wv = ld_f4(w + c);
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long id = ids[row];
+        const int md = modality[row] == 0 ? 0 : 1;
+        F4 e = ld_f4(E + id * D + c), m = ld_f4(Emod + (long long)md * D + c), xv;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv.v[i] = e.v[i] + m.v[i];
+        if (ordinal != nullptr && ordinal[row] >= 0) {
+            const F4 ce = ld_f4(Ecount + (long long)ordinal[row] * D + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv.v[i] += ce.v[i];
+        }
+        float ss[1] = {0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ss[0] += xv.v[i] * xv.v[i];
+        block_sum<1>(ss, scratch, buf);
+        const float r = rsqrtf(ss[0] / (float)D + eps);
+        F4 hv;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hv.v[i] = (xv.v[i] * r) * wv.v[i];
+        if (tc.sel[row]) hv = modulate4(hv, tc, (long long)(row / tc.tokens_per_sample) * tc.ld, c);
+        st_f4(x + (long long)row * D + c, xv);
+        st_bf4(h + (long long)row * D + c, hv);
+        if (threadIdx.x == 0) rstd[row] = r;
+    }
+}
+
+template <bool DROP>
+__global__ void norm_residual_fwd_tc_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ x_in,
+                                            const float* __restrict__ w_a, const float* __restrict__ w_n,
+                                            float* __restrict__ x_out, __nv_bfloat16* __restrict__ h,
+                                            float* __restrict__ rstd_a, float* __restrict__ rstd_x, int rows, int D, float eps,
+                                            uint32_t drop_thresh, float inv_keep, uint64_t seed, uint64_t offset, AdaLN tc) {
+    __shared__ float scratch[2 * 32 * 1];
+    int buf = 0;
+    const int c = threadIdx.x * 4;
+    const F4 wa = ld_f4(w_a + c), wn = ld_f4(w_n + c);
+    const float invD = 1.0f / (float)D;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long off = (long long)row * D + c;
+        const long long boff = (long long)(row / tc.tokens_per_sample) * tc.ld;
+        const F4 av = ld_bf4(a + off), xi = ld_f4(x_in + off);
+        float s[1] = {0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[0] += av.v[i] * av.v[i];
+        block_sum<1>(s, scratch, buf);
+        const float ra = rsqrtf(s[0] * invD + eps);
+        const bool img = tc.img[row] != 0;
+        float coef[4] = {1.f, 1.f, 1.f, 1.f};
+        if (img) {                                   // text tokens: plain branch, neither gate nor dropout (dit.py:246-249)
+            if (DROP) dropout_scales4(seed, offset, (uint32_t)row, threadIdx.x, drop_thresh, inv_keep, coef);
+            if (tc.gate != nullptr) {
+                const F4 g = ld_bf4(tc.gate + boff + c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) coef[i] *= g.v[i];
+            }
+        }
+        F4 xo;
+        s[0] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xo.v[i] = xi.v[i] + (bf16_round(av.v[i] * ra) * wa.v[i]) * coef[i];
+            s[0] += xo.v[i] * xo.v[i];
+        }
+        block_sum<1>(s, scratch, buf);
+        const float rx = rsqrtf(s[0] * invD + eps);
+        F4 hv;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hv.v[i] = (xo.v[i] * rx) * wn.v[i];
+        if (tc.shift != nullptr && tc.sel[row]) hv = modulate4(hv, tc, boff, c);
+        st_f4(x_out + off, xo);
+        st_bf4(h + off, hv);
+        if (threadIdx.x == 0) { rstd_a[row] = ra; rstd_x[row] = rx; }
+    }
+}
+
+// backward of the two kernels above (HAS_BRANCH=false: first norm only).  Per-sample gradients of shift / scale / gate are
+// accumulated with atomics into fp32 [B, ld_d] buffers.
+template <bool HAS_BRANCH, bool DROP>
+__global__ void norm_residual_bwd_tc_kernel(const float* __restrict__ g_out, const __nv_bfloat16* __restrict__ dh,
+                                            const float* __restrict__ x_out, const float* __restrict__ rstd_x,
+                                            const float* __restrict__ w_n, const __nv_bfloat16* __restrict__ a,
+                                            const float* __restrict__ rstd_a, const float* __restrict__ w_a,
+                                            float* __restrict__ g_in, __nv_bfloat16* __restrict__ da, float* __restrict__ dw_n,
+                                            float* __restrict__ dw_a, float* __restrict__ db_a, int rows, int D,
+                                            uint32_t drop_thresh, float inv_keep, uint64_t seed, uint64_t offset, AdaLN tc) {
+    __shared__ float scratch[2 * 32 * 3];
+    int buf = 0;
+    const int c = threadIdx.x * 4;
+    const F4 wn = ld_f4(w_n + c);
+    F4 wa = {{0, 0, 0, 0}};
+    if (HAS_BRANCH) wa = ld_f4(w_a + c);
+    F4 acc_n = {{0, 0, 0, 0}}, acc_a = {{0, 0, 0, 0}}, acc_b = {{0, 0, 0, 0}};
+    // per-sample adaLN gradients stay in registers while this CTA's rows (ascending) belong to one sample; one atomic
+    // per column per (CTA, sample) instead of one per token
+    F4 acc_sh = {{0, 0, 0, 0}}, acc_sc = {{0, 0, 0, 0}}, acc_gt = {{0, 0, 0, 0}};
+    int cur_b = -1;
+    auto flush = [&](int b) {
+        if (b < 0) return;
+        const long long doff = (long long)b * tc.ld_d + c;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (tc.d_shift != nullptr && acc_sh.v[i] != 0.f) atomicAdd(tc.d_shift + doff + i, acc_sh.v[i]);
+            if (tc.d_scale != nullptr && acc_sc.v[i] != 0.f) atomicAdd(tc.d_scale + doff + i, acc_sc.v[i]);
+            if (HAS_BRANCH && tc.d_gate != nullptr && acc_gt.v[i] != 0.f) atomicAdd(tc.d_gate + doff + i, acc_gt.v[i]);
+            acc_sh.v[i] = acc_sc.v[i] = acc_gt.v[i] = 0.f;
+        }
+    };
+    const float invD = 1.0f / (float)D;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long off = (long long)row * D + c;
+        const int b = row / tc.tokens_per_sample;
+        if (b != cur_b) { flush(cur_b); cur_b = b; }
+        const long long boff = (long long)b * tc.ld;
+        const float rx = rstd_x[row];
+        F4 dhv = ld_bf4(dh + off);
+        const F4 xo = ld_f4(x_out + off);
+        F4 go = {{0, 0, 0, 0}};
+        if (g_out != nullptr) go = ld_f4(g_out + off);
+        F4 y;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y.v[i] = xo.v[i] * rx;
+        if (tc.shift != nullptr && tc.sel[row]) {
+            // h = (y * w_n) * bf16(1 + scale) + shift  ->  d_shift += dh, d_scale += dh * (y * w_n), d(y * w_n) = dh * bf16(1 + scale)
+            const F4 sc = ld_bf4(tc.scale + boff + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc_sh.v[i] += dhv.v[i];
+                acc_sc.v[i] += dhv.v[i] * (y.v[i] * wn.v[i]);
+                dhv.v[i] *= bf16_round(1.0f + sc.v[i]);
+            }
+        }
+        F4 av = {{0, 0, 0, 0}}, naf = {{0, 0, 0, 0}}, base;
+        float ra = 0.f, coef[4] = {1.f, 1.f, 1.f, 1.f}, ks[4] = {1.f, 1.f, 1.f, 1.f};
+        bool img = false;
+        F4 gt = {{1.f, 1.f, 1.f, 1.f}};
+        if (HAS_BRANCH) {
+            av = ld_bf4(a + off);
+            ra = rstd_a[row];
+            img = tc.img[row] != 0;
+            if (img) {
+                if (DROP) dropout_scales4(seed, offset, (uint32_t)row, threadIdx.x, drop_thresh, inv_keep, ks);
+                if (tc.gate != nullptr) gt = ld_bf4(tc.gate + boff + c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) coef[i] = ks[i] * gt.v[i];
+            }
+        }
+        float s[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float dy = dhv.v[i] * wn.v[i];
+            s[0] += dy * y.v[i];
+            base.v[i] = go.v[i] + rx * dy;
+            acc_n.v[i] += dhv.v[i] * y.v[i];
+            if (HAS_BRANCH) {
+                naf.v[i] = av.v[i] * ra;
+                s[1] += base.v[i] * wa.v[i] * coef[i] * naf.v[i];
+                s[2] += y.v[i] * wa.v[i] * coef[i] * naf.v[i];
+            }
+        }
+        block_sum<3>(s, scratch, buf);
+        const float m1 = s[0] * invD;
+        F4 g;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g.v[i] = base.v[i] - rx * y.v[i] * m1;
+        st_f4(g_in + off, g);
+        if (HAS_BRANCH) {
+            const float m2 = (s[1] - rx * m1 * s[2]) * invD;
+            F4 dav;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float t = bf16_round(naf.v[i]) * wa.v[i];           // the branch value before gate / dropout
+                acc_a.v[i] += g.v[i] * bf16_round(naf.v[i]) * coef[i];
+                dav.v[i] = ra * (g.v[i] * wa.v[i] * coef[i] - naf.v[i] * m2);
+                acc_b.v[i] += dav.v[i];
+                if (img && tc.gate != nullptr) acc_gt.v[i] += g.v[i] * ks[i] * t;
+            }
+            st_bf4(da + off, dav);
+        }
+    }
+    flush(cur_b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        atomicAdd(dw_n + c + i, acc_n.v[i]);
+        if (HAS_BRANCH) {
+            atomicAdd(dw_a + c + i, acc_a.v[i]);
+            if (db_a != nullptr) atomicAdd(db_a + c + i, acc_b.v[i]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // q/k LayerNorm over the full hidden dim + RoPE   (dit.py:680-682, 724-726; standalone_rotary.py:14-31)
 // ------------------------------------------------------------------------------------------------
 struct QkRaw { uint2 q, k; float4 cs, sn; };
@@ -745,15 +974,30 @@ using namespace ud;
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
-extern "C" int ud_abi_version(void) { return 3; }
+static AdaLN to_adaln(const ud_adaln* t) {
+    AdaLN a;
+    a.sel = t->sel; a.img = t->img;
+    a.shift = CBF(t->shift); a.scale = CBF(t->scale); a.gate = CBF(t->gate);
+    a.ld = t->ld; a.tokens_per_sample = t->tokens_per_sample;
+    a.d_shift = t->d_shift; a.d_scale = t->d_scale; a.d_gate = t->d_gate; a.ld_d = t->ld_d;
+    return a;
+}
+
+extern "C" int ud_abi_version(void) { return 4; }
 extern "C" int ud_device_sm_count(void) { return sm_count(); }
 
 extern "C" int ud_embed_rmsnorm_fwd(const int64_t* ids, const int64_t* modality, const float* E, const float* Emod,
                                     const float* w, float* x, void* h, float* rstd, int rows, int D, float eps,
-                                    const int* ordinal, const float* Ecount, void* stream) {
+                                    const int* ordinal, const float* Ecount, const ud_adaln* tc, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "embed_rmsnorm_fwd")) return -1;
     if (ordinal != nullptr && Ecount == nullptr) return -1;
+    if (tc != nullptr) {
+        embed_rmsnorm_fwd_tc_kernel<<<row_grid(rows, D / 4), D / 4, 0, STREAM(stream)>>>(ids, modality, E, Emod, w, x, BF(h), rstd, rows, D, eps,
+                                                                                       ordinal, Ecount, to_adaln(tc));
+        UD_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     embed_rmsnorm_fwd_kernel<<<row_grid(rows, D / 4), D / 4, 0, STREAM(stream)>>>(ids, modality, E, Emod, w, x, BF(h), rstd, rows, D, eps, ordinal, Ecount);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -773,10 +1017,20 @@ extern "C" int ud_embed_bwd(const int64_t* ids, const int64_t* modality, const f
 
 extern "C" int ud_norm_residual_fwd(const void* a, const float* x_in, const float* w_a, const float* w_n, float* x_out, void* h,
                                     float* rstd_a, float* rstd_x, int rows, int D, float eps, float p_drop, uint64_t seed,
-                                    uint64_t offset, void* stream) {
+                                    uint64_t offset, const ud_adaln* tc, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "norm_residual_fwd")) return -1;
     if (p_drop < 0.f || p_drop >= 1.f) { fprintf(stderr, "unidisc_b200: dropout p must be in [0,1)\n"); return -1; }
+    if (tc != nullptr) {
+        const int g = row_grid(rows, D / 4);
+        if (p_drop > 0.f)
+            norm_residual_fwd_tc_kernel<true><<<g, D / 4, 0, STREAM(stream)>>>(CBF(a), x_in, w_a, w_n, x_out, BF(h), rstd_a, rstd_x, rows, D, eps,
+                                                                              dropout_thresh(p_drop), 1.0f / (1.0f - p_drop), seed, offset, to_adaln(tc));
+        else
+            norm_residual_fwd_tc_kernel<false><<<g, D / 4, 0, STREAM(stream)>>>(CBF(a), x_in, w_a, w_n, x_out, BF(h), rstd_a, rstd_x, rows, D, eps, 0u, 1.f, 0, 0, to_adaln(tc));
+        UD_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     const int grid = row_grid((rows + 3) / 4, D / 4);
     if (p_drop > 0.f)
         norm_residual_fwd_kernel<4, true><<<grid, D / 4, 0, STREAM(stream)>>>(CBF(a), x_in, w_a, w_n, x_out, BF(h), rstd_a, rstd_x, rows, D, eps,
@@ -790,12 +1044,21 @@ extern "C" int ud_norm_residual_fwd(const void* a, const float* x_in, const floa
 extern "C" int ud_norm_residual_bwd(const float* g_out, const void* dh, const float* x_out, const float* rstd_x,
                                     const float* w_n, const void* a, const float* rstd_a, const float* w_a, float* g_in,
                                     void* da, float* dw_n, float* dw_a, float* db_a, int rows, int D, float p_drop,
-                                    uint64_t seed, uint64_t offset, void* stream) {
+                                    uint64_t seed, uint64_t offset, const ud_adaln* tc, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "norm_residual_bwd")) return -1;
     if (p_drop < 0.f || p_drop >= 1.f) { fprintf(stderr, "unidisc_b200: dropout p must be in [0,1)\n"); return -1; }
     int grid = row_grid((rows + 1) / 2, D / 4);
     if (grid > 4 * sm_count()) grid = 4 * sm_count();
+    if (tc != nullptr) {
+        if (p_drop > 0.f)
+            norm_residual_bwd_tc_kernel<true, true><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, db_a, rows, D,
+                                                                                       dropout_thresh(p_drop), 1.0f / (1.0f - p_drop), seed, offset, to_adaln(tc));
+        else
+            norm_residual_bwd_tc_kernel<true, false><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, db_a, rows, D, 0u, 1.f, 0, 0, to_adaln(tc));
+        UD_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     if (p_drop > 0.f)
         norm_residual_bwd_kernel<true, 2, true><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, db_a, rows, D,
                                                                                    dropout_thresh(p_drop), 1.0f / (1.0f - p_drop), seed, offset);
@@ -814,11 +1077,16 @@ extern "C" int ud_dropout_scales(float* out, int rows, int D, float p_drop, uint
 }
 
 extern "C" int ud_rmsnorm_bwd(const float* g_out, const void* dh, const float* x, const float* rstd, const float* w,
-                              float* g_in, float* dw, int rows, int D, void* stream) {
+                              float* g_in, float* dw, int rows, int D, const ud_adaln* tc, void* stream) {
     if (rows <= 0) return 0;
     if (!check_D(D, "rmsnorm_bwd")) return -1;
     int grid = row_grid((rows + 1) / 2, D / 4);
     if (grid > 4 * sm_count()) grid = 4 * sm_count();
+    if (tc != nullptr) {
+        norm_residual_bwd_tc_kernel<false, false><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x, rstd, w, nullptr, nullptr, nullptr, g_in, nullptr, dw, nullptr, nullptr, rows, D, 0u, 1.f, 0, 0, to_adaln(tc));
+        UD_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     norm_residual_bwd_kernel<false, 2, false><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x, rstd, w, nullptr, nullptr, nullptr, g_in, nullptr, dw, nullptr, nullptr, rows, D, 0u, 1.f, 0, 0);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;

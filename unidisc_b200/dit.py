@@ -13,11 +13,12 @@ fp32 buffer (with a bf16 shadow for the tensor cores and a flat fp32 gradient bu
 into), so the optimizer and the DDP all-reduce work on contiguous memory.  There is no eager / CPU fallback.
 
 Supported configuration = the shipped large/small-scale training configs: norm_type=rms, sandwich_normalization,
-qk_norm, rope_2d, modality_embed, multimodal_batches, full_attention, no time-conditioning; `model.dropout` is applied
-to the MLP branch in training mode exactly where the reference does (in-kernel Philox mask, regenerated in backward)
+qk_norm, rope_2d, modality_embed, multimodal_batches, full_attention; `model.dropout` is applied to the MLP branch in
+training mode exactly where the reference does (in-kernel Philox mask, regenerated in backward).  `time_conditioning`
+(adaLN shift / scale / gate from sigma; off in every shipped config) is fused into the same norm kernels.
 `data.require_sample_ids` (interleaved / packed batches): per-image-block RoPE tables, `img_count_embedding` and the
 document mask are derived on the device from `modality` / `sample_ids` (csrc/interleaved.cu).
-(see DESIGN.md for what is not yet covered: adaLN time-conditioning, KV caches).
+(see DESIGN.md for what is not covered: KV caches).
 """
 from __future__ import annotations
 
@@ -75,26 +76,45 @@ class Attention(nn.Module):                                          # parameter
         self.k_norm = nn.LayerNorm(dim)
 
 
+class TimestepEmbedder(nn.Module):                                   # parameters of reference dit.py:415-449
+    def __init__(self, hidden_size, frequency_embedding_size=256):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(frequency_embedding_size, hidden_size, bias=True), nn.SiLU(),
+                                 nn.Linear(hidden_size, hidden_size, bias=True))
+        self.frequency_embedding_size = frequency_embedding_size
+
+
+def _zero_linear(i, o):
+    lin = nn.Linear(i, o, bias=True)                                  # adaLN_modulation: zero-initialised (dit.py:923-925)
+    lin.weight.data.zero_()
+    lin.bias.data.zero_()
+    return lin
+
+
 class DDiTBlock(nn.Module):                                          # parameters of reference dit.py:890-934
-    def __init__(self, dim, n_heads, mlp_ratio=4):
+    def __init__(self, dim, n_heads, mlp_ratio=4, cond_dim=None):
         super().__init__()
         self.attention = Attention(dim, n_heads)
         self.norm1 = RMSNorm(dim)
         self.norm2 = RMSNorm(dim)
         self.mlp = nn.Sequential(nn.Linear(dim, mlp_ratio * dim, bias=True), nn.GELU(approximate="tanh"),
                                  nn.Linear(mlp_ratio * dim, dim, bias=True))
+        if cond_dim is not None:
+            self.adaLN_modulation = _zero_linear(cond_dim, 6 * dim)
         self.post_ff_norm = RMSNorm(dim)
         self.pre_residual_norm = RMSNorm(dim)
 
 
 class DDitFinalLayer(nn.Module):                                     # parameters of reference dit.py:1063-1092
-    def __init__(self, hidden_size, out_channels, zero_linear_init=True):
+    def __init__(self, hidden_size, out_channels, zero_linear_init=True, cond_dim=None):
         super().__init__()
         self.norm_final = RMSNorm(hidden_size)
         self.linear = nn.Linear(hidden_size, out_channels)
         if zero_linear_init:
             self.linear.weight.data.zero_()
         self.linear.bias.data.zero_()
+        if cond_dim is not None:
+            self.adaLN_modulation = _zero_linear(cond_dim, 2 * hidden_size)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -103,8 +123,8 @@ class DDitFinalLayer(nn.Module):                                     # parameter
 # ----------------------------------------------------------------------------------------------------------------
 class _DiTFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, module, indices, modality, sample_ids, save, doc_mask):
-        logits, saved = module._forward_impl(indices, modality, sample_ids, save=save, doc_mask=doc_mask)
+    def forward(ctx, anchor, module, indices, modality, sample_ids, save, doc_mask, sigma):
+        logits, saved = module._forward_impl(indices, modality, sample_ids, save=save, doc_mask=doc_mask, sigma=sigma)
         ctx.module = module
         ctx.saved = saved
         return logits
@@ -116,7 +136,7 @@ class _DiTFunction(torch.autograd.Function):
             raise RuntimeError("unidisc_b200.DIT: backward called on a forward that did not save activations")
         module._backward_impl(saved, dlogits)
         ctx.saved = None
-        return torch.zeros_like(module._anchor), None, None, None, None, None, None
+        return torch.zeros_like(module._anchor), None, None, None, None, None, None, None
 
 
 class DIT(nn.Module):
@@ -134,8 +154,6 @@ class DIT(nn.Module):
         g = lambda o, k, d=None: getattr(o, k, d) if not isinstance(o, dict) else o.get(k, d)
         self.time_conditioning = bool(config.time_conditioning or g(m, "force_time_conditioning", False))
         unsupported = []
-        if self.time_conditioning:
-            unsupported.append("time_conditioning (adaLN)")
         if g(m, "norm_type", "rms") != "rms":
             unsupported.append(f"norm_type={g(m, 'norm_type')}")
         if not g(m, "sandwich_normalization", False):
@@ -170,9 +188,11 @@ class DIT(nn.Module):
 
         self.vocab_embed = EmbeddingLayer(D, vocab_size)
         self.modality_embed = EmbeddingLayer(D, 2)
-        self.blocks = nn.ModuleList([DDiTBlock(D, H) for _ in range(nb)])
-        self.output_layer = DDitFinalLayer(D, vocab_size, zero_linear_init=bool(g(m, "zero_linear_init", True)))
-        self.sigma_map = None
+        cond_dim = int(m.cond_dim) if self.time_conditioning else None
+        self.cond_dim = cond_dim
+        self.blocks = nn.ModuleList([DDiTBlock(D, H, cond_dim=cond_dim) for _ in range(nb)])
+        self.output_layer = DDitFinalLayer(D, vocab_size, zero_linear_init=bool(g(m, "zero_linear_init", True)), cond_dim=cond_dim)
+        self.sigma_map = TimestepEmbedder(cond_dim) if self.time_conditioning else None      # dit.py:1186-1188
 
         lf = g(m, "linear_factor", 1.0)
         ct, st = rope.rope_1d(self.head_dim, self.total_length)
@@ -282,6 +302,9 @@ class DIT(nn.Module):
                 d_n1=gr(p + "norm1.weight"), d_n2=gr(p + "norm2.weight"), d_npre=gr(p + "pre_residual_norm.weight"),
                 d_npost=gr(p + "post_ff_norm.weight"),
             ))
+            if self.time_conditioning:
+                self._blk[-1].update(wada=b16(p + "adaLN_modulation.weight"), bada=b16(p + "adaLN_modulation.bias"),
+                                     d_wada=gr(p + "adaLN_modulation.weight"), d_bada=gr(p + "adaLN_modulation.bias"))
         self._top = dict(
             E=f32("vocab_embed.embedding"), Emod=f32("modality_embed.embedding"), nf=f32("output_layer.norm_final.weight"),
             wh=b16("output_layer.linear.weight"), bh=b16("output_layer.linear.bias"),
@@ -290,6 +313,10 @@ class DIT(nn.Module):
         )
         if self.require_sample_ids:
             self._top["Ecount"], self._top["d_Ecount"] = f32("img_count_embedding"), gr("img_count_embedding")
+        if self.time_conditioning:
+            for key, n in (("sm0", "sigma_map.mlp.0"), ("sm2", "sigma_map.mlp.2"), ("adaf", "output_layer.adaLN_modulation")):
+                self._top["w_" + key], self._top["b_" + key] = b16(n + ".weight"), b16(n + ".bias")
+                self._top["d_w_" + key], self._top["d_b_" + key] = gr(n + ".weight"), gr(n + ".bias")
         self._grad_views = {n: gr(n) for n in self._names}
 
     def _ensure_ready(self):
@@ -352,7 +379,7 @@ class DIT(nn.Module):
     def forward(self, indices, sigma=None, label=None, x_cond=None, attention_mask=None, continuous_mode=False,
                 x_img_emb=None, modality=None, start_pos=None, block_mask=None, update_cache_slice=None, sample_ids=None):
         """Returns logits [B,N,V] in bf16 (what the reference returns under its outer bf16 autocast, model.py:693-729).
-        `sigma` is accepted and ignored (no time-conditioning, as in every shipped training config)."""
+        `sigma` is used only with `time_conditioning` (off in every shipped training config)."""
         if label is not None or x_cond is not None or continuous_mode or x_img_emb is not None or start_pos is not None \
                 or update_cache_slice is not None:
             raise NotImplementedError("unidisc_b200.DIT.forward: label/x_cond/continuous/kv-cache arguments are not supported")
@@ -364,6 +391,8 @@ class DIT(nn.Module):
             raise ValueError("data.require_sample_ids: sample_ids is required")
         if modality is None:
             raise ValueError("modality is required (trainer.multimodal_batches)")
+        if self.time_conditioning and sigma is None:
+            raise ValueError("time_conditioning: sigma is required")
         if not indices.is_cuda:
             raise L.UnidiscB200Error("unidisc_b200.DIT.forward needs CUDA tensors (no CPU fallback)")
         self._ensure_ready()
@@ -372,9 +401,80 @@ class DIT(nn.Module):
         # here a non-None `block_mask` switches the attention kernels' document mask on and the mask itself is derived
         # from `sample_ids` on the fly.  Without require_sample_ids, passing sample_ids alone also enables it.
         doc_mask = sample_ids is not None and (block_mask is not None or not self.require_sample_ids)
-        return _DiTFunction.apply(self._anchor, self, indices, modality, sample_ids, save, doc_mask)
+        return _DiTFunction.apply(self._anchor, self, indices, modality, sample_ids, save, doc_mask,
+                                  sigma if self.time_conditioning else None)
 
-    def _forward_impl(self, indices, modality, sample_ids, save, doc_mask=True):
+    # ------------------------------------------------------------------------------------------------------------
+    # time conditioning (reference dit.py:415-449, 1378-1379, 966-967, 1083-1087).  The conditioning network acts on one
+    # row per SAMPLE ([B, cond_dim], B <= a few dozen): it is evaluated with torch bf16 linears exactly as the reference
+    # does under autocast, and its outputs (shift / scale / gate, bf16 [B, L*6D + 2D]) are consumed per TOKEN inside the
+    # fused norm kernels (csrc/elementwise.cu *_tc_kernel), which also reduce their gradients per sample.
+    # ------------------------------------------------------------------------------------------------------------
+    def _cond_forward(self, sigma, mod_flat, B, N):
+        import torch.nn.functional as F
+        T, D = self._top, self.hidden_size
+        half = self.sigma_map.frequency_embedding_size // 2
+        freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=sigma.device) / half)
+        args = sigma.reshape(-1)[:, None].float() * freqs[None]
+        e = torch.cat([torch.cos(args), torch.sin(args)], dim=-1).to(bf16)
+        h1 = F.linear(e, T["w_sm0"], T["b_sm0"])
+        s1 = F.silu(h1)
+        h2 = F.linear(s1, T["w_sm2"], T["b_sm2"])
+        c = F.silu(h2)                                                        # bf16 [B, cond_dim]
+        cond = torch.cat([F.linear(c, W["wada"], W["bada"]) for W in self._blk] + [F.linear(c, T["w_adaf"], T["b_adaf"])],
+                         dim=1).contiguous()                                  # bf16 [B, L*6D + 2D]
+        is_img = mod_flat == 1
+        # modulate_fused quirk (dit.py:301-304): a batch without any image token modulates EVERY token
+        sel = torch.where(mod_flat.any(), is_img, torch.ones_like(is_img)).to(torch.uint8)
+        return dict(e=e, h1=h1, s1=s1, h2=h2, c=c, cond=cond, sel=sel, img=is_img.to(torch.uint8), N=N,
+                    d_cond=None)
+
+    def _tc(self, C, norm_block=None, gate_block=None, mlp=False, bwd=False):
+        """`ud_adaln` for one fused norm kernel: shift/scale of `norm_block`'s norm1 (mlp=False) / norm2 (mlp=True) — block
+        index L = the final layer — and the MLP gate of `gate_block` applied to the branch the kernel adds."""
+        if C is None:
+            return None
+        D, cond, ld = self.hidden_size, C["cond"], C["cond"].shape[1]
+        kw = dict(ld=ld, tokens_per_sample=C["N"])
+        if bwd:
+            kw["ld_d"] = ld
+        if norm_block is not None:
+            base = norm_block * 6 * D + (3 * D if mlp else 0)
+            kw.update(shift=cond[:, base:], scale=cond[:, base + D:])
+            if bwd:
+                kw.update(d_shift=C["d_cond"][:, base:], d_scale=C["d_cond"][:, base + D:])
+        if gate_block is not None:
+            kw["gate"] = cond[:, gate_block * 6 * D + 5 * D:]
+            if bwd:
+                kw["d_gate"] = C["d_cond"][:, gate_block * 6 * D + 5 * D:]
+        return L.adaln(C["sel"], C["img"], **kw)
+
+    def _adaln_param_grads(self, C, i):
+        """adaLN Linear backward for block i (i = L: final layer) once its slice of d_cond is complete."""
+        D, T = self.hidden_size, self._top
+        lo = i * 6 * D
+        hi = lo + (6 * D if i < self.n_blocks else 2 * D)
+        dc = C["d_cond"][:, lo:hi]
+        if i < self.n_blocks:
+            w, dw, db = self._blk[i]["wada"], self._blk[i]["d_wada"], self._blk[i]["d_bada"]
+        else:
+            w, dw, db = T["w_adaf"], T["d_w_adaf"], T["d_b_adaf"]
+        dw.addmm_(dc.t(), C["c"].float())
+        db.add_(dc.sum(0))
+        C["d_c"].addmm_(dc, w.float())
+
+    def _cond_backward(self, C):
+        import torch.nn.functional as F
+        T = self._top
+        dsilu = lambda pre: (lambda x: torch.sigmoid(x) * (1 + x * (1 - torch.sigmoid(x))))(pre.float())
+        dh2 = C["d_c"] * dsilu(C["h2"])
+        T["d_w_sm2"].addmm_(dh2.t(), C["s1"].float())
+        T["d_b_sm2"].add_(dh2.sum(0))
+        dh1 = (dh2 @ T["w_sm2"].float()) * dsilu(C["h1"])
+        T["d_w_sm0"].addmm_(dh1.t(), C["e"].float())
+        T["d_b_sm0"].add_(dh1.sum(0))
+
+    def _forward_impl(self, indices, modality, sample_ids, save, doc_mask=True, sigma=None):
         B, N = indices.shape
         M, D, H, hd, V = B * N, self.hidden_size, self.n_heads, self.head_dim, self.vocab_size
         T = self._top
@@ -392,25 +492,26 @@ class DIT(nn.Module):
             cos, sin = rope.token_tables(modality, self.rotary_cos_emb_txt, self.rotary_sin_emb_txt, self.rotary_cos_emb_img,
                                          self.rotary_sin_emb_img, self.img_length)
         scale = 1.0 / math.sqrt(hd)
+        C = self._cond_forward(sigma, mod, B, N) if self.time_conditioning else None
         x, h, rstd0 = ops.embed_rmsnorm_fwd(ids, mod, T["E"], T["Emod"], self._blk[0]["n1"], ordinal=ordinal,
-                                            Ecount=T.get("Ecount"))
+                                            Ecount=T.get("Ecount"), tc=self._tc(C, norm_block=0))
         # training-mode dropout of the MLP branch (dit.py:1024-1031): Philox mask keyed by (seed, call counter * L + block)
         p_drop = self.dropout if self.training else 0.0
         self._dropout_calls += 1
         drop_base = self._dropout_calls * self.n_blocks
         saved = dict(ids=ids, mod=mod, sid=sid, cos=cos, sin=sin, B=B, N=N, x0=x, rstd0=rstd0, blocks=[], p_drop=p_drop,
-                     drop_base=drop_base, ordinal=ordinal) if save else None
+                     drop_base=drop_base, ordinal=ordinal, C=C) if save else None
         for i, W in enumerate(self._blk):
             w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
             qkv = ops.gemm(h, W["wqkv"])
             qk, stats = ops.qk_ln_rope_fwd(qkv, W["gq"], W["bq"], W["gk"], W["bk"], cos, sin, hd)
             o, lse = ops.attn_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, N, H, hd, scale, sample_ids=sid)
             a = ops.gemm(o, W["wout"])
-            x1, h2, ra, rx1 = ops.norm_residual_fwd(a, x, W["npre"], W["n2"])
+            x1, h2, ra, rx1 = ops.norm_residual_fwd(a, x, W["npre"], W["n2"], tc=self._tc(C, norm_block=i, mlp=True))
             u, gl = ops.gemm(h2, W["w1"], epi=L.EPI_BF16_GELU, bias=W["b1"])
             d = ops.gemm(gl, W["w2"], bias=W["b2"])
             x2, h_next, rd, rx2 = ops.norm_residual_fwd(d, x1, W["npost"], w_next, p_drop=p_drop, seed=self.dropout_seed,
-                                                        offset=drop_base + i)
+                                                        offset=drop_base + i, tc=self._tc(C, norm_block=i + 1, gate_block=i))
             if save:
                 saved["blocks"].append(dict(h=h, qkv=qkv, qk=qk, stats=stats, o=o, lse=lse, a=a, ra=ra, x1=x1, rx1=rx1, h2=h2,
                                             u=u, g=gl, d=d, rd=rd, x2=x2, rx2=rx2))
@@ -453,6 +554,10 @@ class DIT(nn.Module):
             pending.clear()
         g_res = None       # fp32 gradient flowing down the residual stream
         scale = 1.0 / math.sqrt(hd)
+        C = S.get("C")
+        if C is not None:
+            C["d_cond"] = torch.zeros(C["cond"].shape, device=C["cond"].device, dtype=torch.float32)
+            C["d_c"] = torch.zeros(C["c"].shape, device=C["c"].device, dtype=torch.float32)
         for i in range(self.n_blocks - 1, -1, -1):
             W, A = self._blk[i], S["blocks"][i]
             w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
@@ -460,7 +565,10 @@ class DIT(nn.Module):
             # x2 = x1 + rms(d)*w_post ; h_next = rms(x2)*w_next
             g_res, dd = ops.norm_residual_bwd(g_res, dh, A["x2"], A["rx2"], w_next, A["d"], A["rd"], W["npost"], d_wnext, W["d_npost"],
                                               db_a=W["d_b2"],           # also accumulates mlp.2.bias.grad = colsum(dd)
-                                              p_drop=S["p_drop"], seed=self.dropout_seed, offset=S["drop_base"] + i)
+                                              p_drop=S["p_drop"], seed=self.dropout_seed, offset=S["drop_base"] + i,
+                                              tc=self._tc(C, norm_block=i + 1, gate_block=i, bwd=True))
+            if C is not None and i == self.n_blocks - 1:
+                self._adaln_param_grads(C, self.n_blocks)                 # final layer's shift / scale are complete
             # MLP
             ops.gemm(dd, A["g"], ta=True, tb=True, epi=wacc, out=W["d_w2"])
             du = ops.gemm(dd, W["w2"], tb=True, epi=L.EPI_BF16_DGELU, aux=A["u"])
@@ -469,7 +577,11 @@ class DIT(nn.Module):
             dh2 = ops.gemm(du, W["w1"], tb=True)
             # x1 = x + rms(a)*w_pre ; h2 = rms(x1)*w_n2
             x_in = S["blocks"][i - 1]["x2"] if i > 0 else S["x0"]
-            g_res, da = ops.norm_residual_bwd(g_res, dh2, A["x1"], A["rx1"], W["n2"], A["a"], A["ra"], W["npre"], W["d_n2"], W["d_npre"])
+            g_res, da = ops.norm_residual_bwd(g_res, dh2, A["x1"], A["rx1"], W["n2"], A["a"], A["ra"], W["npre"], W["d_n2"], W["d_npre"],
+                                              tc=self._tc(C, norm_block=i, mlp=True, bwd=True))
+            if C is not None and i + 1 < self.n_blocks:
+                # block i+1's six chunks are final (its norm1 modulation was differentiated by this iteration's first kernel)
+                self._adaln_param_grads(C, i + 1)
             # attention
             ops.gemm(da, A["o"], ta=True, tb=True, epi=wacc, out=W["d_wout"])
             do = ops.gemm(da, W["wout"], tb=True)
@@ -487,7 +599,11 @@ class DIT(nn.Module):
             pending.append(i)
             del x_in
         # first norm + embedding
-        g0 = ops.rmsnorm_bwd(g_res, dh, S["x0"], S["rstd0"], self._blk[0]["n1"], self._blk[0]["d_n1"])
+        g0 = ops.rmsnorm_bwd(g_res, dh, S["x0"], S["rstd0"], self._blk[0]["n1"], self._blk[0]["d_n1"],
+                             tc=self._tc(C, norm_block=0, bwd=True))
+        if C is not None:
+            self._adaln_param_grads(C, 0)
+            self._cond_backward(C)
         ops.embed_bwd(S["ids"], S["mod"], g0, T["d_E"], T["d_Emod"], hot_id=self.mask_index, ordinal=S["ordinal"],
                       dEcount=T.get("d_Ecount"))
         self._shadow_dirty = True      # an optimizer step is expected to follow

@@ -39,13 +39,17 @@ def gemm(a, b, *, ta=False, tb=False, M=None, N=None, K=None, out=None, epi=L.EP
     return out
 
 
-def embed_rmsnorm_fwd(ids, modality, E, Emod, w, eps=1e-6, ordinal=None, Ecount=None):
+def _tc(tc):
+    return tc[0] if tc is not None else None
+
+
+def embed_rmsnorm_fwd(ids, modality, E, Emod, w, eps=1e-6, ordinal=None, Ecount=None, tc=None):
     rows, D = ids.numel(), E.shape[1]
     x = torch.empty((rows, D), device=E.device, dtype=torch.float32)
     h = torch.empty((rows, D), device=E.device, dtype=bf16)
     rstd = torch.empty((rows,), device=E.device, dtype=torch.float32)
     call("ud_embed_rmsnorm_fwd", P(ids), P(modality), P(E), P(Emod), P(w), P(x), P(h), P(rstd), rows, D, eps, P(ordinal),
-         P(Ecount), stream())
+         P(Ecount), _tc(tc), stream())
     return x, h, rstd
 
 
@@ -70,7 +74,7 @@ def interleaved_prep(modality, sample_ids, cos_tab, sin_tab, offsets):
     return cos, sin, ordinal
 
 
-def norm_residual_fwd(a, x_in, w_a, w_n, eps=1e-6, x_out=None, h=None, p_drop=0.0, seed=0, offset=0):
+def norm_residual_fwd(a, x_in, w_a, w_n, eps=1e-6, x_out=None, h=None, p_drop=0.0, seed=0, offset=0, tc=None):
     rows, D = x_in.shape
     if x_out is None:
         x_out = torch.empty_like(x_in)
@@ -79,7 +83,7 @@ def norm_residual_fwd(a, x_in, w_a, w_n, eps=1e-6, x_out=None, h=None, p_drop=0.
     ra = torch.empty((rows,), device=x_in.device, dtype=torch.float32)
     rx = torch.empty((rows,), device=x_in.device, dtype=torch.float32)
     call("ud_norm_residual_fwd", P(a), P(x_in), P(w_a), P(w_n), P(x_out), P(h), P(ra), P(rx), rows, D, eps, float(p_drop),
-         seed, offset, stream())
+         seed, offset, _tc(tc), stream())
     return x_out, h, ra, rx
 
 
@@ -91,22 +95,22 @@ def dropout_scales(rows, D, p_drop, seed, offset, device):
 
 
 def norm_residual_bwd(g_out, dh, x_out, rstd_x, w_n, a, rstd_a, w_a, dw_n, dw_a, g_in=None, da=None, db_a=None, p_drop=0.0,
-                      seed=0, offset=0):
+                      seed=0, offset=0, tc=None):
     rows, D = x_out.shape
     if g_in is None:
         g_in = torch.empty_like(x_out)
     if da is None:
         da = torch.empty((rows, D), device=x_out.device, dtype=bf16)
     call("ud_norm_residual_bwd", P(g_out), P(dh), P(x_out), P(rstd_x), P(w_n), P(a), P(rstd_a), P(w_a), P(g_in), P(da),
-         P(dw_n), P(dw_a), P(db_a), rows, D, float(p_drop), seed, offset, stream())
+         P(dw_n), P(dw_a), P(db_a), rows, D, float(p_drop), seed, offset, _tc(tc), stream())
     return g_in, da
 
 
-def rmsnorm_bwd(g_out, dh, x, rstd, w, dw, g_in=None):
+def rmsnorm_bwd(g_out, dh, x, rstd, w, dw, g_in=None, tc=None):
     rows, D = x.shape
     if g_in is None:
         g_in = torch.empty_like(x)
-    call("ud_rmsnorm_bwd", P(g_out), P(dh), P(x), P(rstd), P(w), P(g_in), P(dw), rows, D, stream())
+    call("ud_rmsnorm_bwd", P(g_out), P(dh), P(x), P(rstd), P(w), P(g_in), P(dw), rows, D, _tc(tc), stream())
     return g_in
 
 
