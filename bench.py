@@ -371,6 +371,40 @@ def main():
             if rank == 0:
                 print(f"[phase] fwd+loss {evs[0].elapsed_time(evs[1]):.2f} ms  bwd {evs[1].elapsed_time(evs[2]):.2f} ms  "
                       f"opt(+allreduce tail) {evs[2].elapsed_time(evs[3]):.2f} ms", file=sys.stderr)
+    if os.environ.get("UD_KERNEL_TIMES") and rank == 0:
+        # debug: in-situ (warm, real clocks) duration of every C-ABI launch of one step, CUDA events around each call
+        for rep in range(2):
+            recs = []
+
+            def timing_call(name, *a):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = orig_call(name, *a)
+                e1.record()
+                tag = name
+                if name == "ud_gemm_bf16":
+                    tag = f"gemm ta{a[0]} tb{a[1]} {a[2]}x{a[3]}x{a[4]} epi{a[11]}"
+                recs.append((tag, e0, e1))
+                return r
+
+            _o.call = timing_call
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            s0.record()
+            step(False)
+            s1.record()
+            torch.cuda.synchronize()
+            _o.call = counting_call
+            if rep == 0:
+                continue
+            agg = {}
+            for tag, e0, e1 in recs:
+                c, t = agg.get(tag, (0, 0.0))
+                agg[tag] = (c + 1, t + e0.elapsed_time(e1))
+            tot = sum(t for _, t in agg.values())
+            print(f"[kernel times] step {s0.elapsed_time(s1):.2f} ms, sum of C-ABI launches {tot:.2f} ms ({len(recs)} launches)", file=sys.stderr)
+            for tag, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                print(f"[kernel times] {tag:48s} n={c:4d} total {t:8.3f} ms  avg {t / c * 1e3:8.1f} us", file=sys.stderr)
     if ddp is not None and ddp.debug_timing:
         ddp._dbg_events = []
         step(False)

@@ -83,6 +83,57 @@ __global__ void k_mma_latency(long long* out, int nmma, int reps) {
     if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tptr); }
 }
 
+
+// MMA-side cost of one attention-backward sub-tile: the tensor pipe's instruction mix issued back to back by one thread,
+// no softmax in between.  VAR 0: current dK/dV kernel (64-query sub-tile): 2 x [8 SS 128x64x16] + 2 x [4 TS 128x128x16, B MN-major]
+// VAR 1: 128-query sub-tile: 2 x [8 SS 128x128x16] + 2 x [8 TS 128x128x16]   VAR 2: SS part of VAR 0   VAR 3: TS part of VAR 0
+// VAR 4: SS part of VAR 1   VAR 5: TS part of VAR 1
+template <int VAR>
+__global__ void k_mma_seq(long long* out, int reps) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint32_t tptr;
+    __shared__ uint64_t bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc<512>(&tptr);
+    fence_proxy_async_smem();
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    if (warp == 1 && lane == 0) {
+        constexpr uint32_t id64 = make_idesc_bf16(128, 64, false, false), id128 = make_idesc_bf16(128, 128, false, false);
+        constexpr uint32_t idacc = make_idesc_bf16(128, 128, false, true);
+        const uint32_t fa = smem_u32(smem), fb = fa + 32768, sa = fa + 65536, sb = sa + 32768;
+        auto kmaj = [](uint32_t base, int ks, int rows) { return make_smem_desc_sw128(base + (ks >> 2) * (rows * 128) + (ks & 3) * 32, 16, 1024); };
+        auto mnmaj = [](uint32_t base, int ks, int rows) { return make_smem_desc_sw128(base + ks * 2048, rows * 128, 1024); };
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            const uint32_t tS = tptr + (r & 1) * 128, tD = tS + 64;
+            if (VAR == 0 || VAR == 2) {
+                for (int ks = 0; ks < 8; ++ks) umma_ss(tS, kmaj(fa, ks, 128), kmaj(sa, ks, 64), id64, ks != 0);
+                for (int ks = 0; ks < 8; ++ks) umma_ss(tD, kmaj(fb, ks, 128), kmaj(sb, ks, 64), id64, ks != 0);
+            }
+            if (VAR == 0 || VAR == 3) {
+                for (int ks = 0; ks < 4; ++ks) umma_ts(tptr + 256, tS + ks * 8, mnmaj(sb, ks, 64), idacc, 1);
+                for (int ks = 0; ks < 4; ++ks) umma_ts(tptr + 384, tD + ks * 8, mnmaj(sa, ks, 64), idacc, 1);
+            }
+            if (VAR == 1 || VAR == 4) {
+                for (int ks = 0; ks < 8; ++ks) umma_ss(tptr, kmaj(fa, ks, 128), kmaj(sa, ks, 128), id128, ks != 0);
+                for (int ks = 0; ks < 8; ++ks) umma_ss(tptr + 128, kmaj(fb, ks, 128), kmaj(sb, ks, 128), id128, ks != 0);
+            }
+            if (VAR == 1 || VAR == 5) {
+                for (int ks = 0; ks < 8; ++ks) umma_ts(tptr + 256, tptr + ks * 8, mnmaj(sb, ks, 128), idacc, 1);
+                for (int ks = 0; ks < 8; ++ks) umma_ts(tptr + 384, tptr + 128 + ks * 8, mnmaj(sa, ks, 128), idacc, 1);
+            }
+        }
+        umma_commit(&bar);
+        while (!mbar_try_wait(&bar, 0)) {}
+        out[blockIdx.x] = (clock64() - t0) / reps;
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tptr); }
+}
+
 // warp 0 lane 0 arrives, warp 1 lane 0 waits: round-trip ping-pong latency
 __global__ void k_mbar_pingpong(long long* out, int reps) {
     __shared__ uint64_t b0, b1;
@@ -138,6 +189,21 @@ int main() {
         k_mma_latency<256><<<sms, 64, 64 * 1024>>>(d, nm, 200); cudaDeviceSynchronize();
         cudaMemcpy(h.data(), d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
         printf("mma issue->commit->wake, %2d MMAs (128xNx16): N=64 %.0f  N=128 %.0f  N=256 %.0f cycles (err=%s)\n", nm, a64, a128, avg(h), cudaGetErrorString(cudaGetLastError()));
+    }
+    {
+        auto run = [&](auto kern, const char* name) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024);
+            kern<<<sms, 64, 164 * 1024>>>(d, 40); cudaDeviceSynchronize();
+            kern<<<sms, 64, 164 * 1024>>>(d, 40); cudaDeviceSynchronize();
+            cudaMemcpy(h.data(), d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+            printf("mma seq %-56s %.0f cycles/rep (err=%s)\n", name, avg(h), cudaGetErrorString(cudaGetLastError()));
+        };
+        run(k_mma_seq<0>, "v2 sub-tile (64q): 16 SS N=64 + 8 TS N=128");
+        run(k_mma_seq<2>, "  SS part: 16 x 128x64x16");
+        run(k_mma_seq<3>, "  TS part: 8 x 128x128x16 (B MN-major)");
+        run(k_mma_seq<1>, "128q sub-tile: 16 SS N=128 + 16 TS N=128");
+        run(k_mma_seq<4>, "  SS part: 16 x 128x128x16");
+        run(k_mma_seq<5>, "  TS part: 16 x 128x128x16 (B MN-major)");
     }
     k_mbar_pingpong<<<sms, 64>>>(d, 1000); cudaDeviceSynchronize();
     cudaMemcpy(h.data(), d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);

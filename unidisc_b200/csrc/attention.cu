@@ -575,7 +575,9 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            // warp-uniform issue loop, one elected lane executes the tcgen05 instructions (see elect_one)
+            const uint32_t leader = elect_one();
             constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
             const uint32_t aQ = smem_u32(sQ);
@@ -584,11 +586,14 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 mbar_wait(&k_full[s], (j >> 1) & 1);
                 tc_fence_after();
                 const uint32_t aK = smem_u32(sK + s * S::TILE_BYTES);
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks)
-                    umma_ss(tS0 + s * 128, desc_kmajor(aQ, ks), desc_kmajor(aK, ks), idesc_s, ks != 0);
-                umma_commit(&s_full[s]);
-                umma_commit(&k_empty[s]);
+                    for (int ks = 0; ks < HD / 16; ++ks)
+                        umma_ss(tS0 + s * 128, desc_kmajor(aQ, ks), desc_kmajor(aK, ks), idesc_s, ks != 0);
+                    umma_commit(&s_full[s]);
+                    umma_commit(&k_empty[s]);
+                }
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             issue_s(0);
@@ -600,11 +605,15 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 mbar_wait(&p_full[s], ph);
                 tc_fence_after();
                 const uint32_t aV = smem_u32(sV + s * S::TILE_BYTES);
+                const uint32_t acc0 = j != 0;
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < ATT_BKV / 16; ++ks)
-                    umma_ts(tO, tP0 + s * 64 + ks * 8, desc_mnmajor(aV, ks), idesc_pv, (j | ks) != 0);
-                umma_commit(&v_empty[s]);
-                umma_commit(pv_done);
+                    for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                        umma_ts(tO, tP0 + s * 64 + ks * 8, desc_mnmajor(aV, ks), idesc_pv, acc0 | (ks != 0));
+                    umma_commit(&v_empty[s]);
+                    umma_commit(pv_done);
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -1078,7 +1087,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            // the whole warp runs this loop (warp-uniform control flow and descriptor arithmetic); one elected lane issues
+            const uint32_t leader = elect_one();
             constexpr uint32_t idesc_sc = make_idesc_bf16(128, 64, false, false);
             constexpr uint32_t idesc_acc = make_idesc_bf16(128, HD, false, true);
             const uint32_t aFA = smem_u32(sFA), aFB = smem_u32(sFB);
@@ -1088,11 +1099,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 tc_fence_after();
                 const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
                 const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tSc, desc_kmajor(aFA, ks), desc_kmajor64(aSA, ks), idesc_sc, ks != 0);
+                    for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tSc, desc_kmajor(aFA, ks), desc_kmajor64(aSA, ks), idesc_sc, ks != 0);
 #pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tDp, desc_kmajor(aFB, ks), desc_kmajor64(aSB, ks), idesc_sc, ks != 0);
-                umma_commit(&sc_full[bf]);
+                    for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tDp, desc_kmajor(aFB, ks), desc_kmajor64(aSB, ks), idesc_sc, ks != 0);
+                    umma_commit(&sc_full[bf]);
+                }
+                __syncwarp();
             };
             mbar_wait(f_full, 0);
             issue_scores(0);
@@ -1104,17 +1118,21 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 tc_fence_after();
                 const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
                 const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
-                if (MODE == 0) {
+                const uint32_t acc0 = i != 0;
+                if (leader) {
+                    if (MODE == 0) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc1, tSc + ks * 8, desc_mnmajor64(aSB, ks), idesc_acc, (i | ks) != 0);
+                        for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc1, tSc + ks * 8, desc_mnmajor64(aSB, ks), idesc_acc, acc0 | (ks != 0));
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, (i | ks) != 0);
-                } else {
+                        for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, acc0 | (ks != 0));
+                    } else {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, (i | ks) != 0);
+                        for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, acc0 | (ks != 0));
+                    }
+                    umma_commit(&st_empty[s]);
+                    umma_commit(&acc_done[bf]);
                 }
-                umma_commit(&st_empty[s]);
-                umma_commit(&acc_done[bf]);
+                __syncwarp();
                 if (i + 2 < T2) {
                     // scores(i+2) overwrite the columns the accumulation MMAs above read P / dS from.  tcgen05.mma issued by
                     // one thread execute in issue order, so no completion wait is needed here (UD_ATTN_BWD_SAFE=1 re-enables it)

@@ -148,6 +148,15 @@ UD_DEVINL void tmem_dealloc(uint32_t taddr) {  // whole warp
 UD_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 UD_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One elected lane of a fully converged warp.  The MMA-issuing warp runs its loop warp-uniformly and only the tcgen05
+// instructions are guarded by this predicate, so descriptor / address arithmetic stays on the uniform datapath (inside an
+// `if (lane == 0)` region every operand is a per-thread register and each tcgen05.mma costs ~15 instructions + R2UR moves).
+UD_DEVINL uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]   (kind::f16: bf16/fp16 inputs, fp32 accumulate)
 UD_DEVINL void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

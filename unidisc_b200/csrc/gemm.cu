@@ -570,7 +570,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== UMMA issuer (leader CTA only) =====================
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {
+            // warp-uniform issue loop (descriptor arithmetic on the uniform datapath); one elected lane executes tcgen05.*
+            const uint32_t leader = elect_one();
             constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
             int s = 0;
             uint32_t ph = 0;
@@ -587,18 +589,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
                     const uint32_t sb = sa + Cfg::A_BYTES;
+                    const uint32_t acc0 = kb != w.k0;
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * (UMMA_K * 128), 8192, 1024)
-                                                 : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
-                        const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), 8192, 1024)
-                                                 : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
-                        umma_ss_2sm(d_tmem, da, db, idesc, (kb != w.k0 || k != 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * (UMMA_K * 128), 8192, 1024)
+                                                     : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
+                            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), 8192, 1024)
+                                                     : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
+                            umma_ss_2sm(d_tmem, da, db, idesc, acc0 | (k != 0));
+                        }
+                        umma_commit_2sm_mc(&empty_bar[s], 0b11);   // frees the stage in BOTH CTAs
                     }
-                    umma_commit_2sm_mc(&empty_bar[s], 0b11);   // frees the stage in BOTH CTAs
+                    __syncwarp();
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                umma_commit_2sm_mc(&tmem_full[as], 0b11);       // accumulator complete -> both epilogues
+                if (leader) umma_commit_2sm_mc(&tmem_full[as], 0b11);       // accumulator complete -> both epilogues
+                __syncwarp();
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
