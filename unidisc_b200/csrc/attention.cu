@@ -330,15 +330,23 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            // warp-uniform issue loop, one elected lane executes the tcgen05 instructions (see elect_one).  Per key tile the
+            // tensor pipe sees  PV_A(j) S_A(j+1) PV_B(j) S_B(j+1): warpgroup A gets its next scores while B still does its
+            // softmax.  MMAs of one thread execute in issue order, so S_t(j+1) may overwrite the P_t(j) columns it aliases
+            // without waiting for PV_t(j) to complete.
+            const uint32_t leader = elect_one();
             constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
             auto issue_s = [&](int t, int j) {
                 const uint32_t aQ = smem_u32(sQ + t * S::TILE_BYTES), aK = smem_u32(sK + (j & 1) * S::TILE_BYTES);
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks)
-                    umma_ss(tmem + t * 128, desc_kmajor(aQ, ks), desc_kmajor(aK, ks), idesc_s, ks != 0);
-                umma_commit(&s_full[t]);
+                    for (int ks = 0; ks < HD / 16; ++ks)
+                        umma_ss(tmem + t * 128, desc_kmajor(aQ, ks), desc_kmajor(aK, ks), idesc_s, ks != 0);
+                    umma_commit(&s_full[t]);
+                }
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             mbar_wait(&k_full[0], 0);
@@ -349,22 +357,24 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 const int s = j & 1;
                 mbar_wait(&v_full[s], (j >> 1) & 1);
                 const uint32_t aV = smem_u32(sV + s * S::TILE_BYTES);
+                const uint32_t acc0 = j != 0;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     mbar_wait(&p_full[t], j & 1);
                     tc_fence_after();
+                    if (leader) {
 #pragma unroll
-                    for (int ks = 0; ks < ATT_BKV / 16; ++ks)
-                        umma_ts(tmem + 256 + t * HD, tmem + t * 128 + ks * 8, desc_mnmajor(aV, ks), idesc_pv, (j | ks) != 0);
-                    umma_commit(&pv_done[t]);
-                }
-                umma_commit(&kv_empty[s]);
-                if (j + 1 < T) {
-                    mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        mbar_wait(&pv_done[t], j & 1);      // P_t(j) (aliased on S_t) fully consumed
-                        tc_fence_after();
+                        for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                            umma_ts(tmem + 256 + t * HD, tmem + t * 128 + ks * 8, desc_mnmajor(aV, ks), idesc_pv, acc0 | (ks != 0));
+                        umma_commit(&pv_done[t]);
+                        if (t == 1) umma_commit(&kv_empty[s]);
+                    }
+                    __syncwarp();
+                    if (j + 1 < T) {
+                        if (t == 0) {
+                            mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                            tc_fence_after();
+                        }
                         issue_s(t, j + 1);
                     }
                 }
@@ -1248,26 +1258,42 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
         tc_fence_after();
         {
             // MODE0: warpgroup 0 stores dK (Acc0), warpgroup 1 stores dV (Acc1).  MODE1: each stores half of dQ's columns.
+            // TMEM gives every thread one ROW; the bf16 rows are staged in the (now idle) fixed-operand tiles with the
+            // 16-byte chunks XOR-swizzled by row, then copied out with whole rows per warp instruction (coalesced 128-byte
+            // lines instead of 32 scattered 16-byte stores per instruction).
             const int a = (MODE == 0) ? wg : 0;
             const uint32_t tA = a == 0 ? tAcc0 : tAcc1;
-            __nv_bfloat16* dst = (a == 0 ? p.out0 : p.out1) + ((long long)b * p.N + row) * (a == 0 ? p.ld0 : p.ld1) + h * HD;
+            uint8_t* stg = (MODE == 0 && wg == 1) ? sFB : sFA;
             const float sc = a == 0 ? p.scale : 1.0f;
+            constexpr int CPR = HD * 2 / 16;                         // 16-byte chunks per row
             const int c_lo = (MODE == 0) ? 0 : wg * (HD / 64), c_hi = (MODE == 0) ? HD / 32 : (wg + 1) * (HD / 64);
 #pragma unroll 1
             for (int c = c_lo; c < c_hi; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tA + c * 32 + lane_off, r);
                 tmem_ld_wait();
-                if (row_ok) {
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        uint4 o4;
-                        o4.x = pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) * sc, __uint_as_float(r[8 * q4 + 1]) * sc);
-                        o4.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * sc, __uint_as_float(r[8 * q4 + 3]) * sc);
-                        o4.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * sc, __uint_as_float(r[8 * q4 + 5]) * sc);
-                        o4.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * sc, __uint_as_float(r[8 * q4 + 7]) * sc);
-                        *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = o4;
-                    }
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 o4;
+                    o4.x = pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) * sc, __uint_as_float(r[8 * q4 + 1]) * sc);
+                    o4.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * sc, __uint_as_float(r[8 * q4 + 3]) * sc);
+                    o4.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * sc, __uint_as_float(r[8 * q4 + 5]) * sc);
+                    o4.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * sc, __uint_as_float(r[8 * q4 + 7]) * sc);
+                    const int ch = c * 4 + q4;
+                    *reinterpret_cast<uint4*>(stg + rloc * (HD * 2) + ((ch ^ (rloc & (CPR - 1))) << 4)) = o4;
+                }
+            }
+            named_bar_sync(1 + wg, 128);
+            const int chunks_w = (c_hi - c_lo) * 4, chunk0 = c_lo * 4;            // this warpgroup's 16-byte chunks per row
+            const long long ldo = a == 0 ? p.ld0 : p.ld1;
+            __nv_bfloat16* base = (a == 0 ? p.out0 : p.out1) + ((long long)b * p.N + t0) * ldo + h * HD;
+#pragma unroll 4
+            for (int it = 0; it < chunks_w; ++it) {
+                const int idx = it * 128 + tid128;
+                const int rr = idx / chunks_w, ch = chunk0 + idx % chunks_w;
+                if (t0 + rr < p.N) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * (HD * 2) + ((ch ^ (rr & (CPR - 1))) << 4));
+                    *reinterpret_cast<uint4*>(base + (long long)rr * ldo + ch * 8) = v;
                 }
             }
         }
