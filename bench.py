@@ -335,6 +335,7 @@ def main():
         last = None
         for _ in range(steps):
             last = step(e2e)
+        opt.join()                      # the streamed optimizer's last update belongs to the timed region
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -366,6 +367,7 @@ def main():
             evs[2].record()
             opt.step()
             opt.zero_grad()
+            opt.join()
             evs[3].record()
             torch.cuda.synchronize()
             if rank == 0:
@@ -392,6 +394,7 @@ def main():
             torch.cuda.synchronize()
             s0.record()
             step(False)
+            opt.join()
             s1.record()
             torch.cuda.synchronize()
             _o.call = counting_call

@@ -163,10 +163,11 @@ int ud_ddpm_update_logits(const int64_t* x, const void* logits_bf16, const void*
  * fused AdamW (torch.optim.AdamW semantics, model_setup.py:385-424) over a flat fp32 buffer, also emitting the bf16
  * shadow copy the GEMMs read.  grad_scale multiplies the gradient (clip coefficient); step is 1-based. */
 int ud_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, int step, const float* grad_scale /*device scalar or NULL*/, void* stream);
+                  float eps, float weight_decay, int step, const float* grad_scale /*device scalar or NULL*/,
+                  int max_ctas /* > 0 caps the grid (side-stream use next to GEMMs) */, void* stream);
 int ud_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 /* sum of squares of a flat fp32 buffer, accumulated into out[0] (out must be zeroed by the caller) */
-int ud_sumsq_f32(const float* g, long long n, float* out, void* stream);
+int ud_sumsq_f32(const float* g, long long n, float* out, int max_ctas, void* stream);
 /* DDP bf16 compress hook (torch default_hooks._compress_hook): dst = bf16(bf16(g) / world) ; and decompress.
  * max_ctas > 0 caps the grid so the side-stream copies leave the SMs to the backward GEMMs they overlap with. */
 int ud_grad_pack_bf16(const float* g, void* dst_bf16, long long n, float inv_world, int max_ctas, void* stream);

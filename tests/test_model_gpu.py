@@ -293,12 +293,15 @@ def test_sampler_end_to_end():
     assert x3.shape == (B, N)
 
 
-def test_fused_adamw_and_clip_vs_torch():
+@pytest.mark.parametrize("overlap", [True, False])
+def test_fused_adamw_and_clip_vs_torch(overlap):
+    """FusedAdamW (+ grad-norm clip) against torch.optim.AdamW + clip_grad_norm_, in the streamed mode (partial gradient
+    norms taken per bucket during backward, update enqueued on a side stream, forward waits per bucket) and the serial one."""
     from oracle import restated as R
     from unidisc_b200.config import make_config
     from unidisc_b200.ddp import FusedAdamW
     from unidisc_b200.model import Diffusion
-    cfg = make_config("small", hidden_size=128, n_blocks=1, n_heads=2, txt_length=64, img_length=64, image_vocab_size=63, text_vocab_size=97)
+    cfg = make_config("small", hidden_size=128, n_blocks=2, n_heads=2, txt_length=64, img_length=64, image_vocab_size=63, text_vocab_size=97)
     torch.manual_seed(0)
     model = Diffusion(cfg, device=dev())
     model.train()
@@ -306,19 +309,31 @@ def test_fused_adamw_and_clip_vs_torch():
     net._ensure_ready()
     ref_params = [torch.nn.Parameter(p.detach().clone()) for p in net.parameters()]
     ref_opt = torch.optim.AdamW(ref_params, lr=1e-3, weight_decay=0.05)
-    opt = FusedAdamW(net, lr=1e-3, weight_decay=0.05, max_grad_norm=1.0)
+    opt = FusedAdamW(net, lr=1e-3, weight_decay=0.05, max_grad_norm=1.0, overlap=overlap)
+    assert opt.overlap == overlap
     ids, modality = R.synthetic_batch(2, 64, 64, model.text_vocab_size, model.vocab_size, seed=1)
     batch = dict(input_ids=ids.to(dev()), modality=modality.to(dev()))
-    for it in range(2):
+    for it in range(3):
         torch.manual_seed(20 + it)
-        model.compute_loss(batch).loss.backward()
+        model.compute_loss(batch).loss.backward()          # the forward consumes the previous step's per-bucket events
         for rp, p in zip(ref_params, net.parameters()):
             rp.grad = p.grad.detach().clone()
-        torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+        ref_norm = torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
         ref_opt.step()
+        if overlap:
+            assert opt._buckets_seen == net.n_blocks + 2      # every bucket's partial norm was taken during backward
         opt.step()
         opt.zero_grad()
+        opt.join()
+        assert torch.allclose(opt.last_grad_norm, ref_norm, rtol=1e-4)
         for rp, p in zip(ref_params, net.parameters()):
             assert torch.allclose(p.detach(), rp.detach(), rtol=1e-4, atol=1e-6)
-        # refresh reference weights to ours to avoid drift in the next forward
     assert torch.equal(net.flat_params_bf16, net.flat_params.to(bf16))
+    # gradient accumulation (two backwards before the step): the per-bucket partial sums are stale, step() must notice
+    torch.manual_seed(40)
+    model.compute_loss(batch).loss.backward()
+    torch.manual_seed(41)
+    model.compute_loss(batch).loss.backward()
+    full = net.flat_grads.double().pow(2).sum().sqrt().float()
+    opt.step()
+    assert torch.allclose(opt.last_grad_norm, full, rtol=1e-4)

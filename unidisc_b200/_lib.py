@@ -39,9 +39,9 @@ _SIGS = {
     "ud_sample_categorical": [_vp, _ll, _vp, _u64, _u64, _vp, _i, _i, _vp],
     "ud_ddpm_update_probs": [_vp, _vp, _ll, _vp, _u64, _u64, _vp, _vp, _i64, _vp, _i, _i, _i, _vp],
     "ud_ddpm_update_logits": [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _i64, _i, _vp, _i, _i, _i, _vp],
-    "ud_adamw_step": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp, _vp],
+    "ud_adamw_step": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp, _i, _vp],
     "ud_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],
-    "ud_sumsq_f32": [_vp, _ll, _vp, _vp],
+    "ud_sumsq_f32": [_vp, _ll, _vp, _i, _vp],
     "ud_grad_pack_bf16": [_vp, _vp, _ll, _f, _i, _vp],
     "ud_grad_unpack_bf16": [_vp, _vp, _ll, _i, _vp],
 }

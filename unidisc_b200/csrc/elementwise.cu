@@ -983,7 +983,7 @@ static AdaLN to_adaln(const ud_adaln* t) {
     return a;
 }
 
-extern "C" int ud_abi_version(void) { return 4; }
+extern "C" int ud_abi_version(void) { return 5; }
 extern "C" int ud_device_sm_count(void) { return sm_count(); }
 
 extern "C" int ud_embed_rmsnorm_fwd(const int64_t* ids, const int64_t* modality, const float* E, const float* Emod,
@@ -1144,12 +1144,16 @@ extern "C" int ud_colsum_bf16(const void* dY, long long ld, float* db, int M, in
     return 0;
 }
 
+// max_ctas > 0 caps the grid: kernels that run on a side stream next to tensor-core GEMMs should take few SM slots / little
+// HBM bandwidth at a time
+static int capped(int grid, int max_ctas) { return (max_ctas > 0 && grid > max_ctas) ? max_ctas : grid; }
+
 extern "C" int ud_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
-                             float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream) {
+                             float beta2, float eps, float weight_decay, int step, const float* grad_scale, int max_ctas, void* stream) {
     if (n <= 0) return 0;
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
-    adamw_kernel<<<flat_grid(n), 256, 0, STREAM(stream)>>>(p, g, m, v, BF(p_bf16), n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale);
+    adamw_kernel<<<capped(flat_grid(n), max_ctas), 256, 0, STREAM(stream)>>>(p, g, m, v, BF(p_bf16), n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1161,15 +1165,12 @@ extern "C" int ud_cast_f32_to_bf16(const float* src, void* dst, long long n, voi
     return 0;
 }
 
-extern "C" int ud_sumsq_f32(const float* g, long long n, float* out, void* stream) {
+extern "C" int ud_sumsq_f32(const float* g, long long n, float* out, int max_ctas, void* stream) {
     if (n <= 0) return 0;
-    sumsq_kernel<<<flat_grid(n), 256, 0, STREAM(stream)>>>(g, n, out);
+    sumsq_kernel<<<capped(flat_grid(n), max_ctas), 256, 0, STREAM(stream)>>>(g, n, out);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
-
-// max_ctas > 0 caps the grid: the DDP side stream runs these next to the backward GEMMs and should take few SM slots
-static int capped(int grid, int max_ctas) { return (max_ctas > 0 && grid > max_ctas) ? max_ctas : grid; }
 
 extern "C" int ud_grad_pack_bf16(const float* g, void* dst, long long n, float inv_world, int max_ctas, void* stream) {
     if (n <= 0) return 0;

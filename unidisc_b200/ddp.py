@@ -83,6 +83,7 @@ class ThinDDP(nn.Module):
         self._comm_stream = None
         self._done_event = None
         module.grad_ready_hook = self._on_grads_ready
+        self.post_bucket_hook = None       # FusedAdamW: hook(block_idx, ranges, on_side_stream) once a bucket's gradients are final
         self.bytes_on_wire_per_step = 0
         self.debug_timing = bool(int(os.environ.get("UD_DDP_DEBUG", "0")))
         self._dbg_events = []
@@ -111,6 +112,8 @@ class ThinDDP(nn.Module):
 
     def _on_grads_ready(self, block_idx):
         if self.world == 1 or not self._sync:
+            if self._sync and self.post_bucket_hook is not None:
+                self.post_bucket_hook(block_idx, self._ranges_by_block.get(block_idx, []), False)
             return
         g = self.module.flat_grads
         cuda = g.is_cuda
@@ -143,6 +146,8 @@ class ThinDDP(nn.Module):
                     seg.div_(self.world)
                     dist.all_reduce(seg, group=self.pg)
                     self.bytes_on_wire_per_step += 4 * (hi - lo)
+            if self.post_bucket_hook is not None:
+                self.post_bucket_hook(block_idx, self._ranges_by_block.get(block_idx, []), True)
             if dbg:
                 c1.record(self._comm_stream)
                 self._dbg_events.append((block_idx, ev, c0, c1))
@@ -154,9 +159,20 @@ class ThinDDP(nn.Module):
 
 
 class FusedAdamW:
-    """AdamW over the DIT's flat fp32 buffers (torch.optim.AdamW semantics, single param group like the reference)."""
+    """AdamW over the DIT's flat fp32 buffers (torch.optim.AdamW semantics, single param group like the reference).
 
-    def __init__(self, module, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=None):
+    `overlap=True` (default on CUDA) streams the optimizer around the compute-bound GEMM phases instead of running it as
+    one exposed HBM-bound block between backward and forward:
+      * the gradient-norm partial sums of a bucket (DiT block / head / rest) are taken on a side stream as soon as the
+        backward (and, under ThinDDP, the all-reduce) has finalised that bucket, i.e. next to the remaining backward GEMMs;
+      * `step()` returns after ENQUEUEING the update on the side stream, bucket by bucket in forward order (embeddings,
+        block 0 ... block L-1, head); the next forward waits on one event per bucket right before it first reads that
+        bucket's weights, so AdamW of block i+1.. runs under the forward GEMMs of blocks ..i.
+    Arithmetic is unchanged (same kernels, same clip coefficient); only the schedule differs.  Anything that reads the
+    parameters outside DIT.forward must call `join()` (DIT.state_dict / flat_params do)."""
+
+    def __init__(self, module, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=None, overlap=None):
+        self.ddp = module if isinstance(module, ThinDDP) else None
         self.module = module.module if isinstance(module, ThinDDP) else module
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
@@ -166,26 +182,118 @@ class FusedAdamW:
         self.exp_avg_sq = torch.zeros_like(p)
         self._sumsq = torch.zeros(1, device=p.device)
         self._scale = torch.ones(1, device=p.device)
-        self.last_grad_norm = None
+        self._norm = None
+        if overlap is None:
+            overlap = p.is_cuda and not bool(int(os.environ.get("UD_OPT_SERIAL", "0")))
+        self.overlap = bool(overlap)
+        self._stream = torch.cuda.Stream() if self.overlap else None
+        # grid cap of the side-stream kernels that run next to tensor-core GEMMs (0 = uncapped): a bandwidth-saturating burst
+        # starves the GEMMs' TMA loads, a throttled stream hides under them (measured)
+        self.side_ctas = int(os.environ.get("UD_OPT_CTAS", 0))
+        self.eager_buckets = int(os.environ.get("UD_OPT_EAGER", 3))      # first buckets the forward needs at once: uncapped
+        self._last_event = None
+        self._buckets_seen = 0
+        self._stages = self._plan_stages() if self.overlap else None
+        if self.overlap and self.max_grad_norm is not None:
+            if self.ddp is not None:
+                self.ddp.post_bucket_hook = self._on_bucket_final
+            else:
+                by_block = {b: self._ranges_of(b) for b in range(-1, self.module.n_blocks + 1)}      # planned once (host cost)
+                self.module.grad_ready_hook = lambda b: self._on_bucket_final(b, by_block[b], False)
+
+    # ---- bucket plan: (name, [ranges]) in the order the forward first reads the weights ----
+    def _ranges_of(self, block_idx):
+        m = self.module
+        if 0 <= block_idx < m.n_blocks:
+            return list(m.block_grad_range(block_idx))
+        named = dict(m.named_parameters())
+        n = "output_layer.linear.weight"
+        head = (m._offs[n], m._offs[n] + (named[n].numel() + 63) // 64 * 64)
+        if block_idx == m.n_blocks:
+            return [head]
+        claimed = sorted([r for i in range(m.n_blocks) for r in m.block_grad_range(i)] + [head])
+        rest, cur = [], 0
+        for lo, hi in claimed:
+            if lo > cur:
+                rest.append((cur, lo))
+            cur = max(cur, hi)
+        if cur < m._flat_g.numel():
+            rest.append((cur, m._flat_g.numel()))
+        return rest
+
+    def _plan_stages(self):
+        m = self.module
+        return [("pre", self._ranges_of(-1))] + [(i, self._ranges_of(i)) for i in range(m.n_blocks)] + [("head", self._ranges_of(m.n_blocks))]
+
+    def _on_bucket_final(self, block_idx, ranges, on_side_stream):
+        """Partial sum of squares of a finalised gradient bucket (overlapped with the rest of the backward)."""
+        g = self.module._flat_g
+        if on_side_stream:                       # ThinDDP's comm stream, already ordered after the bucket's all-reduce
+            for lo, hi in ranges:
+                ops.sumsq(g[lo:hi], self._sumsq, self.side_ctas)
+        else:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                self._stream.wait_event(ev)
+                for lo, hi in ranges:
+                    ops.sumsq(g[lo:hi], self._sumsq, 0 if block_idx == -1 else self.side_ctas)
+        self._buckets_seen += 1
 
     def zero_grad(self, set_to_none: bool = True):
         self.module._force_fresh_grads = True     # next backward overwrites the GEMM grads and re-zeroes the rest
+
+    def join(self):
+        """Make the current stream wait for the enqueued parameter update."""
+        if self._last_event is not None:
+            torch.cuda.current_stream().wait_event(self._last_event)
+
+    @property
+    def last_grad_norm(self):
+        self.join()
+        return self._norm
+
+    def _clip_scale(self, g, partial_ok):
+        """Clip coefficient of torch clip_grad_norm_ from the total gradient norm (device scalar)."""
+        if not partial_ok:
+            self._sumsq.zero_()
+            ops.sumsq(g, self._sumsq)
+        self._norm = self._sumsq.sqrt()
+        torch.clamp(self.max_grad_norm / (self._norm + 1e-6), max=1.0, out=self._scale)
+        return self._scale
 
     @torch.no_grad()
     def step(self):
         m = self.module
         p, g = m._flat_p, m._flat_g              # (not the properties: they would refresh the bf16 shadow we are about to rewrite)
         self.step_count += 1
-        scale = None
-        if self.max_grad_norm is not None:
-            self._sumsq.zero_()
-            ops.sumsq(g, self._sumsq)
-            norm = self._sumsq.sqrt()
-            self.last_grad_norm = norm
-            torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0, out=self._scale)    # torch clip_grad_norm_ coefficient
-            scale = self._scale
-        ops.adamw_step(p, g, self.exp_avg, self.exp_avg_sq, m._flat_bf16, self.lr, self.betas[0], self.betas[1], self.eps,
-                       self.weight_decay, self.step_count, grad_scale=scale)
+        args = (self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count)
+        if not self.overlap:
+            scale = self._clip_scale(g, False) if self.max_grad_norm is not None else None
+            ops.adamw_step(p, g, self.exp_avg, self.exp_avg_sq, m._flat_bf16, *args, grad_scale=scale)
+            m.mark_weights_updated(shadow_is_current=True)
+            return
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)                            # backward (and the DDP tail, which the main stream already waited on) done
+        events = {}
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(ev)
+            scale = None
+            if self.max_grad_norm is not None:
+                # per-bucket partial sums are valid iff every bucket was finalised exactly once since the last step
+                scale = self._clip_scale(g, self._buckets_seen == len(self._stages))
+                self._sumsq.zero_()                # ready for the next backward's partial sums (ordered before every event below)
+            self._buckets_seen = 0
+            for k, (name, ranges) in enumerate(self._stages):
+                for lo, hi in ranges:
+                    ops.adamw_step(p[lo:hi], g[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], m._flat_bf16[lo:hi], *args,
+                                   grad_scale=scale, max_ctas=0 if k < self.eager_buckets else self.side_ctas)
+                e = torch.cuda.Event()
+                e.record(self._stream)
+                events[name] = e
+            self._last_event = events["head"]
+        m._param_events = events                   # DIT.forward waits per bucket; DIT.wait_param_events() for other readers
         m.mark_weights_updated(shadow_is_current=True)
 
     def state_dict(self):

@@ -226,7 +226,8 @@ class DIT(nn.Module):
         self._shadow_dirty = True
         self._anchor = None
         self.training_graph_enabled = True
-        self.grad_ready_hook = None                # thin-DDP: called as hook(lo, hi) when flat grads [lo,hi) are final
+        self.grad_ready_hook = None                # thin-DDP / optimizer: hook(block) when that bucket's flat grads are final
+        self._param_events = None                  # FusedAdamW(overlap): per-bucket "weights updated" events of the last step
         self._grads_attached = False
         if device is not None:
             self.to(device)
@@ -327,6 +328,23 @@ class DIT(nn.Module):
             ops.cast_bf16(self._flat_p, self._flat_bf16)
             self._shadow_dirty = False
 
+    def wait_param_events(self, which=None):
+        """Order the current stream after the streamed optimizer update (FusedAdamW overlap mode): bucket `which`
+        ("pre", block index, "head") or, with None, all of them (and forget them)."""
+        ev = self._param_events
+        if ev is None:
+            return
+        if which is None:
+            for e in ev.values():
+                torch.cuda.current_stream().wait_event(e)
+            self._param_events = None
+        else:
+            torch.cuda.current_stream().wait_event(ev[which])
+
+    def state_dict(self, *a, **k):
+        self.wait_param_events()
+        return super().state_dict(*a, **k)
+
     def mark_weights_updated(self, shadow_is_current: bool = False):
         """Call after the fp32 parameters changed (optimizer step / load_state_dict)."""
         self._shadow_dirty = not shadow_is_current
@@ -352,6 +370,7 @@ class DIT(nn.Module):
     @property
     def flat_params(self):
         self._ensure_ready()
+        self.wait_param_events()
         return self._flat_p
 
     @property
@@ -362,6 +381,7 @@ class DIT(nn.Module):
     @property
     def flat_params_bf16(self):
         self._ensure_ready()
+        self.wait_param_events()
         return self._flat_bf16
 
     def block_grad_range(self, i):
@@ -492,6 +512,10 @@ class DIT(nn.Module):
             cos, sin = rope.token_tables(modality, self.rotary_cos_emb_txt, self.rotary_sin_emb_txt, self.rotary_cos_emb_img,
                                          self.rotary_sin_emb_img, self.img_length)
         scale = 1.0 / math.sqrt(hd)
+        self.wait_param_events("pre")
+        self.wait_param_events(0)              # block 0's norm1 weight is applied by the embedding kernel
+        if self.time_conditioning:
+            self.wait_param_events()           # the conditioning network reads every block's adaLN weights up front
         C = self._cond_forward(sigma, mod, B, N) if self.time_conditioning else None
         x, h, rstd0 = ops.embed_rmsnorm_fwd(ids, mod, T["E"], T["Emod"], self._blk[0]["n1"], ordinal=ordinal,
                                             Ecount=T.get("Ecount"), tc=self._tc(C, norm_block=0))
@@ -503,6 +527,8 @@ class DIT(nn.Module):
                      drop_base=drop_base, ordinal=ordinal, C=C) if save else None
         for i, W in enumerate(self._blk):
             w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
+            if i + 1 < self.n_blocks:
+                self.wait_param_events(i + 1)  # this block's last kernel applies the next block's norm1 weight
             qkv = ops.gemm(h, W["wqkv"])
             qk, stats = ops.qk_ln_rope_fwd(qkv, W["gq"], W["bq"], W["gk"], W["bk"], cos, sin, hd)
             o, lse = ops.attn_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, N, H, hd, scale, sample_ids=sid)
@@ -517,6 +543,7 @@ class DIT(nn.Module):
                                             u=u, g=gl, d=d, rd=rd, x2=x2, rx2=rx2))
             x, h = x2, h_next
         buf = torch.empty((M, self.Vp), device=x.device, dtype=bf16)
+        self.wait_param_events()               # head (last bucket) => everything; the events are dropped
         ops.gemm(h, T["wh"], N=V, out=buf[:, :V], bias=T["bh"])
         if save:
             saved["hf"] = h

@@ -221,9 +221,9 @@ def ddpm_update_logits(x, logits2d, modality, mc_t, mc_s, mask_index, text_vocab
     return out
 
 
-def adamw_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None):
+def adamw_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None, max_ctas=0):
     call("ud_adamw_step", P(p), P(g), P(m), P(v), P(p_bf16), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
-         P(grad_scale), stream())
+         P(grad_scale), max_ctas, stream())
 
 
 def cast_bf16(src, dst):
@@ -231,8 +231,8 @@ def cast_bf16(src, dst):
     return dst
 
 
-def sumsq(g, out):
-    call("ud_sumsq_f32", P(g), g.numel(), P(out), stream())
+def sumsq(g, out, max_ctas=0):
+    call("ud_sumsq_f32", P(g), g.numel(), P(out), max_ctas, stream())
     return out
 
 
