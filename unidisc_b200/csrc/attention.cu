@@ -1049,9 +1049,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
     uint64_t* f_full = bars;                 // 1
     uint64_t* st_full = bars + 1;            // NST
     uint64_t* st_empty = bars + 1 + NST;     // NST
-    uint64_t* sc_full = bars + 1 + 2 * NST;  // 2
-    uint64_t* pr_full = sc_full + 2;         // 2
-    uint64_t* acc_done = pr_full + 2;        // 2
+    uint64_t* s_full = bars + 1 + 2 * NST;   // 2   S^T of a sub-tile in TMEM      (tensor pipe -> softmax warpgroup)
+    uint64_t* dp_full = s_full + 2;          // 2   dP^T of the same sub-tile
+    uint64_t* p_rdy = dp_full + 2;           // 2   bf16 P^T written over S^T        (softmax warpgroup -> tensor pipe)
+    uint64_t* ds_rdy = p_rdy + 2;            // 2   bf16 dS^T written over dP^T
+    uint64_t* acc_done = ds_rdy + 2;         // 2
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_done + 2);
     __shared__ __align__(16) float s_lse[4 * 64];   // per-column metadata of the streamed sub-tile: [warpgroup][2 slots][64]
     __shared__ __align__(16) float s_dlt[4 * 64];   // (two alternating slots per warpgroup: a fast thread may already publish
@@ -1065,7 +1067,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
         tma_prefetch_desc(&tm_fa); tma_prefetch_desc(&tm_fb); tma_prefetch_desc(&tm_sa); tma_prefetch_desc(&tm_sb);
         mbar_init(f_full, 1);
         for (int s = 0; s < NST; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&sc_full[s], 1); mbar_init(&pr_full[s], 128); mbar_init(&acc_done[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1); mbar_init(&dp_full[s], 1); mbar_init(&p_rdy[s], 128); mbar_init(&ds_rdy[s], 128);
+            mbar_init(&acc_done[s], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
@@ -1110,11 +1115,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
                 const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
                 if (leader) {
+                    // S^T and dP^T are signalled separately: the warpgroup starts its exponentials while dP^T is still being
+                    // multiplied
 #pragma unroll
                     for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tSc, desc_kmajor(aFA, ks), desc_kmajor64(aSA, ks), idesc_sc, ks != 0);
+                    umma_commit(&s_full[bf]);
 #pragma unroll
                     for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tDp, desc_kmajor(aFB, ks), desc_kmajor64(aSB, ks), idesc_sc, ks != 0);
-                    umma_commit(&sc_full[bf]);
+                    umma_commit(&dp_full[bf]);
                 }
                 __syncwarp();
             };
@@ -1124,21 +1132,24 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             for (int i = 0; i < T2; ++i) {
                 const int s = i % NST, bf = i & 1;
                 const uint32_t ph = (i >> 1) & 1;
-                mbar_wait(&pr_full[bf], ph);
-                tc_fence_after();
                 const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
                 const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
                 const uint32_t acc0 = i != 0;
-                if (leader) {
-                    if (MODE == 0) {
+                if (MODE == 0) {
+                    // dV += P^T dO as soon as P^T is stored: it runs while the warpgroup still forms dS^T
+                    mbar_wait(&p_rdy[bf], ph);
+                    tc_fence_after();
+                    if (leader) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc1, tSc + ks * 8, desc_mnmajor64(aSB, ks), idesc_acc, acc0 | (ks != 0));
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, acc0 | (ks != 0));
-                    } else {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, acc0 | (ks != 0));
                     }
+                    __syncwarp();
+                }
+                mbar_wait(&ds_rdy[bf], ph);
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, acc0 | (ks != 0));
                     umma_commit(&st_empty[s]);
                     umma_commit(&acc_done[bf]);
                 }
@@ -1195,32 +1206,28 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 named_bar_sync(1 + wg, 128);
                 fetch_meta(i + 2);
             }
-            mbar_wait(&sc_full[bf], (i >> 1) & 1);
+            mbar_wait(&s_full[bf], (i >> 1) & 1);
             tc_fence_after();
             const bool slow = use_ids || (i * 64 + 64 > Ntok) || !row_ok;   // masks needed only on edge tiles / document masks
-            uint32_t rsA[32], rsB[32], rdA[32], rdB[32];
+            uint32_t rsA[32], rsB[32], pk[32];
             tmem_ld_32x32b_x32(tSc + lane_off, rsA);
-            tmem_ld_32x32b_x32(tDp + lane_off, rdA);
             tmem_ld_32x32b_x32(tSc + 32 + lane_off, rsB);
-            tmem_ld_32x32b_x32(tDp + 32 + lane_off, rdB);
-            tmem_ld_wait();                                   // one exposed TMEM latency per sub-tile
-            // P / dS are packed in place into rsA / rdA (chunk 0 -> entries 0..15, chunk 1 -> 16..31).  Interior tiles take the
-            // mask-free instantiation (no per-element compare / select instructions).
-            auto chunk = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c, auto slow_tag) {
+            tmem_ld_wait();
+            // phase 1: P = exp(S * scale - lse), kept in fp32 in rsA / rsB (in place) and packed to bf16 in pk.  Interior tiles
+            // take the mask-free instantiation (no per-element compare / select instructions).
+            auto phase1 = [&](uint32_t (&rs)[32], int c, auto slow_tag) {
                 constexpr bool SLOW = decltype(slow_tag)::value;
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
-                    float l4[4], d4[4];
+                    float l4[4];
                     if (MODE == 0) {
                         const float4 lv = *reinterpret_cast<const float4*>(&s_lse[ms + c * 32 + e4 * 4]);
-                        const float4 dv = *reinterpret_cast<const float4*>(&s_dlt[ms + c * 32 + e4 * 4]);
                         l4[0] = lv.x; l4[1] = lv.y; l4[2] = lv.z; l4[3] = lv.w;
-                        d4[0] = dv.x; d4[1] = dv.y; d4[2] = dv.z; d4[3] = dv.w;
                     } else {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { l4[u] = lse_row; d4[u] = dlt_row; }
+                        for (int u = 0; u < 4; ++u) l4[u] = lse_row;
                     }
-                    float pv[4], dvv[4];
+                    float pv[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         float pr = ex2(fmaf(__uint_as_float(rs[e4 * 4 + u]), scl, -l4[u]));
@@ -1234,24 +1241,59 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                             if (!ok) pr = 0.f;
                         }
                         pv[u] = pr;
-                        dvv[u] = pr * (__uint_as_float(rd[e4 * 4 + u]) - d4[u]);
+                        rs[e4 * 4 + u] = __float_as_uint(pr);
                     }
-                    rsA[c * 16 + e4 * 2] = pack_bf16x2(pv[0], pv[1]); rsA[c * 16 + e4 * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
-                    rdA[c * 16 + e4 * 2] = pack_bf16x2(dvv[0], dvv[1]); rdA[c * 16 + e4 * 2 + 1] = pack_bf16x2(dvv[2], dvv[3]);
+                    if (MODE == 0) {
+                        pk[c * 16 + e4 * 2] = pack_bf16x2(pv[0], pv[1]);
+                        pk[c * 16 + e4 * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+                    }
                 }
             };
             if (slow) {
-                chunk(rsA, rdA, 0, std::true_type{});
-                chunk(rsB, rdB, 1, std::true_type{});
+                phase1(rsA, 0, std::true_type{});
+                phase1(rsB, 1, std::true_type{});
             } else {
-                chunk(rsA, rdA, 0, std::false_type{});
-                chunk(rsB, rdB, 1, std::false_type{});
+                phase1(rsA, 0, std::false_type{});
+                phase1(rsB, 1, std::false_type{});
             }
-            if (MODE == 0) tmem_st_32x32b_x32(tSc + lane_off, rsA);
-            tmem_st_32x32b_x32(tDp + lane_off, rdA);
+            if (MODE == 0) {
+                tmem_st_32x32b_x32(tSc + lane_off, pk);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&p_rdy[bf]);
+            }
+            // phase 2: dS = P * (dP - delta)
+            mbar_wait(&dp_full[bf], (i >> 1) & 1);
+            tc_fence_after();
+            uint32_t rdA[32], rdB[32];
+            tmem_ld_32x32b_x32(tDp + lane_off, rdA);
+            tmem_ld_32x32b_x32(tDp + 32 + lane_off, rdB);
+            tmem_ld_wait();
+            auto phase2 = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c) {
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    float d4[4];
+                    if (MODE == 0) {
+                        const float4 dv = *reinterpret_cast<const float4*>(&s_dlt[ms + c * 32 + e4 * 4]);
+                        d4[0] = dv.x; d4[1] = dv.y; d4[2] = dv.z; d4[3] = dv.w;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) d4[u] = dlt_row;
+                    }
+                    float dvv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        dvv[u] = __uint_as_float(rs[e4 * 4 + u]) * (__uint_as_float(rd[e4 * 4 + u]) - d4[u]);
+                    pk[c * 16 + e4 * 2] = pack_bf16x2(dvv[0], dvv[1]);
+                    pk[c * 16 + e4 * 2 + 1] = pack_bf16x2(dvv[2], dvv[3]);
+                }
+            };
+            phase2(rsA, rdA, 0);
+            phase2(rsB, rdB, 1);
+            tmem_st_32x32b_x32(tDp + lane_off, pk);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&pr_full[bf]);
+            mbar_arrive(&ds_rdy[bf]);
         }
         // ---- write the accumulators (the two warpgroups split the work) ----
         mbar_wait(&acc_done[(T2 - 1) & 1], ((T2 - 1) >> 1) & 1);
