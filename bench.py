@@ -438,6 +438,14 @@ def main():
     gemm_ms = g0.elapsed_time(g1) / iters
     gemm_tflops = 2.0 * M * D * 4 * D / (gemm_ms * 1e-3) / 1e12
     del sets
+    # DRAM traffic of that kernel (dram__bytes_read + dram__bytes_write of one launch) from the committed `ncu --set full` capture
+    gemm_traffic, gemm_traffic_src = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_roofline_ncu.json")))
+        if (M, 4 * D, D) == (10240, 8192, 2048):
+            gemm_traffic, gemm_traffic_src = cap["traffic_bytes"], "profiles/r01_gemm_roofline_ncu.json (ncu --set full, one launch)"
+    except Exception:  # noqa: BLE001
+        pass
 
     # ---- secondary: the HBM-bound fused absorbing sampler (BASELINE.json configs[3]: B=64, N=1280, all rows masked) ----
     sampler_info = None
@@ -493,7 +501,8 @@ def main():
             clocks=clocks,
             roofline=dict(bound="tensor", kernel=f"gemm_kernel<K-major,K-major> M={M} N={4*D} K={D} (MLP up-projection)",
                           achieved=gemm_tflops, peak=pk["bf16_tflops"], unit="TFLOP/s", frac=gemm_tflops / pk["bf16_tflops"],
-                          peak_source=pk["source"] + " (burst: kernel timed alone)", traffic=None, ms_per_launch=gemm_ms),
+                          peak_source=pk["source"] + " (burst: kernel timed alone)", traffic=gemm_traffic, traffic_source=gemm_traffic_src,
+                          algorithmic_bytes=2 * (M * D + 4 * D * D + M * 4 * D), ms_per_launch=gemm_ms),
             step_model_tflops_per_gpu=model_tflops_per_gpu,
             step_frac_of_sustained_peak=model_tflops_per_gpu / pk["bf16_tflops_sustained"],
             flops_per_token_fwd_bwd=fpt,

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel time share of ONE training step
-(the launches between the last two `adamw_kernel` launches).  Usage: python tools/ncu_summary.py launches.csv [out.md]"""
+(the launches between the last two `q_xt_kernel` launches).  Usage: python tools/ncu_summary.py launches.csv [out.md]"""
 import csv
 import re
 import sys
@@ -26,9 +26,12 @@ def main():
         unit = r.get("Metric Unit", "ns")
         scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1e-3)
         rows.append((int(r["ID"]), r["Kernel Name"], v * scale))
-    idx = [i for i, (_, n, _) in enumerate(rows) if "adamw_kernel" in n]
+    # one step = from a q_xt launch (first kernel of compute_loss) up to the next one; the streamed optimizer's kernels of
+    # that step sit between its backward and the next q_xt.  bench.py --steps 1 --warmup 3 launches q_xt 5 times
+    # (3 warm-up, 1 device-timed, 1 end-to-end-timed): the device-timed step is the segment between the last two.
+    idx = [i for i, (_, n, _) in enumerate(rows) if "q_xt_kernel" in n]
     if len(idx) >= 2:
-        seg = rows[idx[-2] + 1: idx[-1] + 1]
+        seg = rows[idx[-2]: idx[-1]]
     else:
         seg = rows
     agg, cnt = defaultdict(float), defaultdict(int)
