@@ -167,7 +167,7 @@ def run_reference_gpu_arm(args, rank, world, local):
         net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     fwd = net
     if args.ref_compile:
-        fwd = torch.compile(net, mode="max-autotune-no-cudagraphs")                   # reference config.yaml:227
+        fwd = torch.compile(net, mode=args.ref_compile_mode)                            # reference config.yaml:227 uses max-autotune-no-cudagraphs
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, fused=True)
     g = torch.Generator().manual_seed(42 + rank)
     ids_h = torch.cat([torch.randint(0, tv - 1, (B, txt), generator=g), torch.randint(tv, V, (B, img), generator=g)], 1).pin_memory()
@@ -209,7 +209,7 @@ def run_reference_gpu_arm(args, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         v = world * B * N / (ms.item() / args.steps * 1e-3)
-        kind = "torch eager" + (" + torch.compile(max-autotune-no-cudagraphs)" if args.ref_compile else "")
+        kind = "torch eager" + (f" + torch.compile({args.ref_compile_mode})" if args.ref_compile else "")
         print(json.dumps(dict(
             impl="reference", device="cuda", metric="joint_token_tokens_per_sec", value=v, unit="tokens/s", n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms.item() / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
@@ -252,6 +252,7 @@ def main():
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="reference arm: host cores (driver contract) or the "
                     "torch-eager restatement on the GPU (the >=1.5x target's denominator)")
     ap.add_argument("--ref-compile", action="store_true", help="with --ref-device cuda: torch.compile the backbone like the reference")
+    ap.add_argument("--ref-compile-mode", default="max-autotune-no-cudagraphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1, help="model.dropout (reference configs/model/extra_large.yaml:9 = 0.1)")
     args = ap.parse_args()
