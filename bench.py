@@ -409,6 +409,20 @@ def main():
             print(f"[kernel times] step {s0.elapsed_time(s1):.2f} ms, sum of C-ABI launches {tot:.2f} ms ({len(recs)} launches)", file=sys.stderr)
             for tag, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 print(f"[kernel times] {tag:48s} n={c:4d} total {t:8.3f} ms  avg {t / c * 1e3:8.1f} us", file=sys.stderr)
+    # debug (UD_OPT_DEBUG=1): when each bucket's AdamW finished vs when the next forward reached the block that needs it
+    if getattr(opt, "debug_timing", False) and opt.overlap and rank == 0:
+        step(False)                                    # step A: its opt.step() records the bucket events ...
+        t0, evA = opt._dbg_step_start, dict(opt._dbg_events)
+        net._dbg_fwd_events = []
+        step(False)                                    # ... that step B's forward waits on
+        fwd_ev, net._dbg_fwd_events = net._dbg_fwd_events, None
+        opt.join()
+        torch.cuda.synchronize()
+        print("[opt timeline] ms after backward end: bucket AdamW done | forward block start", file=sys.stderr)
+        names = ["pre"] + list(range(net.n_blocks)) + ["head"]
+        for k, nme in enumerate(names):
+            f_ms = t0.elapsed_time(fwd_ev[nme]) if isinstance(nme, int) and nme < len(fwd_ev) else float("nan")
+            print(f"[opt timeline] {str(nme):>5s}  adamw_done {t0.elapsed_time(evA[nme]):8.2f}   fwd_block_start {f_ms:8.2f}", file=sys.stderr)
     if ddp is not None and ddp.debug_timing:
         ddp._dbg_events = []
         step(False)

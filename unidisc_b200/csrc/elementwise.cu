@@ -614,6 +614,8 @@ __global__ void qk_ln_rope_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, con
 
 struct QkRawB { uint2 q, k, dq, dk; float4 cs, sn, st; };
 
+// (measured: an R=1 variant held to 64 registers for two CTAs per SM is slower, 127 us vs 106 us — the block-wide reduction
+// per row dominates; R=2 halves the number of reductions)
 template <int R>
 __global__ void qk_ln_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dqk, const __nv_bfloat16* __restrict__ qkv,
                                       const float* __restrict__ stats, const float* __restrict__ gq,
@@ -824,34 +826,48 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              __nv_bfloat16* __restrict__ pb, long long n, float lr, float b1, float b2, float eps, float wd,
                              float bc1, float bc2_sqrt, const float* __restrict__ grad_scale) {
     const float gs = grad_scale ? *grad_scale : 1.0f;
-    const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-        if (i + 4 <= n) {
-            float4 pv = *reinterpret_cast<float4*>(p + i), gv = *reinterpret_cast<const float4*>(g + i);
-            float4 mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
-            float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+    // U independent 16-byte load groups (p, g, m, v) per thread per iteration: when the grid is capped to a couple of CTAs
+    // per SM (side-stream use next to the forward GEMMs) the memory-level parallelism has to come from each thread
+    constexpr int U = 2;
+    const long long tile = (long long)blockDim.x * 4 * U;
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        gg *= gs;
+        pp *= (1.0f - lr * wd);
+        mm = b1 * mm + (1.0f - b1) * gg;
+        vv = b2 * vv + (1.0f - b2) * gg * gg;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        pp -= (lr / bc1) * (mm / denom);
+    };
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        float4 pv[U], gv[U], mv[U], vv[U];
+        long long idx[U];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float gg = gp[k] * gs;
-                pp[k] *= (1.0f - lr * wd);
-                mp[k] = b1 * mp[k] + (1.0f - b1) * gg;
-                vp[k] = b2 * vp[k] + (1.0f - b2) * gg * gg;
-                const float denom = sqrtf(vp[k]) / bc2_sqrt + eps;
-                pp[k] -= (lr / bc1) * (mp[k] / denom);
+        for (int u = 0; u < U; ++u) {
+            idx[u] = base + ((long long)u * blockDim.x + threadIdx.x) * 4;
+            if (idx[u] + 4 <= n) {
+                pv[u] = *reinterpret_cast<const float4*>(p + idx[u]);
+                { const uint4 t = ldg_stream(g + idx[u]); gv[u] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)); }
+                mv[u] = *reinterpret_cast<const float4*>(m + idx[u]);
+                vv[u] = *reinterpret_cast<const float4*>(v + idx[u]);
             }
-            *reinterpret_cast<float4*>(p + i) = pv;
-            *reinterpret_cast<float4*>(m + i) = mv;
-            *reinterpret_cast<float4*>(v + i) = vv;
-            if (pb) *reinterpret_cast<uint2*>(pb + i) = make_uint2(pack_bf16x2(pv.x, pv.y), pack_bf16x2(pv.z, pv.w));
-        } else {
-            for (long long k = i; k < n; ++k) {
-                const float gg = g[k] * gs;
-                float pv = p[k] * (1.0f - lr * wd);
-                const float mm = b1 * m[k] + (1.0f - b1) * gg;
-                const float vv = b2 * v[k] + (1.0f - b2) * gg * gg;
-                pv -= (lr / bc1) * (mm / (sqrtf(vv) / bc2_sqrt + eps));
-                p[k] = pv; m[k] = mm; v[k] = vv;
-                if (pb) pb[k] = __float2bfloat16_rn(pv);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = idx[u];
+            if (i + 4 <= n) {
+                upd(pv[u].x, gv[u].x, mv[u].x, vv[u].x); upd(pv[u].y, gv[u].y, mv[u].y, vv[u].y);
+                upd(pv[u].z, gv[u].z, mv[u].z, vv[u].z); upd(pv[u].w, gv[u].w, mv[u].w, vv[u].w);
+                *reinterpret_cast<float4*>(p + i) = pv[u];
+                *reinterpret_cast<float4*>(m + i) = mv[u];
+                *reinterpret_cast<float4*>(v + i) = vv[u];
+                if (pb) *reinterpret_cast<uint2*>(pb + i) = make_uint2(pack_bf16x2(pv[u].x, pv[u].y), pack_bf16x2(pv[u].z, pv[u].w));
+            } else {
+                for (long long k = i; k < n; ++k) {
+                    float pk = p[k], mk = m[k], vk = v[k];
+                    upd(pk, g[k], mk, vk);
+                    p[k] = pk; m[k] = mk; v[k] = vk;
+                    if (pb) pb[k] = __float2bfloat16_rn(pk);
+                }
             }
         }
     }
@@ -873,13 +889,21 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
     __shared__ float scratch[2 * 32];
     int buf = 0;
     float a[1] = {0.f};
-    const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-        if (i + 4 <= n) {
-            float4 v = *reinterpret_cast<const float4*>(g + i);
-            a[0] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        } else {
-            for (long long k = i; k < n; ++k) a[0] += g[k] * g[k];
+    constexpr int U = 4;                                                     // independent 16-byte loads per thread per iteration
+    const long long tile = (long long)blockDim.x * 4 * U;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        float4 v[U];
+        long long idx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            idx[u] = base + ((long long)u * blockDim.x + threadIdx.x) * 4;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx[u] + 4 <= n) v[u] = *reinterpret_cast<const float4*>(g + idx[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (idx[u] + 4 <= n) a[0] += v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+            else for (long long k = idx[u]; k < n; ++k) a[0] += g[k] * g[k];
         }
     }
     block_sum<1>(a, scratch, buf);

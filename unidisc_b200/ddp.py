@@ -190,7 +190,9 @@ class FusedAdamW:
         # grid cap of the side-stream kernels that run next to tensor-core GEMMs (0 = uncapped): a bandwidth-saturating burst
         # starves the GEMMs' TMA loads, a throttled stream hides under them (measured)
         self.side_ctas = int(os.environ.get("UD_OPT_CTAS", 0))
+        self.sumsq_ctas = int(os.environ.get("UD_OPT_SUMSQ_CTAS", 0))
         self.eager_buckets = int(os.environ.get("UD_OPT_EAGER", 3))      # first buckets the forward needs at once: uncapped
+        self.debug_timing = bool(int(os.environ.get("UD_OPT_DEBUG", "0")))   # timing-enabled bucket events (bench timeline)
         self._last_event = None
         self._buckets_seen = 0
         self._stages = self._plan_stages() if self.overlap else None
@@ -230,14 +232,14 @@ class FusedAdamW:
         g = self.module._flat_g
         if on_side_stream:                       # ThinDDP's comm stream, already ordered after the bucket's all-reduce
             for lo, hi in ranges:
-                ops.sumsq(g[lo:hi], self._sumsq, self.side_ctas)
+                ops.sumsq(g[lo:hi], self._sumsq, self.sumsq_ctas)
         else:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
                 self._stream.wait_event(ev)
                 for lo, hi in ranges:
-                    ops.sumsq(g[lo:hi], self._sumsq, 0 if block_idx == -1 else self.side_ctas)
+                    ops.sumsq(g[lo:hi], self._sumsq, 0 if block_idx == -1 else self.sumsq_ctas)
         self._buckets_seen += 1
 
     def zero_grad(self, set_to_none: bool = True):
@@ -274,8 +276,9 @@ class FusedAdamW:
             m.mark_weights_updated(shadow_is_current=True)
             return
         main = torch.cuda.current_stream()
-        ev = torch.cuda.Event()
+        ev = torch.cuda.Event(enable_timing=self.debug_timing)
         ev.record(main)                            # backward (and the DDP tail, which the main stream already waited on) done
+        self._dbg_step_start = ev
         events = {}
         with torch.cuda.stream(self._stream):
             self._stream.wait_event(ev)
@@ -289,11 +292,12 @@ class FusedAdamW:
                 for lo, hi in ranges:
                     ops.adamw_step(p[lo:hi], g[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], m._flat_bf16[lo:hi], *args,
                                    grad_scale=scale, max_ctas=0 if k < self.eager_buckets else self.side_ctas)
-                e = torch.cuda.Event()
+                e = torch.cuda.Event(enable_timing=self.debug_timing)
                 e.record(self._stream)
                 events[name] = e
             self._last_event = events["head"]
-        m._param_events = events                   # DIT.forward waits per bucket; DIT.wait_param_events() for other readers
+        self._dbg_events = events
+        m._param_events = dict(events)             # DIT.forward waits per bucket; DIT.wait_param_events() for other readers
         m.mark_weights_updated(shadow_is_current=True)
 
     def state_dict(self):

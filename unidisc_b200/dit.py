@@ -228,6 +228,7 @@ class DIT(nn.Module):
         self.training_graph_enabled = True
         self.grad_ready_hook = None                # thin-DDP / optimizer: hook(block) when that bucket's flat grads are final
         self._param_events = None                  # FusedAdamW(overlap): per-bucket "weights updated" events of the last step
+        self._dbg_fwd_events = None                # debug: list collecting a timing event at the start of every block's forward
         self._grads_attached = False
         if device is not None:
             self.to(device)
@@ -529,6 +530,10 @@ class DIT(nn.Module):
             w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
             if i + 1 < self.n_blocks:
                 self.wait_param_events(i + 1)  # this block's last kernel applies the next block's norm1 weight
+            if self._dbg_fwd_events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                self._dbg_fwd_events.append(e)
             qkv = ops.gemm(h, W["wqkv"])
             qk, stats = ops.qk_ln_rope_fwd(qkv, W["gq"], W["bq"], W["gk"], W["bk"], cos, sin, hd)
             o, lse = ops.attn_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, N, H, hd, scale, sample_ids=sid)
