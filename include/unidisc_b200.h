@@ -26,7 +26,8 @@ enum {
     UD_EPI_BF16 = 0,       /* C bf16 = acc (+ bias)                                     nn.Linear, dit.py:642,887,919,1091 */
     UD_EPI_BF16_GELU = 1,  /* C bf16 = u = acc + bias ; aux bf16 = gelu_tanh(u)         mlp.0 + nn.GELU("tanh"), dit.py:917-919 */
     UD_EPI_BF16_DGELU = 2, /* C bf16 = acc * gelu_tanh'(aux)  (aux = saved u)           autograd of the above */
-    UD_EPI_F32 = 3,        /* C fp32 = acc                                              weight gradient */
+    UD_EPI_F32 = 3,        /* C fp32 = acc ; aux (optional) = fp32 device scalar += sum C^2   weight gradient (+ its share of the
+                              gradient norm of clip_grad_norm_, model.py:1518; needs M > 128) */
     UD_EPI_F32_ACC = 4     /* C fp32 += acc                                             weight gradient accumulation (.grad +=) */
 };
 /* C[M,N] = sum_k A(m,k) B(n,k).  ta=0: A is [M,K] (lda);  ta=1: A is [K,M] (lda).  tb=0: B is [N,K];  tb=1: B is [K,N].

@@ -91,6 +91,23 @@ def test_gemm_wgrad_layout(ops, M, N, K):
     assert torch.allclose(out, 2 * ref, rtol=1e-3, atol=2e-3 * math.sqrt(K))
 
 
+@pytest.mark.parametrize("M,N,K", [(200, 328, 520), (1000, 520, 2500), (2048, 2048, 10240), (6144, 2048, 10240)])
+def test_gemm_wgrad_fused_sum_of_squares(ops, M, N, K):
+    """UD_EPI_F32 with aux = fp32 device scalar: the epilogue adds sum(C^2) of what it stores (gradient-norm fusion), on ragged
+    edges (zero-filled rows / columns contribute nothing) and on stream-K split tiles; the accumulate epilogue rejects it."""
+    from unidisc_b200._lib import EPI_F32, EPI_F32_ACC, UnidiscB200Error
+    dy, x = rnd(K, M, seed=5, scale=0.1, dtype=bf16), rnd(K, N, seed=6, scale=0.1, dtype=bf16)
+    acc = torch.full((1,), 3.0, device=dev())
+    out = torch.empty((M, (N + 3) // 4 * 4), device=dev(), dtype=torch.float32)[:, :N]
+    ops.gemm(dy, x, ta=True, tb=True, epi=EPI_F32, out=out, aux=acc)
+    ops.gemm(dy, x, ta=True, tb=True, epi=EPI_F32, out=out, aux=acc)
+    torch.cuda.synchronize()
+    want = 3.0 + 2 * out.double().pow(2).sum().item()
+    assert abs(acc.item() - want) <= 1e-4 * want, (acc.item(), want)
+    with pytest.raises(UnidiscB200Error):
+        ops.gemm(dy, x, ta=True, tb=True, epi=EPI_F32_ACC, out=out, aux=acc)
+
+
 @pytest.mark.parametrize("case", ["fwd_n2048", "dgrad_n2048", "wgrad_64tiles", "wgrad_192tiles", "gelu_tail", "ragged"])
 def test_gemm_streamk_tail(ops, case):
     """Shapes whose last wave of 256x256 tiles is partial: the tail tiles' k-blocks are shared between all clusters

@@ -622,6 +622,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         e.N = p.N; e.ldc = p.ldc; e.ld_aux = p.ld_aux; e.C = reinterpret_cast<char*>(p.C); e.aux = reinterpret_cast<char*>(p.aux);
         e.bias = p.bias;
         const bool has_bias = (EPI != UD_EPI_F32 && EPI != UD_EPI_F32_ACC) && e.bias != nullptr;
+        float ssq = 0.f;                       // UD_EPI_F32 + aux: sum of squares of everything this thread stores (gradient norm)
         WorkIter it(p, cluster_id, num_clusters, num_kb);
         WorkItem w;
         while (it.next(w)) {
@@ -730,6 +731,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                             tmem_ld_32x32b_x32(tacc + cc * 32, r);
                             tmem_ld_wait();
                             add_partials(r, cc);
+                            if constexpr (EPI == UD_EPI_F32) {
+                                // rows >= M and columns >= N of the accumulator are exact zeros (TMA zero-fills out-of-bounds operands)
+                                if (e.aux != nullptr) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) ssq = fmaf(__uint_as_float(r[j]), __uint_as_float(r[j]), ssq);
+                                }
+                            }
                             if (col0 + 32 <= e.N) {
                                 uint4 u[8];
 #pragma unroll
@@ -837,6 +845,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 }
             }
             if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        if constexpr (EPI == UD_EPI_F32) {
+            if (e.aux != nullptr) {                // one atomic per epilogue warp per launch
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+                if (lane == 0 && ssq != 0.f) atomicAdd(reinterpret_cast<float*>(e.aux), ssq);
+            }
         }
     }
 
@@ -1070,6 +1085,10 @@ extern "C" int ud_gemm_bf16(int ta, int tb, int M, int N, int K, const void* A, 
     if ((reinterpret_cast<uintptr_t>(C) & 15) || (ldc % 4) != 0) {
         fprintf(stderr, "unidisc_b200: GEMM output needs a 16-byte aligned base and ldc %% 4 == 0\n");
         return -6;
+    }
+    if (aux != nullptr && (epi == UD_EPI_F32_ACC || (epi == UD_EPI_F32 && !two_cta))) {
+        fprintf(stderr, "unidisc_b200: the fused sum of squares (aux with an fp32 epilogue) needs UD_EPI_F32 and M > 128\n");
+        return -7;
     }
     GemmParams p;
     p.M = M; p.N = N; p.K = K;

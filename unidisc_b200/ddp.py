@@ -201,7 +201,14 @@ class FusedAdamW:
                 self.ddp.post_bucket_hook = self._on_bucket_final
             else:
                 by_block = {b: self._ranges_of(b) for b in range(-1, self.module.n_blocks + 1)}      # planned once (host cost)
-                self.module.grad_ready_hook = lambda b: self._on_bucket_final(b, by_block[b], False)
+                big_end = self.module._big_end
+                small_only = {b: [r for r in rs if r[0] >= big_end] for b, rs in by_block.items()}
+                # single GPU: the wgrad GEMM epilogues add sum(dW^2) of the GEMM weights straight into the accumulator
+                # (DIT.grad_sumsq_acc); only the small parameters still need a pass
+                if not bool(int(os.environ.get("UD_NO_FUSED_SUMSQ", "0"))):
+                    self.module.grad_sumsq_acc = self._sumsq
+                self.module.grad_ready_hook = lambda b: self._on_bucket_final(
+                    b, small_only[b] if self.module._last_bwd_fused_sumsq else by_block[b], False)
 
     # ---- bucket plan: (name, [ranges]) in the order the forward first reads the weights ----
     def _ranges_of(self, block_idx):

@@ -229,6 +229,8 @@ class DIT(nn.Module):
         self.grad_ready_hook = None                # thin-DDP / optimizer: hook(block) when that bucket's flat grads are final
         self._param_events = None                  # FusedAdamW(overlap): per-bucket "weights updated" events of the last step
         self._dbg_fwd_events = None                # debug: list collecting a timing event at the start of every block's forward
+        self.grad_sumsq_acc = None                 # FusedAdamW (N=1): fp32 scalar the wgrad GEMM epilogues add sum(dW^2) into
+        self._last_bwd_fused_sumsq = False
         self._grads_attached = False
         if device is not None:
             self.to(device)
@@ -561,6 +563,10 @@ class DIT(nn.Module):
         T = self._top
         fresh = self._attach_grads()
         wacc = L.EPI_F32 if fresh else L.EPI_F32_ACC
+        # gradient-norm fusion: when the weight gradients are written (not accumulated) their squares are summed by the GEMM
+        # epilogue that stores them, so the optimizer never re-reads the 5.6 GB of GEMM-weight gradients for clip_grad_norm_
+        gacc = self.grad_sumsq_acc if (fresh and self.hidden_size > 128) else None      # (the fused epilogue needs M > 128)
+        self._last_bwd_fused_sumsq = gacc is not None
         # logits gradient in the padded [M, Vp] layout (produced in place by the fused SUBS-NLL backward when possible)
         if dlogits.dtype == bf16 and dlogits.dim() == 3 and dlogits.stride() == (N * self.Vp, self.Vp, 1):
             dl = dlogits.as_strided((M, self.Vp), (self.Vp, 1))[:, :V]
@@ -569,7 +575,7 @@ class DIT(nn.Module):
             buf[:, :V].copy_(dlogits.reshape(M, V))
             dl = buf[:, :V]
         # head
-        ops.gemm(dl, S["hf"], ta=True, tb=True, M=V, N=D, K=M, epi=wacc, out=T["d_wh"])
+        ops.gemm(dl, S["hf"], ta=True, tb=True, M=V, N=D, K=M, epi=wacc, out=T["d_wh"], aux=gacc)
         ops.colsum(dl, T["d_bh"], M, V)
         dh = ops.gemm(dl, T["wh"], tb=True, M=M, N=D, K=V)
         S["logits_buf"] = None
@@ -602,9 +608,9 @@ class DIT(nn.Module):
             if C is not None and i == self.n_blocks - 1:
                 self._adaln_param_grads(C, self.n_blocks)                 # final layer's shift / scale are complete
             # MLP
-            ops.gemm(dd, A["g"], ta=True, tb=True, epi=wacc, out=W["d_w2"])
+            ops.gemm(dd, A["g"], ta=True, tb=True, epi=wacc, out=W["d_w2"], aux=gacc)
             du = ops.gemm(dd, W["w2"], tb=True, epi=L.EPI_BF16_DGELU, aux=A["u"])
-            ops.gemm(du, A["h2"], ta=True, tb=True, epi=wacc, out=W["d_w1"])
+            ops.gemm(du, A["h2"], ta=True, tb=True, epi=wacc, out=W["d_w1"], aux=gacc)
             ops.colsum(du, W["d_b1"])
             dh2 = ops.gemm(du, W["w1"], tb=True)
             # x1 = x + rms(a)*w_pre ; h2 = rms(x1)*w_n2
@@ -615,7 +621,7 @@ class DIT(nn.Module):
                 # block i+1's six chunks are final (its norm1 modulation was differentiated by this iteration's first kernel)
                 self._adaln_param_grads(C, i + 1)
             # attention
-            ops.gemm(da, A["o"], ta=True, tb=True, epi=wacc, out=W["d_wout"])
+            ops.gemm(da, A["o"], ta=True, tb=True, epi=wacc, out=W["d_wout"], aux=gacc)
             do = ops.gemm(da, W["wout"], tb=True)
             dqk = torch.empty((M, 2 * D), device=do.device, dtype=bf16)
             dqkv = torch.empty((M, 3 * D), device=do.device, dtype=bf16)
@@ -625,7 +631,7 @@ class DIT(nn.Module):
                          B, N, H, hd, scale, sample_ids=S["sid"])
             ops.qk_ln_rope_bwd(dqk, qkv, A["stats"], W["gq"], W["gk"], S["cos"], S["sin"], dqkv, W["d_gq"], W["d_bq"], W["d_gk"],
                                W["d_bk"], hd)
-            ops.gemm(dqkv, A["h"], ta=True, tb=True, epi=wacc, out=W["d_wqkv"])
+            ops.gemm(dqkv, A["h"], ta=True, tb=True, epi=wacc, out=W["d_wqkv"], aux=gacc)
             dh = ops.gemm(dqkv, W["wqkv"], tb=True)
             S["blocks"][i] = None      # release this block's activations
             pending.append(i)
