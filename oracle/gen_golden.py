@@ -447,6 +447,76 @@ def gen_timecond():
                         modality_txt=_np(mod_t), ref_logits_txt_fp32=_np(ref_t), **{"P::" + k: _np(v) for k, v in P.items()})
 
 
+CFG1 = dict(D=384, H=6, L=6, txt=60, img=196, text_vocab_size=32001, vocab_size=48385, mask_index=32000, B=4)
+
+
+def cfg1_params(seed=123):
+    """Deterministic parameters for the BASELINE.json configs[0]-sized model (37 M of them: too large to commit, so both the
+    generator and the tests rebuild them from the seed with the CPU generator)."""
+    ocfg = R.OracleConfig(CFG1["D"], CFG1["H"], CFG1["L"], CFG1["txt"], CFG1["img"], CFG1["vocab_size"], CFG1["text_vocab_size"],
+                          CFG1["mask_index"])
+    return ocfg, R.init_params(ocfg, seed=seed)
+
+
+def gen_cfg1():
+    """BASELINE.json configs[0] (the reference's own CPU-runnable parity case): DiT-S depth 6, dim 384, 6 heads, seq_len 256,
+    batch 4, fp32, eager, real vocabulary (32001 text + 16384 image ids).  The image span is 196 = 14 x 14 tokens and the text
+    span 60, because the reference asserts a square image length for its 2-D RoPE (models/dit.py:1048); 64 + 192 cannot be run.
+    Stores the inputs, the random draws, sub-sampled reference logits (every 4th token, every 61st vocabulary entry), whole-
+    tensor checksums and the reference compute_loss outputs."""
+    c = CFG1
+    ocfg, P = cfg1_params()
+    ref_cfg = RL.make_ref_config(c["D"], c["H"], c["L"], c["txt"], c["img"])
+    dit = RL.build_reference_dit(ref_cfg, c["vocab_size"], c["text_vocab_size"], c["mask_index"], dtype=torch.float32)
+    missing = dit.load_state_dict(P, strict=True)
+    dit.eval()
+    B, N = c["B"], c["txt"] + c["img"]
+    x0, modality = R.synthetic_batch(B, c["txt"], c["img"], c["text_vocab_size"], c["vocab_size"], seed=7)
+    g = torch.Generator().manual_seed(8)
+    u_t = torch.rand(B, generator=g)
+    rand_move = torch.rand(B, N, generator=g)
+    t = R.sample_t(u_t)
+    sigma, _ = R.loglinear_noise(t)
+    xt, move, _ = R.q_xt(x0, 1 - torch.exp(-sigma[:, None]), rand_move, c["mask_index"])
+    with torch.no_grad():
+        ref_logits = dit(xt, None, modality=modality)
+    mine = R.dit_forward(ocfg, P, xt, modality, mode="fp32")
+    err = (mine - ref_logits).abs().max().item()
+    print(f"[cfg1 fp32] max|restated - reference| = {err:.3e} (ref absmax {ref_logits.abs().max():.3f})")
+    assert err < 5e-5, err
+    # reference compute_loss on the same draws (torch.rand order of model.py:844 -> :439 replayed through the global generator)
+    found = RL._extract_functions(os.path.join(RL.REFERENCE_ROOT, "model.py"), ["forward", "compute_loss", "get_cond_dict"])
+    gg = RL._exec_functions(found, dict(Loss=lambda **k: SimpleNamespace(**k), utils=SimpleNamespace(print_nans=lambda *a: None),
+                                       get_block_mask=None, get_interleaved_block_mask=None, shard_output=None))
+    cfgd = dict(txt=c["txt"], img=c["img"], mask_index=c["mask_index"], text_vocab_size=c["text_vocab_size"], vocab_size=c["vocab_size"])
+    s3, _ = make_fake_self(cfgd, ref_dit=dit, img_loss_weight=0.6)
+    s3.forward = lambda *a, **k: gg["forward"](s3, *a, **k)
+    s3.get_cond_dict = lambda b: gg["get_cond_dict"](s3, b)
+    am = torch.ones(B, N, dtype=torch.bool)
+    am[2, 50:58] = False
+    batch = dict(input_ids=x0, attention_mask=am, modality=modality, modality_mask=torch.stack([modality == 0, modality == 1], dim=-1))
+    torch.manual_seed(21)
+    with torch.no_grad():
+        Lr = gg["compute_loss"](s3, batch, prefix="train", batch_idx=-1)
+    torch.manual_seed(21)
+    u2 = torch.rand(B)
+    rm2 = torch.rand(B, N)
+    m2 = R.training_loss(ocfg, P, x0, modality, am, u2, rm2, mode="fp32", img_loss_weight=0.6)
+    e = abs(m2["loss"].item() - Lr.loss.item())
+    print(f"[cfg1 compute_loss] ref {Lr.loss.item():.6f} restated {m2['loss'].item():.6f} |d|={e:.2e}")
+    assert e < 1e-4 * max(1.0, abs(Lr.loss.item()))
+    np.savez_compressed(os.path.join(OUT, "cfg1.npz"),
+                        cfg=np.array([c[k] for k in ["D", "H", "L", "txt", "img", "vocab_size", "text_vocab_size", "mask_index"]]),
+                        param_seed=np.array([123]), x0=_np(x0), modality=_np(modality), u_t=_np(u_t), rand_move=_np(rand_move),
+                        xt=_np(xt), ref_logits_sub=_np(ref_logits[:, ::4, ::61]),
+                        ref_logits_sum=np.array([ref_logits.double().sum().item(), ref_logits.double().abs().sum().item()]),
+                        ref_logits_rowmax=_np(ref_logits.max(dim=-1).values), ref_logits_argmax=_np(ref_logits.argmax(dim=-1)),
+                        loss_am=_np(am), loss_u_t=_np(u2), loss_rand_move=_np(rm2),
+                        loss_ref=np.array([Lr.loss.item(), Lr.txt_loss.item(), Lr.img_loss.item()]), loss_nlls_ref=_np(Lr.nlls),
+                        param_checksum=np.array([sum(v.double().sum().item() for v in P.values())]))
+
+
+
 def _with_length(ocfg, N):
     """OracleConfig whose `length` (txt_length + img_length) equals the packed sequence length N."""
     import dataclasses
@@ -455,9 +525,13 @@ def _with_length(ocfg, N):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+        gen_cfg1()
+        return
     gen_diffusion_fns(*gen_dit())
     gen_interleaved()
     gen_timecond()
+    gen_cfg1()
     print("golden fixtures written to", OUT)
 
 

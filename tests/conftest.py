@@ -48,3 +48,9 @@ def golden_interleaved():
 def golden_timecond():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "timecond.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_cfg1():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "cfg1.npz"))

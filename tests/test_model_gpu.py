@@ -337,3 +337,56 @@ def test_fused_adamw_and_clip_vs_torch(overlap):
     full = net.flat_grads.double().pow(2).sum().sqrt().float()
     opt.step()
     assert torch.allclose(opt.last_grad_norm, full, rtol=1e-4)
+
+
+def test_cfg1_reference_parity_run_on_gpu(golden_cfg1, monkeypatch):
+    """BASELINE.json configs[0] (DiT-S depth 6 / dim 384 / 6 heads of 64, seq_len 256 = 60 text + 14x14 image tokens, batch 4, real
+    vocabulary): CUDA logits and compute_loss against the unmodified reference's fp32 outputs (tests/golden/cfg1.npz) and the
+    bf16-mode oracle; q_xt bit-exact on the reference's draws."""
+    from oracle import restated as R
+    from oracle.gen_golden import cfg1_params
+    from unidisc_b200.config import make_config
+    from unidisc_b200.model import Diffusion
+    g = golden_cfg1
+    ocfg, P = cfg1_params(int(g["param_seed"][0]))
+    D, H, L, txt, img, V, tv, mi = [int(v) for v in g["cfg"]]
+    cfg = make_config("small", hidden_size=D, n_blocks=L, n_heads=H, txt_length=txt, img_length=img, image_vocab_size=V - tv,
+                      text_vocab_size=tv, img_loss_weight=0.6)
+    model = Diffusion(cfg, device=dev())
+    assert (model.vocab_size, model.text_vocab_size, model.mask_index) == (V, tv, mi)
+    r = model.backbone.load_state_dict(P)
+    assert not r.missing_keys and not r.unexpected_keys
+    model.eval()
+    x0, modality = torch.from_numpy(g["x0"]).to(dev()), torch.from_numpy(g["modality"]).to(dev())
+    xt_ref = torch.from_numpy(g["xt"])
+    # forward on the reference's x_t
+    with torch.no_grad():
+        out = model.backbone(xt_ref.to(dev()), None, modality=modality).float().cpu()
+    sub = torch.from_numpy(g["ref_logits_sub"])
+    e_ref = (out[:, ::4, ::61] - sub).abs()
+    orc = R.dit_forward(ocfg, P, xt_ref, modality.cpu(), mode="bf16").float()
+    e_orc = (out - orc).abs()
+    print(f"cfg1 logits: max|cuda-oracle_bf16|={e_orc.max():.4f} mean={e_orc.mean():.5f}; max|cuda-reference_fp32|(sub)={e_ref.max():.4f} "
+          f"mean={e_ref.mean():.5f}")
+    assert e_orc.max() < 6e-2 and e_orc.mean() < 4e-3
+    assert e_ref.max() < 8e-2 and e_ref.mean() < 6e-3
+    agree = (out.argmax(-1).numpy() == g["ref_logits_argmax"]).mean()
+    assert agree > 0.97, agree
+    # compute_loss on the reference's draws (torch.rand is called for t, then for the move mask: model.py:844, :439)
+    draws = [torch.from_numpy(g["loss_u_t"]).to(dev()), torch.from_numpy(g["loss_rand_move"]).to(dev())]
+    real_rand = torch.rand
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: draws.pop(0) if draws else real_rand(*a, **k))
+    am = torch.from_numpy(g["loss_am"]).to(dev())
+    model.train()
+    Lc = model.compute_loss(dict(input_ids=x0, modality=modality, attention_mask=am))
+    monkeypatch.undo()
+    assert not draws
+    ref = g["loss_ref"]
+    ob = R.training_loss(ocfg, P, x0.cpu(), modality.cpu(), am.cpu(), torch.from_numpy(g["loss_u_t"]), torch.from_numpy(g["loss_rand_move"]),
+                         mode="bf16", img_loss_weight=0.6)
+    got = float(Lc.loss.detach())
+    print(f"cfg1 loss cuda={got:.5f} oracle_bf16={float(ob['loss']):.5f} reference_fp32={ref[0]:.5f}")
+    assert abs(got - float(ob["loss"])) < 1e-3 * abs(float(ob["loss"])) + 2e-3
+    assert abs(got - ref[0]) < 1e-2 * abs(ref[0])
+    assert abs(float(Lc.txt_loss) - ref[1]) < 1e-2 * abs(ref[1]) + 1e-3 and abs(float(Lc.img_loss) - ref[2]) < 1e-2 * abs(ref[2]) + 1e-3
+    assert torch.allclose(Lc.nlls.detach().cpu(), torch.from_numpy(g["loss_nlls_ref"]), rtol=3e-2, atol=8e-2)

@@ -195,3 +195,41 @@ def test_time_conditioning_matches_reference(golden_timecond):
     # bf16-emulating mode stays close to the fp32 reference
     out_bf = R.dit_forward(cfg, P, torch.from_numpy(g["ids"]), torch.from_numpy(g["modality"]), mode="bf16", sigma=sigma).float()
     assert (out_bf - torch.from_numpy(g["ref_logits_fp32"])).abs().max().item() < 0.08
+
+
+def _cfg1(g):
+    """Parameters of the BASELINE.json configs[0]-sized fixture are rebuilt from their seed (37 M values, not committed)."""
+    from oracle.gen_golden import cfg1_params
+    ocfg, P = cfg1_params(int(g["param_seed"][0]))
+    assert [int(v) for v in g["cfg"]] == [ocfg.hidden_size, ocfg.n_heads, ocfg.n_blocks, ocfg.txt_length, ocfg.img_length,
+                                          ocfg.vocab_size, ocfg.text_vocab_size, ocfg.mask_index]
+    chk = sum(v.double().sum().item() for v in P.values())
+    assert abs(chk - float(g["param_checksum"][0])) < 1e-6 * max(1.0, abs(chk)), "seeded parameter generator changed"
+    return ocfg, P
+
+
+def test_cfg1_reference_parity_run(golden_cfg1):
+    """BASELINE.json configs[0]: DiT-S depth 6 / dim 384 / 6 heads, seq_len 256 (60 text + 196 = 14x14 image tokens), batch 4,
+    fp32 CPU eager, real vocabulary — the oracle against logits and compute_loss outputs of the unmodified reference."""
+    g = golden_cfg1
+    ocfg, P = _cfg1(g)
+    x0, modality = torch.from_numpy(g["x0"]), torch.from_numpy(g["modality"])
+    # q_xt on the stored draws is bit-exact
+    t = R.sample_t(torch.from_numpy(g["u_t"]))
+    sigma, _ = R.loglinear_noise(t)
+    xt, _, _ = R.q_xt(x0, 1 - torch.exp(-sigma[:, None]), torch.from_numpy(g["rand_move"]), ocfg.mask_index)
+    assert np.array_equal(xt.numpy(), g["xt"])
+    logits = R.dit_forward(ocfg, P, xt, modality, mode="fp32")
+    assert (logits[:, ::4, ::61] - torch.from_numpy(g["ref_logits_sub"])).abs().max().item() < 5e-5
+    assert (logits.max(dim=-1).values - torch.from_numpy(g["ref_logits_rowmax"])).abs().max().item() < 5e-5
+    s, a = g["ref_logits_sum"]
+    assert abs(logits.double().abs().sum().item() - a) < 1e-6 * a
+    assert abs(logits.double().sum().item() - s) < 1e-6 * a
+    agree = (logits.argmax(dim=-1).numpy() == g["ref_logits_argmax"]).mean()
+    assert agree > 0.999, agree                      # (near-ties may flip at 1e-6)
+    out = R.training_loss(ocfg, P, x0, modality, torch.from_numpy(g["loss_am"]), torch.from_numpy(g["loss_u_t"]),
+                          torch.from_numpy(g["loss_rand_move"]), mode="fp32", img_loss_weight=0.6)
+    ref = g["loss_ref"]
+    assert abs(out["loss"].item() - ref[0]) < 1e-4 * max(1.0, abs(ref[0]))
+    assert abs(out["txt_loss"].item() - ref[1]) < 1e-4 and abs(out["img_loss"].item() - ref[2]) < 1e-4
+    assert torch.allclose(out["nlls"], torch.from_numpy(g["loss_nlls_ref"]), rtol=1e-4, atol=1e-3)
