@@ -811,6 +811,12 @@ struct AttnBwdParams {
     long long ld0, ld1;
     const int64_t* sample_ids;
     int safe_order;
+    // v2 dQ kernel only: it forms delta = rowsum(dO * O) for its own 128 query rows (and publishes it for the dK/dV kernel,
+    // which runs after it), so no separate pass over O and dO is launched
+    const __nv_bfloat16* o;
+    const __nv_bfloat16* d_o;
+    long long ldo;
+    float* delta_out;
 };
 
 template <int HD, int MODE>
@@ -1176,7 +1182,26 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
         int sid_row = 0;
         if (use_ids) sid_row = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
         float lse_row = 0.f, dlt_row = 0.f;
-        if (MODE == 1 && row < p.N) { lse_row = p.lse[bh * p.N + row] * LOG2E; dlt_row = p.delta[bh * p.N + row]; }
+        if (MODE == 1 && row < p.N) {
+            lse_row = p.lse[bh * p.N + row] * LOG2E;
+            if (p.o != nullptr) {
+                // delta of this thread's query row, straight from O and dO (both warpgroups own the same rows and compute it
+                // redundantly; warpgroup 0 publishes it)
+                const uint4* po = reinterpret_cast<const uint4*>(p.o + ((long long)b * p.N + row) * p.ldo + h * HD);
+                const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((long long)b * p.N + row) * p.ldo + h * HD);
+                float acc = 0.f;
+#pragma unroll 4
+                for (int j = 0; j < HD / 8; ++j) {
+                    const uint4 a = po[j], g = pd[j];
+                    acc += bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y)
+                         + bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
+                }
+                dlt_row = acc;
+                if (wg == 0) p.delta_out[bh * p.N + row] = acc;
+            } else {
+                dlt_row = p.delta[bh * p.N + row];
+            }
+        }
         const bool row_ok = row < p.N;
         const int bf = wg;
         const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
@@ -1400,6 +1425,17 @@ static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const v
                            long long ldo, AttnBwdParams p, __nv_bfloat16* dq, __nv_bfloat16* dk, long long lddqk,
                            __nv_bfloat16* dv, long long lddv, cudaStream_t stream) {
     static const bool use_v1 = getenv("UD_ATTN_BWD_V1") != nullptr;     // A/B switch: strictly alternating v1 kernel
+    // The v2 dQ kernel can form delta itself (UD_ATTN_FUSED_DELTA=1), but measured at B8 H16 N1280 hd128 the per-thread row reads
+    // delay every CTA's first sub-tile: 458.6 us fused vs 445.4 us with the separate 33 us pass, so the pass stays the default.
+    static const bool sep_delta = getenv("UD_ATTN_FUSED_DELTA") == nullptr;
+    if (use_v1 || sep_delta) {
+        const long long warps = (long long)p.B * p.N * p.H;
+        const int threads = 256;
+        const long long blocks = (warps * 32 + threads - 1) / threads;
+        attn_delta_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p.o, p.d_o, p.ldo, p.delta_out, p.B, p.N, p.H, HD);
+        UD_CUDA_CHECK(cudaGetLastError());
+        p.o = nullptr;                        // kernels read p.delta
+    }
     CUtensorMap tq, tk, tv, tdo, tq64, tk64, tv64, tdo64;
     const int D = p.H * HD;
     int rc;
@@ -1437,9 +1473,10 @@ static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const v
         UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2_kernel<HD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr2 = true;
     }
-    attn_bwd2_kernel<HD, 0><<<grid, 320, smem, stream>>>(tk, tv, tq64, tdo64, p0);
-    UD_CUDA_CHECK(cudaGetLastError());
+    // dQ first: it also produces delta, which the dK/dV kernel reads per streamed query column
     attn_bwd2_kernel<HD, 1><<<grid, 320, smem, stream>>>(tq, tdo, tk64, tv64, p1);
+    UD_CUDA_CHECK(cudaGetLastError());
+    attn_bwd2_kernel<HD, 0><<<grid, 320, smem, stream>>>(tk, tv, tq64, tdo64, p0);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1471,15 +1508,11 @@ extern "C" int ud_attn_bwd(const void* q, const void* k, long long ldqk, const v
                            void* stream) {
     if (B <= 0 || N <= 0) return 0;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    {
-        const long long warps = (long long)B * N * H;
-        const int threads = 256;
-        const long long blocks = (warps * 32 + threads - 1) / threads;
-        attn_delta_kernel<<<(unsigned)blocks, threads, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(o),
-                                                                reinterpret_cast<const __nv_bfloat16*>(d_o), ldo, delta, B, N, H, head_dim);
-        UD_CUDA_CHECK(cudaGetLastError());
-    }
     AttnBwdParams p;
+    p.o = reinterpret_cast<const __nv_bfloat16*>(o);
+    p.d_o = reinterpret_cast<const __nv_bfloat16*>(d_o);
+    p.ldo = ldo;
+    p.delta_out = delta;
     p.B = B; p.N = N; p.H = H;
     p.scale = scale;
     p.scale_log2 = scale * LOG2E;
