@@ -42,7 +42,8 @@ def main():
         if r > 0:
             times.append(e0.elapsed_time(e1))
     assert x.shape == (B, N) and int((x == model.mask_index).sum()) == 0
-    assert bool(((x[:, :txt] < model.text_vocab_size) & (x[:, txt:] >= model.text_vocab_size)).all()), "tokens left their modality's vocabulary"
+    assert bool((x[:, :txt] < model.text_vocab_size).all()) and bool((x[:, txt:] >= model.text_vocab_size).all()), \
+        "tokens left their modality's vocabulary"
     ms = min(times)
     fwd_flops = B * N * (cfg.model.n_blocks * (24 * cfg.model.hidden_size ** 2 + 4 * N * cfg.model.hidden_size) + 2 * cfg.model.hidden_size * model.vocab_size)
     print(json.dumps(dict(workload=f"{a.preset} 64-step absorbing sampling", predictor=a.predictor, batch=B, seq_len=N, steps=a.steps, nfe=nfe,
