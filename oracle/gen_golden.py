@@ -517,6 +517,86 @@ def gen_cfg1():
 
 
 
+def _ub_cases():
+    """Synthetic dataloader batches for update_batch (tokenised paths), with their config switches."""
+    g = torch.Generator().manual_seed(31)
+    txt, img, tv = 12, 16, 97
+    cases = {}
+    # (a) pre-tokenised unified sample: int32 ids, text padding mask
+    tam = torch.ones(3, txt, dtype=torch.int32)
+    tam[1, 9:] = 0
+    cases["pretok"] = (dict(txt_input_ids=torch.randint(0, tv - 1, (3, txt), generator=g, dtype=torch.int32), txt_attention_mask=tam,
+                            img_input_ids=torch.randint(0, 63, (3, img), generator=g, dtype=torch.int32)),
+                       dict(), txt, img)
+    # (b) the same with packed-sample ids (data.require_sample_ids, trainer.interleaved) and an explicit modality with -1 padding
+    sid = torch.zeros(3, txt + img, dtype=torch.int32)
+    sid[0, 20:] = 1
+    sid[2, 5:] = 2
+    mod = torch.cat([torch.zeros(3, txt, dtype=torch.int32), torch.ones(3, img, dtype=torch.int32)], 1)
+    mod[1, 9:12] = -1
+    cases["pretok_sid"] = (dict(txt_input_ids=torch.randint(0, tv - 1, (3, txt), generator=g, dtype=torch.int32), txt_attention_mask=tam.clone(),
+                                img_input_ids=torch.randint(0, 63, (3, img), generator=g, dtype=torch.int32), sample_ids=sid, modality=mod),
+                           dict(trainer=dict(interleaved=True), data=dict(require_sample_ids=True)), txt, img)
+    # (c) joint multimodal batch with un-shifted image ids (trainer.force_shift_image_batches) and interleaved blocks
+    mod2 = torch.zeros(2, txt + img, dtype=torch.int64)
+    mod2[0, 4:20] = 1
+    mod2[1, :16] = 1
+    ids2 = torch.where(mod2 == 1, torch.randint(0, 63, (2, txt + img), generator=g), torch.randint(0, tv - 1, (2, txt + img), generator=g))
+    cases["joint"] = (dict(input_ids=ids2.to(torch.int32), modality=mod2, attention_mask=torch.ones(2, txt + img, dtype=torch.int64)),
+                      dict(trainer=dict(force_shift_image_batches=True, interleaved=True)), txt, img)
+    return cases, tv
+
+
+def _ub_config(txt, img, over):
+    cfg = dict(parameterization="subs", backbone="dit",
+               eval=dict(), data=dict(require_sample_ids=False, txt_only=False),
+               trainer=dict(image_mode="discrete", multimodal_batches=True, interleaved=False, ignore_text_in_unified=False,
+                            ar_inpainting=False),
+               model=dict(txt_length=txt, img_length=img, length=txt + img, unified_model=True))
+    for sec, kv in over.items():
+        cfg[sec].update(kv)
+    return cfg
+
+
+def gen_update_batch():
+    """Diffusion.update_batch (model.py:157-395) on tokenised batches: the reference function itself (extracted from model.py,
+    fake self) vs unidisc_b200.model.update_batch; every output tensor must be identical."""
+    from unidisc.utils.tensor_utils import get_contiguous_blocks
+    from unidisc_b200.model import update_batch as mine_fn
+
+    class TensorDict(dict):                      # stands in for tensordict.TensorDict (only constructed for the block metadata)
+        def __init__(self, d=None, batch_size=None):
+            super().__init__(d or {})
+
+    found = RL._extract_functions(os.path.join(RL.REFERENCE_ROOT, "model.py"), ["update_batch"])
+    gg = RL._exec_functions(found, dict(TensorDict=TensorDict, get_contiguous_blocks=get_contiguous_blocks, get_image_batch=None))
+    cases, tv = _ub_cases()
+    out = {}
+    for name, (batch, over, txt, img) in cases.items():
+        cfg = _ub_config(txt, img, over)
+        s = SimpleNamespace(config=RL.to_attrdict(cfg), image_model=True, is_compiled=True, text_vocab_size=tv, device=torch.device("cpu"),
+                            training=True, unified_model=True)
+        s.txt_sl = lambda b: b["modality_mask"][..., 0]
+        s.img_sl = lambda b: b["modality_mask"][..., 1]
+        ref = gg["update_batch"](s, {k: v.clone() for k, v in batch.items()})
+        mine = mine_fn({k: v.clone() for k, v in batch.items()}, RL.to_attrdict(cfg), text_vocab_size=tv, device=torch.device("cpu"))
+        flat = lambda d: {k if not isinstance(v, dict) else None: v for k, v in d.items()}
+        keys = sorted(k for k, v in ref.items() if isinstance(v, torch.Tensor))
+        assert keys == sorted(k for k, v in mine.items() if isinstance(v, torch.Tensor)), (keys, sorted(mine))
+        for k in keys:
+            assert ref[k].dtype == mine[k].dtype and torch.equal(ref[k], mine[k]), (name, k)
+            out[f"{name}::out::{k}"] = _np(ref[k])
+        if "interleaved_metadata" in ref:
+            for k in ("batch_indices", "start_positions", "end_positions"):
+                assert torch.equal(ref["interleaved_metadata"][k], mine["interleaved_metadata"][k]), (name, k)
+                out[f"{name}::meta::{k}"] = _np(ref["interleaved_metadata"][k])
+        for k, v in batch.items():
+            out[f"{name}::in::{k}"] = _np(v)
+        print(f"[update_batch {name}] {len(keys)} tensors identical" + (" + block metadata" if "interleaved_metadata" in ref else ""))
+    np.savez_compressed(os.path.join(OUT, "update_batch.npz"), text_vocab_size=np.array([tv]), **out)
+
+
+
 def _with_length(ocfg, N):
     """OracleConfig whose `length` (txt_length + img_length) equals the packed sequence length N."""
     import dataclasses
@@ -528,10 +608,15 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
         gen_cfg1()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "update_batch":
+        RL.load_reference_diffusion_methods()          # installs the import shims / sys.path for the reference tree
+        gen_update_batch()
+        return
     gen_diffusion_fns(*gen_dit())
     gen_interleaved()
     gen_timecond()
     gen_cfg1()
+    gen_update_batch()
     print("golden fixtures written to", OUT)
 
 

@@ -1,6 +1,7 @@
 """CPU: the restated oracle (oracle/restated.py) against the committed golden vectors that
 oracle/gen_golden.py produced by running the unmodified reference code (tests/golden/*.npz)."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import restated as R
@@ -233,3 +234,34 @@ def test_cfg1_reference_parity_run(golden_cfg1):
     assert abs(out["loss"].item() - ref[0]) < 1e-4 * max(1.0, abs(ref[0]))
     assert abs(out["txt_loss"].item() - ref[1]) < 1e-4 and abs(out["img_loss"].item() - ref[2]) < 1e-4
     assert torch.allclose(out["nlls"], torch.from_numpy(g["loss_nlls_ref"]), rtol=1e-4, atol=1e-3)
+
+
+def test_update_batch_matches_reference():
+    """Batch contract: unidisc_b200.model.update_batch against the outputs of the reference's own
+    Diffusion.update_batch (model.py:157-395) on tokenised dataloader batches — every tensor identical, dtypes included."""
+    import os
+    from oracle.gen_golden import _ub_cases, _ub_config
+    from oracle.ref_loader import to_attrdict
+    from unidisc_b200.model import update_batch
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "update_batch.npz"))
+    cases, tv = _ub_cases()
+    assert tv == int(g["text_vocab_size"][0])
+    for name, (batch, over, txt, img) in cases.items():
+        for k, v in batch.items():                                   # the seeded inputs are the ones the fixture was made from
+            assert np.array_equal(v.numpy(), g[f"{name}::in::{k}"]), (name, k)
+        out = update_batch({k: v.clone() for k, v in batch.items()}, to_attrdict(_ub_config(txt, img, over)), text_vocab_size=tv,
+                           device=torch.device("cpu"))
+        want = {k.split("::")[2]: g[k] for k in g.files if k.startswith(f"{name}::out::")}
+        assert sorted(want) == sorted(k for k, v in out.items() if isinstance(v, torch.Tensor)), name
+        for k, w in want.items():
+            assert out[k].numpy().dtype == w.dtype and np.array_equal(out[k].numpy(), w), (name, k)
+        for k in [k for k in g.files if k.startswith(f"{name}::meta::")]:
+            assert np.array_equal(out["interleaved_metadata"][k.split("::")[2]].numpy(), g[k]), (name, k)
+    # image ids are shifted into the joint vocabulary, padding is excluded, modality -1 is folded into text
+    o = update_batch({k: v.clone() for k, v in cases["pretok_sid"][0].items()},
+                     to_attrdict(_ub_config(12, 16, cases["pretok_sid"][1])), text_vocab_size=tv, device=torch.device("cpu"))
+    assert int(o["input_ids"][:, 12:].min()) >= tv and int(o["modality"].min()) == 0
+    assert bool((o["sample_ids"][~o["attention_mask"]] == -1).all())
+    with pytest.raises(NotImplementedError):
+        update_batch(dict(img=torch.zeros(1, 3, 8, 8), input_ids=torch.zeros(1, 28), modality=torch.ones(1, 28)),
+                     to_attrdict(_ub_config(12, 16, {})), text_vocab_size=tv, device=torch.device("cpu"))

@@ -150,6 +150,100 @@ class _SubsNLL(torch.autograd.Function):
         return logits, None, None, None, None, None, None
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# batch contract: reference Diffusion.update_batch, model.py:157-395 — pre-tokenised datasets
+# ----------------------------------------------------------------------------------------------------------------
+def contiguous_blocks(ids: torch.Tensor):
+    """Runs of equal values along the sequence: (batch_indices, start_positions, end_positions) of every run whose value is
+    >= 0 (reference unidisc/utils/tensor_utils.py:24-44)."""
+    diff = ids[:, 1:] != ids[:, :-1]
+    diff = torch.nn.functional.pad(diff, (1, 0), mode="constant", value=True)
+    starts = diff.nonzero(as_tuple=False)
+    ends = torch.nn.functional.pad(diff[:, 1:], (0, 1), mode="constant", value=True).nonzero(as_tuple=False)
+    bi, sp, ep = starts[:, 0], starts[:, 1], ends[:, 1] + 1
+    valid = ids[bi, sp] >= 0
+    return bi[valid], sp[valid], ep[valid]
+
+
+def update_batch(batch, config, *, text_vocab_size: int, device, training: bool = True):
+    """Dataloader batch -> the dict `compute_loss` consumes (reference model.py:157-395), for the tokenised paths of the shipped
+    configs: (a) `txt_input_ids` / `txt_attention_mask` / `img_input_ids` (image ids are shifted by `text_vocab_size`,
+    model.py:200), (b) already joint `input_ids` + `modality` (trainer.multimodal_batches).  Adds `modality`, `modality_mask`
+    (one-hot bool [B,N,2]), `batch_contains_img`, `txt_sl` / `img_sl`, normalises dtypes, applies the `sample_ids` / padding
+    rules of data.require_sample_ids and attaches the interleaved block metadata.  Raw-image batches (VAE tokenisation,
+    model.py:215-283), class labels and the AR flip are outside the hot path and raise."""
+    if batch is None:
+        return batch
+    g = _g
+    tr, md, data = config.trainer, config.model, g(config, "data")
+    if g(g(config, "eval"), "big_seq_len_eval", False) or g(tr, "image_mode", "discrete") == "continuous" or g(tr, "add_label", False) \
+            or g(md, "img_cond", False) or g(tr, "force_remove_img_tokens", False):
+        raise NotImplementedError("unidisc_b200.update_batch: big_seq_len_eval / continuous / add_label / img_cond / "
+                                  "force_remove_img_tokens are not on the hot path")
+    batch = dict(batch.items())
+    if "txt_input_ids" in batch or "img_input_ids" in batch:                           # model.py:183-210
+        for key in ("img_input_ids", "txt_input_ids", "sample_ids"):
+            if key in batch:
+                if isinstance(batch[key], list):
+                    batch[key] = torch.stack(batch[key], dim=0)
+                batch[key] = batch[key].to(torch.int64)
+        img_input_ids = batch.pop("img_input_ids")
+        batch["input_ids"] = img_input_ids
+        batch["attention_mask"] = torch.ones_like(img_input_ids).to(torch.bool)
+        if "txt_input_ids" in batch:
+            batch["input_ids"] = torch.cat([batch["txt_input_ids"], batch["input_ids"] + text_vocab_size], dim=-1)
+            batch["attention_mask"] = torch.cat([batch["txt_attention_mask"], batch["attention_mask"]], dim=-1)
+        batch["input_ids"] = batch["input_ids"].to(torch.int64)
+        if "modality" not in batch:
+            if g(tr, "ignore_text_in_unified", False):
+                modality = torch.ones_like(batch["input_ids"], dtype=torch.int64)
+            else:
+                assert md.txt_length > 0 and md.img_length > 0
+                modality = torch.zeros_like(batch["input_ids"], dtype=torch.int64)
+                modality[:, -img_input_ids.shape[-1]:] = 1
+            batch["modality"] = modality
+    elif g(tr, "multimodal_batches", False) and not g(tr, "use_legacy_update_batch_fn", False):   # model.py:212-256
+        if "img" in batch:
+            raise NotImplementedError("unidisc_b200.update_batch: raw-image batches need the VAE tokeniser (model.py:215-232)")
+        batch["input_ids"] = batch["input_ids"].to(torch.int64)
+        if "sample_ids" in batch:
+            batch["sample_ids"] = batch["sample_ids"].to(torch.int64)
+        if g(tr, "force_shift_image_batches", False):
+            batch["input_ids"] = torch.where(batch["modality"] == 1, batch["input_ids"] + text_vocab_size, batch["input_ids"])
+    else:
+        raise NotImplementedError("unidisc_b200.update_batch: only tokenised batches (txt/img_input_ids or multimodal_batches)")
+    if batch["input_ids"].shape[1] != md.length and not g(tr, "ar_inpainting", False):     # model.py:284-287
+        raise AssertionError(f"input ids are not the correct length input ids shape: {batch['input_ids'].shape}, model length: {md.length}")
+    batch["modality"] = batch["modality"].to(torch.int64)                                   # model.py:293-316
+    if g(tr, "multimodal_batches", False) and batch["modality"].ndim == 2 and batch["modality"].shape[-1] == 1:
+        batch["modality"] = batch["modality"].repeat(1, md.length)
+    batch["modality"][batch["modality"] == -1] = 0
+    assert batch["modality"].min() == 0 and batch["modality"].max() == 1
+    batch["modality_mask"] = torch.nn.functional.one_hot(batch["modality"], num_classes=2).to(torch.bool)
+    batch["batch_contains_img"] = (batch["modality"] == 1).any(dim=-1)
+    batch["txt_sl"] = batch["modality_mask"][..., 0]
+    batch["img_sl"] = batch["modality_mask"][..., 1]
+    for key in batch.keys():                                                                # model.py:338-341
+        if isinstance(batch[key], torch.Tensor):
+            batch[key] = batch[key].to(device)
+    if g(tr, "force_full_attention_mask", False):
+        batch["attention_mask"] = torch.ones_like(batch["attention_mask"], dtype=torch.bool)
+    batch["attention_mask"] = batch["attention_mask"].to(torch.bool)
+    if g(data, "require_sample_ids", False):                                                # model.py:351-354
+        assert "sample_ids" in batch
+        batch["sample_ids"][~(batch["attention_mask"].bool())] = -1
+        batch["attention_mask"][batch["sample_ids"] == -1] = False
+    if g(tr, "rand_flip_ar_prob", None) is not None and g(config, "parameterization", "subs") == "ar":
+        raise NotImplementedError("unidisc_b200.update_batch: AR flip (model.py:358-374)")
+    if g(tr, "interleaved", False):                                                         # model.py:376-393
+        if "sample_ids" not in batch:
+            batch["sample_ids"] = torch.zeros_like(batch["modality"], dtype=torch.int64)
+        bi, sp, ep = contiguous_blocks(batch["modality"])
+        batch["interleaved_metadata"] = dict(batch_indices=bi, start_positions=sp, end_positions=ep)
+    return batch
+
+
+
 class Diffusion(nn.Module):
     def __init__(self, config, tokenizer=None, device=None, vocab_size: Optional[int] = None,
                  text_vocab_size: Optional[int] = None, mask_index: Optional[int] = None):
@@ -202,6 +296,9 @@ class Diffusion(nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     # training side
     # ------------------------------------------------------------------------------------------------------------
+    def update_batch(self, batch):                                    # reference model.py:157-395
+        return update_batch(batch, self.config, text_vocab_size=self.text_vocab_size, device=self.device, training=self.training)
+
     def _sample_t(self, n, device):                                   # reference model.py:589-619
         _eps_t = torch.rand(n, device=device)
         if self.antithetic_sampling:
