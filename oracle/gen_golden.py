@@ -597,6 +597,38 @@ def gen_update_batch():
 
 
 
+def gen_first_hitting():
+    """_first_hitting_update (model_eval.py:3004-3043) given p_x0: the reference function (fake self whose _ddpm_forward returns
+    fixed probabilities) vs unidisc_b200.model.first_hitting_select fed with the same draws."""
+    from unidisc_b200.model import first_hitting_select
+    B, N, V, mi = 3, 40, 50, 49
+    cfgd = dict(txt=16, img=24, mask_index=mi, text_vocab_size=30, vocab_size=V)
+    s, M = make_fake_self(cfgd, ref_dit=None)
+    g = torch.Generator().manual_seed(41)
+    x = torch.randint(0, mi, (B, N), generator=g)
+    x[torch.rand(B, N, generator=g) < 0.6] = mi
+    x[2, :] = torch.randint(0, mi, (N,), generator=g)          # a fully unmasked row (num_unmask clamps to 0)
+    probs = torch.softmax(torch.randn(B, N, V, generator=g) * 2, -1)
+    probs[..., mi] = 0
+    s._ddpm_forward = lambda *a, **k: probs.clone()
+    sched = M.adap_sche(x, 6, mi, mode="arccos")
+    tt, dt = torch.full((B, 1), 0.6), (1 - 1e-5) / 6
+    out = dict(x=_np(x), probs=_np(probs), schedule=_np(sched))
+    for step in (0, 3, 5):
+        torch.manual_seed(50 + step)
+        ref, nfe = M._first_hitting_update(s, x.clone(), tt, dt, schedule=sched, step=step)
+        torch.manual_seed(50 + step)
+        u = torch.rand_like(probs)
+        rv = torch.rand(B, N)
+        mine = first_hitting_select(x.clone(), R.sample_categorical(probs, u), sched[:, step], rv, mi)
+        assert nfe == 1 and torch.equal(mine, ref), step
+        assert int(((ref != x) & (x != mi)).sum()) == 0               # unmasked tokens are carried over
+        out.update({f"u_{step}": _np(u), f"rv_{step}": _np(rv), f"ref_{step}": _np(ref)})
+    print("[first_hitting] 3 steps identical to the reference")
+    np.savez_compressed(os.path.join(OUT, "first_hitting.npz"), mask_index=np.array([mi]), **out)
+
+
+
 def _with_length(ocfg, N):
     """OracleConfig whose `length` (txt_length + img_length) equals the packed sequence length N."""
     import dataclasses
@@ -608,6 +640,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
         gen_cfg1()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "first_hitting":
+        gen_first_hitting()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "update_batch":
         RL.load_reference_diffusion_methods()          # installs the import shims / sys.path for the reference tree
         gen_update_batch()
@@ -617,6 +652,7 @@ def main():
     gen_timecond()
     gen_cfg1()
     gen_update_batch()
+    gen_first_hitting()
     print("golden fixtures written to", OUT)
 
 

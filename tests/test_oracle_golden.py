@@ -265,3 +265,23 @@ def test_update_batch_matches_reference():
     with pytest.raises(NotImplementedError):
         update_batch(dict(img=torch.zeros(1, 3, 8, 8), input_ids=torch.zeros(1, 28), modality=torch.ones(1, 28)),
                      to_attrdict(_ub_config(12, 16, {})), text_vocab_size=tv, device=torch.device("cpu"))
+
+
+def test_first_hitting_update_matches_reference():
+    """First-hitting sampler step (model_eval.py:3004-3043): unidisc_b200.model.first_hitting_select on the reference's draws
+    (categorical sample of p_x0, then the random choice of which masked positions to reveal) — bit-exact tokens."""
+    import os
+    from unidisc_b200.model import first_hitting_select
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "first_hitting.npz"))
+    mi = int(g["mask_index"][0])
+    x, probs, sched = torch.from_numpy(g["x"]), torch.from_numpy(g["probs"]), torch.from_numpy(g["schedule"])
+    for step in (0, 3, 5):
+        xs = R.sample_categorical(probs, torch.from_numpy(g[f"u_{step}"]))
+        out = first_hitting_select(x.clone(), xs, sched[:, step], torch.from_numpy(g[f"rv_{step}"]), mi)
+        assert np.array_equal(out.numpy(), g[f"ref_{step}"]), step
+        newly = (out != x)
+        assert bool((x[newly] == mi).all())                                   # only masked positions change
+        want = torch.minimum(sched[:, step], (x == mi).sum(-1))
+        assert torch.equal(newly.sum(-1), want.to(newly.sum(-1).dtype))      # exactly the scheduled number per row
+    # nothing to reveal -> unchanged
+    assert torch.equal(first_hitting_select(x.clone(), x, torch.zeros(x.shape[0], dtype=torch.int32), torch.rand(x.shape), mi), x)

@@ -244,6 +244,24 @@ def update_batch(batch, config, *, text_vocab_size: int, device, training: bool 
 
 
 
+def first_hitting_select(x, x_sampled, num_unmask, random_values, mask_index):
+    """Selection step of the first-hitting sampler (reference model_eval.py:3028-3043): per row, `num_unmask` of the still
+    masked positions — the ones with the largest `random_values` — take their sampled token; everything else is kept.
+    Pure tensor logic (any device); `random_values = torch.rand_like(copy_flag, dtype=float32)` in the reference."""
+    copy_flag = x != mask_index
+    num_unmask = torch.minimum(num_unmask, (~copy_flag).sum(dim=-1))
+    if torch.all(num_unmask <= 0):
+        return x
+    rv = torch.where(~copy_flag, random_values, -1)
+    _, indices = torch.sort(rv, dim=-1, descending=True)
+    range_tensor = torch.arange(copy_flag.shape[-1], device=copy_flag.device).expand(copy_flag.shape)
+    final_mask = range_tensor < num_unmask[:, None]
+    result = torch.zeros_like(copy_flag)
+    result.scatter_(-1, indices, final_mask)
+    return torch.where(result, x_sampled, x)
+
+
+
 class Diffusion(nn.Module):
     def __init__(self, config, tokenizer=None, device=None, vocab_size: Optional[int] = None,
                  text_vocab_size: Optional[int] = None, mask_index: Optional[int] = None):
@@ -571,6 +589,17 @@ class Diffusion(nn.Module):
         return torch.where(conf >= tresh.expand_as(conf), pred_code, x), 1
 
     @torch.no_grad()
+    def _first_hitting_update(self, x, t, dt, schedule=None, step=None, **kwargs):   # reference model_eval.py:3004-3043
+        copy_flag = x != self.mask_index
+        num_unmask = torch.minimum(schedule[:, step].to(x.device), (~copy_flag).sum(dim=-1))
+        p_x0 = self._ddpm_forward(x, t, None, **{k: kwargs.get(k) for k in ("x0", "x0_unmask", "modality")})
+        x_sampled = ops.sample_categorical(p_x0, u=torch.rand_like(p_x0))            # model_utils.py:95-97, same draw order
+        if torch.all(num_unmask <= 0):
+            return x, 1
+        random_values = torch.rand_like(copy_flag, dtype=torch.float32)
+        return first_hitting_select(x, x_sampled, num_unmask, random_values, self.mask_index), 1
+
+    @torch.no_grad()
     def _sample(self, num_steps=None, eps=1e-5, text_only=True, x0=None, x0_unmask=None, batch_size_per_gpu=None,
                 example_batch=None, sample_batch_idx=None, sample_modality=None, sample_ids=None, return_raw_data=False,
                 return_nfe=False, **kwargs):
@@ -590,7 +619,7 @@ class Diffusion(nn.Module):
         num_steps = int(min(num_steps, int((~x0_unmask).sum(dim=-1).min())))
         x = torch.where(x0_unmask, x0, x)
         schedule = None
-        if self.sampler in ("maskgit",):
+        if self.sampler in ("maskgit", "first_hitting"):                             # model_eval.py:2274
             schedule = self.adap_sche(x, num_steps, self.mask_index, mode="arccos")
         timesteps = torch.linspace(1, eps, num_steps + 1, device=self.device)
         dt = (1 - eps) / num_steps
@@ -600,6 +629,8 @@ class Diffusion(nn.Module):
             t = timesteps[i] * torch.ones(B, 1, device=self.device)
             if self.sampler == "maskgit":
                 x, n = self._maskgit_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, schedule=schedule, step=i, modality=modality)
+            elif self.sampler == "first_hitting":                                    # model_eval.py:2373-2374
+                x, n = self._first_hitting_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, schedule=schedule, step=i, modality=modality)
             elif self.sampler == "ddpm":
                 x, n = self._ddpm_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, modality=modality, parity_noise=parity)
             elif self.sampler == "ddpm_cache":
