@@ -308,10 +308,12 @@ class FusedAdamW:
         m.mark_weights_updated(shadow_is_current=True)
 
     def state_dict(self):
+        self.join()                                # the moments may still be in flight on the optimizer stream
         return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, lr=self.lr, betas=self.betas,
                     eps=self.eps, weight_decay=self.weight_decay)
 
     def load_state_dict(self, sd):
+        self.join()
         self.step_count = sd["step"]
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
