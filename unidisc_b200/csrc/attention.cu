@@ -1374,6 +1374,359 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
     }
 }
 
+// EXPERIMENTAL (not launched by default; UD_ATTN_BWD_DQ3=1 selects it for the dQ kernel, not yet validated on hardware): the
+// same kernel with NBUF score buffers and NST_ smem stages as template parameters.  The dQ kernel owns a single accumulator
+// (HD TMEM columns), so three 128-column score buffers fit (3 * 128 + HD <= 512): with two warpgroups alternating over three
+// buffers the scores of a warpgroup's NEXT sub-tile are already in TMEM when it finishes the current one, which takes the
+// S -> softmax -> accumulate round trip (about 3000 cycles for two sub-tiles, tools/ubench.cu) off the critical path.
+template <int HD, int NST_>
+struct AttnBwd2xSmem {
+    static constexpr int FIX_BYTES = 128 * HD * 2;
+    static constexpr int SUB_BYTES = 64 * HD * 2;
+    static constexpr int SUB_BOX = 64 * 128;
+    static constexpr int NBOX = HD / 64;
+    static constexpr int BYTES = 2 * FIX_BYTES + NST_ * 2 * SUB_BYTES + 1024 + 512;      // + alignment slack + barriers
+};
+
+template <int HD, int MODE, int NBUF, int NST_>
+__global__ void __launch_bounds__(320, 1)
+attn_bwd2x_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fb,
+                 const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const AttnBwdParams p) {
+    using S = AttnBwd2xSmem<HD, NST_>;
+    constexpr int NST = NST_;
+    static_assert(NBUF * 128 + (MODE == 0 ? 2 : 1) * HD <= 512, "score buffers + accumulators exceed the 512 TMEM columns");
+    static_assert((1 + 2 * NST + 5 * NBUF) * 8 + 4 <= 512, "barrier block larger than its reservation");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sFA = smem;
+    uint8_t* sFB = sFA + S::FIX_BYTES;
+    uint8_t* sST = sFB + S::FIX_BYTES;                   // stage s: [SA | SB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sST + NST * 2 * S::SUB_BYTES);
+    uint64_t* f_full = bars;                 // 1
+    uint64_t* st_full = bars + 1;            // NST
+    uint64_t* st_empty = bars + 1 + NST;     // NST
+    uint64_t* s_full = bars + 1 + 2 * NST;   // NBUF   S^T of a sub-tile in TMEM      (tensor pipe -> softmax warpgroup)
+    uint64_t* dp_full = s_full + NBUF;       // NBUF   dP^T of the same sub-tile
+    uint64_t* p_rdy = dp_full + NBUF;        // NBUF   bf16 P^T written over S^T        (softmax warpgroup -> tensor pipe)
+    uint64_t* ds_rdy = p_rdy + NBUF;         // NBUF   bf16 dS^T written over dP^T
+    uint64_t* acc_done = ds_rdy + NBUF;      // NBUF
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_done + NBUF);
+    // per-column metadata of the streamed sub-tile: [warpgroup][2 slots][64] (only the dK/dV kernel needs lse / delta per column)
+    __shared__ __align__(16) float s_lse[MODE == 0 ? 4 * 64 : 4];
+    __shared__ __align__(16) float s_dlt[MODE == 0 ? 4 * 64 : 4];
+    __shared__ __align__(16) int s_sid[4 * 64];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int T2 = (p.N + 63) / 64;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_fa); tma_prefetch_desc(&tm_fb); tma_prefetch_desc(&tm_sa); tma_prefetch_desc(&tm_sb);
+        mbar_init(f_full, 1);
+        for (int s = 0; s < NST; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
+        for (int s = 0; s < NBUF; ++s) {
+            mbar_init(&s_full[s], 1); mbar_init(&dp_full[s], 1); mbar_init(&p_rdy[s], 128); mbar_init(&ds_rdy[s], 128);
+            mbar_init(&acc_done[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+    const uint32_t tAcc0 = tmem + NBUF * 128, tAcc1 = tmem + NBUF * 128 + HD;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(f_full, 2 * S::FIX_BYTES);
+#pragma unroll
+            for (int bx = 0; bx < S::NBOX; ++bx) {
+                tma_load_3d(sFA + bx * (128 * 128), &tm_fa, f_full, h * HD + bx * 64, t0, b);
+                tma_load_3d(sFB + bx * (128 * 128), &tm_fb, f_full, h * HD + bx * 64, t0, b);
+            }
+            for (int i = 0; i < T2; ++i) {
+                const int s = i % NST;
+                mbar_wait(&st_empty[s], ((i / NST) & 1) ^ 1);
+                mbar_expect_tx(&st_full[s], 2 * S::SUB_BYTES);
+                uint8_t* sa = sST + s * 2 * S::SUB_BYTES;
+                uint8_t* sb = sa + S::SUB_BYTES;
+#pragma unroll
+                for (int bx = 0; bx < S::NBOX; ++bx) {
+                    tma_load_3d(sa + bx * S::SUB_BOX, &tm_sa, &st_full[s], h * HD + bx * 64, i * 64, b);
+                    tma_load_3d(sb + bx * S::SUB_BOX, &tm_sb, &st_full[s], h * HD + bx * 64, i * 64, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        {
+            // the whole warp runs this loop (warp-uniform control flow and descriptor arithmetic); one elected lane issues
+            const uint32_t leader = elect_one();
+            constexpr uint32_t idesc_sc = make_idesc_bf16(128, 64, false, false);
+            constexpr uint32_t idesc_acc = make_idesc_bf16(128, HD, false, true);
+            const uint32_t aFA = smem_u32(sFA), aFB = smem_u32(sFB);
+            auto issue_scores = [&](int i) {
+                const int s = i % NST, bf = i % NBUF;
+                mbar_wait(&st_full[s], (i / NST) & 1);
+                tc_fence_after();
+                const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
+                const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
+                if (leader) {
+                    // S^T and dP^T are signalled separately: the warpgroup starts its exponentials while dP^T is still being
+                    // multiplied
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tSc, desc_kmajor(aFA, ks), desc_kmajor64(aSA, ks), idesc_sc, ks != 0);
+                    umma_commit(&s_full[bf]);
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tDp, desc_kmajor(aFB, ks), desc_kmajor64(aSB, ks), idesc_sc, ks != 0);
+                    umma_commit(&dp_full[bf]);
+                }
+                __syncwarp();
+            };
+            mbar_wait(f_full, 0);
+#pragma unroll
+            for (int i0 = 0; i0 < NBUF; ++i0)
+                if (i0 < T2) issue_scores(i0);
+            for (int i = 0; i < T2; ++i) {
+                const int s = i % NST, bf = i % NBUF;
+                const uint32_t ph = (i / NBUF) & 1;
+                const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
+                const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
+                const uint32_t acc0 = i != 0;
+                if (MODE == 0) {
+                    // dV += P^T dO as soon as P^T is stored: it runs while the warpgroup still forms dS^T
+                    mbar_wait(&p_rdy[bf], ph);
+                    tc_fence_after();
+                    if (leader) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc1, tSc + ks * 8, desc_mnmajor64(aSB, ks), idesc_acc, acc0 | (ks != 0));
+                    }
+                    __syncwarp();
+                }
+                mbar_wait(&ds_rdy[bf], ph);
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, acc0 | (ks != 0));
+                    umma_commit(&st_empty[s]);
+                    umma_commit(&acc_done[bf]);
+                }
+                __syncwarp();
+                if (i + NBUF < T2) {
+                    // scores(i+NBUF) overwrite the columns the accumulation MMAs above read P / dS from.  tcgen05.mma issued by
+                    // one thread execute in issue order, so no completion wait is needed here (UD_ATTN_BWD_SAFE=1 re-enables it)
+                    if (p.safe_order) mbar_wait(&acc_done[bf], ph);
+                    issue_scores(i + NBUF);
+                }
+            }
+        }
+    } else {
+        // two softmax warpgroups (warps 2-5 and 6-9): warpgroup g owns the sub-tiles i == g (mod 2); sub-tile i lives in score
+        // buffer i % NBUF
+        const int wg = (warp - 2) >> 2;
+        const int qd = warp & 3;
+        const int rloc = qd * 32 + lane;
+        const int row = t0 + rloc;   // MODE0: key index ; MODE1: query index
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const int tid128 = (threadIdx.x - 64) & 127;
+        const bool use_ids = p.sample_ids != nullptr;
+        const long long bh = (long long)b * p.H + h;
+        int sid_row = 0;
+        if (use_ids) sid_row = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
+        float lse_row = 0.f, dlt_row = 0.f;
+        if (MODE == 1 && row < p.N) {
+            lse_row = p.lse[bh * p.N + row] * LOG2E;
+            if (p.o != nullptr) {
+                // delta of this thread's query row, straight from O and dO (both warpgroups own the same rows and compute it
+                // redundantly; warpgroup 0 publishes it)
+                const uint4* po = reinterpret_cast<const uint4*>(p.o + ((long long)b * p.N + row) * p.ldo + h * HD);
+                const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((long long)b * p.N + row) * p.ldo + h * HD);
+                float acc = 0.f;
+#pragma unroll 4
+                for (int j = 0; j < HD / 8; ++j) {
+                    const uint4 a = po[j], g = pd[j];
+                    acc += bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y)
+                         + bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
+                }
+                dlt_row = acc;
+                if (wg == 0) p.delta_out[bh * p.N + row] = acc;
+            } else {
+                dlt_row = p.delta[bh * p.N + row];
+            }
+        }
+        const bool row_ok = row < p.N;
+        const float scl = p.scale_log2;
+        const int Ntok = p.N;
+        // metadata of this warpgroup's next sub-tile is fetched one iteration ahead (global latency off the critical path)
+        float pf_lse = INFINITY, pf_dlt = 0.f;
+        int pf_sid = -2;
+        auto fetch_meta = [&](int i) {
+            if ((MODE == 0 || use_ids) && tid128 < 64 && i < T2) {
+                const int cidx = i * 64 + tid128;
+                if (MODE == 0) {
+                    pf_lse = cidx < Ntok ? p.lse[bh * Ntok + cidx] * LOG2E : INFINITY;
+                    pf_dlt = cidx < Ntok ? p.delta[bh * Ntok + cidx] : 0.f;
+                }
+                if (use_ids) pf_sid = cidx < Ntok ? (int)p.sample_ids[(long long)b * Ntok + cidx] : -2;
+            }
+        };
+        fetch_meta(wg);
+        for (int i = wg; i < T2; i += 2) {
+            const int ms = (wg * 2 + ((i >> 1) & 1)) * 64;    // metadata slot of this sub-tile
+            const int bf = i % NBUF;
+            const uint32_t bph = (i / NBUF) & 1;
+            const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
+            if (MODE == 0 || use_ids) {
+                if (tid128 < 64) {
+                    if (MODE == 0) { s_lse[ms + tid128] = pf_lse; s_dlt[ms + tid128] = pf_dlt; }
+                    if (use_ids) s_sid[ms + tid128] = pf_sid;
+                }
+                named_bar_sync(1 + wg, 128);
+                fetch_meta(i + 2);
+            }
+            mbar_wait(&s_full[bf], bph);
+            tc_fence_after();
+            const bool slow = use_ids || (i * 64 + 64 > Ntok) || !row_ok;   // masks needed only on edge tiles / document masks
+            uint32_t rsA[32], rsB[32], pk[32];
+            tmem_ld_32x32b_x32(tSc + lane_off, rsA);
+            tmem_ld_32x32b_x32(tSc + 32 + lane_off, rsB);
+            tmem_ld_wait();
+            // phase 1: P = exp(S * scale - lse), kept in fp32 in rsA / rsB (in place) and packed to bf16 in pk.  Interior tiles
+            // take the mask-free instantiation (no per-element compare / select instructions).
+            auto phase1 = [&](uint32_t (&rs)[32], int c, auto slow_tag) {
+                constexpr bool SLOW = decltype(slow_tag)::value;
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    float l4[4];
+                    if (MODE == 0) {
+                        const float4 lv = *reinterpret_cast<const float4*>(&s_lse[ms + c * 32 + e4 * 4]);
+                        l4[0] = lv.x; l4[1] = lv.y; l4[2] = lv.z; l4[3] = lv.w;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) l4[u] = lse_row;
+                    }
+                    float pv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float pr = ex2(fmaf(__uint_as_float(rs[e4 * 4 + u]), scl, -l4[u]));
+                        if (SLOW) {
+                            const int col = c * 32 + e4 * 4 + u;
+                            bool ok = row_ok && (i * 64 + col < Ntok);
+                            if (use_ids) {
+                                const int sq = s_sid[ms + col];
+                                ok = ok && sq == sid_row && sid_row != -1;
+                            }
+                            if (!ok) pr = 0.f;
+                        }
+                        pv[u] = pr;
+                        rs[e4 * 4 + u] = __float_as_uint(pr);
+                    }
+                    if (MODE == 0) {
+                        pk[c * 16 + e4 * 2] = pack_bf16x2(pv[0], pv[1]);
+                        pk[c * 16 + e4 * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+                    }
+                }
+            };
+            if (slow) {
+                phase1(rsA, 0, std::true_type{});
+                phase1(rsB, 1, std::true_type{});
+            } else {
+                phase1(rsA, 0, std::false_type{});
+                phase1(rsB, 1, std::false_type{});
+            }
+            if (MODE == 0) {
+                tmem_st_32x32b_x32(tSc + lane_off, pk);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&p_rdy[bf]);
+            }
+            // phase 2: dS = P * (dP - delta)
+            mbar_wait(&dp_full[bf], bph);
+            tc_fence_after();
+            uint32_t rdA[32], rdB[32];
+            tmem_ld_32x32b_x32(tDp + lane_off, rdA);
+            tmem_ld_32x32b_x32(tDp + 32 + lane_off, rdB);
+            tmem_ld_wait();
+            auto phase2 = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c) {
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    float d4[4];
+                    if (MODE == 0) {
+                        const float4 dv = *reinterpret_cast<const float4*>(&s_dlt[ms + c * 32 + e4 * 4]);
+                        d4[0] = dv.x; d4[1] = dv.y; d4[2] = dv.z; d4[3] = dv.w;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) d4[u] = dlt_row;
+                    }
+                    float dvv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        dvv[u] = __uint_as_float(rs[e4 * 4 + u]) * (__uint_as_float(rd[e4 * 4 + u]) - d4[u]);
+                    pk[c * 16 + e4 * 2] = pack_bf16x2(dvv[0], dvv[1]);
+                    pk[c * 16 + e4 * 2 + 1] = pack_bf16x2(dvv[2], dvv[3]);
+                }
+            };
+            phase2(rsA, rdA, 0);
+            phase2(rsB, rdB, 1);
+            tmem_st_32x32b_x32(tDp + lane_off, pk);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&ds_rdy[bf]);
+        }
+        // ---- write the accumulators (the two warpgroups split the work) ----
+        mbar_wait(&acc_done[(T2 - 1) % NBUF], ((T2 - 1) / NBUF) & 1);
+        tc_fence_after();
+        {
+            // MODE0: warpgroup 0 stores dK (Acc0), warpgroup 1 stores dV (Acc1).  MODE1: each stores half of dQ's columns.
+            // TMEM gives every thread one ROW; the bf16 rows are staged in the (now idle) fixed-operand tiles with the
+            // 16-byte chunks XOR-swizzled by row, then copied out with whole rows per warp instruction (coalesced 128-byte
+            // lines instead of 32 scattered 16-byte stores per instruction).
+            const int a = (MODE == 0) ? wg : 0;
+            const uint32_t tA = a == 0 ? tAcc0 : tAcc1;
+            uint8_t* stg = (MODE == 0 && wg == 1) ? sFB : sFA;
+            const float sc = a == 0 ? p.scale : 1.0f;
+            constexpr int CPR = HD * 2 / 16;                         // 16-byte chunks per row
+            const int c_lo = (MODE == 0) ? 0 : wg * (HD / 64), c_hi = (MODE == 0) ? HD / 32 : (wg + 1) * (HD / 64);
+#pragma unroll 1
+            for (int c = c_lo; c < c_hi; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tA + c * 32 + lane_off, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 o4;
+                    o4.x = pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) * sc, __uint_as_float(r[8 * q4 + 1]) * sc);
+                    o4.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * sc, __uint_as_float(r[8 * q4 + 3]) * sc);
+                    o4.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * sc, __uint_as_float(r[8 * q4 + 5]) * sc);
+                    o4.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * sc, __uint_as_float(r[8 * q4 + 7]) * sc);
+                    const int ch = c * 4 + q4;
+                    *reinterpret_cast<uint4*>(stg + rloc * (HD * 2) + ((ch ^ (rloc & (CPR - 1))) << 4)) = o4;
+                }
+            }
+            named_bar_sync(1 + wg, 128);
+            const int chunks_w = (c_hi - c_lo) * 4, chunk0 = c_lo * 4;            // this warpgroup's 16-byte chunks per row
+            const long long ldo = a == 0 ? p.ld0 : p.ld1;
+            __nv_bfloat16* base = (a == 0 ? p.out0 : p.out1) + ((long long)b * p.N + t0) * ldo + h * HD;
+#pragma unroll 4
+            for (int it = 0; it < chunks_w; ++it) {
+                const int idx = it * 128 + tid128;
+                const int rr = idx / chunks_w, ch = chunk0 + idx % chunks_w;
+                if (t0 + rr < p.N) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * (HD * 2) + ((ch ^ (rr & (CPR - 1))) << 4));
+                    *reinterpret_cast<uint4*>(base + (long long)rr * ldo + ch * 8) = v;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
 template <int HD>
 static int attn_smem_bytes(int ntiles) { return ntiles * AttnSmem<HD>::TILE_BYTES + 1024 + 4096; }
 
@@ -1474,7 +1827,18 @@ static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const v
         attr2 = true;
     }
     // dQ first: it also produces delta, which the dK/dV kernel reads per streamed query column
-    attn_bwd2_kernel<HD, 1><<<grid, 320, smem, stream>>>(tq, tdo, tk64, tv64, p1);
+    static const bool dq3 = getenv("UD_ATTN_BWD_DQ3") != nullptr;      // experimental three-score-buffer dQ kernel (see attn_bwd2x_kernel)
+    if (dq3) {
+        const int smem3 = AttnBwd2xSmem<HD, 5>::BYTES;
+        static bool attr3 = false;
+        if (!attr3) {
+            UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2x_kernel<HD, 1, 3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+            attr3 = true;
+        }
+        attn_bwd2x_kernel<HD, 1, 3, 5><<<grid, 320, smem3, stream>>>(tq, tdo, tk64, tv64, p1);
+    } else {
+        attn_bwd2_kernel<HD, 1><<<grid, 320, smem, stream>>>(tq, tdo, tk64, tv64, p1);
+    }
     UD_CUDA_CHECK(cudaGetLastError());
     attn_bwd2_kernel<HD, 0><<<grid, 320, smem, stream>>>(tk, tv, tq64, tdo64, p0);
     UD_CUDA_CHECK(cudaGetLastError());
