@@ -173,6 +173,9 @@ int ud_sumsq_f32(const float* g, long long n, float* out, int max_ctas, void* st
  * max_ctas > 0 caps the grid so the side-stream copies leave the SMs to the backward GEMMs they overlap with. */
 int ud_grad_pack_bf16(const float* g, void* dst_bf16, long long n, float inv_world, int max_ctas, void* stream);
 int ud_grad_unpack_bf16(const void* src_bf16, float* g, long long n, int max_ctas, void* stream);
+/* decompress and, on the way, sumsq[0] += sum of squares of the fp32 gradients written (the all-reduced gradient's share of the
+ * norm clip_grad_norm_ needs, model.py:1518) */
+int ud_grad_unpack_bf16_sumsq(const void* src_bf16, float* g, long long n, int max_ctas, float* sumsq, void* stream);
 
 #ifdef __cplusplus
 }

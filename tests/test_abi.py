@@ -44,7 +44,7 @@ def built_lib():
 def test_header_declares_what_the_binding_binds():
     from unidisc_b200 import _lib
     protos = _prototypes()
-    assert len(protos) >= 27
+    assert len(protos) >= 28
     assert set(protos) == set(_lib._SIGS), (set(protos) ^ set(_lib._SIGS))
     assert set(_lib.EXPORTED_SYMBOLS) == set(protos)
     for name, params in protos.items():
@@ -62,7 +62,7 @@ def test_library_loads_and_exports_every_declared_symbol(built_lib):
     for name in _prototypes():
         assert hasattr(h, name), f"{built_lib} does not export {name}"
     h.ud_abi_version.restype = ctypes.c_int
-    assert h.ud_abi_version() == 5            # bumped whenever a prototype changes (include/unidisc_b200.h)
+    assert h.ud_abi_version() == 6            # bumped whenever a prototype changes (include/unidisc_b200.h)
 
 
 def test_adaln_struct_layout_matches_header():

@@ -44,6 +44,7 @@ _SIGS = {
     "ud_sumsq_f32": [_vp, _ll, _vp, _i, _vp],
     "ud_grad_pack_bf16": [_vp, _vp, _ll, _f, _i, _vp],
     "ud_grad_unpack_bf16": [_vp, _vp, _ll, _i, _vp],
+    "ud_grad_unpack_bf16_sumsq": [_vp, _vp, _ll, _i, _vp, _vp],
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS.keys())

@@ -959,6 +959,41 @@ __global__ void grad_unpack_kernel(const __nv_bfloat16* __restrict__ s, float* _
     }
 }
 
+// the same with the gradient norm's partial sum taken on the way: out[0] += sum of squares of everything written to g
+__global__ void grad_unpack_sumsq_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ g, long long n,
+                                         float* __restrict__ out) {
+    __shared__ float scratch[2 * 32];
+    int buf = 0;
+    float a[1] = {0.f};
+    const long long tile = (long long)blockDim.x * 16;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        uint2 v[4];
+        long long idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            idx[u] = base + ((long long)u * blockDim.x + threadIdx.x) * 4;
+            if (idx[u] + 4 <= n) v[u] = *reinterpret_cast<const uint2*>(s + idx[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = idx[u];
+            if (i + 4 <= n) {
+                const float4 f = make_float4(bf16lo(v[u].x), bf16hi(v[u].x), bf16lo(v[u].y), bf16hi(v[u].y));
+                *reinterpret_cast<float4*>(g + i) = f;
+                a[0] += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+            } else {
+                for (long long k = i; k < n; ++k) {
+                    const float f = __bfloat162float(s[k]);
+                    g[k] = f;
+                    a[0] += f * f;
+                }
+            }
+        }
+    }
+    block_sum<1>(a, scratch, buf);
+    if (threadIdx.x == 0 && a[0] != 0.f) atomicAdd(out, a[0]);
+}
+
 // materialises the dropout keep-scales the fused norm kernels regenerate on the fly (for parity tests / debugging)
 __global__ void dropout_scale_kernel(float* __restrict__ out, int rows, int D, uint32_t thresh, float inv_keep, uint64_t seed,
                                      uint64_t offset) {
@@ -1007,7 +1042,7 @@ static AdaLN to_adaln(const ud_adaln* t) {
     return a;
 }
 
-extern "C" int ud_abi_version(void) { return 5; }
+extern "C" int ud_abi_version(void) { return 6; }
 extern "C" int ud_device_sm_count(void) { return sm_count(); }
 
 extern "C" int ud_embed_rmsnorm_fwd(const int64_t* ids, const int64_t* modality, const float* E, const float* Emod,
@@ -1199,6 +1234,14 @@ extern "C" int ud_sumsq_f32(const float* g, long long n, float* out, int max_cta
 extern "C" int ud_grad_pack_bf16(const float* g, void* dst, long long n, float inv_world, int max_ctas, void* stream) {
     if (n <= 0) return 0;
     grad_pack_kernel<<<capped(flat_grid(n / 4 + 1), max_ctas), 256, 0, STREAM(stream)>>>(g, BF(dst), n, inv_world);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_grad_unpack_bf16_sumsq(const void* src, float* g, long long n, int max_ctas, float* sumsq, void* stream) {
+    if (n <= 0) return 0;
+    if (sumsq == nullptr) return -1;
+    grad_unpack_sumsq_kernel<<<capped(flat_grid(n / 4 + 1), max_ctas), 256, 0, STREAM(stream)>>>(CBF(src), g, n, sumsq);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -48,7 +48,9 @@ class ThinDDP(nn.Module):
         # wide kernel disturbs the overlapped backward less than a long narrow one, see nccl_options)
         self.side_ctas = int(os.environ.get("UD_DDP_SIDE_CTAS", 0)) if side_ctas is None else int(side_ctas)
         self._pack = _pack or (lambda g, d, w: ops.grad_pack(g, d, w, self.side_ctas))
-        self._unpack = _unpack or (lambda s, g: ops.grad_unpack(s, g, self.side_ctas))
+        # `sumsq_target` (FusedAdamW, UD_DDP_FUSED_SUMSQ=1, experimental): the decompression also accumulates the gradient norm
+        self.sumsq_target = None
+        self._unpack = _unpack or (lambda s, g: ops.grad_unpack(s, g, self.side_ctas, sumsq=self.sumsq_target))
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.bf16_compress = bf16_compress
         self._sync = True
@@ -199,6 +201,8 @@ class FusedAdamW:
         if self.overlap and self.max_grad_norm is not None:
             if self.ddp is not None:
                 self.ddp.post_bucket_hook = self._on_bucket_final
+                if bool(int(os.environ.get("UD_DDP_FUSED_SUMSQ", "0"))) and self.ddp.bf16_compress and self.ddp.world > 1:
+                    self.ddp.sumsq_target = self._sumsq        # grad_unpack adds the squares; the hook only counts the bucket
             else:
                 by_block = {b: self._ranges_of(b) for b in range(-1, self.module.n_blocks + 1)}      # planned once (host cost)
                 big_end = self.module._big_end
@@ -237,7 +241,9 @@ class FusedAdamW:
     def _on_bucket_final(self, block_idx, ranges, on_side_stream):
         """Partial sum of squares of a finalised gradient bucket (overlapped with the rest of the backward)."""
         g = self.module._flat_g
-        if on_side_stream:                       # ThinDDP's comm stream, already ordered after the bucket's all-reduce
+        if on_side_stream and self.ddp is not None and self.ddp.sumsq_target is not None:
+            pass                                 # the squares were summed by grad_unpack on the same stream
+        elif on_side_stream:                     # ThinDDP's comm stream, already ordered after the bucket's all-reduce
             for lo, hi in ranges:
                 ops.sumsq(g[lo:hi], self._sumsq, self.sumsq_ctas)
         else:

@@ -240,5 +240,8 @@ def grad_pack(g, dst, inv_world, max_ctas=0):
     call("ud_grad_pack_bf16", P(g), P(dst), g.numel(), inv_world, max_ctas, stream())
 
 
-def grad_unpack(src, g, max_ctas=0):
+def grad_unpack(src, g, max_ctas=0, sumsq=None):
+    if sumsq is not None:
+        call("ud_grad_unpack_bf16_sumsq", P(src), P(g), g.numel(), max_ctas, P(sumsq), stream())
+        return
     call("ud_grad_unpack_bf16", P(src), P(g), g.numel(), max_ctas, stream())
