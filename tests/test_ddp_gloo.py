@@ -84,16 +84,32 @@ def _worker(rank, world, port, q):
         for i in [m.n_blocks] + list(range(m.n_blocks - 1, -1, -1)) + [-1]:
             m.grad_ready_hook(i)
     ok_nosync = torch.equal(m.flat_grads, grads)
+    # post-bucket hook (the streamed optimizer's gradient-norm partial sums): once per bucket, AFTER that bucket's all-reduce
+    seen = []
+
+    def post(block_idx, ranges, on_side_stream):
+        ok = all(torch.equal(m.flat_grads[lo:hi], expect.float()[lo:hi]) for lo, hi in ranges)
+        seen.append((block_idx, on_side_stream, ok, sum(hi - lo for lo, hi in ranges)))
+
+    ddp.post_bucket_hook = post
     for i in [m.n_blocks] + list(range(m.n_blocks - 1, -1, -1)) + [-1]:     # order used by DIT._backward_impl
         m.grad_ready_hook(i)
     got = m.flat_grads.clone()
+    ok_post = ([b for b, _, _, _ in seen] == [m.n_blocks] + list(range(m.n_blocks - 1, -1, -1)) + [-1]
+               and all(side and ok for _, side, ok, _ in seen) and sum(n for _, _, _, n in seen) == got.numel())
+    # an optimizer handed the bare module must chain behind the DDP hook, never replace it
+    from unidisc_b200.ddp import FusedAdamW
+    opt = FusedAdamW(m, max_grad_norm=1.0)
+    ok_chain = opt.ddp is ddp and getattr(m.grad_ready_hook, "__self__", None) is ddp and not opt.overlap
+    opt2 = FusedAdamW(ddp, max_grad_norm=1.0)
+    ok_chain = ok_chain and opt2.ddp is ddp and opt2.module is m
     # every element reduced exactly once
     covered = torch.zeros_like(got, dtype=torch.int32)
     for rs in ddp._ranges_by_block.values():
         for lo, hi in rs:
             covered[lo:hi] += 1
     q.put((rank, ok_bcast, ok_nosync, bool((covered == 1).all()), float((got - expect.float()).abs().max()),
-           ddp.bytes_on_wire_per_step, 2 * got.numel()))
+           ddp.bytes_on_wire_per_step, 2 * got.numel(), ok_post, ok_chain))
     dist.destroy_process_group()
 
 
@@ -108,7 +124,9 @@ def test_thin_ddp_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, ok_bcast, ok_nosync, covered_once, err, wire, expect_wire in res:
+    for rank, ok_bcast, ok_nosync, covered_once, err, wire, expect_wire, ok_post, ok_chain in res:
+        assert ok_post, "post_bucket_hook must fire once per bucket, on the communication path, after the bucket's all-reduce"
+        assert ok_chain, "FusedAdamW must chain behind ThinDDP's gradient hook (replacing it disables the all-reduce)"
         assert ok_bcast, "weights must be broadcast from rank 0"
         assert ok_nosync, "no_sync() must suppress the all-reduce"
         assert covered_once, "every gradient element must be all-reduced exactly once"

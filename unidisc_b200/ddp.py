@@ -176,6 +176,12 @@ class FusedAdamW:
     def __init__(self, module, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=None, overlap=None):
         self.ddp = module if isinstance(module, ThinDDP) else None
         self.module = module.module if isinstance(module, ThinDDP) else module
+        if self.ddp is None:
+            # handed the bare DIT although a ThinDDP wraps it: its grad_ready_hook must stay in place (replacing it would
+            # silently switch the gradient all-reduce off), so the optimizer chains behind it
+            owner = getattr(getattr(self.module, "grad_ready_hook", None), "__self__", None)
+            if isinstance(owner, ThinDDP):
+                self.ddp = owner
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.step_count = 0
@@ -204,6 +210,8 @@ class FusedAdamW:
                 if bool(int(os.environ.get("UD_DDP_FUSED_SUMSQ", "0"))) and self.ddp.bf16_compress and self.ddp.world > 1:
                     self.ddp.sumsq_target = self._sumsq        # grad_unpack adds the squares; the hook only counts the bucket
             else:
+                if self.module.grad_ready_hook is not None:
+                    raise RuntimeError("FusedAdamW(overlap): DIT.grad_ready_hook is already taken by something that is not a ThinDDP")
                 by_block = {b: self._ranges_of(b) for b in range(-1, self.module.n_blocks + 1)}      # planned once (host cost)
                 big_end = self.module._big_end
                 small_only = {b: [r for r in rs if r[0] >= big_end] for b, rs in by_block.items()}
