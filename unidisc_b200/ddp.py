@@ -117,7 +117,11 @@ class ThinDDP(nn.Module):
             if self._sync and self.post_bucket_hook is not None:
                 self.post_bucket_hook(block_idx, self._ranges_by_block.get(block_idx, []), False)
             return
-        g = self.module.flat_grads
+        # (not the `flat_grads` property: it refreshes the bf16 weight shadow when the backward has just marked it stale — an
+        #  8.4 GB cast per step that the optimizer overwrites right after)
+        g = getattr(self.module, "_flat_g", None)
+        if g is None:
+            g = self.module.flat_grads
         cuda = g.is_cuda
         if self._stage is None:
             self._stage = torch.empty(self._max_range, device=g.device, dtype=bf16 if self.bf16_compress else torch.float32)
