@@ -214,7 +214,8 @@ class FusedAdamW:
                 if bool(int(os.environ.get("UD_DDP_FUSED_SUMSQ", "0"))) and self.ddp.bf16_compress and self.ddp.world > 1:
                     self.ddp.sumsq_target = self._sumsq        # grad_unpack adds the squares; the hook only counts the bucket
             else:
-                if self.module.grad_ready_hook is not None:
+                prev = self.module.grad_ready_hook
+                if prev is not None and not getattr(prev, "_ud_fused_adamw", False):
                     raise RuntimeError("FusedAdamW(overlap): DIT.grad_ready_hook is already taken by something that is not a ThinDDP")
                 by_block = {b: self._ranges_of(b) for b in range(-1, self.module.n_blocks + 1)}      # planned once (host cost)
                 big_end = self.module._big_end
@@ -223,8 +224,10 @@ class FusedAdamW:
                 # (DIT.grad_sumsq_acc); only the small parameters still need a pass
                 if not bool(int(os.environ.get("UD_NO_FUSED_SUMSQ", "0"))):
                     self.module.grad_sumsq_acc = self._sumsq
-                self.module.grad_ready_hook = lambda b: self._on_bucket_final(
+                hook = lambda b: self._on_bucket_final(
                     b, small_only[b] if self.module._last_bwd_fused_sumsq else by_block[b], False)
+                hook._ud_fused_adamw = True          # a later FusedAdamW on the same module may replace this hook
+                self.module.grad_ready_hook = hook
 
     # ---- bucket plan: (name, [ranges]) in the order the forward first reads the weights ----
     def _ranges_of(self, block_idx):
