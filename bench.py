@@ -28,6 +28,10 @@ WORKLOADS = {
     "unidisc-1.4B": ("extra_large", 8, 256, 1024),
     "dit-b": ("small", 32, 256, 1024),
     "tiny": ("small", 2, 64, 64),     # CI-sized sanity run, never a bench line
+    # BASELINE.json configs[4]: packed / interleaved documents, seq_len 4096, bs 2 per GPU, document-masked attention
+    "unidisc-1.4B-interleaved": ("extra_large", 2, 3072, 1024),
+    # BASELINE.json configs[3]: 64-step absorbing denoising, batch 64 (a "step" = one whole sampling run of the batch)
+    "unidisc-1.4B-sample": ("extra_large", 64, 256, 1024),
 }
 TEXT_VOCAB, IMAGE_VOCAB = 32001, 16384
 
@@ -94,7 +98,42 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path (q_xt -> DIT -> SUBS -> weighted NLL, fwd+bwd), host cores
 # --------------------------------------------------------------------------------------------------------------
-def cpu_reference_tokens_per_sec(workload, budget_s=25.0):
+CPU_THREADS = 16          # fixed, so the CPU figure is comparable between boxes (hosts of this pool have 16-32 cores)
+
+
+def cpu_reference_forward(workload):
+    """Forward pass of the UNMODIFIED reference backbone (`models.dit.DIT` staged in baseline/_ref by
+    baseline/install_reference.py) on the host cores: real depth, B=1, the reference's CPU default (bf16 autocast,
+    SURVEY.md section 0 row 10), eval mode.  The reference's eager BACKWARD raises on CPU (in-place q/k-norm write), so the
+    training-step figure comes from the port (cpu_reference_tokens_per_sec) and this is reported beside it."""
+    from oracle import ref_loader as RL
+    from unidisc_b200.config import MODEL_PRESETS
+    if not RL.reference_available():
+        return dict(value=None, unit="tokens/s (forward only)", sample=f"reference backbone not staged at {RL.REFERENCE_ROOT}")
+    preset, _, txt, img = WORKLOADS[workload]
+    D, L, H = MODEL_PRESETS[preset]
+    V, tv, mi = TEXT_VOCAB + IMAGE_VOCAB, TEXT_VOCAB, TEXT_VOCAB - 1
+    N = txt + img
+    torch.set_num_threads(min(CPU_THREADS, os.cpu_count() or 1))
+    rcfg = RL.make_ref_config(D, H, L, txt, img, dropout=0.0)
+    model = RL.build_reference_dit(rcfg, V, tv, mi, dtype=None)
+    model.eval()
+    g = torch.Generator().manual_seed(42)
+    ids = torch.cat([torch.randint(0, tv - 1, (1, txt), generator=g), torch.randint(tv, V, (1, img), generator=g)], 1)
+    mod = torch.cat([torch.zeros(1, txt, dtype=torch.int64), torch.ones(1, img, dtype=torch.int64)], 1)
+    best = None
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        for _ in range(2):
+            t0 = time.perf_counter()
+            model(ids, None, modality=mod)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    del model
+    return dict(value=N / best, unit="tokens/s (forward only)", cores=torch.get_num_threads(), kind="reference",
+                sample=f"unmodified models.dit.DIT ({RL.REFERENCE_ROOT}), depth {L}, B=1 N={N} V={V}, CPU bf16 autocast, eval, best of 2 ({best:.2f}s)")
+
+
+def cpu_reference_tokens_per_sec(workload, budget_s=25.0, with_reference_forward=True):
     """Times the oracle restatement (oracle/restated.py, eager torch fp32 on the host cores) of the reference training
     path on a bounded sample: per-GPU batch 1 at the workload's D/N/V, depth 1 and 3 blocks, fwd+bwd; the per-block and
     the embed+head+loss costs are separated and extrapolated linearly to the workload's depth."""
@@ -103,7 +142,7 @@ def cpu_reference_tokens_per_sec(workload, budget_s=25.0):
     preset, _, txt, img = WORKLOADS[workload]
     from unidisc_b200.config import MODEL_PRESETS
     D, L, H = MODEL_PRESETS[preset]
-    cores = os.cpu_count() or 1
+    cores = min(CPU_THREADS, os.cpu_count() or 1)
     torch.set_num_threads(cores)
     V, tv, mi = TEXT_VOCAB + IMAGE_VOCAB, TEXT_VOCAB, TEXT_VOCAB - 1
     N = txt + img
@@ -130,18 +169,33 @@ def cpu_reference_tokens_per_sec(workload, budget_s=25.0):
     per_block = max((t3 - t1) / 2.0, 1e-6)
     fixed = max(t1 - per_block, 0.0)
     t_full = fixed + L * per_block
-    return dict(value=N / t_full, unit="tokens/s", cores=cores, kind="port",
-                sample=f"oracle/restated.py eager-torch fp32 fwd+bwd, B=1 N={N} D={D} V={V}; measured depth 1 ({t1:.2f}s) and 3 ({t3:.2f}s), "
-                       f"extrapolated linearly to depth {L} ({t_full:.1f}s/step); no optimizer step on the CPU arm")
+    out = dict(value=N / t_full, unit="tokens/s", cores=cores, kind="port",
+               sample=f"oracle/restated.py eager-torch fp32 fwd+bwd, B=1 N={N} D={D} V={V}; measured depth 1 ({t1:.2f}s) and 3 ({t3:.2f}s), "
+                      f"extrapolated linearly to depth {L} ({t_full:.1f}s/step); no optimizer step on the CPU arm; {cores} threads (fixed)")
+    if with_reference_forward:
+        try:
+            out["reference_forward"] = cpu_reference_forward(workload)
+        except Exception as e:  # noqa: BLE001
+            out["reference_forward"] = dict(value=None, sample=f"failed: {type(e).__name__}: {e}")
+    return out
 
 
 def run_reference_gpu_arm(args, rank, world, local):
-    """`--impl reference --ref-device cuda`: the reference's own torch path on the GPU — oracle/torch_eager.py, the library-op
-    restatement of models/dit.py + model.py::compute_loss (nn.Linear / F.layer_norm / F.scaled_dot_product_attention under
-    torch.autocast(bf16), materialised SUBS log-probs, torch.optim.AdamW(fused) + clip_grad_norm_, torch DDP with the BF16
-    compress hook for N>1: reference main.py:641-656, model_setup.py:385-424,703) on the same workload, same timing rules.
-    This is the denominator of BASELINE.json's ">= 1.5x the reference's torch-sdpa GPU path" target; the driver's
-    reference arm stays the CPU one."""
+    """`--impl reference --ref-device cuda`: the reference's own torch path on the GPU, the denominator of BASELINE.json's
+    ">= 1.5x the reference's torch-sdpa GPU path" target (the driver's reference arm stays the CPU one).
+
+    --ref-kind stock (default): the UNMODIFIED `models.dit.DIT` staged under baseline/_ref/ (baseline/install_reference.py),
+      instantiated like model_setup.py:149-161 (dtype=None, fp32 parameters) and run under the outer
+      `torch.autocast(bf16)` of model.py:693-696 with UNIDISC_FORCE_CUDNN_SPDA_CONTEXT=1 (cuDNN SDPA, dit.py:816-829),
+      torch.optim.AdamW(fused) + clip_grad_norm_(1.0) (model_setup.py:385-424, model.py:1518), torch DDP with
+      gradient_as_bucket_view / static_graph and the BF16 compress hook for N > 1 (main.py:641-656), optionally
+      torch.compile(mode=max-autotune-no-cudagraphs) with the reference's inductor settings (utils.py:502-527,
+      configs/config.yaml:227).  The loss around it (q_xt, SUBS on the materialised [B,N,V] tensor, weighted NLL) is the
+      library-op restatement of model.py::compute_loss in oracle/torch_eager.py (model.py itself needs accelerate / hydra /
+      tensordict, absent from this image).
+    --ref-kind restated: oracle/torch_eager.py's restatement of the backbone as well (round-1 cross-check)."""
+    if args.ref_sdpa == "cudnn":
+        os.environ["UNIDISC_FORCE_CUDNN_SPDA_CONTEXT"] = "1"          # read at import time by models/dit.py:21
     import torch.distributed as dist
     from oracle import restated as R
     from oracle import torch_eager as TE
@@ -155,19 +209,39 @@ def run_reference_gpu_arm(args, rank, world, local):
     preset, bpg, txt, img = WORKLOADS[args.workload]
     D, L, H = MODEL_PRESETS[preset]
     V, tv, mi = TEXT_VOCAB + IMAGE_VOCAB, TEXT_VOCAB, TEXT_VOCAB - 1
-    N, B = txt + img, bpg
+    N, B = txt + img, (args.batch or bpg)
     torch.manual_seed(0)
-    ocfg = R.OracleConfig(D, H, L, txt, img, V, tv, mi)
-    model = TE.EagerDIT(ocfg, dropout=args.dropout).to(dev)
+    torch.set_float32_matmul_precision("medium")                      # reference utils.py:425-438 (called from main.py:550)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    if args.ref_kind == "stock":
+        from oracle import ref_loader as RL
+        rcfg = RL.make_ref_config(D, H, L, txt, img, dropout=args.dropout)
+        rcfg.model.force_optimized_native_attn = args.ref_sdpa == "cudnn"
+        model = RL.build_reference_dit(rcfg, V, tv, mi, dtype=None).to(dev)
+        src = f"unmodified models.dit.DIT from {RL.REFERENCE_ROOT}"
+        call_backbone = lambda net, xt, modality: net(xt, None, modality=modality)
+    else:
+        ocfg = R.OracleConfig(D, H, L, txt, img, V, tv, mi)
+        model = TE.EagerDIT(ocfg, dropout=args.dropout).to(dev)
+        src = "oracle/torch_eager.py (restated backbone)"
+        call_backbone = lambda net, xt, modality: net(xt, modality)
     model.train()
     net = model
     if world > 1:
         from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True, static_graph=True)
         net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     fwd = net
     if args.ref_compile:
-        fwd = torch.compile(net, mode=args.ref_compile_mode)                            # reference config.yaml:227 uses max-autotune-no-cudagraphs
+        if args.ref_sd3_config:                                       # reference utils.py:511-516 (trainer.sd3_compile_config, default on)
+            import torch._inductor.config as ic
+            ic.conv_1x1_as_mm = True
+            ic.coordinate_descent_tuning = True
+            ic.epilogue_fusion = False
+            ic.coordinate_descent_check_all_directions = True
+        fwd = torch.compile(net, mode=args.ref_compile_mode)          # reference utils.py:524: the (DDP-wrapped) backbone is compiled
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, fused=True)
     g = torch.Generator().manual_seed(42 + rank)
     ids_h = torch.cat([torch.randint(0, tv - 1, (B, txt), generator=g), torch.randint(tv, V, (B, img), generator=g)], 1).pin_memory()
@@ -176,7 +250,7 @@ def run_reference_gpu_arm(args, rank, world, local):
 
     class _W(torch.nn.Module):                     # lets DDP / compile wrap the backbone while the loss code calls model(xt, modality)
         def forward(self, xt, modality):
-            return fwd(xt, modality)
+            return call_backbone(fwd, xt, modality)
 
     def step():
         ids, mod, am = ids_h.to(dev, non_blocking=True), mod_h.to(dev, non_blocking=True), am_h.to(dev, non_blocking=True)
@@ -187,8 +261,11 @@ def run_reference_gpu_arm(args, rank, world, local):
         opt.zero_grad(set_to_none=True)
         return float(loss.detach())
 
+    t_w0 = time.perf_counter()
     for _ in range(args.warmup):
         step()
+    torch.cuda.synchronize()
+    warm_s = time.perf_counter() - t_w0
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -209,15 +286,16 @@ def run_reference_gpu_arm(args, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         v = world * B * N / (ms.item() / args.steps * 1e-3)
-        kind = "torch eager" + (f" + torch.compile({args.ref_compile_mode})" if args.ref_compile else "")
+        kind = "eager" + (f" + torch.compile({args.ref_compile_mode}{', sd3 inductor config' if args.ref_sd3_config else ''})" if args.ref_compile else "")
         print(json.dumps(dict(
             impl="reference", device="cuda", metric="joint_token_tokens_per_sec", value=v, unit="tokens/s", n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms.item() / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
             data="synthetic", config=dict(workload=args.workload, seq_len=N, per_gpu_batch=B, global_batch=world * B, vocab=V,
                                           parallelism=f"dp{world}", optimizer="torch AdamW(fused)+clip_grad_norm_(1.0)", dropout=args.dropout,
-                                          note=f"oracle/torch_eager.py ({kind}, SDPA, autocast bf16) — the reference's torch path restated, on the GPU"),
+                                          backbone=src, mode=kind, sdpa=args.ref_sdpa,
+                                          ddp="torch DDP + bf16_compress_hook, static_graph" if world > 1 else None),
             e2e=dict(value=v, unit="tokens/s", h2d_bytes_per_step=ids_h.numel() * 16 + am_h.numel(), d2h_bytes_per_step=4, loss=last),
-            gpu_launches=0, clocks=clocks, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30)))
+            gpu_launches=0, clocks=clocks, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30, warmup_wall_s=warm_s)))
     if world > 1:
         dist.destroy_process_group()
 
@@ -226,9 +304,9 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     vals = []
-    for _ in range(max(1, min(args.steps, 2))):
-        vals.append(cpu_reference_tokens_per_sec(args.workload))
-    cb = vals[-1]
+    for i in range(max(1, min(args.steps, 2))):
+        vals.append(cpu_reference_tokens_per_sec(args.workload, with_reference_forward=(i == 0)))
+    cb = dict(vals[-1], reference_forward=vals[0].get("reference_forward"))
     v = max(x["value"] for x in vals)
     preset, bpg, txt, img = WORKLOADS[args.workload]
     line = dict(impl="reference", metric="joint_token_tokens_per_sec", value=v, unit="tokens/s", n_gpus=args.gpus, steps=args.steps,
@@ -237,6 +315,137 @@ def run_reference_arm(args, rank, world):
                 cpu_baseline=dict(cb, value=v), e2e=dict(value=v, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: UniDisc-1.4B inference, 64-step absorbing denoising, seq_len 1280, bs 64, one B200
+# --------------------------------------------------------------------------------------------------------------
+def run_sampling_workload(args, rank, world, local):
+    """A "step" is one complete `Diffusion._sample` call on a batch of 64 all-mask sequences: 64 x [backbone forward ->
+    fused vocabulary pass (SUBS softmax -> absorbing update / MaskGIT draw + selection)] + the noise-removal forward.
+    N > 1 = independent replicas (no collective).  value = sampled tokens per second over all ranks."""
+    import torch.distributed as dist
+    from unidisc_b200 import _lib as Lb
+    from unidisc_b200 import ops
+    from unidisc_b200.config import make_config
+    from unidisc_b200.model import Diffusion
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    preset, B, txt, img = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    cfg = make_config(preset, txt_length=txt, img_length=img, predictor=args.predictor, sampling_steps=args.sampling_steps, seed=42 + rank)
+    torch.manual_seed(0)
+    model = Diffusion(cfg, device=dev)
+    model.eval()
+    N = txt + img
+    D, Lyr, V = cfg.model.hidden_size, cfg.model.n_blocks, model.vocab_size
+    mod_h = torch.cat([torch.zeros(B, txt, dtype=torch.int64), torch.ones(B, img, dtype=torch.int64)], 1).pin_memory()
+    mod_d = mod_h.to(dev)
+    out_h = torch.empty(B, N, dtype=torch.int64).pin_memory()
+    launches = [0]
+    orig_call = Lb.call
+
+    def counting_call(name, *a):
+        launches[0] += 1
+        return orig_call(name, *a)
+
+    ops.call = counting_call
+
+    def run(e2e):
+        modality = mod_h.to(dev, non_blocking=True) if e2e else mod_d
+        x, nfe = model._sample(num_steps=args.sampling_steps, batch_size_per_gpu=B, sample_modality=modality, return_nfe=True)
+        if e2e:
+            out_h.copy_(x, non_blocking=True)            # device -> host read of the sampled tokens
+        return x, nfe
+
+    def timed(e2e, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches[0] = 0
+        e0.record()
+        for _ in range(steps):
+            x, nfe = run(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), x, nfe
+
+    for _ in range(max(1, args.warmup)):
+        run(True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, x, nfe = timed(False, args.steps)
+    n_launch = launches[0]
+    ms_e2e, x, nfe = timed(True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    assert x.shape == (B, N) and int((x == model.mask_index).sum()) == 0, "sampling left masked tokens"
+    assert bool((x[:, :txt] < model.text_vocab_size).all()) and bool((x[:, txt:] >= model.text_vocab_size).all()), \
+        "tokens left their modality's vocabulary"
+    # ---- the vocabulary-pass kernel alone (HBM roofline): this predictor's kernel on a resident [B*N, Vp] bf16 logits buffer ----
+    pk = peaks()
+    tv = model.text_vocab_size
+    lg = torch.empty(B * N, model.backbone.Vp, device=dev, dtype=torch.bfloat16)
+    for c in range(0, B * N, 8192):
+        lg[c:c + 8192].normal_(0, 3)
+    xs = torch.full((B, N), model.mask_index, dtype=torch.int64, device=dev)
+    tt = torch.full((B,), 0.7, device=dev)
+    num = torch.full((B,), 20, dtype=torch.int32, device=dev)
+
+    def vocab_pass(i):
+        if args.predictor == "maskgit":
+            ops.maskgit_update(xs, lg, mod_d.view(-1), tt, num, model.mask_index, tv, V, r_temp=10.0, seed=1, offset=i)
+        else:
+            ops.ddpm_update_logits(xs, lg, mod_d.view(-1), tt, tt - 0.01, model.mask_index, tv, V, seed=1, offset=i)
+
+    for i in range(3):
+        vocab_pass(i)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(8):
+        vocab_pass(3 + i)
+    s1.record()
+    torch.cuda.synchronize()
+    sms = s0.elapsed_time(s1) / 8
+    alg_bytes = B * (txt * tv + img * (V - tv)) * 2 + B * N * 8 * 2
+    del lg
+    fwd_flops = B * N * flops_per_token_fwd(D, Lyr, N, V)
+    per_batch_ms = ms_dev / args.steps
+    value = world * B * N / (per_batch_ms * 1e-3)
+    if rank == 0:
+        line = dict(
+            metric="sampled_tokens_per_sec", value=value, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=max(1, args.warmup),
+            ms_per_step=per_batch_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+            config=dict(workload=args.workload, model=f"DiT D={D} L={Lyr} H={cfg.model.n_heads}", seq_len=N, per_gpu_batch=B, vocab=V,
+                        predictor=args.predictor, denoising_steps=args.sampling_steps, nfe=nfe, noise_removal=True,
+                        parallelism=f"replicas x{world}", step="one 64-step sampling run of the whole batch (warm-up in the same unit)",
+                        l2="logits 7.9 GB and activations per forward >> 126 MB L2 (no flush needed)"),
+            e2e=dict(value=world * B * N / (ms_e2e / args.steps * 1e-3), unit="tokens/s", ms_per_step=ms_e2e / args.steps,
+                     h2d_bytes_per_step=mod_h.numel() * 8, d2h_bytes_per_step=out_h.numel() * 8),
+            gpu_launches=n_launch // max(args.steps, 1), clocks=clocks,
+            ms_per_denoising_step=per_batch_ms / (nfe + 1), samples_per_s=world * B / (per_batch_ms * 1e-3),
+            backbone_tflops_per_gpu=(nfe + 1) * fwd_flops / (per_batch_ms * 1e-3) / 1e12,
+            backbone_frac_of_sustained_peak=(nfe + 1) * fwd_flops / (per_batch_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+            roofline=dict(bound="hbm", kernel=("maskgit draw + selection" if args.predictor == "maskgit" else "ddpm_update_logits_fast_kernel")
+                          + " (vocabulary pass, Philox noise, all rows masked)", achieved=alg_bytes / (sms * 1e-3) / 1e9, peak=pk["hbm_gbs"],
+                          unit="GB/s", frac=alg_bytes / (sms * 1e-3) / 1e9 / pk["hbm_gbs"], peak_source=pk["source"], traffic=None,
+                          algorithmic_bytes=alg_bytes, ms_per_launch=sms),
+            peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, cpu_baseline=None)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -253,8 +462,16 @@ def main():
                     "torch-eager restatement on the GPU (the >=1.5x target's denominator)")
     ap.add_argument("--ref-compile", action="store_true", help="with --ref-device cuda: torch.compile the backbone like the reference")
     ap.add_argument("--ref-compile-mode", default="max-autotune-no-cudagraphs")
+    ap.add_argument("--ref-kind", default="stock", choices=["stock", "restated"], help="with --ref-device cuda: the unmodified "
+                    "models.dit.DIT staged in baseline/_ref (default) or the oracle/torch_eager.py restatement")
+    ap.add_argument("--ref-sdpa", default="cudnn", choices=["cudnn", "default"], help="UNIDISC_FORCE_CUDNN_SPDA_CONTEXT=1 (reference "
+                    "setting for optimized native attention) or torch's default SDPA backend choice")
+    ap.add_argument("--ref-sd3-config", type=int, default=1, help="with --ref-compile: the reference's inductor settings (utils.py:511-516)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1, help="model.dropout (reference configs/model/extra_large.yaml:9 = 0.1)")
+    ap.add_argument("--predictor", default="ddpm_cache", choices=["ddpm_cache", "ddpm", "maskgit"], help="sampling workload only")
+    ap.add_argument("--sampling-steps", type=int, default=64, help="sampling workload only")
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -264,6 +481,9 @@ def main():
             run_reference_gpu_arm(args, rank, world, local)
         else:
             run_reference_arm(args, rank, world)
+        return
+    if args.workload == "unidisc-1.4B-sample":
+        run_sampling_workload(args, rank, world, local)
         return
     assert args.warmup >= 3 or args.workload == "tiny", "timing rules: W >= 3"
 
@@ -281,9 +501,15 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev, pg_options=nccl_options())
     preset, bpg, txt, img = WORKLOADS[args.workload]
+    if args.batch:
+        bpg = args.batch
     small = args.workload == "tiny"
+    packed = args.workload.endswith("-interleaved")
+    extra = dict(hidden_size=256, n_blocks=2, n_heads=4) if small else {}
+    if packed:       # reference configs/experiments/*interleaved*: sample ids from the packing collate + FlexAttention document mask
+        extra.update(data__require_sample_ids=True, trainer__interleaved=True, trainer__interleaved_training_flex_attention=True)
     cfg = make_config(preset, txt_length=txt, img_length=img, dropout=args.dropout, image_vocab_size=IMAGE_VOCAB if not small else 255,
-                      text_vocab_size=TEXT_VOCAB if not small else 257, **(dict(hidden_size=256, n_blocks=2, n_heads=4) if small else {}))
+                      text_vocab_size=TEXT_VOCAB if not small else 257, **extra)
     torch.manual_seed(0)
     model = Diffusion(cfg, device=dev)
     model.train()
@@ -300,11 +526,20 @@ def main():
     D, Lyr = cfg.model.hidden_size, cfg.model.n_blocks
 
     g = torch.Generator().manual_seed(42 + rank)                      # mirrors reference main.py:1062 (seed + rank)
-    ids_h = torch.cat([torch.randint(0, tv - 1, (B, txt), generator=g), torch.randint(tv, V, (B, img), generator=g)], 1).pin_memory()
-    mod_h = torch.cat([torch.zeros(B, txt, dtype=torch.int64), torch.ones(B, img, dtype=torch.int64)], 1).pin_memory()
-    am_h = torch.ones(B, N, dtype=torch.bool).pin_memory()
+    sid_h = sid_d = None
+    attn_pairs = float(N)                                             # mean number of keys a query attends to (dense: N)
+    if packed:
+        from unidisc_b200.synth import packed_batch
+        ids_h, mod_h, sid_h, am_h, doc_lens = packed_batch(B, N, tv, V, seed=42 + rank)
+        ids_h, mod_h, sid_h, am_h = ids_h.pin_memory(), mod_h.pin_memory(), sid_h.pin_memory(), am_h.pin_memory()
+        sid_d = sid_h.to(dev)
+        attn_pairs = sum(x * x for lens in doc_lens for x in lens) / float(B * N)     # cfg5: 4 N D -> 4 D sum(len_i^2) / N
+    else:
+        ids_h = torch.cat([torch.randint(0, tv - 1, (B, txt), generator=g), torch.randint(tv, V, (B, img), generator=g)], 1).pin_memory()
+        mod_h = torch.cat([torch.zeros(B, txt, dtype=torch.int64), torch.ones(B, img, dtype=torch.int64)], 1).pin_memory()
+        am_h = torch.ones(B, N, dtype=torch.bool).pin_memory()
     ids_d, mod_d, am_d = ids_h.to(dev), mod_h.to(dev), am_h.to(dev)
-    h2d = ids_h.numel() * 8 + mod_h.numel() * 8 + am_h.numel()
+    h2d = ids_h.numel() * 8 + mod_h.numel() * 8 + am_h.numel() + (sid_h.numel() * 8 if packed else 0)
 
     launches = [0]
     orig_call = Lb.call
@@ -321,8 +556,12 @@ def main():
         if e2e:
             batch = dict(input_ids=ids_h.to(dev, non_blocking=True), modality=mod_h.to(dev, non_blocking=True),
                          attention_mask=am_h.to(dev, non_blocking=True))
+            if packed:
+                batch["sample_ids"] = sid_h.to(dev, non_blocking=True)
         else:
             batch = dict(input_ids=ids_d, modality=mod_d, attention_mask=am_d)
+            if packed:
+                batch["sample_ids"] = sid_d
         losses = model.compute_loss(batch)
         losses.loss.backward()
         opt.step()
@@ -351,22 +590,9 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), float(last)
 
-    try:
-        for _ in range(args.warmup):
-            step(True)
-        torch.cuda.synchronize()
-    except Exception as e:  # noqa: BLE001
-        # safety net for the multi-GPU runs: a host-side failure of the streamed optimizer behind ThinDDP (every rank runs the
-        # same code, so every rank lands here) falls back to the blocking optimizer instead of losing the measurement
-        if world == 1 or not opt.overlap:
-            raise
-        print(f"[bench] streamed optimizer failed under DDP ({type(e).__name__}: {e}); falling back to the blocking optimizer", file=sys.stderr)
-        ddp.post_bucket_hook, ddp.sumsq_target = None, None
-        net._param_events = None
-        opt = make_opt(False)
-        for _ in range(args.warmup):
-            step(True)
-        torch.cuda.synchronize()
+    for _ in range(args.warmup):          # (a failure here fails the run: no silent change of the optimizer schedule)
+        step(True)
+    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -510,7 +736,7 @@ def main():
             sampler_info = dict(error=str(e))
 
     tok_step = world * B * N
-    fpt = 3 * flops_per_token_fwd(D, Lyr, N, V)
+    fpt = 3 * flops_per_token_fwd(D, Lyr, attn_pairs, V)
     value = tok_step / (ms_dev / args.steps * 1e-3)
     e2e_v = tok_step / (ms_e2e / args.steps * 1e-3)
     model_tflops_per_gpu = value / world * fpt / 1e12
@@ -527,7 +753,8 @@ def main():
             ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
             config=dict(workload=args.workload, model=f"DiT D={D} L={Lyr} H={cfg.model.n_heads}", seq_len=N, per_gpu_batch=B,
                         global_batch=world * B, vocab=V, parallelism=f"dp{world}", optimizer="AdamW+clip(1.0)", optimizer_schedule="streamed" if opt.overlap else "blocking",
-                        dropout=args.dropout,
+                        dropout=args.dropout, **(dict(packing="documents = text U[32,512] + image {256,1024} tokens, tail padding; "
+                                                              f"mean attended keys per query {attn_pairs:.0f} of {N}") if packed else {}),
                         l2="activations and weights per step >> 126 MB L2 (no flush needed)"),
             e2e=dict(value=e2e_v, unit="tokens/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                      loss=loss_e2e),

@@ -116,9 +116,15 @@ int ud_qk_ln_rope_bwd(const void* dqk_bf16, const void* qkv_bf16, const float* s
 /* ---- attention (tcgen05, bidirectional softmax(QK^T/sqrt(hd))V, optional document mask) ----------------------
  * replaces torch SDPA / FlexAttention (dit.py:775-829).  q,k: bf16 [B*N, ldqk] (head h at column h*hd), v: bf16 with ldv,
  * o: bf16 [B*N, ldo]; lse: fp32 [B,H,N] (natural log, scaled scores).  sample_ids: int64 [B,N] or NULL
- * (mask = same id and id != -1, model_utils.py:740-771). */
+ * (mask = same id and id != -1, model_utils.py:740-771).  With sample_ids every CTA visits only the key tiles whose id range
+ * overlaps its query tile's (the block skipping of the reference's BlockMask): cost ~ sum(len_i^2), not N^2. */
 int ud_attn_fwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, void* o, long long ldo, float* lse,
                 const int64_t* sample_ids, int B, int N, int H, int head_dim, float scale, void* stream);
+/* partial-query attention against a K/V cache (inference: dit.py:588-614 `update_kv_cache`, 793-812 image-K/V cache of the
+ * FlexAttention path): Nq query tokens per sample attend to Nk cached key/value tokens, no mask.  q: bf16 [B*Nq, ldq];
+ * k, v: bf16 [B*Nk, ldk / ldv] (head h at column h*hd); o: bf16 [B*Nq, ldo]; lse: fp32 [B,H,Nq]. */
+int ud_attn_fwd_kv(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
+                   long long ldo, float* lse, int B, int Nq, int Nk, int H, int head_dim, float scale, void* stream);
 /* backward: writes dq,dk (bf16, ld lddqk) and dv (bf16, ld lddv).  delta: fp32 [B,H,N] scratch. */
 int ud_attn_bwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const void* o, const void* d_o,
                 long long ldo, const float* lse, float* delta, void* dq, void* dk, long long lddqk, void* dv, long long lddv,
@@ -159,6 +165,21 @@ int ud_ddpm_update_logits(const int64_t* x, const void* logits_bf16, const void*
                           const float* cfg_w, const int64_t* modality, const float* u, uint64_t seed, uint64_t offset,
                           const float* mc_t, const float* mc_s, int64_t mask_index, int text_vocab, int64_t* out, int B, int N,
                           int V, void* stream);
+
+/* MaskGIT step (model_eval.py:3045-3114) in two launches: (1) per masked token row, one vocabulary pass: SUBS softmax p,
+ * pred = torch.multinomial(p, 1) (= argmax_v p_v / E_v with E ~ Exp(1): ATen's single-draw multinomial), conf = log p_pred +
+ * r_temp * gumbel * t (float64, as the reference's np.random.gumbel draw promotes it; -inf on unmasked rows);  (2) per sample,
+ * the num_unmask[b] (clamped to the number of masked tokens) most confident rows take their prediction, everything else keeps
+ * x.  e_noise fp32 [B*N, V] + gumbel fp64 [B*N] supplied = bit-parity mode; both NULL = in-kernel Philox draws.
+ * t: fp32 [B]; num_unmask: int32 [B] (= schedule[:, step]); pred (int64 [B*N]) and conf (fp64 [B*N]) are outputs/scratch. */
+int ud_maskgit_update(const int64_t* x, const void* logits_bf16, const void* logits_uncond_bf16, long long ldv,
+                      const float* cfg_w, const int64_t* modality, const float* e_noise, const double* gumbel, uint64_t seed,
+                      uint64_t offset, const float* t, float r_temp, const int* num_unmask, int64_t mask_index, int text_vocab,
+                      int64_t* pred, double* conf, int64_t* out, int B, int N, int V, void* stream);
+/* arg-max over the vocabulary of the SUBS log-probs with carry-over (x where xt != mask): the noise-removal pass of `_sample`
+ * (model_eval.py:2440-2446) without materialising [rows, V] log-probs */
+int ud_subs_argmax(const void* logits_bf16, long long ldv, const int64_t* xt, const int64_t* modality, int64_t* out, int rows,
+                   int V, int text_vocab, int mask_index, void* stream);
 
 /* ---- optimizer / DDP helpers ----------------------------------------------------------------------------------
  * fused AdamW (torch.optim.AdamW semantics, model_setup.py:385-424) over a flat fp32 buffer, also emitting the bf16

@@ -629,6 +629,63 @@ def gen_first_hitting():
 
 
 
+def gen_sampler_logits():
+    """Samplers driven from LOGITS (the fused kernels' input): the reference chain `_subs_parameterization(logits).exp()` ->
+    `_ddpm_caching_update` / `_ddpm_update` / `_maskgit_update` (model.py:621-658, model_eval.py:2042-2104, 3045-3114) executed
+    on bf16-representable fp32 logits, with the noise tensors the reference draws (torch.rand_like, the Exp(1) tensor inside
+    torch.multinomial, np.random.gumbel) replayed and stored.  -> tests/golden/sampler_logits.npz"""
+    cfgd = dict(txt=16, img=32, mask_index=96, text_vocab_size=97, vocab_size=160)
+    B, N, V, tv, mi = 3, 48, 160, 97, 96
+    s, M = make_fake_self(cfgd, ref_dit=None)
+    g = torch.Generator().manual_seed(61)
+    logits = (torch.randn(B, N, V, generator=g) * 3).bfloat16().float()
+    modality = torch.cat([torch.zeros(B, 16, dtype=torch.int64), torch.ones(B, 32, dtype=torch.int64)], 1)
+    x0 = torch.where(modality == 0, torch.randint(0, tv - 1, (B, N), generator=g), torch.randint(tv, V, (B, N), generator=g))
+    x = x0.clone()
+    x[0, torch.rand(N, generator=g) < 0.7] = mi
+    x[1, torch.rand(N, generator=g) < 0.15] = mi
+    # sample 2 stays fully unmasked: every update must carry it over
+    p = s._subs_parameterization(logits.clone(), xt=x, batch=None, modality=modality).exp()
+    assert torch.equal(p, R.subs_parameterization(logits, x, modality, mi, tv).exp())
+    s._ddpm_forward = lambda *a, **k: p.clone()
+    tt = torch.tensor([[0.8], [0.35], [0.6]])
+    dt = (1 - 1e-5) / 16
+    out = dict(logits=_np(logits), modality=_np(modality), x=_np(x), t=_np(tt), dt=np.array(dt), cfg=np.array([V, tv, mi]))
+    torch.manual_seed(62)
+    _, xn_ref, _ = M._ddpm_caching_update(s, x, tt, dt, p_x0=None)
+    torch.manual_seed(62)
+    u = torch.rand_like(p)
+    assert torch.equal(R.ddpm_caching_update(x, tt, dt, p.clone(), u, mi), xn_ref)
+    out.update(cache_u=_np(u), cache_ref=_np(xn_ref))
+    torch.manual_seed(63)
+    xn2_ref, _ = M._ddpm_update(s, x, tt, dt)
+    torch.manual_seed(63)
+    u2 = torch.rand_like(p)
+    assert torch.equal(R.ddpm_update(x, tt, dt, p.clone(), u2, mi), xn2_ref)
+    out.update(ddpm_u=_np(u2), ddpm_ref=_np(xn2_ref))
+    # maskgit at three schedule steps
+    s.config.eval["maskgit_r_temp"] = 10
+    sched = M.adap_sche(x, 8, mi, mode="arccos")
+    out["schedule"] = _np(sched)
+    for step in (0, 4, 7):
+        torch.manual_seed(70 + step)
+        np.random.seed(70 + step)
+        ref, nfe = M._maskgit_update(s, x.clone(), tt, dt, schedule=sched, step=step)
+        torch.manual_seed(70 + step)
+        np.random.seed(70 + step)
+        e_noise = torch.empty_like(p.view(-1, V)).exponential_(1)             # the draw inside torch.multinomial
+        gum = torch.from_numpy(np.random.gumbel(size=(B, N)))
+        torch.manual_seed(70 + step)
+        pred_ref = torch.multinomial(p.view(-1, V), 1)[:, 0].view(B, N)
+        assert torch.equal(R.multinomial_from_exponential(p, e_noise), pred_ref), "torch.multinomial != argmax(p / Exp(1))"
+        mine = R.maskgit_update_from_noise(x, tt, p, e_noise, gum, sched[:, step], mi, r_temp=10)
+        assert nfe == 1 and torch.equal(mine, ref), step
+        assert int(((ref != x) & (x != mi)).sum()) == 0
+        out.update({f"mg_e_{step}": _np(e_noise), f"mg_gumbel_{step}": _np(gum), f"mg_ref_{step}": _np(ref), f"mg_pred_{step}": _np(pred_ref)})
+    print("[sampler_logits] ddpm_cache / ddpm / maskgit(3 steps) identical to the reference; multinomial == argmax(p/Exp(1))")
+    np.savez_compressed(os.path.join(OUT, "sampler_logits.npz"), **out)
+
+
 def _with_length(ocfg, N):
     """OracleConfig whose `length` (txt_length + img_length) equals the packed sequence length N."""
     import dataclasses
@@ -643,6 +700,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "first_hitting":
         gen_first_hitting()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "sampler_logits":
+        gen_sampler_logits()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "update_batch":
         RL.load_reference_diffusion_methods()          # installs the import shims / sys.path for the reference tree
         gen_update_batch()
@@ -653,6 +713,7 @@ def main():
     gen_cfg1()
     gen_update_batch()
     gen_first_hitting()
+    gen_sampler_logits()
     print("golden fixtures written to", OUT)
 
 

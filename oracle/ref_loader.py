@@ -29,7 +29,15 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("UNIDISC_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    """/root/reference in the build container; on the GPU box (where it does not exist) the verbatim copy of the backbone's
+    import closure that baseline/install_reference.py staged under baseline/_ref/ (backbone only: model.py & co are not there)."""
+    if os.path.isfile("/root/reference/models/dit.py"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+REFERENCE_ROOT = os.environ.get("UNIDISC_REFERENCE_ROOT") or _default_root()
 
 
 def reference_available() -> bool:

@@ -541,6 +541,19 @@ def maskgit_update(x, t, p_x0, pred_code, gumbel, num_unmask, mask_index, r_temp
     return torch.where(sel, pred_code, x)
 
 
+def multinomial_from_exponential(p_x0, e_noise):
+    """`torch.multinomial(p.view(-1, V), 1)` (model_eval.py:3073) given the Exp(1) tensor it draws internally: ATen's
+    single-sample path is `q = empty_like(p).exponential_(1); argmax(p / q)` (aten/src/ATen/native/TensorCompare /
+    Distributions `multinomial`), on CPU and CUDA alike."""
+    V = p_x0.shape[-1]
+    return (p_x0.reshape(-1, V) / e_noise.reshape(-1, V)).argmax(dim=-1).view(p_x0.shape[:-1])
+
+
+def maskgit_update_from_noise(x, t, p_x0, e_noise, gumbel, num_unmask, mask_index, r_temp=10.0):
+    """model_eval.py:3045-3114 driven by the two raw noise tensors (Exp(1) [B,N,V] fp32 and Gumbel [B,N] fp64)."""
+    return maskgit_update(x, t, p_x0, multinomial_from_exponential(p_x0, e_noise), gumbel, num_unmask, mask_index, r_temp=r_temp)
+
+
 # --------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md §8d) and parameter init mirroring the reference module
 # --------------------------------------------------------------------------------------

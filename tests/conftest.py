@@ -54,3 +54,9 @@ def golden_timecond():
 def golden_cfg1():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "cfg1.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_sampler_logits():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "sampler_logits.npz"))

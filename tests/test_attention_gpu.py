@@ -128,3 +128,66 @@ def test_attn_bwd_document_mask():
     (o_ref * do.float()).sum().backward()
     for got, ref, nm in ((dqk[:, :D], q32.grad, "dq"), (dqk[:, D:], k32.grad, "dk"), (dqkv[:, 2 * D:], v32.grad, "dv")):
         assert torch.allclose(got.float(), ref, rtol=3e-2, atol=2e-2), (nm, (got.float() - ref).abs().max())
+
+
+def _packed_sids(B, N, seed):
+    from unidisc_b200.synth import packed_batch
+    _, _, sid, _, lens = packed_batch(B, N, 97, 160, seed)
+    return sid, lens
+
+
+@pytest.mark.parametrize("N,hd", [(4096, 128), (1100, 64)])
+def test_attn_document_mask_packed_tile_skipping(N, hd):
+    """BASELINE cfg5 layout (packed documents of text U[32,512] + image 256/1024, tail padding) at full length: the kernels
+    visit only the key tiles whose sample-id range overlaps the query tile's; forward and backward must equal the dense
+    masked fp32 reference.  Row 1 carries NON-monotonic ids (documents relabelled), row 2 is all padding."""
+    from unidisc_b200 import ops
+    B, H = 3, 2
+    qk, qkv, D = _mk(B, N, H, hd, seed=11)
+    sid, lens = _packed_sids(B, N, seed=4)
+    perm = torch.tensor([5, 2, 9, 0, 7, 3, 1, 8, 6, 4, 11, 10, 12, 13, 14, 15])
+    sid[1] = torch.where(sid[1] >= 0, perm[sid[1].clamp(min=0)], sid[1])
+    sid[2] = -1
+    sid = sid.to(dev())
+    q, k, v = qk[:, :D], qk[:, D:], qkv[:, 2 * D:]
+    scale = 1.0 / math.sqrt(hd)
+    o, lse = ops.attn_fwd(q, k, v, B, N, H, hd, scale, sample_ids=sid)
+    do = torch.randn(B * N, D, generator=torch.Generator().manual_seed(1)).to(bf16).to(dev())
+    dqk = torch.full((B * N, 2 * D), float("nan"), device=dev(), dtype=bf16)
+    dqkv = torch.full((B * N, 3 * D), float("nan"), device=dev(), dtype=bf16)
+    ops.attn_bwd(q, k, v, o, do, lse, dqk[:, :D], dqk[:, D:], dqkv[:, 2 * D:], B, N, H, hd, scale, sample_ids=sid)
+    torch.cuda.synchronize()
+    q32, k32, v32 = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    o_ref, lse_ref = _ref(q32, k32, v32, B, N, H, hd, sample_ids=sid)
+    (o_ref * do.float()).sum().backward()
+    assert torch.isfinite(o.float()).all()
+    assert torch.allclose(o.float(), o_ref.detach(), rtol=2e-2, atol=8e-3), (o.float() - o_ref).abs().max()
+    valid = (sid != -1)[:, None, :].expand(B, H, N)
+    assert torch.allclose(lse[valid], lse_ref.detach()[valid], rtol=1e-3, atol=2e-3)
+    pad = (sid == -1).reshape(-1)
+    assert (o[pad].float() == 0).all(), "padding queries produce zero attention output"
+    for got, ref, nm in ((dqk[:, :D], q32.grad, "dq"), (dqk[:, D:], k32.grad, "dk"), (dqkv[:, 2 * D:], v32.grad, "dv")):
+        assert torch.isfinite(got.float()).all(), nm
+        assert torch.allclose(got.float(), ref, rtol=3e-2, atol=2e-2), (nm, (got.float() - ref).abs().max())
+        assert (got[pad].float() == 0).all(), f"{nm}: padding rows get zero gradient"
+
+
+@pytest.mark.parametrize("Nq,Nk,hd", [(256, 1280, 128), (64, 200, 64), (128, 128, 64)])
+def test_attn_fwd_kv_partial_query(Nq, Nk, hd):
+    """partial-query attention against cached K/V (inference caches): the Nq text queries attend to all Nk cached keys."""
+    from unidisc_b200 import ops
+    B, H = 2, 2
+    D = H * hd
+    g = torch.Generator().manual_seed(6)
+    q = torch.randn(B * Nq, D, generator=g).to(bf16).to(dev())
+    kc = torch.randn(B * Nk, D + 64, generator=g).to(bf16).to(dev())[:, :D]          # cache rows with their own pitch
+    vc = torch.randn(B * Nk, D, generator=g).to(bf16).to(dev())
+    o, lse = ops.attn_fwd_kv(q, kc, vc, B, Nq, Nk, H, hd, 1.0 / math.sqrt(hd))
+    torch.cuda.synchronize()
+    qh = q.float().view(B, Nq, H, hd).permute(0, 2, 1, 3)
+    kh = kc.float().reshape(B, Nk, H, hd).permute(0, 2, 1, 3)
+    vh = vc.float().view(B, Nk, H, hd).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(hd)
+    o_ref = (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(B * Nq, D)
+    assert torch.allclose(o.float(), o_ref, rtol=2e-2, atol=8e-3), (o.float() - o_ref).abs().max()
+    assert torch.allclose(lse, torch.logsumexp(s, -1), rtol=1e-3, atol=2e-3)

@@ -99,6 +99,25 @@ def test_samplers_bit_exact(golden_fns, golden_dit):
     assert np.array_equal(mg.numpy(), g["mg_ref"])
 
 
+def test_samplers_from_logits_bit_exact(golden_sampler_logits):
+    """oracle chain SUBS(logits).exp() -> ddpm_cache / ddpm / maskgit against the reference's outputs on its own noise draws
+    (the Exp(1) tensor inside torch.multinomial and the np.random.gumbel draw are stored in the fixture)."""
+    g = golden_sampler_logits
+    V, tv, mi = [int(v) for v in g["cfg"]]
+    lg, mod, x = torch.from_numpy(g["logits"]), torch.from_numpy(g["modality"]), torch.from_numpy(g["x"])
+    t, dt = torch.from_numpy(g["t"]), float(g["dt"])
+    p = R.subs_parameterization(lg, x, mod, mi, tv).exp()
+    assert np.array_equal(R.ddpm_caching_update(x, t, dt, p.clone(), torch.from_numpy(g["cache_u"]), mi).numpy(), g["cache_ref"])
+    assert np.array_equal(R.ddpm_update(x, t, dt, p.clone(), torch.from_numpy(g["ddpm_u"]), mi).numpy(), g["ddpm_ref"])
+    sch = R.adap_sche(x, 8, mi)
+    assert np.array_equal(sch.numpy(), g["schedule"])
+    for step in (0, 4, 7):
+        e, gum = torch.from_numpy(g[f"mg_e_{step}"]), torch.from_numpy(g[f"mg_gumbel_{step}"])
+        assert np.array_equal(R.multinomial_from_exponential(p, e).numpy(), g[f"mg_pred_{step}"])
+        out = R.maskgit_update_from_noise(x, t, p, e, gum, sch[:, step], mi, r_temp=10)
+        assert np.array_equal(out.numpy(), g[f"mg_ref_{step}"])
+
+
 def test_ddpm_forward_and_cfg(golden_fns, golden_dit):
     g, gd = golden_fns, golden_dit
     cfg, P = _cfg(gd), _params(gd)

@@ -30,6 +30,7 @@ _SIGS = {
     "ud_qk_ln_rope_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     "ud_qk_ln_rope_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "ud_attn_fwd": [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "ud_attn_fwd_kv": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "ud_attn_bwd": [_vp, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],
     "ud_colsum_bf16": [_vp, _ll, _vp, _i, _i, _vp],
     "ud_subs_nll_fwd": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -39,6 +40,8 @@ _SIGS = {
     "ud_sample_categorical": [_vp, _ll, _vp, _u64, _u64, _vp, _i, _i, _vp],
     "ud_ddpm_update_probs": [_vp, _vp, _ll, _vp, _u64, _u64, _vp, _vp, _i64, _vp, _i, _i, _i, _vp],
     "ud_ddpm_update_logits": [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _i64, _i, _vp, _i, _i, _i, _vp],
+    "ud_maskgit_update": [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _f, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "ud_subs_argmax": [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "ud_adamw_step": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp, _i, _vp],
     "ud_cast_f32_to_bf16": [_vp, _vp, _ll, _vp],
     "ud_sumsq_f32": [_vp, _ll, _vp, _i, _vp],

@@ -31,13 +31,78 @@ UD_DEVINL float ex2(float x) {
 }
 
 struct AttnParams {
-    int B, N, H;
+    int B, N, H;       // N = number of QUERY tokens per sample
+    int Nk;            // number of key/value tokens per sample (== N except for partial-query attention against a K/V cache)
     float scale_log2;  // softmax scale * log2(e)
     __nv_bfloat16* o;
     long long ldo;
     float* lse;  // [B,H,N]
-    const int64_t* sample_ids;  // [B,N] or null
+    const int64_t* sample_ids;  // [B,N] or null (needs Nk == N)
 };
+
+// ------------------------------------------------------------------------------------------------
+// Document-mask tile lists.  The reference's FlexAttention BlockMask (model_utils.py:740-771: same sample id, id != -1)
+// SKIPS (q-block, kv-block) pairs that cannot match, so a packed batch costs sum(len_i^2), not N^2.  Here every CTA derives
+// in its prologue, from the sample ids of its batch row (N int64, L2-resident), the list of streamed tiles whose valid-id
+// range [min, max] overlaps the range of its fixed 128-row tile; tiles outside are neither loaded nor multiplied.  A pair of
+// tiles that both lie inside ONE document (uniform, equal ids, no padding) is flagged mask-free and takes the unmasked
+// softmax instantiation.
+// ------------------------------------------------------------------------------------------------
+static constexpr int MAX_DOC_TILES = 512;
+struct DocTiles {
+    int n;
+    uint16_t idx[MAX_DOC_TILES];
+    uint8_t nomask[MAX_DOC_TILES];
+    uint8_t code[MAX_DOC_TILES];
+};
+
+template <int SUB_ROWS>
+UD_DEVINL void doc_tile_list(const int64_t* __restrict__ ids, int N, int f0, int nsub, DocTiles& tl) {   // whole CTA
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    int fmn = 0x7fffffff, fmx = -1;
+    bool funi = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = f0 + k * 32 + lane;
+        const int v = r < N ? (int)ids[r] : -1;
+        if (v >= 0) { fmn = min(fmn, v); fmx = max(fmx, v); } else funi = false;
+    }
+    fmn = __reduce_min_sync(0xffffffffu, fmn);
+    fmx = __reduce_max_sync(0xffffffffu, fmx);
+    funi = __all_sync(0xffffffffu, funi) && fmn == fmx;
+    for (int t = warp; t < nsub; t += nwarps) {
+        int smn = 0x7fffffff, smx = -1;
+        bool suni = true;
+#pragma unroll
+        for (int k = 0; k < SUB_ROWS / 32; ++k) {
+            const int r = t * SUB_ROWS + k * 32 + lane;
+            const int v = r < N ? (int)ids[r] : -1;
+            if (v >= 0) { smn = min(smn, v); smx = max(smx, v); } else suni = false;
+        }
+        smn = __reduce_min_sync(0xffffffffu, smn);
+        smx = __reduce_max_sync(0xffffffffu, smx);
+        suni = __all_sync(0xffffffffu, suni) && smn == smx;
+        const bool act = smx >= fmn && smn <= fmx;          // (a side without any valid id never overlaps)
+        if (lane == 0) tl.code[t] = act ? ((funi && suni && smn == fmn) ? 2 : 1) : 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int cnt = 0;
+        for (int base = 0; base < nsub; base += 32) {
+            const int t = base + lane;
+            const int c = t < nsub ? tl.code[t] : 0;
+            const uint32_t m = __ballot_sync(0xffffffffu, c != 0);
+            if (c != 0) {
+                const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                tl.idx[pos] = (uint16_t)t;
+                tl.nomask[pos] = c == 2;
+            }
+            cnt += __popc(m);
+        }
+        if (lane == 0) tl.n = cnt;
+    }
+    __syncthreads();
+}
 
 template <int HD>
 struct AttnSmem {
@@ -54,464 +119,6 @@ UD_DEVINL uint64_t desc_kmajor(uint32_t tile_base, int ks) {
 UD_DEVINL uint64_t desc_mnmajor(uint32_t tile_base, int ks) {
     return make_smem_desc_sw128(tile_base + ks * 2048, 128 * 128, 1024);
 }
-
-template <int HD>
-__global__ void __launch_bounds__(192, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
-    using S = AttnSmem<HD>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + S::TILE_BYTES;            // [2] stages
-    uint8_t* sV = sK + 2 * S::TILE_BYTES;        // [2] stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * S::TILE_BYTES);
-    uint64_t* q_full = bars;           // 1
-    uint64_t* k_full = bars + 1;       // 2
-    uint64_t* v_full = bars + 3;       // 2
-    uint64_t* kv_empty = bars + 5;     // 2
-    uint64_t* s_full = bars + 7;       // 2
-    uint64_t* p_full = bars + 9;       // 2
-    uint64_t* pv_done = bars + 11;     // 1
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
-    int* sid_k = reinterpret_cast<int*>(bars + 14);  // [2][128]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
-    const int T = (p.N + ATT_BKV - 1) / ATT_BKV;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&k_full[s], 1); mbar_init(&v_full[s], 1); mbar_init(&kv_empty[s], 1);
-            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128);
-        }
-        mbar_init(pv_done, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_ptr_smem;
-    const uint32_t tS0 = tmem, tO = tmem + 256, tP0 = tmem + 256 + HD;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(q_full, S::TILE_BYTES);
-#pragma unroll
-            for (int bx = 0; bx < S::NBOX; ++bx) tma_load_3d(sQ + bx * S::BOX_BYTES, &tm_q, q_full, h * HD + bx * 64, q0, b);
-            for (int j = 0; j < T; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(&kv_empty[s], ph ^ 1);
-                mbar_expect_tx(&k_full[s], S::TILE_BYTES);
-#pragma unroll
-                for (int bx = 0; bx < S::NBOX; ++bx)
-                    tma_load_3d(sK + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_k, &k_full[s], h * HD + bx * 64, j * ATT_BKV, b);
-                mbar_expect_tx(&v_full[s], S::TILE_BYTES);
-#pragma unroll
-                for (int bx = 0; bx < S::NBOX; ++bx)
-                    tma_load_3d(sV + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_v, &v_full[s], h * HD + bx * 64, j * ATT_BKV, b);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
-            const uint32_t aQ = smem_u32(sQ);
-            auto issue_s = [&](int j) {
-                const int s = j & 1;
-                mbar_wait(&k_full[s], (j >> 1) & 1);
-                tc_fence_after();
-                const uint32_t aK = smem_u32(sK + s * S::TILE_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks)
-                    umma_ss(tS0 + s * 128, desc_kmajor(aQ, ks), desc_kmajor(aK, ks), idesc_s, ks != 0);
-                umma_commit(&s_full[s]);
-            };
-            mbar_wait(q_full, 0);
-            issue_s(0);
-            for (int j = 0; j < T; ++j) {
-                if (j + 1 < T) issue_s(j + 1);
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(&v_full[s], ph);
-                mbar_wait(&p_full[s], ph);
-                tc_fence_after();
-                const uint32_t aV = smem_u32(sV + s * S::TILE_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < ATT_BKV / 16; ++ks)
-                    umma_ts(tO, tP0 + s * 64 + ks * 8, desc_mnmajor(aV, ks), idesc_pv, (j | ks) != 0);
-                umma_commit(&kv_empty[s]);
-                umma_commit(pv_done);
-            }
-        }
-    } else {
-        // ===================== softmax warps =====================
-        const int qd = warp & 3;
-        const int rloc = qd * 32 + lane;          // row inside the tile == TMEM lane
-        const int row = q0 + rloc;
-        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const bool use_ids = p.sample_ids != nullptr;
-        int sid_q = 0;
-        if (use_ids) sid_q = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
-        const int tid128 = threadIdx.x - 64;
-        float m_used = -INFINITY, l = 0.f;
-        for (int j = 0; j < T; ++j) {
-            const int s = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            if (use_ids) {
-                const int kk = j * ATT_BKV + tid128;
-                sid_k[s * 128 + tid128] = kk < p.N ? (int)p.sample_ids[(long long)b * p.N + kk] : -2;
-                named_bar_sync(1, 128);
-            }
-            mbar_wait(&s_full[s], ph);
-            tc_fence_after();
-            float v[128];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tS0 + s * 128 + c * 32 + lane_off, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[c * 32 + i] = __uint_as_float(r[i]) * p.scale_log2;
-            }
-            const int kbase = j * ATT_BKV;
-            if (use_ids || kbase + ATT_BKV > p.N) {
-#pragma unroll
-                for (int i = 0; i < 128; ++i) {
-                    bool ok = kbase + i < p.N;
-                    if (use_ids) ok = ok && (sid_k[s * 128 + i] == sid_q) && (sid_q != -1);
-                    if (!ok) v[i] = -INFINITY;
-                }
-            }
-            float mx = v[0];
-#pragma unroll
-            for (int i = 1; i < 128; ++i) mx = fmaxf(mx, v[i]);
-            const float m_new = fmaxf(m_used, mx);
-            const bool grow = m_new > m_used + 8.0f;   // also true for -inf -> finite
-            if (__any_sync(0xffffffffu, grow)) {
-                const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_new);
-                if (j > 0) {
-                    mbar_wait(pv_done, (j - 1) & 1);   // O must be quiescent before it is rescaled
-                    tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < HD / 32; ++c) {
-                        uint32_t r[32];
-                        tmem_ld_32x32b_x32(tO + c * 32 + lane_off, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                        tmem_st_32x32b_x32(tO + c * 32 + lane_off, r);
-                    }
-                    tmem_st_wait();
-                }
-                l *= alpha;
-                m_used = m_new;
-            }
-            const float mref = (m_used == -INFINITY) ? 0.f : m_used;
-            uint32_t pk_lo[32], pk_hi[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float p0 = ex2(v[2 * i] - mref), p1 = ex2(v[2 * i + 1] - mref);
-                const float p2 = ex2(v[64 + 2 * i] - mref), p3 = ex2(v[64 + 2 * i + 1] - mref);
-                l += (p0 + p1) + (p2 + p3);
-                pk_lo[i] = pack_bf16x2(p0, p1);
-                pk_hi[i] = pack_bf16x2(p2, p3);
-            }
-            tmem_st_32x32b_x32(tP0 + s * 64 + lane_off, pk_lo);
-            tmem_st_32x32b_x32(tP0 + s * 64 + 32 + lane_off, pk_hi);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_full[s]);
-        }
-        // ---- epilogue: O / l, lse ----
-        mbar_wait(pv_done, (T - 1) & 1);
-        tc_fence_after();
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
-        __nv_bfloat16* orow = p.o + ((long long)b * p.N + row) * p.ldo + h * HD;
-#pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tO + c * 32 + lane_off, r);
-            tmem_ld_wait();
-            if (row < p.N) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 o4;
-                    o4.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
-                    o4.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
-                    o4.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
-                    o4.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = o4;
-                }
-            }
-        }
-        if (row < p.N) p.lse[((long long)b * p.H + h) * p.N + row] = l > 0.f ? (m_used + log2f(l)) * LN2 : INFINITY;
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem);
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// Forward v2: one CTA owns TWO 128-query tiles (A, B) and two softmax warpgroups, so the tensor core works on one tile
-// (S = QK^T, O += PV) while the other tile's warpgroup does the exp / row-sum arithmetic, and every SM sub-partition
-// has two softmax warps.  P (bf16) is written over the first 64 columns of its own S buffer (read back by the TS MMA).
-//   TMEM: S_A[128] S_B[128] O_A[HD] O_B[HD]          smem: Q_A Q_B | 2 stages of (K, V)
-// ------------------------------------------------------------------------------------------------
-template <int HD>
-__global__ void __launch_bounds__(320, 1)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                 const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
-    using S = AttnSmem<HD>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                           // [2] tiles
-    uint8_t* sK = sQ + 2 * S::TILE_BYTES;         // [2] stages
-    uint8_t* sV = sK + 2 * S::TILE_BYTES;         // [2] stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * S::TILE_BYTES);
-    uint64_t* q_full = bars;           // 1
-    uint64_t* k_full = bars + 1;       // 2
-    uint64_t* v_full = bars + 3;       // 2
-    uint64_t* kv_empty = bars + 5;     // 2
-    uint64_t* s_full = bars + 7;       // 2 (per tile)
-    uint64_t* p_full = bars + 9;       // 2 (per tile)
-    uint64_t* pv_done = bars + 11;     // 2 (per tile)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
-    __shared__ int sid_k[2 * 2 * 128];   // [warpgroup][stage][128]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
-    const int T = (p.N + ATT_BKV - 1) / ATT_BKV;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&k_full[s], 1); mbar_init(&v_full[s], 1); mbar_init(&kv_empty[s], 1);
-            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&pv_done[s], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_ptr_smem;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(q_full, 2 * S::TILE_BYTES);
-#pragma unroll
-            for (int t = 0; t < 2; ++t)
-#pragma unroll
-                for (int bx = 0; bx < S::NBOX; ++bx)
-                    tma_load_3d(sQ + t * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_q, q_full, h * HD + bx * 64, q0 + t * 128, b);
-            for (int j = 0; j < T; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(&kv_empty[s], ph ^ 1);
-                mbar_expect_tx(&k_full[s], S::TILE_BYTES);
-#pragma unroll
-                for (int bx = 0; bx < S::NBOX; ++bx)
-                    tma_load_3d(sK + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_k, &k_full[s], h * HD + bx * 64, j * ATT_BKV, b);
-                mbar_expect_tx(&v_full[s], S::TILE_BYTES);
-#pragma unroll
-                for (int bx = 0; bx < S::NBOX; ++bx)
-                    tma_load_3d(sV + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_v, &v_full[s], h * HD + bx * 64, j * ATT_BKV, b);
-            }
-        }
-    } else if (warp == 1) {
-        {
-            // warp-uniform issue loop, one elected lane executes the tcgen05 instructions (see elect_one).  Per key tile the
-            // tensor pipe sees  PV_A(j) S_A(j+1) PV_B(j) S_B(j+1): warpgroup A gets its next scores while B still does its
-            // softmax.  MMAs of one thread execute in issue order, so S_t(j+1) may overwrite the P_t(j) columns it aliases
-            // without waiting for PV_t(j) to complete.
-            const uint32_t leader = elect_one();
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
-            auto issue_s = [&](int t, int j) {
-                const uint32_t aQ = smem_u32(sQ + t * S::TILE_BYTES), aK = smem_u32(sK + (j & 1) * S::TILE_BYTES);
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks)
-                        umma_ss(tmem + t * 128, desc_kmajor(aQ, ks), desc_kmajor(aK, ks), idesc_s, ks != 0);
-                    umma_commit(&s_full[t]);
-                }
-                __syncwarp();
-            };
-            mbar_wait(q_full, 0);
-            mbar_wait(&k_full[0], 0);
-            tc_fence_after();
-            issue_s(0, 0);
-            issue_s(1, 0);
-            for (int j = 0; j < T; ++j) {
-                const int s = j & 1;
-                mbar_wait(&v_full[s], (j >> 1) & 1);
-                const uint32_t aV = smem_u32(sV + s * S::TILE_BYTES);
-                const uint32_t acc0 = j != 0;
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    mbar_wait(&p_full[t], j & 1);
-                    tc_fence_after();
-                    if (leader) {
-#pragma unroll
-                        for (int ks = 0; ks < ATT_BKV / 16; ++ks)
-                            umma_ts(tmem + 256 + t * HD, tmem + t * 128 + ks * 8, desc_mnmajor(aV, ks), idesc_pv, acc0 | (ks != 0));
-                        umma_commit(&pv_done[t]);
-                        if (t == 1) umma_commit(&kv_empty[s]);
-                    }
-                    __syncwarp();
-                    if (j + 1 < T) {
-                        if (t == 0) {
-                            mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-                            tc_fence_after();
-                        }
-                        issue_s(t, j + 1);
-                    }
-                }
-            }
-        }
-    } else {
-        const int wg = (warp - 2) >> 2;              // tile index
-        const int qd = warp & 3;
-        const int rloc = qd * 32 + lane;
-        const int row = q0 + wg * 128 + rloc;
-        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const uint32_t tS = tmem + wg * 128, tO = tmem + 256 + wg * HD;
-        const bool use_ids = p.sample_ids != nullptr;
-        int sid_q = 0;
-        if (use_ids) sid_q = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
-        const int tid128 = (threadIdx.x - 64) & 127;
-        const float scl = p.scale_log2;
-        const int Ntok = p.N;
-        float m_used = -INFINITY, l = 0.f;
-        for (int j = 0; j < T; ++j) {
-            const int s = j & 1;
-            int* sk = sid_k + (wg * 2 + s) * 128;
-            if (use_ids) {
-                const int kk = j * ATT_BKV + tid128;
-                sk[tid128] = kk < Ntok ? (int)p.sample_ids[(long long)b * Ntok + kk] : -2;
-                named_bar_sync(1 + wg, 128);
-            }
-            mbar_wait(&s_full[wg], j & 1);
-            tc_fence_after();
-            const int kbase = j * ATT_BKV;
-            const bool slow = use_ids || (kbase + ATT_BKV > Ntok);
-            // the whole S row (128 fp32) is fetched with four back-to-back tcgen05.ld and ONE wait: TMEM load latency is
-            // paid once per tile instead of once per chunk
-            uint32_t r0[32], r1[32], r2[32], r3[32];
-            tmem_ld_32x32b_x32(tS + 0 + lane_off, r0);
-            tmem_ld_32x32b_x32(tS + 32 + lane_off, r1);
-            tmem_ld_32x32b_x32(tS + 64 + lane_off, r2);
-            tmem_ld_32x32b_x32(tS + 96 + lane_off, r3);
-            tmem_ld_wait();
-            if (slow) {
-                auto maskchunk = [&](uint32_t (&r)[32], int cb) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        bool ok = kbase + cb + i < Ntok;
-                        if (use_ids) ok = ok && sk[cb + i] == sid_q && sid_q != -1;
-                        if (!ok) r[i] = 0xff800000u;   // -inf
-                    }
-                };
-                maskchunk(r0, 0); maskchunk(r1, 32); maskchunk(r2, 64); maskchunk(r3, 96);
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r1[i]));
-                mx2 = fmaxf(mx2, __uint_as_float(r2[i])); mx3 = fmaxf(mx3, __uint_as_float(r3[i]));
-            }
-            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scl;
-            const float m_new = fmaxf(m_used, mx);
-            const bool grow = m_new > m_used + 8.0f;   // also true for -inf -> finite
-            if (__any_sync(0xffffffffu, grow)) {
-                const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_new);
-                if (j > 0) {
-                    mbar_wait(&pv_done[wg], (j - 1) & 1);   // O must be quiescent before it is rescaled
-                    tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < HD / 32; ++c) {
-                        uint32_t r[32];
-                        tmem_ld_32x32b_x32(tO + c * 32 + lane_off, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                        tmem_st_32x32b_x32(tO + c * 32 + lane_off, r);
-                    }
-                    tmem_st_wait();
-                }
-                l *= alpha;
-                m_used = m_new;
-            }
-            const float mref = (m_used == -INFINITY) ? 0.f : m_used;
-            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-            // probabilities are packed IN PLACE (r0/r2 become the two 32-column P stores) to keep the live set at 128 registers
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float a0 = ex2(fmaf(__uint_as_float(r0[2 * i]), scl, -mref)), a1 = ex2(fmaf(__uint_as_float(r0[2 * i + 1]), scl, -mref));
-                const float c0 = ex2(fmaf(__uint_as_float(r2[2 * i]), scl, -mref)), c1 = ex2(fmaf(__uint_as_float(r2[2 * i + 1]), scl, -mref));
-                l0 += a0 + a1; l2 += c0 + c1;
-                r0[i] = pack_bf16x2(a0, a1);
-                r2[i] = pack_bf16x2(c0, c1);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float b0 = ex2(fmaf(__uint_as_float(r1[2 * i]), scl, -mref)), b1 = ex2(fmaf(__uint_as_float(r1[2 * i + 1]), scl, -mref));
-                const float d0 = ex2(fmaf(__uint_as_float(r3[2 * i]), scl, -mref)), d1 = ex2(fmaf(__uint_as_float(r3[2 * i + 1]), scl, -mref));
-                l1 += b0 + b1; l3 += d0 + d1;
-                r0[16 + i] = pack_bf16x2(b0, b1);
-                r2[16 + i] = pack_bf16x2(d0, d1);
-            }
-            tmem_st_32x32b_x32(tS + lane_off, r0);          // P columns [0,32)  = keys 0..63
-            tmem_st_32x32b_x32(tS + 32 + lane_off, r2);     // P columns [32,64) = keys 64..127
-            l += (l0 + l1) + (l2 + l3);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_full[wg]);
-        }
-        // ---- epilogue: O / l, lse ----
-        mbar_wait(&pv_done[wg], (T - 1) & 1);
-        tc_fence_after();
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
-        __nv_bfloat16* orow = p.o + ((long long)b * p.N + row) * p.ldo + h * HD;
-#pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tO + c * 32 + lane_off, r);
-            tmem_ld_wait();
-            if (row < p.N) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 o4;
-                    o4.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
-                    o4.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
-                    o4.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
-                    o4.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = o4;
-                }
-            }
-        }
-        if (row < p.N) p.lse[((long long)b * p.H + h) * p.N + row] = l > 0.f ? (m_used + log2f(l)) * LN2 : INFINITY;
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem);
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------
 // Forward v3: the v1 dataflow (one 128-query tile per CTA, double-buffered S and P in TMEM so QK^T of tile j+1 runs under
@@ -542,10 +149,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
     __shared__ int sid_k[2 * 128];            // [stage][128]
     __shared__ float xch[2 * 2 * 128];        // [stage][warpgroup][row]: partial row maxima (and final row sums)
+    __shared__ DocTiles tl;                   // active key tiles of this query tile (document mask only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
-    const int T = (p.N + ATT_BKV - 1) / ATT_BKV;
+    const int Tall = (p.Nk + ATT_BKV - 1) / ATT_BKV;
+    const bool use_ids = p.sample_ids != nullptr;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
@@ -563,15 +172,20 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_smem;
     const uint32_t tS0 = tmem, tO = tmem + 256, tP0 = tmem + 256 + HD;
+    if (use_ids) doc_tile_list<ATT_BKV>(p.sample_ids + (long long)b * p.N, p.N, q0, Tall, tl);
+    // T = number of key tiles this CTA visits; iteration jj works on key tile tile_of(jj) (stage / phase bookkeeping is in jj)
+    const int T = use_ids ? tl.n : Tall;
+    auto tile_of = [&](int jj) { return use_ids ? (int)tl.idx[jj] : jj; };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0 && T > 0) {
             mbar_expect_tx(q_full, S::TILE_BYTES);
 #pragma unroll
             for (int bx = 0; bx < S::NBOX; ++bx) tma_load_3d(sQ + bx * S::BOX_BYTES, &tm_q, q_full, h * HD + bx * 64, q0, b);
-            for (int j = 0; j < T; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
+            for (int jj = 0; jj < T; ++jj) {
+                const int j = tile_of(jj);
+                const int s = jj & 1;
+                const uint32_t ph = (jj >> 1) & 1;
                 mbar_wait(&k_empty[s], ph ^ 1);
                 mbar_expect_tx(&k_full[s], S::TILE_BYTES);
 #pragma unroll
@@ -585,7 +199,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        {
+        if (T > 0) {
             // warp-uniform issue loop, one elected lane executes the tcgen05 instructions (see elect_one)
             const uint32_t leader = elect_one();
             constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
@@ -632,16 +246,17 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const int rloc = qd * 32 + lane;          // row inside the tile == TMEM lane
         const int row = q0 + rloc;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const bool use_ids = p.sample_ids != nullptr;
         int sid_q = 0;
         if (use_ids) sid_q = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
         const int tid256 = threadIdx.x - 64;
         const float scl = p.scale_log2;
-        const int Ntok = p.N;
+        const int Ntok = p.Nk;
         float m_used = -INFINITY, l = 0.f;
-        for (int j = 0; j < T; ++j) {
-            const int s = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
+        for (int jj = 0; jj < T; ++jj) {
+            const int j = tile_of(jj);
+            const int s = jj & 1;
+            const uint32_t ph = (jj >> 1) & 1;
+            const bool use_ids = p.sample_ids != nullptr && !tl.nomask[jj];     // this tile pair needs the per-element mask
             if (use_ids && tid256 < 128) {
                 const int kk = j * ATT_BKV + tid256;
                 sid_k[s * 128 + tid256] = kk < Ntok ? (int)p.sample_ids[(long long)b * Ntok + kk] : -2;
@@ -689,8 +304,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             const bool grow = m_new > m_used + 8.0f;      // identical decision in both warpgroups (same inputs)
             if (__any_sync(0xffffffffu, grow)) {
                 const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_new);
-                if (j > 0) {
-                    mbar_wait(pv_done, (j - 1) & 1);       // O must be quiescent before it is rescaled
+                if (jj > 0) {
+                    mbar_wait(pv_done, (jj - 1) & 1);      // O must be quiescent before it is rescaled
                     tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < HD / 64; ++c) {   // each warpgroup rescales its half of O's columns
@@ -732,7 +347,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         xs[wg * 128 + rloc] = l;
         named_bar_sync(1, 256);
         const float lt = xs[rloc] + xs[128 + rloc];
-        mbar_wait(pv_done, (T - 1) & 1);
+        if (T > 0) mbar_wait(pv_done, (T - 1) & 1);
         tc_fence_after();
         const float inv = lt > 0.f ? 1.0f / lt : 0.f;
         __nv_bfloat16* orow = p.o + ((long long)b * p.N + row) * p.ldo + h * HD + wg * (HD / 2);
@@ -741,6 +356,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             uint32_t r[32];
             tmem_ld_32x32b_x32(tO + wg * (HD / 2) + c * 32 + lane_off, r);
             tmem_ld_wait();
+            if (inv == 0.f) {                              // fully masked row (padding): O was never written / holds no mass
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = 0u;
+            }
             if (row < p.N) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -819,205 +438,6 @@ struct AttnBwdParams {
     float* delta_out;
 };
 
-template <int HD, int MODE>
-__global__ void __launch_bounds__(192, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fb,
-                const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const AttnBwdParams p) {
-    // fixed operands: fa, fb (MODE0: K_j, V_j ; MODE1: Q_i, dO_i); streamed: sa, sb (MODE0: Q_i, dO_i ; MODE1: K_j, V_j)
-    using S = AttnSmem<HD>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sFA = smem;
-    uint8_t* sFB = sFA + S::TILE_BYTES;
-    uint8_t* sSA = sFB + S::TILE_BYTES;      // [2]
-    uint8_t* sSB = sSA + 2 * S::TILE_BYTES;  // [2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sSB + 2 * S::TILE_BYTES);
-    uint64_t* f_full = bars;          // 1
-    uint64_t* st_full = bars + 1;     // 2
-    uint64_t* st_empty = bars + 3;    // 2
-    uint64_t* sc_full = bars + 5;     // 1  scores ready (commit)
-    uint64_t* pr_full = bars + 6;     // 1  probabilities written (128 arrivals)
-    uint64_t* acc_done = bars + 7;    // 1  accumulating MMAs retired (commit)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
-    float* s_lse = reinterpret_cast<float*>(bars + 10);   // [2][128]  (MODE0: per streamed query)
-    float* s_dlt = s_lse + 256;                           // [2][128]
-    int* s_sid = reinterpret_cast<int*>(s_dlt + 256);     // [2][128]  sample id of the streamed rows
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-    const int T = (p.N + 127) / 128;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_fa); tma_prefetch_desc(&tm_fb); tma_prefetch_desc(&tm_sa); tma_prefetch_desc(&tm_sb);
-        mbar_init(f_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
-        mbar_init(sc_full, 1); mbar_init(pr_full, 128); mbar_init(acc_done, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_ptr_smem;
-    const uint32_t tSc = tmem, tDp = tmem + 128, tAcc0 = tmem + 256, tAcc1 = tmem + 256 + HD;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(f_full, 2 * S::TILE_BYTES);
-#pragma unroll
-            for (int bx = 0; bx < S::NBOX; ++bx) {
-                tma_load_3d(sFA + bx * S::BOX_BYTES, &tm_fa, f_full, h * HD + bx * 64, t0, b);
-                tma_load_3d(sFB + bx * S::BOX_BYTES, &tm_fb, f_full, h * HD + bx * 64, t0, b);
-            }
-            for (int i = 0; i < T; ++i) {
-                const int s = i & 1;
-                mbar_wait(&st_empty[s], ((i >> 1) & 1) ^ 1);
-                mbar_expect_tx(&st_full[s], 2 * S::TILE_BYTES);
-#pragma unroll
-                for (int bx = 0; bx < S::NBOX; ++bx) {
-                    tma_load_3d(sSA + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_sa, &st_full[s], h * HD + bx * 64, i * 128, b);
-                    tma_load_3d(sSB + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_sb, &st_full[s], h * HD + bx * 64, i * 128, b);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_sc = make_idesc_bf16(128, 128, false, false);
-            constexpr uint32_t idesc_acc = make_idesc_bf16(128, HD, false, true);
-            const uint32_t aFA = smem_u32(sFA), aFB = smem_u32(sFB);
-            mbar_wait(f_full, 0);
-            for (int i = 0; i < T; ++i) {
-                const int s = i & 1;
-                mbar_wait(&st_full[s], (i >> 1) & 1);
-                if (i > 0) mbar_wait(acc_done, (i - 1) & 1);   // previous probabilities (aliased columns) fully consumed
-                tc_fence_after();
-                const uint32_t aSA = smem_u32(sSA + s * S::TILE_BYTES), aSB = smem_u32(sSB + s * S::TILE_BYTES);
-                // scores: Sc = FA . SA^T ; Dp = FB . SB^T     (all K-major, reduction over head_dim)
-#pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tSc, desc_kmajor(aFA, ks), desc_kmajor(aSA, ks), idesc_sc, ks != 0);
-#pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tDp, desc_kmajor(aFB, ks), desc_kmajor(aSB, ks), idesc_sc, ks != 0);
-                umma_commit(sc_full);
-                mbar_wait(pr_full, i & 1);
-                tc_fence_after();
-                if (MODE == 0) {
-                    // dV += Pt . dO_i (B = SB MN-major) ; dK += dSt . Q_i (B = SA MN-major)
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) umma_ts(tAcc1, tSc + ks * 8, desc_mnmajor(aSB, ks), idesc_acc, (i | ks) != 0);
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor(aSA, ks), idesc_acc, (i | ks) != 0);
-                } else {
-                    // dQ += dS . K_j (B = SA MN-major)
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor(aSA, ks), idesc_acc, (i | ks) != 0);
-                }
-                umma_commit(&st_empty[s]);
-                umma_commit(acc_done);
-            }
-        }
-    } else {
-        const int qd = warp & 3;
-        const int rloc = qd * 32 + lane;
-        const int row = t0 + rloc;   // MODE0: key index ; MODE1: query index
-        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const int tid128 = threadIdx.x - 64;
-        const bool use_ids = p.sample_ids != nullptr;
-        const long long bh = (long long)b * p.H + h;
-        int sid_row = 0;
-        if (use_ids) sid_row = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
-        float lse_row = 0.f, dlt_row = 0.f;
-        if (MODE == 1 && row < p.N) { lse_row = p.lse[bh * p.N + row] * LOG2E; dlt_row = p.delta[bh * p.N + row]; }
-        for (int i = 0; i < T; ++i) {
-            const int s = i & 1;
-            // per-column metadata of the streamed tile
-            {
-                const int cidx = i * 128 + tid128;
-                if (MODE == 0) {
-                    s_lse[s * 128 + tid128] = cidx < p.N ? p.lse[bh * p.N + cidx] * LOG2E : INFINITY;
-                    s_dlt[s * 128 + tid128] = cidx < p.N ? p.delta[bh * p.N + cidx] : 0.f;
-                }
-                if (use_ids) s_sid[s * 128 + tid128] = cidx < p.N ? (int)p.sample_ids[(long long)b * p.N + cidx] : -2;
-                named_bar_sync(1, 128);
-            }
-            mbar_wait(sc_full, i & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t rs[32], rd[32];
-                tmem_ld_32x32b_x32(tSc + c * 32 + lane_off, rs);
-                tmem_ld_32x32b_x32(tDp + c * 32 + lane_off, rd);
-                tmem_ld_wait();
-                uint32_t pp[16], dd[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float pv[2], dv[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int col = c * 32 + 2 * e + u;
-                        const int cidx = i * 128 + col;
-                        bool ok;
-                        float lse2, dl;
-                        if (MODE == 0) {
-                            ok = (cidx < p.N) && (row < p.N);
-                            if (use_ids) { const int sq = s_sid[s * 128 + col]; ok = ok && sq == sid_row && sq != -1; }
-                            lse2 = s_lse[s * 128 + col]; dl = s_dlt[s * 128 + col];
-                        } else {
-                            ok = (cidx < p.N) && (row < p.N);
-                            if (use_ids) ok = ok && s_sid[s * 128 + col] == sid_row && sid_row != -1;
-                            lse2 = lse_row; dl = dlt_row;
-                        }
-                        const float sc = __uint_as_float(rs[2 * e + u]) * p.scale_log2;
-                        const float pr = ok ? ex2(sc - lse2) : 0.f;
-                        pv[u] = pr;
-                        dv[u] = pr * (__uint_as_float(rd[2 * e + u]) - dl);
-                    }
-                    pp[e] = pack_bf16x2(pv[0], pv[1]);
-                    dd[e] = pack_bf16x2(dv[0], dv[1]);
-                }
-                if (MODE == 0) tmem_st_32x32b_x16(tSc + c * 16 + lane_off, pp);
-                tmem_st_32x32b_x16(tDp + c * 16 + lane_off, dd);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(pr_full);
-        }
-        // ---- write the accumulators ----
-        mbar_wait(acc_done, (T - 1) & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int a = 0; a < (MODE == 0 ? 2 : 1); ++a) {
-            const uint32_t tA = a == 0 ? tAcc0 : tAcc1;
-            __nv_bfloat16* dst = (a == 0 ? p.out0 : p.out1) + ((long long)b * p.N + row) * (a == 0 ? p.ld0 : p.ld1) + h * HD;
-            const float sc = a == 0 ? p.scale : 1.0f;   // dK, dQ carry the softmax scale; dV does not
-#pragma unroll
-            for (int c = 0; c < HD / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tA + c * 32 + lane_off, r);
-                tmem_ld_wait();
-                if (row < p.N) {
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        uint4 o4;
-                        o4.x = pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) * sc, __uint_as_float(r[8 * q4 + 1]) * sc);
-                        o4.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * sc, __uint_as_float(r[8 * q4 + 3]) * sc);
-                        o4.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * sc, __uint_as_float(r[8 * q4 + 5]) * sc);
-                        o4.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * sc, __uint_as_float(r[8 * q4 + 7]) * sc);
-                        *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = o4;
-                    }
-                }
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem);
-    }
-}
-
-
 // ------------------------------------------------------------------------------------------------
 // Backward v2: same maths as attn_bwd_kernel, but the streamed operand is cut into 64-row sub-tiles and the score
 // accumulators are double-buffered in TMEM, so the tensor core (scores of sub-tile i+2, accumulation of sub-tile i)
@@ -1064,10 +484,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
     __shared__ __align__(16) float s_lse[4 * 64];   // per-column metadata of the streamed sub-tile: [warpgroup][2 slots][64]
     __shared__ __align__(16) float s_dlt[4 * 64];   // (two alternating slots per warpgroup: a fast thread may already publish
     __shared__ __align__(16) int s_sid[4 * 64];     //  sub-tile i+2 while a slow one still reads sub-tile i)
+    __shared__ DocTiles tl;                         // active streamed sub-tiles of this fixed tile (document mask only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-    const int T2 = (p.N + 63) / 64;
+    const int T2all = (p.N + 63) / 64;
+    const bool use_ids = p.sample_ids != nullptr;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_fa); tma_prefetch_desc(&tm_fb); tma_prefetch_desc(&tm_sa); tma_prefetch_desc(&tm_sb);
@@ -1085,9 +507,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_smem;
     const uint32_t tAcc0 = tmem + 256, tAcc1 = tmem + 256 + HD;
+    if (use_ids) doc_tile_list<64>(p.sample_ids + (long long)b * p.N, p.N, t0, T2all, tl);
+    // T2 = number of streamed 64-row sub-tiles this CTA visits; iteration ii works on sub-tile sub_of(ii) (stage / buffer /
+    // phase bookkeeping is in ii, coordinates and per-column metadata in the sub-tile index)
+    const int T2 = use_ids ? tl.n : T2all;
+    auto sub_of = [&](int ii) { return use_ids ? (int)tl.idx[ii] : ii; };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0 && T2 > 0) {
             mbar_expect_tx(f_full, 2 * S::FIX_BYTES);
 #pragma unroll
             for (int bx = 0; bx < S::NBOX; ++bx) {
@@ -1096,19 +523,20 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             }
             for (int i = 0; i < T2; ++i) {
                 const int s = i % NST;
+                const int sub = sub_of(i);
                 mbar_wait(&st_empty[s], ((i / NST) & 1) ^ 1);
                 mbar_expect_tx(&st_full[s], 2 * S::SUB_BYTES);
                 uint8_t* sa = sST + s * 2 * S::SUB_BYTES;
                 uint8_t* sb = sa + S::SUB_BYTES;
 #pragma unroll
                 for (int bx = 0; bx < S::NBOX; ++bx) {
-                    tma_load_3d(sa + bx * S::SUB_BOX, &tm_sa, &st_full[s], h * HD + bx * 64, i * 64, b);
-                    tma_load_3d(sb + bx * S::SUB_BOX, &tm_sb, &st_full[s], h * HD + bx * 64, i * 64, b);
+                    tma_load_3d(sa + bx * S::SUB_BOX, &tm_sa, &st_full[s], h * HD + bx * 64, sub * 64, b);
+                    tma_load_3d(sb + bx * S::SUB_BOX, &tm_sb, &st_full[s], h * HD + bx * 64, sub * 64, b);
                 }
             }
         }
     } else if (warp == 1) {
-        {
+        if (T2 > 0) {
             // the whole warp runs this loop (warp-uniform control flow and descriptor arithmetic); one elected lane issues
             const uint32_t leader = elect_one();
             constexpr uint32_t idesc_sc = make_idesc_bf16(128, 64, false, false);
@@ -1177,7 +605,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
         const int row = t0 + rloc;   // MODE0: key index ; MODE1: query index
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         const int tid128 = (threadIdx.x - 64) & 127;
-        const bool use_ids = p.sample_ids != nullptr;
         const long long bh = (long long)b * p.H + h;
         int sid_row = 0;
         if (use_ids) sid_row = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
@@ -1210,9 +637,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
         // metadata of this warpgroup's next sub-tile is fetched one iteration ahead (global latency off the critical path)
         float pf_lse = INFINITY, pf_dlt = 0.f;
         int pf_sid = -2;
-        auto fetch_meta = [&](int i) {
-            if ((MODE == 0 || use_ids) && tid128 < 64 && i < T2) {
-                const int cidx = i * 64 + tid128;
+        auto fetch_meta = [&](int ii) {
+            if ((MODE == 0 || use_ids) && tid128 < 64 && ii < T2) {
+                const int cidx = sub_of(ii) * 64 + tid128;
                 if (MODE == 0) {
                     pf_lse = cidx < Ntok ? p.lse[bh * Ntok + cidx] * LOG2E : INFINITY;
                     pf_dlt = cidx < Ntok ? p.delta[bh * Ntok + cidx] : 0.f;
@@ -1221,19 +648,22 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             }
         };
         fetch_meta(wg);
-        for (int i = wg; i < T2; i += 2) {
-            const int ms = (wg * 2 + ((i >> 1) & 1)) * 64;    // metadata slot of this sub-tile
+        for (int ii = wg; ii < T2; ii += 2) {
+            const int i = sub_of(ii);                          // streamed sub-tile index (coordinates)
+            const int ms = (wg * 2 + ((ii >> 1) & 1)) * 64;   // metadata slot of this sub-tile
             if (MODE == 0 || use_ids) {
                 if (tid128 < 64) {
                     if (MODE == 0) { s_lse[ms + tid128] = pf_lse; s_dlt[ms + tid128] = pf_dlt; }
                     if (use_ids) s_sid[ms + tid128] = pf_sid;
                 }
                 named_bar_sync(1 + wg, 128);
-                fetch_meta(i + 2);
+                fetch_meta(ii + 2);
             }
-            mbar_wait(&s_full[bf], (i >> 1) & 1);
+            mbar_wait(&s_full[bf], (ii >> 1) & 1);
             tc_fence_after();
-            const bool slow = use_ids || (i * 64 + 64 > Ntok) || !row_ok;   // masks needed only on edge tiles / document masks
+            // masks are needed only on edge tiles and on tile pairs that straddle a document boundary / hold padding
+            const bool doc_mask = use_ids && !tl.nomask[ii];
+            const bool slow = doc_mask || (i * 64 + 64 > Ntok) || !row_ok;
             uint32_t rsA[32], rsB[32], pk[32];
             tmem_ld_32x32b_x32(tSc + lane_off, rsA);
             tmem_ld_32x32b_x32(tSc + 32 + lane_off, rsB);
@@ -1259,7 +689,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                         if (SLOW) {
                             const int col = c * 32 + e4 * 4 + u;
                             bool ok = row_ok && (i * 64 + col < Ntok);
-                            if (use_ids) {
+                            if (doc_mask) {
                                 const int sq = s_sid[ms + col];
                                 ok = ok && sq == sid_row && sid_row != -1;
                             }
@@ -1288,7 +718,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 mbar_arrive(&p_rdy[bf]);
             }
             // phase 2: dS = P * (dP - delta)
-            mbar_wait(&dp_full[bf], (i >> 1) & 1);
+            mbar_wait(&dp_full[bf], (ii >> 1) & 1);
             tc_fence_after();
             uint32_t rdA[32], rdB[32];
             tmem_ld_32x32b_x32(tDp + lane_off, rdA);
@@ -1321,7 +751,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             mbar_arrive(&ds_rdy[bf]);
         }
         // ---- write the accumulators (the two warpgroups split the work) ----
-        mbar_wait(&acc_done[(T2 - 1) & 1], ((T2 - 1) >> 1) & 1);
+        if (T2 > 0) mbar_wait(&acc_done[(T2 - 1) & 1], ((T2 - 1) >> 1) & 1);
         tc_fence_after();
         {
             // MODE0: warpgroup 0 stores dK (Acc0), warpgroup 1 stores dV (Acc1).  MODE1: each stores half of dQ's columns.
@@ -1339,359 +769,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tA + c * 32 + lane_off, r);
                 tmem_ld_wait();
+                if (T2 == 0) {                                  // no matching tile at all (padding): the gradient is zero
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    uint4 o4;
-                    o4.x = pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) * sc, __uint_as_float(r[8 * q4 + 1]) * sc);
-                    o4.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * sc, __uint_as_float(r[8 * q4 + 3]) * sc);
-                    o4.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * sc, __uint_as_float(r[8 * q4 + 5]) * sc);
-                    o4.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * sc, __uint_as_float(r[8 * q4 + 7]) * sc);
-                    const int ch = c * 4 + q4;
-                    *reinterpret_cast<uint4*>(stg + rloc * (HD * 2) + ((ch ^ (rloc & (CPR - 1))) << 4)) = o4;
+                    for (int e = 0; e < 32; ++e) r[e] = 0u;
                 }
-            }
-            named_bar_sync(1 + wg, 128);
-            const int chunks_w = (c_hi - c_lo) * 4, chunk0 = c_lo * 4;            // this warpgroup's 16-byte chunks per row
-            const long long ldo = a == 0 ? p.ld0 : p.ld1;
-            __nv_bfloat16* base = (a == 0 ? p.out0 : p.out1) + ((long long)b * p.N + t0) * ldo + h * HD;
-#pragma unroll 4
-            for (int it = 0; it < chunks_w; ++it) {
-                const int idx = it * 128 + tid128;
-                const int rr = idx / chunks_w, ch = chunk0 + idx % chunks_w;
-                if (t0 + rr < p.N) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * (HD * 2) + ((ch ^ (rr & (CPR - 1))) << 4));
-                    *reinterpret_cast<uint4*>(base + (long long)rr * ldo + ch * 8) = v;
-                }
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem);
-    }
-}
-
-// EXPERIMENTAL (not launched by default; UD_ATTN_BWD_DQ3=1 selects it for the dQ kernel, not yet validated on hardware): the
-// same kernel with NBUF score buffers and NST_ smem stages as template parameters.  The dQ kernel owns a single accumulator
-// (HD TMEM columns), so three 128-column score buffers fit (3 * 128 + HD <= 512): with two warpgroups alternating over three
-// buffers the scores of a warpgroup's NEXT sub-tile are already in TMEM when it finishes the current one, which takes the
-// S -> softmax -> accumulate round trip (about 3000 cycles for two sub-tiles, tools/ubench.cu) off the critical path.
-template <int HD, int NST_>
-struct AttnBwd2xSmem {
-    static constexpr int FIX_BYTES = 128 * HD * 2;
-    static constexpr int SUB_BYTES = 64 * HD * 2;
-    static constexpr int SUB_BOX = 64 * 128;
-    static constexpr int NBOX = HD / 64;
-    static constexpr int BYTES = 2 * FIX_BYTES + NST_ * 2 * SUB_BYTES + 1024 + 512;      // + alignment slack + barriers
-};
-
-template <int HD, int MODE, int NBUF, int NST_>
-__global__ void __launch_bounds__(320, 1)
-attn_bwd2x_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fb,
-                 const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const AttnBwdParams p) {
-    using S = AttnBwd2xSmem<HD, NST_>;
-    constexpr int NST = NST_;
-    static_assert(NBUF * 128 + (MODE == 0 ? 2 : 1) * HD <= 512, "score buffers + accumulators exceed the 512 TMEM columns");
-    static_assert((1 + 2 * NST + 5 * NBUF) * 8 + 4 <= 512, "barrier block larger than its reservation");
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sFA = smem;
-    uint8_t* sFB = sFA + S::FIX_BYTES;
-    uint8_t* sST = sFB + S::FIX_BYTES;                   // stage s: [SA | SB]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sST + NST * 2 * S::SUB_BYTES);
-    uint64_t* f_full = bars;                 // 1
-    uint64_t* st_full = bars + 1;            // NST
-    uint64_t* st_empty = bars + 1 + NST;     // NST
-    uint64_t* s_full = bars + 1 + 2 * NST;   // NBUF   S^T of a sub-tile in TMEM      (tensor pipe -> softmax warpgroup)
-    uint64_t* dp_full = s_full + NBUF;       // NBUF   dP^T of the same sub-tile
-    uint64_t* p_rdy = dp_full + NBUF;        // NBUF   bf16 P^T written over S^T        (softmax warpgroup -> tensor pipe)
-    uint64_t* ds_rdy = p_rdy + NBUF;         // NBUF   bf16 dS^T written over dP^T
-    uint64_t* acc_done = ds_rdy + NBUF;      // NBUF
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_done + NBUF);
-    // per-column metadata of the streamed sub-tile: [warpgroup][2 slots][64] (only the dK/dV kernel needs lse / delta per column)
-    __shared__ __align__(16) float s_lse[MODE == 0 ? 4 * 64 : 4];
-    __shared__ __align__(16) float s_dlt[MODE == 0 ? 4 * 64 : 4];
-    __shared__ __align__(16) int s_sid[4 * 64];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-    const int T2 = (p.N + 63) / 64;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_fa); tma_prefetch_desc(&tm_fb); tma_prefetch_desc(&tm_sa); tma_prefetch_desc(&tm_sb);
-        mbar_init(f_full, 1);
-        for (int s = 0; s < NST; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
-        for (int s = 0; s < NBUF; ++s) {
-            mbar_init(&s_full[s], 1); mbar_init(&dp_full[s], 1); mbar_init(&p_rdy[s], 128); mbar_init(&ds_rdy[s], 128);
-            mbar_init(&acc_done[s], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_ptr_smem;
-    const uint32_t tAcc0 = tmem + NBUF * 128, tAcc1 = tmem + NBUF * 128 + HD;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(f_full, 2 * S::FIX_BYTES);
-#pragma unroll
-            for (int bx = 0; bx < S::NBOX; ++bx) {
-                tma_load_3d(sFA + bx * (128 * 128), &tm_fa, f_full, h * HD + bx * 64, t0, b);
-                tma_load_3d(sFB + bx * (128 * 128), &tm_fb, f_full, h * HD + bx * 64, t0, b);
-            }
-            for (int i = 0; i < T2; ++i) {
-                const int s = i % NST;
-                mbar_wait(&st_empty[s], ((i / NST) & 1) ^ 1);
-                mbar_expect_tx(&st_full[s], 2 * S::SUB_BYTES);
-                uint8_t* sa = sST + s * 2 * S::SUB_BYTES;
-                uint8_t* sb = sa + S::SUB_BYTES;
-#pragma unroll
-                for (int bx = 0; bx < S::NBOX; ++bx) {
-                    tma_load_3d(sa + bx * S::SUB_BOX, &tm_sa, &st_full[s], h * HD + bx * 64, i * 64, b);
-                    tma_load_3d(sb + bx * S::SUB_BOX, &tm_sb, &st_full[s], h * HD + bx * 64, i * 64, b);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        {
-            // the whole warp runs this loop (warp-uniform control flow and descriptor arithmetic); one elected lane issues
-            const uint32_t leader = elect_one();
-            constexpr uint32_t idesc_sc = make_idesc_bf16(128, 64, false, false);
-            constexpr uint32_t idesc_acc = make_idesc_bf16(128, HD, false, true);
-            const uint32_t aFA = smem_u32(sFA), aFB = smem_u32(sFB);
-            auto issue_scores = [&](int i) {
-                const int s = i % NST, bf = i % NBUF;
-                mbar_wait(&st_full[s], (i / NST) & 1);
-                tc_fence_after();
-                const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
-                const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
-                if (leader) {
-                    // S^T and dP^T are signalled separately: the warpgroup starts its exponentials while dP^T is still being
-                    // multiplied
-#pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tSc, desc_kmajor(aFA, ks), desc_kmajor64(aSA, ks), idesc_sc, ks != 0);
-                    umma_commit(&s_full[bf]);
-#pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tDp, desc_kmajor(aFB, ks), desc_kmajor64(aSB, ks), idesc_sc, ks != 0);
-                    umma_commit(&dp_full[bf]);
-                }
-                __syncwarp();
-            };
-            mbar_wait(f_full, 0);
-#pragma unroll
-            for (int i0 = 0; i0 < NBUF; ++i0)
-                if (i0 < T2) issue_scores(i0);
-            for (int i = 0; i < T2; ++i) {
-                const int s = i % NST, bf = i % NBUF;
-                const uint32_t ph = (i / NBUF) & 1;
-                const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
-                const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
-                const uint32_t acc0 = i != 0;
-                if (MODE == 0) {
-                    // dV += P^T dO as soon as P^T is stored: it runs while the warpgroup still forms dS^T
-                    mbar_wait(&p_rdy[bf], ph);
-                    tc_fence_after();
-                    if (leader) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc1, tSc + ks * 8, desc_mnmajor64(aSB, ks), idesc_acc, acc0 | (ks != 0));
-                    }
-                    __syncwarp();
-                }
-                mbar_wait(&ds_rdy[bf], ph);
-                tc_fence_after();
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, acc0 | (ks != 0));
-                    umma_commit(&st_empty[s]);
-                    umma_commit(&acc_done[bf]);
-                }
-                __syncwarp();
-                if (i + NBUF < T2) {
-                    // scores(i+NBUF) overwrite the columns the accumulation MMAs above read P / dS from.  tcgen05.mma issued by
-                    // one thread execute in issue order, so no completion wait is needed here (UD_ATTN_BWD_SAFE=1 re-enables it)
-                    if (p.safe_order) mbar_wait(&acc_done[bf], ph);
-                    issue_scores(i + NBUF);
-                }
-            }
-        }
-    } else {
-        // two softmax warpgroups (warps 2-5 and 6-9): warpgroup g owns the sub-tiles i == g (mod 2); sub-tile i lives in score
-        // buffer i % NBUF
-        const int wg = (warp - 2) >> 2;
-        const int qd = warp & 3;
-        const int rloc = qd * 32 + lane;
-        const int row = t0 + rloc;   // MODE0: key index ; MODE1: query index
-        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const int tid128 = (threadIdx.x - 64) & 127;
-        const bool use_ids = p.sample_ids != nullptr;
-        const long long bh = (long long)b * p.H + h;
-        int sid_row = 0;
-        if (use_ids) sid_row = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
-        float lse_row = 0.f, dlt_row = 0.f;
-        if (MODE == 1 && row < p.N) {
-            lse_row = p.lse[bh * p.N + row] * LOG2E;
-            if (p.o != nullptr) {
-                // delta of this thread's query row, straight from O and dO (both warpgroups own the same rows and compute it
-                // redundantly; warpgroup 0 publishes it)
-                const uint4* po = reinterpret_cast<const uint4*>(p.o + ((long long)b * p.N + row) * p.ldo + h * HD);
-                const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((long long)b * p.N + row) * p.ldo + h * HD);
-                float acc = 0.f;
-#pragma unroll 4
-                for (int j = 0; j < HD / 8; ++j) {
-                    const uint4 a = po[j], g = pd[j];
-                    acc += bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y)
-                         + bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
-                }
-                dlt_row = acc;
-                if (wg == 0) p.delta_out[bh * p.N + row] = acc;
-            } else {
-                dlt_row = p.delta[bh * p.N + row];
-            }
-        }
-        const bool row_ok = row < p.N;
-        const float scl = p.scale_log2;
-        const int Ntok = p.N;
-        // metadata of this warpgroup's next sub-tile is fetched one iteration ahead (global latency off the critical path)
-        float pf_lse = INFINITY, pf_dlt = 0.f;
-        int pf_sid = -2;
-        auto fetch_meta = [&](int i) {
-            if ((MODE == 0 || use_ids) && tid128 < 64 && i < T2) {
-                const int cidx = i * 64 + tid128;
-                if (MODE == 0) {
-                    pf_lse = cidx < Ntok ? p.lse[bh * Ntok + cidx] * LOG2E : INFINITY;
-                    pf_dlt = cidx < Ntok ? p.delta[bh * Ntok + cidx] : 0.f;
-                }
-                if (use_ids) pf_sid = cidx < Ntok ? (int)p.sample_ids[(long long)b * Ntok + cidx] : -2;
-            }
-        };
-        fetch_meta(wg);
-        for (int i = wg; i < T2; i += 2) {
-            const int ms = (wg * 2 + ((i >> 1) & 1)) * 64;    // metadata slot of this sub-tile
-            const int bf = i % NBUF;
-            const uint32_t bph = (i / NBUF) & 1;
-            const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
-            if (MODE == 0 || use_ids) {
-                if (tid128 < 64) {
-                    if (MODE == 0) { s_lse[ms + tid128] = pf_lse; s_dlt[ms + tid128] = pf_dlt; }
-                    if (use_ids) s_sid[ms + tid128] = pf_sid;
-                }
-                named_bar_sync(1 + wg, 128);
-                fetch_meta(i + 2);
-            }
-            mbar_wait(&s_full[bf], bph);
-            tc_fence_after();
-            const bool slow = use_ids || (i * 64 + 64 > Ntok) || !row_ok;   // masks needed only on edge tiles / document masks
-            uint32_t rsA[32], rsB[32], pk[32];
-            tmem_ld_32x32b_x32(tSc + lane_off, rsA);
-            tmem_ld_32x32b_x32(tSc + 32 + lane_off, rsB);
-            tmem_ld_wait();
-            // phase 1: P = exp(S * scale - lse), kept in fp32 in rsA / rsB (in place) and packed to bf16 in pk.  Interior tiles
-            // take the mask-free instantiation (no per-element compare / select instructions).
-            auto phase1 = [&](uint32_t (&rs)[32], int c, auto slow_tag) {
-                constexpr bool SLOW = decltype(slow_tag)::value;
-#pragma unroll
-                for (int e4 = 0; e4 < 8; ++e4) {
-                    float l4[4];
-                    if (MODE == 0) {
-                        const float4 lv = *reinterpret_cast<const float4*>(&s_lse[ms + c * 32 + e4 * 4]);
-                        l4[0] = lv.x; l4[1] = lv.y; l4[2] = lv.z; l4[3] = lv.w;
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) l4[u] = lse_row;
-                    }
-                    float pv[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float pr = ex2(fmaf(__uint_as_float(rs[e4 * 4 + u]), scl, -l4[u]));
-                        if (SLOW) {
-                            const int col = c * 32 + e4 * 4 + u;
-                            bool ok = row_ok && (i * 64 + col < Ntok);
-                            if (use_ids) {
-                                const int sq = s_sid[ms + col];
-                                ok = ok && sq == sid_row && sid_row != -1;
-                            }
-                            if (!ok) pr = 0.f;
-                        }
-                        pv[u] = pr;
-                        rs[e4 * 4 + u] = __float_as_uint(pr);
-                    }
-                    if (MODE == 0) {
-                        pk[c * 16 + e4 * 2] = pack_bf16x2(pv[0], pv[1]);
-                        pk[c * 16 + e4 * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
-                    }
-                }
-            };
-            if (slow) {
-                phase1(rsA, 0, std::true_type{});
-                phase1(rsB, 1, std::true_type{});
-            } else {
-                phase1(rsA, 0, std::false_type{});
-                phase1(rsB, 1, std::false_type{});
-            }
-            if (MODE == 0) {
-                tmem_st_32x32b_x32(tSc + lane_off, pk);
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(&p_rdy[bf]);
-            }
-            // phase 2: dS = P * (dP - delta)
-            mbar_wait(&dp_full[bf], bph);
-            tc_fence_after();
-            uint32_t rdA[32], rdB[32];
-            tmem_ld_32x32b_x32(tDp + lane_off, rdA);
-            tmem_ld_32x32b_x32(tDp + 32 + lane_off, rdB);
-            tmem_ld_wait();
-            auto phase2 = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c) {
-#pragma unroll
-                for (int e4 = 0; e4 < 8; ++e4) {
-                    float d4[4];
-                    if (MODE == 0) {
-                        const float4 dv = *reinterpret_cast<const float4*>(&s_dlt[ms + c * 32 + e4 * 4]);
-                        d4[0] = dv.x; d4[1] = dv.y; d4[2] = dv.z; d4[3] = dv.w;
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) d4[u] = dlt_row;
-                    }
-                    float dvv[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        dvv[u] = __uint_as_float(rs[e4 * 4 + u]) * (__uint_as_float(rd[e4 * 4 + u]) - d4[u]);
-                    pk[c * 16 + e4 * 2] = pack_bf16x2(dvv[0], dvv[1]);
-                    pk[c * 16 + e4 * 2 + 1] = pack_bf16x2(dvv[2], dvv[3]);
-                }
-            };
-            phase2(rsA, rdA, 0);
-            phase2(rsB, rdB, 1);
-            tmem_st_32x32b_x32(tDp + lane_off, pk);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&ds_rdy[bf]);
-        }
-        // ---- write the accumulators (the two warpgroups split the work) ----
-        mbar_wait(&acc_done[(T2 - 1) % NBUF], ((T2 - 1) / NBUF) & 1);
-        tc_fence_after();
-        {
-            // MODE0: warpgroup 0 stores dK (Acc0), warpgroup 1 stores dV (Acc1).  MODE1: each stores half of dQ's columns.
-            // TMEM gives every thread one ROW; the bf16 rows are staged in the (now idle) fixed-operand tiles with the
-            // 16-byte chunks XOR-swizzled by row, then copied out with whole rows per warp instruction (coalesced 128-byte
-            // lines instead of 32 scattered 16-byte stores per instruction).
-            const int a = (MODE == 0) ? wg : 0;
-            const uint32_t tA = a == 0 ? tAcc0 : tAcc1;
-            uint8_t* stg = (MODE == 0 && wg == 1) ? sFB : sFA;
-            const float sc = a == 0 ? p.scale : 1.0f;
-            constexpr int CPR = HD * 2 / 16;                         // 16-byte chunks per row
-            const int c_lo = (MODE == 0) ? 0 : wg * (HD / 64), c_hi = (MODE == 0) ? HD / 32 : (wg + 1) * (HD / 64);
-#pragma unroll 1
-            for (int c = c_lo; c < c_hi; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tA + c * 32 + lane_off, r);
-                tmem_ld_wait();
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     uint4 o4;
@@ -1736,39 +817,19 @@ static int make_head_tmap(CUtensorMap* tm, const void* base, long long ld, int B
 }
 
 template <int HD>
-static int launch_attn_fwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const AttnParams& p,
-                           cudaStream_t stream) {
-    static const int variant = getenv("UD_ATTN_FWD") ? atoi(getenv("UD_ATTN_FWD")) : 3;   // 3 = eight softmax warps (default); 1, 2 = A/B variants
-    const bool use_v1 = variant == 1;
+static int launch_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                           const AttnParams& p, cudaStream_t stream) {
     CUtensorMap tq, tk, tv;
     const int D = p.H * HD;
-    int rc = make_head_tmap(&tq, q, ldqk, p.B, p.N, D);
+    int rc = make_head_tmap(&tq, q, ldq, p.B, p.N, D);
     if (rc) return rc;
-    if ((rc = make_head_tmap(&tk, k, ldqk, p.B, p.N, D))) return rc;
-    if ((rc = make_head_tmap(&tv, v, ldv, p.B, p.N, D))) return rc;
-    if (use_v1) {
-        const int smem = attn_smem_bytes<HD>(5);
-        static bool attr = false;
-        if (!attr) { UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-        dim3 grid((p.N + ATT_BQ - 1) / ATT_BQ, p.H, p.B);
-        attn_fwd_kernel<HD><<<grid, 192, smem, stream>>>(tq, tk, tv, p);
-        UD_CUDA_CHECK(cudaGetLastError());
-        return 0;
-    }
-    if (variant == 3) {
-        const int smem3 = attn_smem_bytes<HD>(5);
-        static bool attr3 = false;
-        if (!attr3) { UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); attr3 = true; }
-        dim3 grid3((p.N + ATT_BQ - 1) / ATT_BQ, p.H, p.B);
-        attn_fwd3_kernel<HD><<<grid3, 320, smem3, stream>>>(tq, tk, tv, p);
-        UD_CUDA_CHECK(cudaGetLastError());
-        return 0;
-    }
-    const int smem = attn_smem_bytes<HD>(6);
-    static bool attr2 = false;
-    if (!attr2) { UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr2 = true; }
-    dim3 grid((p.N + 255) / 256, p.H, p.B);
-    attn_fwd2_kernel<HD><<<grid, 320, smem, stream>>>(tq, tk, tv, p);
+    if ((rc = make_head_tmap(&tk, k, ldk, p.B, p.Nk, D))) return rc;
+    if ((rc = make_head_tmap(&tv, v, ldv, p.B, p.Nk, D))) return rc;
+    const int smem3 = attn_smem_bytes<HD>(5);
+    static bool attr3 = false;
+    if (!attr3) { UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); attr3 = true; }
+    dim3 grid3((p.N + ATT_BQ - 1) / ATT_BQ, p.H, p.B);
+    attn_fwd3_kernel<HD><<<grid3, 320, smem3, stream>>>(tq, tk, tv, p);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1777,11 +838,10 @@ template <int HD>
 static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const void* d_o,
                            long long ldo, AttnBwdParams p, __nv_bfloat16* dq, __nv_bfloat16* dk, long long lddqk,
                            __nv_bfloat16* dv, long long lddv, cudaStream_t stream) {
-    static const bool use_v1 = getenv("UD_ATTN_BWD_V1") != nullptr;     // A/B switch: strictly alternating v1 kernel
-    // The v2 dQ kernel can form delta itself (UD_ATTN_FUSED_DELTA=1), but measured at B8 H16 N1280 hd128 the per-thread row reads
+    // The dQ kernel can form delta itself (UD_ATTN_FUSED_DELTA=1), but measured at B8 H16 N1280 hd128 the per-thread row reads
     // delay every CTA's first sub-tile: 458.6 us fused vs 445.4 us with the separate 33 us pass, so the pass stays the default.
     static const bool sep_delta = getenv("UD_ATTN_FUSED_DELTA") == nullptr;
-    if (use_v1 || sep_delta) {
+    if (sep_delta) {
         const long long warps = (long long)p.B * p.N * p.H;
         const int threads = 256;
         const long long blocks = (warps * 32 + threads - 1) / threads;
@@ -1801,20 +861,6 @@ static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const v
     p0.out0 = dk; p0.ld0 = lddqk; p0.out1 = dv; p0.ld1 = lddv;
     AttnBwdParams p1 = p;
     p1.out0 = dq; p1.ld0 = lddqk; p1.out1 = nullptr; p1.ld1 = 0;
-    if (use_v1) {
-        const int smem = attn_smem_bytes<HD>(6);
-        static bool attr = false;
-        if (!attr) {
-            UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<HD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<HD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr = true;
-        }
-        attn_bwd_kernel<HD, 0><<<grid, 192, smem, stream>>>(tk, tv, tq, tdo, p0);
-        UD_CUDA_CHECK(cudaGetLastError());
-        attn_bwd_kernel<HD, 1><<<grid, 192, smem, stream>>>(tq, tdo, tk, tv, p1);
-        UD_CUDA_CHECK(cudaGetLastError());
-        return 0;
-    }
     if ((rc = make_head_tmap(&tq64, q, ldqk, p.B, p.N, D, 64))) return rc;
     if ((rc = make_head_tmap(&tk64, k, ldqk, p.B, p.N, D, 64))) return rc;
     if ((rc = make_head_tmap(&tv64, v, ldv, p.B, p.N, D, 64))) return rc;
@@ -1827,18 +873,7 @@ static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const v
         attr2 = true;
     }
     // dQ first: it also produces delta, which the dK/dV kernel reads per streamed query column
-    static const bool dq3 = getenv("UD_ATTN_BWD_DQ3") != nullptr;      // experimental three-score-buffer dQ kernel (see attn_bwd2x_kernel)
-    if (dq3) {
-        const int smem3 = AttnBwd2xSmem<HD, 5>::BYTES;
-        static bool attr3 = false;
-        if (!attr3) {
-            UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2x_kernel<HD, 1, 3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-            attr3 = true;
-        }
-        attn_bwd2x_kernel<HD, 1, 3, 5><<<grid, 320, smem3, stream>>>(tq, tdo, tk64, tv64, p1);
-    } else {
-        attn_bwd2_kernel<HD, 1><<<grid, 320, smem, stream>>>(tq, tdo, tk64, tv64, p1);
-    }
+    attn_bwd2_kernel<HD, 1><<<grid, 320, smem, stream>>>(tq, tdo, tk64, tv64, p1);
     UD_CUDA_CHECK(cudaGetLastError());
     attn_bwd2_kernel<HD, 0><<<grid, 320, smem, stream>>>(tk, tv, tq64, tdo64, p0);
     UD_CUDA_CHECK(cudaGetLastError());
@@ -1849,21 +884,36 @@ static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const v
 
 using namespace ud;
 
-extern "C" int ud_attn_fwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, void* o, long long ldo,
-                           float* lse, const int64_t* sample_ids, int B, int N, int H, int head_dim, float scale, void* stream) {
-    if (B <= 0 || N <= 0) return 0;
+static int attn_fwd_entry(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
+                          long long ldo, float* lse, const int64_t* sample_ids, int B, int Nq, int Nk, int H, int head_dim,
+                          float scale, void* stream) {
+    if (B <= 0 || Nq <= 0 || Nk <= 0) return 0;
+    if (sample_ids != nullptr && (Nq != Nk || (Nk + 63) / 64 > MAX_DOC_TILES)) {
+        fprintf(stderr, "unidisc_b200: document-masked attention needs Nq == Nk <= %d\n", MAX_DOC_TILES * 64);
+        return -1;
+    }
     AttnParams p;
-    p.B = B; p.N = N; p.H = H;
+    p.B = B; p.N = Nq; p.Nk = Nk; p.H = H;
     p.scale_log2 = scale * LOG2E;
     p.o = reinterpret_cast<__nv_bfloat16*>(o);
     p.ldo = ldo;
     p.lse = lse;
     p.sample_ids = sample_ids;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (head_dim == 128) return launch_attn_fwd<128>(q, k, ldqk, v, ldv, p, s);
-    if (head_dim == 64) return launch_attn_fwd<64>(q, k, ldqk, v, ldv, p, s);
+    if (head_dim == 128) return launch_attn_fwd<128>(q, ldq, k, ldk, v, ldv, p, s);
+    if (head_dim == 64) return launch_attn_fwd<64>(q, ldq, k, ldk, v, ldv, p, s);
     fprintf(stderr, "unidisc_b200: attention supports head_dim 64 and 128 (got %d)\n", head_dim);
     return -1;
+}
+
+extern "C" int ud_attn_fwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, void* o, long long ldo,
+                           float* lse, const int64_t* sample_ids, int B, int N, int H, int head_dim, float scale, void* stream) {
+    return attn_fwd_entry(q, ldqk, k, ldqk, v, ldv, o, ldo, lse, sample_ids, B, N, N, H, head_dim, scale, stream);
+}
+
+extern "C" int ud_attn_fwd_kv(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
+                              long long ldo, float* lse, int B, int Nq, int Nk, int H, int head_dim, float scale, void* stream) {
+    return attn_fwd_entry(q, ldq, k, ldk, v, ldv, o, ldo, lse, nullptr, B, Nq, Nk, H, head_dim, scale, stream);
 }
 
 extern "C" int ud_attn_bwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const void* o,
@@ -1871,6 +921,10 @@ extern "C" int ud_attn_bwd(const void* q, const void* k, long long ldqk, const v
                            void* dv, long long lddv, const int64_t* sample_ids, int B, int N, int H, int head_dim, float scale,
                            void* stream) {
     if (B <= 0 || N <= 0) return 0;
+    if (sample_ids != nullptr && (N + 63) / 64 > MAX_DOC_TILES) {
+        fprintf(stderr, "unidisc_b200: document-masked attention needs N <= %d\n", MAX_DOC_TILES * 64);
+        return -1;
+    }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     AttnBwdParams p;
     p.o = reinterpret_cast<const __nv_bfloat16*>(o);

@@ -235,8 +235,40 @@ __global__ void sample_probs_kernel(const int64_t* __restrict__ x, const float* 
     }
 }
 
-// Fused fast path: bf16 logits (+ optional CFG pair) -> SUBS softmax -> absorbing update.  The row's valid range is
-// staged once in shared memory as fp32 (HBM is read exactly once), then reduced for the lse and scanned for the arg-max.
+// Stage one row's valid vocabulary range [lo,hi) in shared memory as fp32 (CFG-combined when CFG) and return the row's
+// log-sum-exp over it (mask column excluded): HBM is read exactly once per row.  Block-wide; `sm` = 64 floats of scratch.
+template <bool CFG>
+UD_DEVINL float stage_row_lse(float* srow, float* sm, const __nv_bfloat16* rc, const __nv_bfloat16* ru, float w, int lo, int hi,
+                              int mask_index) {
+    MaxSum acc = {-INFINITY, 0.f};
+    __syncthreads();  // srow reuse across rows
+    auto put = [&](int v, float lcv, float luv) {
+        float l = lcv;
+        if (CFG) l = __fsub_rn(__fmul_rn(1.0f + w, lcv), __fmul_rn(w, luv));     // model_eval.py:1812 (torch: two products, one subtraction)
+        srow[v - lo] = l;
+        if (v != mask_index) ms_add(acc, l);
+    };
+    const int lo_al = min(hi, (lo + 7) & ~7), hi_al = max(lo_al, hi & ~7);
+    for (int v = lo + threadIdx.x; v < lo_al; v += blockDim.x)
+        put(v, __bfloat162float(rc[v]), CFG ? __bfloat162float(ru[v]) : 0.f);
+    for (int v = lo_al + threadIdx.x * 8; v < hi_al; v += blockDim.x * 8) {
+        const uint4 a = ldg_stream(rc + v);
+        uint4 bq = make_uint4(0, 0, 0, 0);
+        if (CFG) bq = ldg_stream(ru + v);
+        put(v + 0, bf16lo(a.x), bf16lo(bq.x)); put(v + 1, bf16hi(a.x), bf16hi(bq.x));
+        put(v + 2, bf16lo(a.y), bf16lo(bq.y)); put(v + 3, bf16hi(a.y), bf16hi(bq.y));
+        put(v + 4, bf16lo(a.z), bf16lo(bq.z)); put(v + 5, bf16hi(a.z), bf16hi(bq.z));
+        put(v + 6, bf16lo(a.w), bf16lo(bq.w)); put(v + 7, bf16hi(a.w), bf16hi(bq.w));
+    }
+    for (int v = hi_al + threadIdx.x; v < hi; v += blockDim.x)
+        put(v, __bfloat162float(rc[v]), CFG ? __bfloat162float(ru[v]) : 0.f);
+    const MaxSum t = block_ms(acc, sm);      // (its barriers also publish srow to the whole block)
+    return t.m + logf(t.s);
+}
+
+// Fused path with SUPPLIED noise (bit-parity mode): bf16 logits (+ optional CFG pair) -> SUBS softmax -> absorbing update
+// in the reference's fp32 operation order: q_v = exp(l_v - lse) * (mc_t - mc_s), q_mask = mc_s, arg-max of
+// q_v / (1e-10 - log(u_v + 1e-10))   (model_eval.py:2091-2094, model_utils.py:95-97).
 template <bool CFG>
 __global__ void ddpm_update_logits_kernel(const int64_t* __restrict__ x, const __nv_bfloat16* __restrict__ lc,
                                           const __nv_bfloat16* __restrict__ lu, long long ldv, const float* __restrict__ cfg_w,
@@ -256,47 +288,121 @@ __global__ void ddpm_update_logits_kernel(const int64_t* __restrict__ x, const _
         const int b = r / N;
         int lo, hi;
         valid_range(modality[r], V, text_vocab, lo, hi);
-        const __nv_bfloat16* rc = lc + (long long)r * ldv;
-        const __nv_bfloat16* ru = CFG ? lu + (long long)r * ldv : nullptr;
-        const float w = CFG ? cfg_w[b] : 0.f;
-        MaxSum acc = {-INFINITY, 0.f};
-        __syncthreads();  // srow reuse across rows
-        auto put = [&](int v, float lcv, float luv) {
-            float l = lcv;
-            if (CFG) l = (1.0f + w) * lcv - w * luv;                     // model_eval.py:1812
-            srow[v - lo] = l;
-            if (v != mask_index) ms_add(acc, l);
-        };
-        {
-            const int lo_al = min(hi, (lo + 7) & ~7), hi_al = max(lo_al, hi & ~7);
-            for (int v = lo + threadIdx.x; v < lo_al; v += blockDim.x)
-                put(v, __bfloat162float(rc[v]), CFG ? __bfloat162float(ru[v]) : 0.f);
-            for (int v = lo_al + threadIdx.x * 8; v < hi_al; v += blockDim.x * 8) {
-                const uint4 a = ldg_stream(rc + v);
-                uint4 bq = make_uint4(0, 0, 0, 0);
-                if (CFG) bq = ldg_stream(ru + v);
-                put(v + 0, bf16lo(a.x), bf16lo(bq.x)); put(v + 1, bf16hi(a.x), bf16hi(bq.x));
-                put(v + 2, bf16lo(a.y), bf16lo(bq.y)); put(v + 3, bf16hi(a.y), bf16hi(bq.y));
-                put(v + 4, bf16lo(a.z), bf16lo(bq.z)); put(v + 5, bf16hi(a.z), bf16hi(bq.z));
-                put(v + 6, bf16lo(a.w), bf16lo(bq.w)); put(v + 7, bf16hi(a.w), bf16hi(bq.w));
-            }
-            for (int v = hi_al + threadIdx.x; v < hi; v += blockDim.x)
-                put(v, __bfloat162float(rc[v]), CFG ? __bfloat162float(ru[v]) : 0.f);
-        }
-        const MaxSum t = block_ms(acc, sm);
-        const float lse = t.m + logf(t.s);
-        const float d = mc_t[b] - mc_s[b], ms = mc_s[b];
+        const float lse = stage_row_lse<CFG>(srow, sm, lc + (long long)r * ldv, CFG ? lu + (long long)r * ldv : nullptr,
+                                             CFG ? cfg_w[b] : 0.f, lo, hi, (int)mask_index);
+        const float d = __fsub_rn(mc_t[b], mc_s[b]), ms = mc_s[b];
         const float* ur = u ? u + (long long)r * V : nullptr;
         ArgMax a = {-INFINITY, 0x7fffffff};
         for (int v = lo + threadIdx.x; v < hi; v += blockDim.x) {
             if (v == mask_index) continue;
             const float uu = ur ? ur[v] : philox_uniform(seed, offset, (uint64_t)r * V + v);
-            am_upd(a, __fdiv_rn(expf(srow[v - lo] - lse) * d, gumbel_norm(uu)), v);
+            am_upd(a, __fdiv_rn(__fmul_rn(expf(__fsub_rn(srow[v - lo], lse)), d), gumbel_norm(uu)), v);
         }
         if (threadIdx.x == 0) {  // the mask column keeps probability mc_s (model_eval.py:2066,2092)
             const float uu = ur ? ur[mask_index] : philox_uniform(seed, offset, (uint64_t)r * V + mask_index);
             am_upd(a, __fdiv_rn(ms, gumbel_norm(uu)), (int)mask_index);
         }
+        a = block_argmax(a, smv, smi);
+        if (threadIdx.x == 0) out[r] = a.i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaskGIT step (model_eval.py:3045-3114), supplied-noise (bit-parity) draw: per masked token row
+//   pred = torch.multinomial(p, 1) = argmax_v p_v / E_v,  E ~ Exp(1)   (ATen multinomial's single-draw path: q.exponential_(1); argmax(p / q))
+//   conf = log(p_pred) + r_temp * gumbel * t   (float64 like the reference, whose np.random.gumbel draw promotes the sum)
+// with p = exp(SUBS log-softmax) computed in one vocabulary pass; conf = -inf on rows that are already unmasked.
+// ------------------------------------------------------------------------------------------------
+template <bool CFG>
+__global__ void maskgit_draw_kernel(const int64_t* __restrict__ x, const __nv_bfloat16* __restrict__ lc,
+                                    const __nv_bfloat16* __restrict__ lu, long long ldv, const float* __restrict__ cfg_w,
+                                    const int64_t* __restrict__ modality, const float* __restrict__ e_noise,
+                                    const double* __restrict__ gumbel, const float* __restrict__ t, float r_temp,
+                                    int64_t mask_index, int text_vocab, int64_t* __restrict__ pred, double* __restrict__ conf,
+                                    int R, int N, int V) {
+    extern __shared__ float srow[];
+    __shared__ float sm[64];
+    __shared__ float smv[32];
+    __shared__ int smi[32];
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        const long long xr = x[r];
+        if (xr != mask_index) {
+            if (threadIdx.x == 0) { pred[r] = xr; conf[r] = -INFINITY; }
+            continue;
+        }
+        const int b = r / N;
+        int lo, hi;
+        valid_range(modality[r], V, text_vocab, lo, hi);
+        const float lse = stage_row_lse<CFG>(srow, sm, lc + (long long)r * ldv, CFG ? lu + (long long)r * ldv : nullptr,
+                                             CFG ? cfg_w[b] : 0.f, lo, hi, (int)mask_index);
+        const float* er = e_noise + (long long)r * V;
+        ArgMax a = {-INFINITY, 0x7fffffff};
+        for (int v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+            if (v == mask_index) continue;
+            am_upd(a, __fdiv_rn(expf(__fsub_rn(srow[v - lo], lse)), er[v]), v);
+        }
+        a = block_argmax(a, smv, smi);
+        if (threadIdx.x == 0) {
+            const float p = expf(__fsub_rn(srow[a.i - lo], lse));
+            pred[r] = a.i;
+            conf[r] = (double)logf(p) + ((double)r_temp * gumbel[r]) * (double)t[b];
+        }
+    }
+}
+
+// MaskGIT selection: per sample keep the num_unmask[b] most confident predictions (ties at the threshold are all kept, like
+// the reference's `conf >= k-th largest`).  One CTA per sample; conf staged in shared memory; rank by counting.
+__global__ void maskgit_select_kernel(const int64_t* __restrict__ x, const int64_t* __restrict__ pred,
+                                      const double* __restrict__ conf, const int* __restrict__ num_unmask, int64_t mask_index,
+                                      int64_t* __restrict__ out, int N) {
+    extern __shared__ double sconf[];
+    __shared__ int s_cnt;
+    const int b = blockIdx.x;
+    const int64_t* xb = x + (long long)b * N;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        sconf[i] = conf[(long long)b * N + i];
+        local += xb[i] == mask_index;
+    }
+    local = (int)warp_sum((float)local);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    const int k = min(num_unmask[b], s_cnt);                        // model_eval.py:3069
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const double ci = sconf[i];
+        int greater = 0;
+        if (k > 0) {
+            for (int j = 0; j < N; ++j) greater += sconf[j] > ci;
+        }
+        const bool sel = k > 0 && greater < k && ci == ci;          // conf >= k-th largest value  (NaN never selected)
+        out[(long long)b * N + i] = sel ? pred[(long long)b * N + i] : xb[i];
+    }
+}
+
+// arg-max of the SUBS log-probs with carry-over (noise-removal pass of `_sample`, model_eval.py:2440-2446): x where already
+// unmasked, else argmax_v (l_v - lse) over the valid vocabulary (first index on ties, like torch.argmax)
+__global__ void subs_argmax_kernel(const __nv_bfloat16* __restrict__ logits, long long ldv, const int64_t* __restrict__ xt,
+                                   const int64_t* __restrict__ modality, int64_t* __restrict__ out, int rows, int V,
+                                   int text_vocab, int mask_index) {
+    __shared__ float sm[64];
+    __shared__ float smv[32];
+    __shared__ int smi[32];
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const long long xr = xt[r];
+        if (xr != mask_index) {
+            if (threadIdx.x == 0) out[r] = xr;
+            continue;
+        }
+        int lo, hi;
+        valid_range(modality[r], V, text_vocab, lo, hi);
+        const __nv_bfloat16* row = logits + (long long)r * ldv;
+        const MaxSum t = block_ms(row_lse_bf16(row, lo, hi, mask_index), sm);
+        const float lse = t.m + logf(t.s);
+        ArgMax a = {-INFINITY, 0x7fffffff};
+        for (int v = lo + threadIdx.x; v < hi; v += blockDim.x)
+            if (v != mask_index) am_upd(a, __bfloat162float(row[v]) - lse, v);
         a = block_argmax(a, smv, smi);
         if (threadIdx.x == 0) out[r] = a.i;
     }
@@ -313,13 +419,16 @@ UD_DEVINL float u01_from_bits(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1
 UD_DEVINL float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 UD_DEVINL float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-template <bool CFG>
+// MODE 0: absorbing update (out = next token).  MODE 1: MaskGIT draw (model_eval.py:3072-3076): out = pred ~ p (no "stay"
+// option), conf = log p_pred + r_temp * Gumbel * t with an in-kernel Gumbel draw; mc_t then carries t[b], mc_s is unused.
+template <bool CFG, int MODE>
 __global__ void __launch_bounds__(256)
 ddpm_update_logits_fast_kernel(const int64_t* __restrict__ x, const __nv_bfloat16* __restrict__ lc,
                                const __nv_bfloat16* __restrict__ lu, long long ldv, const float* __restrict__ cfg_w,
                                const int64_t* __restrict__ modality, uint64_t seed, uint64_t offset,
                                const float* __restrict__ mc_t, const float* __restrict__ mc_s, int64_t mask_index,
-                               int text_vocab, int64_t* __restrict__ out, int R, int N, int V) {
+                               int text_vocab, int64_t* __restrict__ out, int R, int N, int V, float r_temp,
+                               double* __restrict__ conf) {
     // ONE WARP PER ROW: no shared memory, no block barriers; 64 independent rows in flight per SM hide the HBM latency and
     // the short serial tail (final draw by lane 0).
     constexpr float L2E = 1.4426950408889634f, LN2_ = 0.6931471805599453f;
@@ -330,7 +439,7 @@ ddpm_update_logits_fast_kernel(const int64_t* __restrict__ x, const __nv_bfloat1
     for (int r = gw; r < R; r += nw) {
         const long long xr = x[r];
         if (xr != mask_index) {
-            if (lane == 0) out[r] = xr;
+            if (lane == 0) { out[r] = xr; if (MODE == 1) conf[r] = -INFINITY; }
             continue;
         }
         const int b = r / N;
@@ -402,10 +511,13 @@ ddpm_update_logits_fast_kernel(const int64_t* __restrict__ x, const __nv_bfloat1
         }
         if (lane == 0) {
             const float lse2 = m2 + lg2f(ssum);                                   // log2 of the row's sum of exp(l)
-            const float d = mc_t[b] - mc_s[b], msk = mc_s[b];
             const uint4 fin = philox4x32_10(make_uint4((uint32_t)r, 0xffffffffu, 0u, (uint32_t)offset), key);
-            const float gscore = best + lg2f(fmaxf(d, 0.f)) - lse2;               // log2(q_group) + Gumbel (log2 units)
-            const float stay = lg2f(fmaxf(msk, 0.f)) - lg2f(-LN2_ * lg2f(u01_from_bits(fin.x)));
+            float gscore = 0.f, stay = -INFINITY, chosen_l2 = -INFINITY;
+            if (MODE == 0) {
+                const float d = mc_t[b] - mc_s[b], msk = mc_s[b];
+                gscore = best + lg2f(fmaxf(d, 0.f)) - lse2;                           // log2(q_group) + Gumbel (log2 units)
+                stay = lg2f(fmaxf(msk, 0.f)) - lg2f(-LN2_ * lg2f(u01_from_bits(fin.x)));
+            }
             int64_t res = mask_index;
             if (best_v != 0x7fffffff && !(stay > gscore)) {
                 // draw the token inside the winning group: Gumbel-max over its (up to 8) valid columns
@@ -427,10 +539,14 @@ ddpm_update_logits_fast_kernel(const int64_t* __restrict__ x, const __nv_bfloat1
                     const int c = v + i;
                     if (c < lo || c >= hi || c == mask_index) continue;
                     const float sc = l2[i] * L2E - lg2f(-LN2_ * lg2f(u01_from_bits(rr[i])));
-                    if (sc > bs) { bs = sc; res = c; }
+                    if (sc > bs) { bs = sc; res = c; chosen_l2 = l2[i] * L2E; }
                 }
             }
             out[r] = res;
+            if (MODE == 1) {
+                const float gum = -logf(-logf(u01_from_bits(fin.x)));                 // standard Gumbel (np.random.gumbel's law)
+                conf[r] = (double)((chosen_l2 - lse2) * LN2_) + ((double)r_temp * (double)gum) * (double)mc_t[b];
+            }
         }
     }
 }
@@ -523,9 +639,9 @@ extern "C" int ud_ddpm_update_logits(const int64_t* x, const void* logits, const
         long long want = ((long long)R * 32 + 255) / 256;          // one warp per row, 8 warps per CTA
         const int grid = (int)(want < (long long)sm_count() * 8 ? want : (long long)sm_count() * 8);
         if (cfg)
-            ddpm_update_logits_fast_kernel<true><<<grid, 256, 0, STREAM(stream)>>>(x, CBF(logits), CBF(logits_uncond), ldv, cfg_w, modality, seed, offset, mc_t, mc_s, mask_index, text_vocab, out, R, N, V);
+            ddpm_update_logits_fast_kernel<true, 0><<<grid, 256, 0, STREAM(stream)>>>(x, CBF(logits), CBF(logits_uncond), ldv, cfg_w, modality, seed, offset, mc_t, mc_s, mask_index, text_vocab, out, R, N, V, 0.f, nullptr);
         else
-            ddpm_update_logits_fast_kernel<false><<<grid, 256, 0, STREAM(stream)>>>(x, CBF(logits), nullptr, ldv, nullptr, modality, seed, offset, mc_t, mc_s, mask_index, text_vocab, out, R, N, V);
+            ddpm_update_logits_fast_kernel<false, 0><<<grid, 256, 0, STREAM(stream)>>>(x, CBF(logits), nullptr, ldv, nullptr, modality, seed, offset, mc_t, mc_s, mask_index, text_vocab, out, R, N, V, 0.f, nullptr);
         UD_CUDA_CHECK(cudaGetLastError());
         return 0;
     }
@@ -537,6 +653,55 @@ extern "C" int ud_ddpm_update_logits(const int64_t* x, const void* logits, const
         if (!attr[0]) { UD_CUDA_CHECK(cudaFuncSetAttribute(ddpm_update_logits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[0] = true; }
         ddpm_update_logits_kernel<false><<<rows_grid(R), 512, smem, STREAM(stream)>>>(x, CBF(logits), nullptr, ldv, nullptr, modality, u, seed, offset, mc_t, mc_s, mask_index, text_vocab, out, R, N, V);
     }
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_maskgit_update(const int64_t* x, const void* logits, const void* logits_uncond, long long ldv, const float* cfg_w,
+                                 const int64_t* modality, const float* e_noise, const double* gumbel, uint64_t seed,
+                                 uint64_t offset, const float* t, float r_temp, const int* num_unmask, int64_t mask_index,
+                                 int text_vocab, int64_t* pred, double* conf, int64_t* out, int B, int N, int V, void* stream) {
+    const int R = B * N;
+    if (R <= 0) return 0;
+    if (ldv % 8 != 0) { fprintf(stderr, "unidisc_b200: maskgit needs ldv %% 8 == 0\n"); return -1; }
+    if ((e_noise == nullptr) != (gumbel == nullptr)) { fprintf(stderr, "unidisc_b200: maskgit needs both noise tensors or neither\n"); return -1; }
+    const bool cfg = logits_uncond != nullptr;
+    if (e_noise == nullptr) {        // in-kernel Philox: single-pass warp-per-row draw
+        long long want = ((long long)R * 32 + 255) / 256;
+        const int grid = (int)(want < (long long)sm_count() * 8 ? want : (long long)sm_count() * 8);
+        if (cfg)
+            ddpm_update_logits_fast_kernel<true, 1><<<grid, 256, 0, STREAM(stream)>>>(x, CBF(logits), CBF(logits_uncond), ldv, cfg_w, modality, seed, offset, t, nullptr, mask_index, text_vocab, pred, R, N, V, r_temp, conf);
+        else
+            ddpm_update_logits_fast_kernel<false, 1><<<grid, 256, 0, STREAM(stream)>>>(x, CBF(logits), nullptr, ldv, nullptr, modality, seed, offset, t, nullptr, mask_index, text_vocab, pred, R, N, V, r_temp, conf);
+    } else {
+        int widest = V;
+        if (text_vocab > 0) widest = text_vocab > V - text_vocab ? text_vocab : V - text_vocab;
+        const size_t smem = (size_t)widest * sizeof(float);
+        if (smem > 200 * 1024) { fprintf(stderr, "unidisc_b200: vocabulary range too wide for the maskgit draw (%d)\n", widest); return -1; }
+        static bool attr[2] = {false, false};
+        if (cfg) {
+            if (!attr[1]) { UD_CUDA_CHECK(cudaFuncSetAttribute(maskgit_draw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[1] = true; }
+            maskgit_draw_kernel<true><<<rows_grid(R), 512, smem, STREAM(stream)>>>(x, CBF(logits), CBF(logits_uncond), ldv, cfg_w, modality, e_noise, gumbel, t, r_temp, mask_index, text_vocab, pred, conf, R, N, V);
+        } else {
+            if (!attr[0]) { UD_CUDA_CHECK(cudaFuncSetAttribute(maskgit_draw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[0] = true; }
+            maskgit_draw_kernel<false><<<rows_grid(R), 512, smem, STREAM(stream)>>>(x, CBF(logits), nullptr, ldv, nullptr, modality, e_noise, gumbel, t, r_temp, mask_index, text_vocab, pred, conf, R, N, V);
+        }
+    }
+    UD_CUDA_CHECK(cudaGetLastError());
+    const size_t smem_sel = (size_t)N * sizeof(double);
+    if (smem_sel > 200 * 1024) { fprintf(stderr, "unidisc_b200: sequence too long for the maskgit selection (%d)\n", N); return -1; }
+    static bool attr_sel = false;
+    if (smem_sel > 48 * 1024 && !attr_sel) { UD_CUDA_CHECK(cudaFuncSetAttribute(maskgit_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_sel = true; }
+    maskgit_select_kernel<<<B, 1024, smem_sel, STREAM(stream)>>>(x, pred, conf, num_unmask, mask_index, out, N);
+    UD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ud_subs_argmax(const void* logits, long long ldv, const int64_t* xt, const int64_t* modality, int64_t* out, int rows,
+                              int V, int text_vocab, int mask_index, void* stream) {
+    if (rows <= 0) return 0;
+    if (ldv % 8 != 0) { fprintf(stderr, "unidisc_b200: subs_argmax needs ldv %% 8 == 0\n"); return -1; }
+    subs_argmax_kernel<<<rows_grid(rows), ROW_THREADS, 0, STREAM(stream)>>>(CBF(logits), ldv, xt, modality, out, rows, V, text_vocab, mask_index);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -380,7 +380,7 @@ class Diffusion(nn.Module):
         B, N, V = logits.shape
         ldv = logits.stride(1)
         l2 = logits.as_strided((B * N, ldv), (ldv, 1))
-        tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", True) else -1
+        tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", False) else -1
         out = ops.subs_logprobs(l2, None if xt is None else xt.reshape(-1).contiguous(), modality.reshape(-1).contiguous(), V, tv,
                                 self.mask_index)
         return out.view(B, N, V)
@@ -397,7 +397,7 @@ class Diffusion(nn.Module):
         return self._subs_parameterization(logits, xt=x, batch=batch, modality=modality)
 
     def _log_p_x0(self, logits, xt, x0, modality):
-        tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", True) else -1
+        tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", False) else -1
         return _SubsNLL.apply(logits, xt, x0, modality, self.vocab_size, tv, self.mask_index)
 
     def compute_loss(self, batch, prefix="train", batch_idx=-1):
@@ -471,45 +471,31 @@ class Diffusion(nn.Module):
         return (cfg * (1 - t))[:, None]
 
     def _ddpm_forward(self, x, t, sigma_t, x0=None, x0_unmask=None, force_cfg=None, **kwargs):
-        """reference model_eval.py:1761-1833: returns p_x0 [B,N,V] (fp32)."""
+        """reference model_eval.py:1761-1833: returns p_x0 [B,N,V] (fp32, materialised — the API-parity path; the samplers'
+        default paths consume the logits directly)."""
         modality = kwargs.get("modality")
-        w = None
-        if _g(_g(self.config, "eval"), "cfg", None) is not None and x0_unmask is not None and x0_unmask.sum() > 0:
-            w = self.get_cfg_weight(t.reshape(-1))
-        if w is not None and (w > 0).any():
-            x_uncond = x.clone()
-            x_uncond[x0_unmask] = self.mask_index
-            lg = self.backbone(torch.cat([x, x_uncond], 0), None, modality=torch.cat([modality, modality], 0)).float()
-            lc, lu = lg.chunk(2, dim=0)
-            out = ((1 + w.unsqueeze(-1)) * lc - w.unsqueeze(-1) * lu).to(bf16)      # model_eval.py:1812 (then SUBS, xt=None)
-            B, N, V = out.shape
-            buf = torch.zeros((B * N, self.backbone.Vp), device=out.device, dtype=bf16)
-            buf[:, :V] = out.reshape(B * N, V)
-            logits = buf.view(B, N, -1)[:, :, :V]
-            return self._subs_parameterization(logits, xt=None, modality=modality).exp()
-        return self.forward(x=x, sigma=sigma_t, modality=modality).exp()
-
-    def _fused_absorbing_update(self, x, t, mc_t, mc_s, x0=None, x0_unmask=None, modality=None, u=None):
-        """backbone -> (CFG) -> SUBS softmax -> q_xs -> Gumbel arg-max -> copy-through in ONE vocabulary pass."""
         B, N = x.shape
+        lc, lu, w = self._sampling_logits(x, t, x0_unmask, modality, kwargs.get("sample_ids"))
         V = self.vocab_size
-        cfg = _g(_g(self.config, "eval"), "cfg", None)
-        use_cfg = cfg is not None and x0_unmask is not None and bool(x0_unmask.any())
-        if use_cfg:
-            x_uncond = torch.where(x0_unmask, torch.full_like(x, self.mask_index), x)
-            lg = self.backbone(torch.cat([x, x_uncond], 0), None, modality=torch.cat([modality, modality], 0))
-            ldv = lg.stride(1)
-            l2 = lg.as_strided((2 * B * N, ldv), (ldv, 1))
-            lc, lu = l2[: B * N], l2[B * N:]
-            w = (cfg * (1 - t.reshape(-1))).float().contiguous()
-        else:
-            lg = self.backbone(x, None, modality=modality)
-            ldv = lg.stride(1)
-            lc, lu, w = lg.as_strided((B * N, ldv), (ldv, 1)), None, None
+        if lu is not None and bool((w > 0).any()):
+            out = ((1 + w[:, None, None]) * lc[:, :V].float().view(B, N, V) - w[:, None, None] * lu[:, :V].float().view(B, N, V)).to(bf16)
+            buf = torch.zeros((B * N, self.backbone.Vp), device=out.device, dtype=bf16)   # model_eval.py:1812 (then SUBS, xt=None)
+            buf[:, :V] = out.reshape(B * N, V)
+            return self._subs_parameterization(buf.view(B, N, -1)[:, :, :V], xt=None, modality=modality).exp()
+        ldv = lc.stride(0)
+        return self._subs_parameterization(lc.as_strided((B, N, V), (N * ldv, ldv, 1)), xt=x, modality=modality).exp()
+
+    def _fused_absorbing_update(self, x, t, mc_t, mc_s, x0=None, x0_unmask=None, modality=None, u=None, sample_ids=None,
+                                logits_cache=None, return_cache=False):
+        """backbone -> (CFG) -> SUBS softmax -> q_xs -> Gumbel arg-max -> copy-through in ONE vocabulary pass.
+        `logits_cache` = the (lc, lu, w) of a previous call on an unchanged x: the backbone forward is skipped (ddpm_cache)."""
+        lc, lu, w = logits_cache if logits_cache is not None else self._sampling_logits(x, t, x0_unmask, modality, sample_ids)
+        if return_cache:
+            return (lc, lu, w), self._fused_absorbing_update(x, t, mc_t, mc_s, modality=modality, u=u, logits_cache=(lc, lu, w))
         self._rng_offset += 1
-        tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", True) else -1
+        tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", False) else -1
         return ops.ddpm_update_logits(x, lc, modality.reshape(-1).contiguous(), mc_t.float().contiguous(), mc_s.float().contiguous(),
-                                      self.mask_index, tv, V, logits_uncond=lu, cfg_w=w, u=u,
+                                      self.mask_index, tv, self.vocab_size, logits_uncond=lu, cfg_w=w, u=u,
                                       seed=int(_g(self.config, "seed", 42)), offset=self._rng_offset)
 
     @torch.no_grad()
@@ -522,16 +508,22 @@ class Diffusion(nn.Module):
             p_x0 = self._ddpm_forward(x, t, None, **kwargs)
             u = torch.rand_like(p_x0)
             return ops.ddpm_update_probs(x, p_x0, mc_t.contiguous(), mc_s.contiguous(), self.mask_index, u=u.view(-1, u.shape[-1])), 1
-        return self._fused_absorbing_update(x, tt, mc_t, mc_s, **{k: kwargs.get(k) for k in ("x0", "x0_unmask", "modality")}), 1
+        return self._fused_absorbing_update(x, tt, mc_t, mc_s, **{k: kwargs.get(k) for k in ("x0", "x0_unmask", "modality", "sample_ids")}), 1
 
     @torch.no_grad()
     def _ddpm_caching_update(self, x, t, dt, p_x0=None, x0=None, x0_unmask=None, modality=None, **kwargs):
-        """reference model_eval.py:2072-2104.  With p_x0 given (or parity_noise=True) the update consumes a materialised
-        fp32 p_x0 and torch.rand noise exactly like the reference; otherwise the fused single-pass kernel is used and
-        the returned cache is None (the fused path never materialises p_x0)."""
+        """reference model_eval.py:2072-2104.  With a p_x0 TENSOR given (or parity_noise=True) the update consumes a
+        materialised fp32 p_x0 and torch.rand noise exactly like the reference; otherwise the fused single-pass kernel is
+        used and the returned cache is the raw bf16 logits of this step's forward (never a materialised p_x0): handing it back
+        while x is unchanged skips the backbone exactly where the reference reuses p_x0_cache (CFG weights follow t, as the
+        reference's cached p_x0 does not — the cache is only reused without CFG)."""
         tt = t.reshape(-1)
         mc_t, mc_s = tt, tt - dt
         nfe = 0
+        if isinstance(p_x0, tuple):                              # logits cache of the fused path
+            if p_x0[1] is None:
+                return p_x0, self._fused_absorbing_update(x, tt, mc_t, mc_s, modality=modality, logits_cache=p_x0), 0
+            p_x0 = None
         if p_x0 is not None or kwargs.get("parity_noise", False):
             if p_x0 is None:
                 p_x0 = self._ddpm_forward(x, t, None, x0=x0, x0_unmask=x0_unmask, modality=modality)
@@ -540,7 +532,9 @@ class Diffusion(nn.Module):
             xn = ops.ddpm_update_probs(x, p_x0, mc_t.float().contiguous(), mc_s.float().contiguous(), self.mask_index,
                                        u=u.view(-1, u.shape[-1]))
             return p_x0, xn, nfe
-        return None, self._fused_absorbing_update(x, tt, mc_t, mc_s, x0=x0, x0_unmask=x0_unmask, modality=modality), 1
+        cache, xn = self._fused_absorbing_update(x, tt, mc_t, mc_s, x0=x0, x0_unmask=x0_unmask, modality=modality,
+                                                 sample_ids=kwargs.get("sample_ids"), return_cache=True)
+        return cache, xn, 1
 
     @staticmethod
     def adap_sche(x, step, mask_index, mode="arccos"):                               # reference model_eval.py:2964-3001
@@ -569,24 +563,56 @@ class Diffusion(nn.Module):
             out.append(sche.int())
         return torch.stack(out, dim=0)
 
+    def _sampling_logits(self, x, t, x0_unmask, modality, sample_ids=None):
+        """backbone forward of a sampling step (+ the CFG pair of model_eval.py:1763-1812): returns (lc, lu, w) as 2-D views of
+        the padded bf16 logits buffer; lu / w are None without classifier-free guidance."""
+        B, N = x.shape
+        sigma = self._sampling_sigma(t)
+        cfg = _g(_g(self.config, "eval"), "cfg", None)
+        use_cfg = cfg is not None and x0_unmask is not None and bool(x0_unmask.any())
+        kw = dict(sample_ids=sample_ids) if sample_ids is not None else {}
+        if use_cfg:
+            x_uncond = torch.where(x0_unmask, torch.full_like(x, self.mask_index), x)
+            if sample_ids is not None:
+                kw = dict(sample_ids=torch.cat([sample_ids, sample_ids], 0))
+            lg = self.backbone(torch.cat([x, x_uncond], 0), None if sigma is None else torch.cat([sigma, sigma], 0),
+                               modality=torch.cat([modality, modality], 0), **kw)
+            ldv = lg.stride(1)
+            l2 = lg.as_strided((2 * B * N, ldv), (ldv, 1))
+            return l2[: B * N], l2[B * N:], (cfg * (1 - t.reshape(-1))).float().contiguous()
+        lg = self.backbone(x, sigma, modality=modality, **kw)
+        ldv = lg.stride(1)
+        return lg.as_strided((B * N, ldv), (ldv, 1)), None, None
+
+    def _sampling_sigma(self, t):
+        """sigma handed to the backbone while sampling (model_eval.py:3060: sigma_t unless trainer.force_null_sigma); only a
+        time-conditioned backbone looks at it."""
+        if not self.time_conditioning or _g(self.config.trainer, "force_null_sigma", False):
+            return None
+        return self.noise(t.reshape(-1))[0]
+
     @torch.no_grad()
-    def _maskgit_update(self, x, t, dt, schedule=None, step=None, **kwargs):         # reference model_eval.py:3045-3114
+    def _maskgit_update(self, x, t, dt, schedule=None, step=None, parity_noise=None, **kwargs):
+        """reference model_eval.py:3045-3114 as two kernels (csrc/loss_sampler.cu): one vocabulary pass per masked row (SUBS
+        softmax -> multinomial draw -> confidence) and a per-sample k-th-largest selection; the [B,N,V] probability tensor,
+        torch.multinomial and torch.topk of the reference never materialise.  `parity_noise=(E, gumbel)`: the Exp(1) tensor
+        torch.multinomial draws internally (fp32 [B,N,V]) and the np.random.gumbel draw (fp64 [B,N]) — bit-exact mode."""
         copy_flag = x != self.mask_index
         r_temp = _g(_g(self.config, "eval"), "maskgit_r_temp", 10)
-        num_unmask = torch.minimum(schedule[:, step].to(x.device), (~copy_flag).sum(dim=-1))
-        if torch.all(num_unmask <= 0):
+        sched = schedule[:, step].to(x.device).to(torch.int32).contiguous()
+        num_unmask = torch.minimum(sched, (~copy_flag).sum(dim=-1).to(torch.int32))
+        if torch.all(num_unmask <= 0):                                               # model_eval.py:3070-3071
             return x, 0
-        p_x0 = self._ddpm_forward(x, t, None, **{k: kwargs.get(k) for k in ("x0", "x0_unmask", "modality")})
-        pred_code = torch.multinomial(p_x0.view(-1, p_x0.shape[-1]), 1)[:, 0].view(p_x0.shape[:-1])
-        conf = torch.gather(p_x0, -1, pred_code.unsqueeze(-1)).squeeze(-1)
-        rand = r_temp * torch.from_numpy(np.random.gumbel(size=pred_code.shape)).to(x.device) * t
-        conf = torch.log(conf.squeeze()) + rand
-        conf = torch.where(copy_flag, -torch.inf, conf)
-        k = int(num_unmask.max().item())
-        tresh, _ = torch.topk(conf, k=k, dim=-1)
-        tresh = tresh.gather(-1, torch.clamp(num_unmask - 1, min=0)[:, None])
-        tresh = torch.where((num_unmask <= 0)[:, None], torch.inf, tresh)
-        return torch.where(conf >= tresh.expand_as(conf), pred_code, x), 1
+        modality = kwargs.get("modality")
+        lc, lu, w = self._sampling_logits(x, t, kwargs.get("x0_unmask"), modality, kwargs.get("sample_ids"))
+        self._rng_offset += 1
+        tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", False) else -1
+        e_noise, gumbel = parity_noise if parity_noise is not None else (None, None)
+        out, _, _ = ops.maskgit_update(x, lc, modality.reshape(-1).contiguous(), t.reshape(-1).float().contiguous(), sched, self.mask_index,
+                                       tv, self.vocab_size, r_temp=float(r_temp), logits_uncond=lu, cfg_w=w,
+                                       e_noise=None if e_noise is None else e_noise.reshape(-1, e_noise.shape[-1]), gumbel=gumbel,
+                                       seed=int(_g(self.config, "seed", 42)), offset=self._rng_offset)
+        return out, 1
 
     @torch.no_grad()
     def _first_hitting_update(self, x, t, dt, schedule=None, step=None, **kwargs):   # reference model_eval.py:3004-3043
@@ -628,14 +654,15 @@ class Diffusion(nn.Module):
         for i in range(num_steps):
             t = timesteps[i] * torch.ones(B, 1, device=self.device)
             if self.sampler == "maskgit":
-                x, n = self._maskgit_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, schedule=schedule, step=i, modality=modality)
+                x, n = self._maskgit_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, schedule=schedule, step=i, modality=modality,
+                                            sample_ids=sample_ids)
             elif self.sampler == "first_hitting":                                    # model_eval.py:2373-2374
                 x, n = self._first_hitting_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, schedule=schedule, step=i, modality=modality)
             elif self.sampler == "ddpm":
                 x, n = self._ddpm_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, modality=modality, parity_noise=parity)
             elif self.sampler == "ddpm_cache":
                 p_cache, x_next, n = self._ddpm_caching_update(x, t, dt, p_x0=p_cache, x0=x0, x0_unmask=x0_unmask,
-                                                               modality=modality, parity_noise=parity)
+                                                               modality=modality, parity_noise=parity, sample_ids=sample_ids)
                 if p_cache is not None and (not torch.equal(x_next, x) or self.time_conditioning):
                     p_cache = None
                 x = x_next
@@ -644,12 +671,15 @@ class Diffusion(nn.Module):
             nfe += n
             x = torch.where(x0_unmask, x0, x)
         if _g(_g(self.config, "sampling"), "noise_removal", True):                   # model_eval.py:2440-2446
-            lg = self.backbone(x, None, modality=modality)
+            t_last = timesteps[-1] * torch.ones(B, 1, device=self.device)
+            lg = self.backbone(x, self._sampling_sigma(t_last), modality=modality,
+                               **(dict(sample_ids=sample_ids) if sample_ids is not None else {}))
             ldv = lg.stride(1)
             l2 = lg.as_strided((B * N, ldv), (ldv, 1))
-            # argmax of SUBS log-probs with carry-over == x where unmasked, else argmax over the valid vocabulary
-            lp = self._subs_parameterization(lg, xt=x, modality=modality)
-            x = lp.argmax(dim=-1)
-            del l2
+            # argmax of the SUBS log-probs with carry-over: x where unmasked, else argmax over the valid vocabulary — one
+            # vocabulary pass, the fp32 [B,N,V] log-prob tensor is not materialised
+            tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", False) else -1
+            x = ops.subs_argmax(l2, x.reshape(-1).contiguous(), modality.reshape(-1).contiguous(), self.vocab_size, tv,
+                                self.mask_index).view(B, N)
         x = torch.where(x0_unmask, x0, x)
         return (x, nfe) if return_nfe else x

@@ -144,6 +144,17 @@ def attn_fwd(q, k, v, B, N, H, head_dim, scale, sample_ids=None, o=None):
     return o, lse
 
 
+def attn_fwd_kv(q, k, v, B, Nq, Nk, H, head_dim, scale, o=None):
+    """partial-query attention against cached K/V: q [B*Nq, >=H*hd], k/v [B*Nk, >=H*hd] bf16 views. Returns o [B*Nq, H*hd], lse."""
+    D = H * head_dim
+    if o is None:
+        o = torch.empty((B * Nq, D), device=q.device, dtype=bf16)
+    lse = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32)
+    call("ud_attn_fwd_kv", P(q), q.stride(0), P(k), k.stride(0), P(v), v.stride(0), P(o), o.stride(0), P(lse), B, Nq, Nk, H, head_dim,
+         scale, stream())
+    return o, lse
+
+
 def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, N, H, head_dim, scale, sample_ids=None):
     _chk(dq.stride(0) == dk.stride(0), "dq and dk must share a row stride")
     _chk(o.stride(0) == do.stride(0), "o and do must share a row stride")
@@ -218,6 +229,32 @@ def ddpm_update_logits(x, logits2d, modality, mc_t, mc_s, mask_index, text_vocab
     out = torch.empty_like(x)
     call("ud_ddpm_update_logits", P(x), P(logits2d), P(logits_uncond), logits2d.stride(0), P(cfg_w), P(modality), P(u), seed,
          offset, P(mc_t), P(mc_s), mask_index, text_vocab, P(out), B, N, V, stream())
+    return out
+
+
+def maskgit_update(x, logits2d, modality, t, num_unmask, mask_index, text_vocab, V, r_temp=10.0, logits_uncond=None, cfg_w=None,
+                   e_noise=None, gumbel=None, seed=0, offset=0):
+    """One MaskGIT step (reference model_eval.py:3045-3114) from raw bf16 logits.  t: fp32 [B]; num_unmask: int32 [B];
+    e_noise fp32 [B*N,V] (Exp(1), the draw inside torch.multinomial) + gumbel fp64 [B,N] (np.random.gumbel) = parity mode.
+    Returns (x_next, pred_code, conf)."""
+    B, N = x.shape
+    _chk(num_unmask.dtype == torch.int32 and t.dtype == torch.float32, "maskgit: t fp32 [B], num_unmask int32 [B]")
+    _chk((e_noise is None) == (gumbel is None), "maskgit: supply both noise tensors or neither")
+    if gumbel is not None:
+        _chk(gumbel.dtype == torch.float64 and e_noise.dtype == torch.float32, "maskgit: gumbel fp64, e_noise fp32")
+        gumbel, e_noise = gumbel.contiguous(), e_noise.contiguous()
+    out = torch.empty_like(x)
+    pred = torch.empty_like(x)
+    conf = torch.empty((B, N), device=x.device, dtype=torch.float64)
+    call("ud_maskgit_update", P(x), P(logits2d), P(logits_uncond), logits2d.stride(0), P(cfg_w), P(modality), P(e_noise), P(gumbel),
+         seed, offset, P(t), float(r_temp), P(num_unmask), mask_index, text_vocab, P(pred), P(conf), P(out), B, N, V, stream())
+    return out, pred, conf
+
+
+def subs_argmax(logits2d, xt, modality, V, text_vocab, mask_index):
+    rows = xt.numel()
+    out = torch.empty((rows,), device=xt.device, dtype=torch.int64)
+    call("ud_subs_argmax", P(logits2d), logits2d.stride(0), P(xt), P(modality), P(out), rows, V, text_vocab, mask_index, stream())
     return out
 
 
