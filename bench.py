@@ -211,8 +211,10 @@ def run_reference_gpu_arm(args, rank, world, local):
     V, tv, mi = TEXT_VOCAB + IMAGE_VOCAB, TEXT_VOCAB, TEXT_VOCAB - 1
     N, B = txt + img, (args.batch or bpg)
     torch.manual_seed(0)
-    torch.set_float32_matmul_precision("medium")                      # reference utils.py:425-438 (called from main.py:550)
-    torch.backends.cuda.matmul.allow_tf32 = True
+    # reference utils.py:425-438 (called from main.py:550).  It also sets the legacy `cuda.matmul.allow_tf32 = True`; on this
+    # image's torch 2.11 mixing the legacy and the new matmul-precision API makes inductor's max-autotune raise, and "medium"
+    # already implies TF32 matmuls, so only the new API is used.
+    torch.set_float32_matmul_precision("medium")
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
     if args.ref_kind == "stock":

@@ -121,10 +121,12 @@ int ud_qk_ln_rope_bwd(const void* dqk_bf16, const void* qkv_bf16, const float* s
 int ud_attn_fwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, void* o, long long ldo, float* lse,
                 const int64_t* sample_ids, int B, int N, int H, int head_dim, float scale, void* stream);
 /* partial-query attention against a K/V cache (inference: dit.py:588-614 `update_kv_cache`, 793-812 image-K/V cache of the
- * FlexAttention path): Nq query tokens per sample attend to Nk cached key/value tokens, no mask.  q: bf16 [B*Nq, ldq];
- * k, v: bf16 [B*Nk, ldk / ldv] (head h at column h*hd); o: bf16 [B*Nq, ldo]; lse: fp32 [B,H,Nq]. */
-int ud_attn_fwd_kv(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
-                   long long ldo, float* lse, int B, int Nq, int Nk, int H, int head_dim, float scale, void* stream);
+ * FlexAttention path): Nq query tokens per sample attend to Nk key/value tokens, no mask.  Every operand is a token-major bf16
+ * matrix with row pitch ld* and a per-sample stride *_bs (both in elements; *_bs = 0 means rows * ld, i.e. dense), so sub-ranges
+ * of a sequence (the text rows of q, the image rows of a cache) are addressed in place.  lse: fp32 [B,H,Nq]. */
+int ud_attn_fwd_kv(const void* q, long long ldq, long long q_bs, const void* k, long long ldk, long long k_bs, const void* v,
+                   long long ldv, long long v_bs, void* o, long long ldo, long long o_bs, float* lse, int B, int Nq, int Nk, int H,
+                   int head_dim, float scale, void* stream);
 /* backward: writes dq,dk (bf16, ld lddqk) and dv (bf16, ld lddv).  delta: fp32 [B,H,N] scratch. */
 int ud_attn_bwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const void* o, const void* d_o,
                 long long ldo, const float* lse, float* delta, void* dq, void* dk, long long lddqk, void* dv, long long lddv,

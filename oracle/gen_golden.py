@@ -686,6 +686,69 @@ def gen_sampler_logits():
     np.savez_compressed(os.path.join(OUT, "sampler_logits.npz"), **out)
 
 
+def gen_attn_cache():
+    """Inference attention caching (eval.attention_caching, model_eval.py:2297-2367 + dit.py:793-812): the UNMODIFIED reference
+    DIT (use_flex_attention, eager flex on CPU) run through one caching cycle — step 0 full attention, step 1 masked attention
+    (`get_block_mask(txt_dropout=False, img_dropout=True)`, model_utils.py:721-738) that stores the image K/V, step 2 text-only
+    forward writing the cache's text slice — against the restatement.  Parameters = tests/golden/dit_small.npz.
+    -> tests/golden/attn_cache.npz"""
+    from torch.nn.attention.flex_attention import create_block_mask
+    gd = np.load(os.path.join(OUT, "dit_small.npz"))
+    D, H, L, txt, img, V, tv, mi = [int(v) for v in gd["cfg"]]
+    P = {k[3:]: torch.from_numpy(gd[k]) for k in gd.files if k.startswith("P::")}
+    ref_cfg = RL.make_ref_config(D, H, L, txt, img)
+    ref_cfg.model.use_flex_attention = True
+    torch.manual_seed(0)
+    dit = RL.build_reference_dit(ref_cfg, V, tv, mi, dtype=torch.float32)
+    dit.load_state_dict(P)
+    dit.eval()
+    found = RL._extract_functions(os.path.join(RL.REFERENCE_ROOT, "model_utils.py"), ["_attn_mask", "get_block_mask"])
+    gm = RL._exec_functions(found, dict(create_block_mask=create_block_mask))
+    ocfg = R.OracleConfig(D, H, L, txt, img, V, tv, mi)
+    B, N = 2, txt + img
+    ids, modality = R.synthetic_batch(B, txt, img, tv, V, seed=7)
+    g = torch.Generator().manual_seed(8)
+    x0 = ids.clone()
+    x0[torch.rand(B, N, generator=g) < 0.6] = mi
+    x1 = x0.clone()
+    x1[:, 5:40:3] = ids[:, 5:40:3]                      # a few text tokens get revealed between the steps
+    x2 = x1.clone()
+    x2[:, 2:60:4] = ids[:, 2:60:4]
+    txt_sl = slice(None, txt)
+    out = dict(x0=_np(x0), x1=_np(x1), x2=_np(x2), modality=_np(modality))
+    with torch.no_grad():
+        dit.set_flex_attention_cache(B, N, torch.device("cpu"), torch.float32)
+        r0 = dit(x0, None, modality=modality, block_mask=True, update_cache_slice=None)                       # step 0
+        bm = gm["get_block_mask"](txt_batch_attn_dropout=torch.zeros(B, dtype=torch.bool),
+                                  img_batch_attn_dropout=torch.ones(B, dtype=torch.bool), txt_length=txt, batch_size=B, seq_len=N,
+                                  device=torch.device("cpu"))
+        r1 = dit(x1, None, modality=modality, block_mask=bm, update_cache_slice=slice(0, N))                   # step 1
+        ck1 = [blk.attention.cache_k.clone() for blk in dit.blocks]
+        r2 = dit(x2[:, txt_sl], None, modality=modality[:, txt_sl], block_mask=True, update_cache_slice=txt_sl)  # step 2
+        ck2 = [blk.attention.cache_k.clone() for blk in dit.blocks]
+        cv2 = [blk.attention.cache_v.clone() for blk in dit.blocks]
+    cache = {}
+    m0 = R.dit_forward(ocfg, P, x0, modality, mode="fp32")
+    m1 = R.dit_forward(ocfg, P, x1, modality, mode="fp32", attn_mask=R.caching_step_mask(txt, N), kv_cache=cache, cache_op="store")
+    e_ck1 = max((cache[i]["k"] - ck1[i]).abs().max().item() for i in range(L))
+    m2 = R.dit_forward(ocfg, P, x2[:, txt_sl], modality[:, txt_sl], mode="fp32", kv_cache=cache, cache_op="update", update_slice=txt_sl)
+    e_ck2 = max((cache[i]["k"] - ck2[i]).abs().max().item() for i in range(L))
+    e_cv2 = max((cache[i]["v"] - cv2[i]).abs().max().item() for i in range(L))
+    errs = [(m0 - r0).abs().max().item(), (m1 - r1).abs().max().item(), (m2 - r2).abs().max().item()]
+    print(f"[attn_cache] max|restated - reference| logits step0/1/2 = {errs[0]:.2e} / {errs[1]:.2e} / {errs[2]:.2e}; "
+          f"cache K after step 1 {e_ck1:.2e}, K/V after step 2 {e_ck2:.2e} / {e_cv2:.2e}")
+    assert max(errs) < 3e-5 and max(e_ck1, e_ck2, e_cv2) < 1e-5
+    # the variant that attends to the updated cache (documented intent, dit.py:795-797) must differ from the shipped dataflow
+    cache_b = {i: dict(k=ck1[i].clone(), v=cache[i]["v"].clone()) for i in range(L)}
+    m2b = R.dit_forward(ocfg, P, x2[:, txt_sl], modality[:, txt_sl], mode="fp32", kv_cache=cache_b, cache_op="update", update_slice=txt_sl,
+                        attend_cache=True)
+    assert (m2b - r2).abs().max().item() > 1e-3
+    sub = lambda t: _np(t[:, :, ::7])                                     # sub-sampled logits keep the fixture small
+    out.update(ref_step0=sub(r0), ref_step1=sub(r1), ref_step2=sub(r2), ref_cache_k_blk1=_np(ck2[1][:, :, ::5, ::3]),
+               ref_cache_v_blk1=_np(cv2[1][:, :, ::5, ::3]))
+    np.savez_compressed(os.path.join(OUT, "attn_cache.npz"), **out)
+
+
 def _with_length(ocfg, N):
     """OracleConfig whose `length` (txt_length + img_length) equals the packed sequence length N."""
     import dataclasses
@@ -703,6 +766,10 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "sampler_logits":
         gen_sampler_logits()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "attn_cache":
+        RL.load_reference_diffusion_methods()
+        gen_attn_cache()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "update_batch":
         RL.load_reference_diffusion_methods()          # installs the import shims / sys.path for the reference tree
         gen_update_batch()
@@ -714,6 +781,7 @@ def main():
     gen_update_batch()
     gen_first_hitting()
     gen_sampler_logits()
+    gen_attn_cache()
     print("golden fixtures written to", OUT)
 
 

@@ -238,7 +238,9 @@ def attention_core(q, k, v, scale):
 
 
 def block_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], i: int, x, cos, sin, mode, sample_ids=None,
-                  taps: Optional[dict] = None, drop_scale: Optional[torch.Tensor] = None, c=None, modality=None):
+                  taps: Optional[dict] = None, drop_scale: Optional[torch.Tensor] = None, c=None, modality=None,
+                  attn_mask=None, kv_cache: Optional[dict] = None, cache_op: Optional[str] = None, update_slice=None,
+                  attend_cache: bool = False):
     """DDiTBlock.forward dit.py:948-1033 (rms, sandwich, qk_norm, no time-conditioning) with
     Attention.forward dit.py:616-887 (sdpa branch)."""
     pre = f"blocks.{i}."
@@ -262,7 +264,23 @@ def block_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], i: int, x, cos,
     if mode == "bf16":
         q, k = _bf(q), _bf(k)
     qh, kh, vh = (t.permute(0, 2, 1, 3) for t in (q, k, v))
-    if sample_ids is None:
+    if kv_cache is not None and cache_op is not None:
+        # inference image-K/V cache of the FlexAttention path, dit.py:793-806.  "store" (step 1 of a caching cycle): the cache
+        # becomes this step's full K, V.  "update" (steps 2..): the text-only forward writes its K, V into the cache's text
+        # slice; the reference then calls flex_attention with the LOCAL k, v (dit.py:812 — the cache is written, not read);
+        # attend_cache=True attends to the updated cache instead (what its comment at dit.py:795-797 describes).
+        if cache_op == "store":
+            kv_cache[i] = dict(k=kh.clone(), v=vh.clone())
+        elif cache_op == "update":
+            kv_cache[i]["k"][:, :, update_slice] = kh.to(kv_cache[i]["k"].dtype)
+            kv_cache[i]["v"][:, :, update_slice] = vh.to(kv_cache[i]["v"].dtype)
+            if attend_cache:
+                kh, vh = kv_cache[i]["k"], kv_cache[i]["v"]
+    if attn_mask is not None:
+        s = (qh.float() @ kh.float().transpose(-1, -2)) / math.sqrt(hd)
+        s = s.masked_fill(~attn_mask, float("-inf"))
+        o = torch.softmax(s, dim=-1) @ vh.float()
+    elif sample_ids is None:
         o = attention_core(qh, kh, vh, 1.0 / math.sqrt(hd))                          # step 5
     else:
         # document mask (model_utils.py:740-771): (sid[q]==sid[kv]) & (sid[q] != -1)
@@ -301,8 +319,17 @@ def block_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], i: int, x, cos,
     return x2
 
 
+def caching_step_mask(txt_length: int, N: int, device=None):
+    """model_utils.py:721-738 `_attn_mask(txt_batch_dropout=False, img_batch_dropout=True)` — the mask of step 1 of an
+    attention-caching cycle (model_eval.py:2329-2338): image queries see image keys only, text queries see everything."""
+    qi = torch.arange(N, device=device)[:, None]
+    ki = torch.arange(N, device=device)[None, :]
+    return ((qi >= txt_length) & (ki >= txt_length)) | (qi < txt_length)
+
+
 def dit_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], indices, modality, mode="fp32", sample_ids=None,
-                taps: Optional[dict] = None, return_hidden=False, drop_scales=None, sigma=None):
+                taps: Optional[dict] = None, return_hidden=False, drop_scales=None, sigma=None, attn_mask=None,
+                kv_cache: Optional[dict] = None, cache_op: Optional[str] = None, update_slice=None, attend_cache=False):
     """DIT.forward dit.py:1324-1500 (discrete, multimodal_batches, modality_embed, rope_2d, no time-cond).
 
     indices, modality: int64 [B,N].  Returns logits [B,N,V] (bf16 in mode="bf16", fp32 otherwise).
@@ -320,7 +347,9 @@ def dit_forward(cfg: OracleConfig, P: Dict[str, torch.Tensor], indices, modality
     c = conditioning_vector(P, sigma, mode) if cfg.time_conditioning else None       # dit.py:1378-1379
     for i in range(cfg.n_blocks):
         x = block_forward(cfg, P, i, x, cos, sin, mode, sample_ids=sample_ids, taps=taps,
-                          drop_scale=None if drop_scales is None else drop_scales[i], c=c, modality=modality)
+                          drop_scale=None if drop_scales is None else drop_scales[i], c=c, modality=modality,
+                          attn_mask=attn_mask, kv_cache=kv_cache, cache_op=cache_op, update_slice=update_slice,
+                          attend_cache=attend_cache)
     if return_hidden:
         return x
     hf = _rmsnorm(x, P["output_layer.norm_final.weight"], cfg.rms_eps, mode)          # dit.py:1089

@@ -60,3 +60,9 @@ def golden_cfg1():
 def golden_sampler_logits():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "sampler_logits.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_attn_cache():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "attn_cache.npz"))

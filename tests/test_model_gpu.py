@@ -390,3 +390,65 @@ def test_cfg1_reference_parity_run_on_gpu(golden_cfg1, monkeypatch):
     assert abs(got - ref[0]) < 1e-2 * abs(ref[0])
     assert abs(float(Lc.txt_loss) - ref[1]) < 1e-2 * abs(ref[1]) + 1e-3 and abs(float(Lc.img_loss) - ref[2]) < 1e-2 * abs(ref[2]) + 1e-3
     assert torch.allclose(Lc.nlls.detach().cpu(), torch.from_numpy(g["loss_nlls_ref"]), rtol=3e-2, atol=8e-2)
+
+
+def test_attention_caching_cycle_vs_reference_golden(golden_attn_cache, golden_dit):
+    """inference attention caching (f3): DIT.set_flex_attention_cache + the three steps of a caching cycle against the
+    unmodified reference's logits (tests/golden/attn_cache.npz) and the oracle in bf16 mode; then the cache-attending variant
+    (eval.attention_caching_attend_cache) against the oracle's attend_cache restatement."""
+    from oracle import restated as R
+    from unidisc_b200.config import make_config
+    from unidisc_b200.dit import DIT, TextFullImageSelfMask
+    g, gd = golden_attn_cache, golden_dit
+    D, H, L, txt, img, V, tv, mi = [int(v) for v in gd["cfg"]]
+    P = {k[3:]: torch.from_numpy(gd[k]) for k in gd.files if k.startswith("P::")}
+    ocfg = R.OracleConfig(D, H, L, txt, img, V, tv, mi)
+    N = txt + img
+    sl = slice(None, txt)
+    x0, x1, x2, mod = (torch.from_numpy(g[k]) for k in ("x0", "x1", "x2", "modality"))
+    B = x0.shape[0]
+    for attend in (False, True):
+        cfg = make_config("small", hidden_size=D, n_blocks=L, n_heads=H, txt_length=txt, img_length=img, image_vocab_size=V - tv,
+                          text_vocab_size=tv, eval__attention_caching_attend_cache=attend)
+        m = DIT(cfg, vocab_size=V, text_vocab_size=tv, mask_index=mi).to(dev())
+        m.load_state_dict(P)
+        m.eval()
+        with torch.no_grad():
+            m.set_flex_attention_cache(B, N, dev())
+            o0 = m(x0.to(dev()), None, modality=mod.to(dev()), block_mask=True, update_cache_slice=None).float().cpu()
+            o1 = m(x1.to(dev()), None, modality=mod.to(dev()), block_mask=TextFullImageSelfMask(txt), update_cache_slice=slice(0, N)).float().cpu()
+            o2 = m(x2[:, sl].contiguous().to(dev()), None, modality=mod[:, sl].contiguous().to(dev()), block_mask=True,
+                   update_cache_slice=sl).float().cpu()
+            ck = m._kv_cache["k"][1].float().cpu().view(B, N, H, D // H).permute(0, 2, 1, 3)
+        cache = {}
+        r0 = R.dit_forward(ocfg, P, x0, mod, mode="bf16").float()
+        r1 = R.dit_forward(ocfg, P, x1, mod, mode="bf16", attn_mask=R.caching_step_mask(txt, N), kv_cache=cache, cache_op="store").float()
+        r2 = R.dit_forward(ocfg, P, x2[:, sl], mod[:, sl], mode="bf16", kv_cache=cache, cache_op="update", update_slice=sl,
+                           attend_cache=attend).float()
+        for got, ref, nm in ((o0, r0, "step0"), (o1, r1, "step1"), (o2, r2, "step2")):
+            e = (got - ref).abs()
+            assert e.max() < 4e-2 and e.mean() < 4e-3, f"attend={attend} {nm}: max {e.max():.4f} mean {e.mean():.5f}"
+        assert (ck - cache[1]["k"].float()).abs().max() < 3e-2, "cached K (after LayerNorm + RoPE) of block 1"
+        if not attend:                                   # the reference's own dataflow: compare with ITS fp32 logits too
+            for got, key in ((o0, "ref_step0"), (o1, "ref_step1"), (o2, "ref_step2")):
+                assert np.abs(got[:, :, ::7].numpy() - g[key]).max() < 6e-2, key
+        else:                                            # attending the cache must change the text logits
+            assert (o2 - R.dit_forward(ocfg, P, x2[:, sl], mod[:, sl], mode="bf16").float()).abs().max() > 1e-2
+
+
+def test_sample_with_attention_caching_runs():
+    from unidisc_b200.config import make_config
+    from unidisc_b200.model import Diffusion
+    cfg = make_config("small", hidden_size=128, n_blocks=2, n_heads=2, txt_length=64, img_length=64, image_vocab_size=63,
+                      text_vocab_size=97, sampling_steps=12, eval__attention_caching=True, eval__attention_caching_txt_to_img_ratio=4)
+    torch.manual_seed(0)
+    model = Diffusion(cfg, device=dev())
+    model.eval()
+    B, N = 2, 128
+    modality = torch.cat([torch.zeros(B, 64, dtype=torch.int64), torch.ones(B, 64, dtype=torch.int64)], 1).to(dev())
+    for pred in ("ddpm_cache", "maskgit"):
+        model.sampler = pred
+        x = model._sample(num_steps=12, batch_size_per_gpu=B, sample_modality=modality)
+        assert x.shape == (B, N) and (x != model.mask_index).all()
+        assert (x[:, :64] < model.text_vocab_size - 1).all() and (x[:, 64:] >= model.text_vocab_size).all()
+    assert model.backbone._kv_cache is None and model._backbone_kwargs == {}

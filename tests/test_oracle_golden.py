@@ -118,6 +118,24 @@ def test_samplers_from_logits_bit_exact(golden_sampler_logits):
         assert np.array_equal(out.numpy(), g[f"mg_ref_{step}"])
 
 
+def test_attention_caching_cycle_matches_reference(golden_attn_cache, golden_dit):
+    """oracle restatement of the inference attention-caching cycle (model_eval.py:2297-2367, dit.py:793-812) against the
+    unmodified reference DIT's logits and cache contents (step 0 full, step 1 masked + store, step 2 text-only + update)."""
+    g, gd = golden_attn_cache, golden_dit
+    cfg, P = _cfg(gd), _params(gd)
+    txt, N = cfg.txt_length, cfg.length
+    x0, x1, x2, mod = (torch.from_numpy(g[k]) for k in ("x0", "x1", "x2", "modality"))
+    sl = slice(None, txt)
+    cache = {}
+    m0 = R.dit_forward(cfg, P, x0, mod, mode="fp32")
+    m1 = R.dit_forward(cfg, P, x1, mod, mode="fp32", attn_mask=R.caching_step_mask(txt, N), kv_cache=cache, cache_op="store")
+    m2 = R.dit_forward(cfg, P, x2[:, sl], mod[:, sl], mode="fp32", kv_cache=cache, cache_op="update", update_slice=sl)
+    for got, key in ((m0, "ref_step0"), (m1, "ref_step1"), (m2, "ref_step2")):
+        assert np.abs(got[:, :, ::7].numpy() - g[key]).max() < 3e-5, key
+    assert np.abs(cache[1]["k"][:, :, ::5, ::3].numpy() - g["ref_cache_k_blk1"]).max() < 1e-5
+    assert np.abs(cache[1]["v"][:, :, ::5, ::3].numpy() - g["ref_cache_v_blk1"]).max() < 1e-5
+
+
 def test_ddpm_forward_and_cfg(golden_fns, golden_dit):
     g, gd = golden_fns, golden_dit
     cfg, P = _cfg(gd), _params(gd)

@@ -35,7 +35,7 @@ def rb(*s):
 
 
 def main():
-    which = sys.argv[1:] or ["attn", "rows", "gemm"]
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["attn", "rows", "gemm"]
     if "attn" in which:
         qk, qkv = rb(M, 2 * D), rb(M, 3 * D)
         q, k, v = qk[:, :D], qk[:, D:], qkv[:, 2 * D:]
@@ -48,6 +48,27 @@ def main():
         dqk, dqkv = torch.empty_like(qk), torch.empty_like(qkv)
         t = timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, dqk[:, :D], dqk[:, D:], dqkv[:, 2 * D:], B, N, H, hd, sc))
         print(f"attn_bwd  {t*1e3:8.1f} us  {2.5*fl/t/1e9:7.1f} TFLOP/s (5-GEMM flops)   [UD_ATTN_BWD_V1={os.environ.get('UD_ATTN_BWD_V1')}]")
+    if "attn" in which and "--vs-cudnn" in sys.argv:
+        # the bar (reference models/dit.py:816-829: SDPA forced onto the cuDNN backend): same B8 H16 N1280 hd128 tensors, fwd and fwd+bwd
+        import torch.nn.functional as F
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        for backend in (SDPBackend.CUDNN_ATTENTION, SDPBackend.FLASH_ATTENTION):
+            try:
+                qh, kh, vh = (t.reshape(B, N, H, hd).permute(0, 2, 1, 3).detach().clone().requires_grad_(True) for t in (q, k, v))
+                with sdpa_kernel(backends=[backend]):
+                    t_f = timeit(lambda: F.scaled_dot_product_attention(qh, kh, vh))
+                    oo = F.scaled_dot_product_attention(qh, kh, vh)
+                    go = torch.randn_like(oo)
+
+                    def fb():
+                        o2 = F.scaled_dot_product_attention(qh, kh, vh)
+                        o2.backward(go)
+                        qh.grad = kh.grad = vh.grad = None
+                    t_fb = timeit(fb)
+                print(f"torch SDPA {backend.name:18s} fwd {t_f*1e3:8.1f} us {fl/t_f/1e9:7.1f} TFLOP/s | fwd+bwd {t_fb*1e3:8.1f} us -> bwd {(t_fb-t_f)*1e3:8.1f} us "
+                      f"{2.5*fl/(t_fb-t_f)/1e9:7.1f} TFLOP/s (5-GEMM flops)")
+            except Exception as e:  # noqa: BLE001
+                print(f"torch SDPA {backend.name}: unavailable ({type(e).__name__}: {str(e)[:120]})")
     if "rows" in which:
         a, x = rb(M, D), torch.randn(M, D, device=dev)
         w = torch.ones(D, device=dev)

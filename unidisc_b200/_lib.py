@@ -30,7 +30,7 @@ _SIGS = {
     "ud_qk_ln_rope_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     "ud_qk_ln_rope_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "ud_attn_fwd": [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp],
-    "ud_attn_fwd_kv": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _i, _f, _vp],
+    "ud_attn_fwd_kv": [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _ll, _ll, _vp, _ll, _ll, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "ud_attn_bwd": [_vp, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],
     "ud_colsum_bf16": [_vp, _ll, _vp, _i, _i, _vp],
     "ud_subs_nll_fwd": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

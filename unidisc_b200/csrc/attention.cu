@@ -36,6 +36,7 @@ struct AttnParams {
     float scale_log2;  // softmax scale * log2(e)
     __nv_bfloat16* o;
     long long ldo;
+    long long o_bs;    // elements between the first output rows of consecutive samples (N * ldo for a dense [B*N, ldo] matrix)
     float* lse;  // [B,H,N]
     const int64_t* sample_ids;  // [B,N] or null (needs Nk == N)
 };
@@ -350,7 +351,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (T > 0) mbar_wait(pv_done, (T - 1) & 1);
         tc_fence_after();
         const float inv = lt > 0.f ? 1.0f / lt : 0.f;
-        __nv_bfloat16* orow = p.o + ((long long)b * p.N + row) * p.ldo + h * HD + wg * (HD / 2);
+        __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)row * p.ldo + h * HD + wg * (HD / 2);
 #pragma unroll
         for (int c = 0; c < HD / 64; ++c) {
             uint32_t r[32];
@@ -811,20 +812,22 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
 template <int HD>
 static int attn_smem_bytes(int ntiles) { return ntiles * AttnSmem<HD>::TILE_BYTES + 1024 + 4096; }
 
-static int make_head_tmap(CUtensorMap* tm, const void* base, long long ld, int B, int N, int D, int box_rows = 128) {
-    // dims: (column, token, batch); box = 64 columns x box_rows tokens x 1 batch
-    return make_tmap_3d_bf16(tm, base, (uint64_t)D, (uint64_t)N, (uint64_t)B, (uint64_t)ld, (uint64_t)ld * N, 64, box_rows, 1);
+static int make_head_tmap(CUtensorMap* tm, const void* base, long long ld, int B, int N, int D, int box_rows = 128,
+                          long long batch_stride = 0) {
+    // dims: (column, token, batch); box = 64 columns x box_rows tokens x 1 batch.  batch_stride (elements) defaults to N * ld.
+    return make_tmap_3d_bf16(tm, base, (uint64_t)D, (uint64_t)N, (uint64_t)B, (uint64_t)ld,
+                             (uint64_t)(batch_stride > 0 ? batch_stride : ld * N), 64, box_rows, 1);
 }
 
 template <int HD>
 static int launch_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
-                           const AttnParams& p, cudaStream_t stream) {
+                           const AttnParams& p, cudaStream_t stream, long long q_bs = 0, long long k_bs = 0, long long v_bs = 0) {
     CUtensorMap tq, tk, tv;
     const int D = p.H * HD;
-    int rc = make_head_tmap(&tq, q, ldq, p.B, p.N, D);
+    int rc = make_head_tmap(&tq, q, ldq, p.B, p.N, D, 128, q_bs);
     if (rc) return rc;
-    if ((rc = make_head_tmap(&tk, k, ldk, p.B, p.Nk, D))) return rc;
-    if ((rc = make_head_tmap(&tv, v, ldv, p.B, p.Nk, D))) return rc;
+    if ((rc = make_head_tmap(&tk, k, ldk, p.B, p.Nk, D, 128, k_bs))) return rc;
+    if ((rc = make_head_tmap(&tv, v, ldv, p.B, p.Nk, D, 128, v_bs))) return rc;
     const int smem3 = attn_smem_bytes<HD>(5);
     static bool attr3 = false;
     if (!attr3) { UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); attr3 = true; }
@@ -886,7 +889,7 @@ using namespace ud;
 
 static int attn_fwd_entry(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
                           long long ldo, float* lse, const int64_t* sample_ids, int B, int Nq, int Nk, int H, int head_dim,
-                          float scale, void* stream) {
+                          float scale, void* stream, long long q_bs = 0, long long k_bs = 0, long long v_bs = 0, long long o_bs = 0) {
     if (B <= 0 || Nq <= 0 || Nk <= 0) return 0;
     if (sample_ids != nullptr && (Nq != Nk || (Nk + 63) / 64 > MAX_DOC_TILES)) {
         fprintf(stderr, "unidisc_b200: document-masked attention needs Nq == Nk <= %d\n", MAX_DOC_TILES * 64);
@@ -897,11 +900,12 @@ static int attn_fwd_entry(const void* q, long long ldq, const void* k, long long
     p.scale_log2 = scale * LOG2E;
     p.o = reinterpret_cast<__nv_bfloat16*>(o);
     p.ldo = ldo;
+    p.o_bs = o_bs > 0 ? o_bs : (long long)Nq * ldo;
     p.lse = lse;
     p.sample_ids = sample_ids;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (head_dim == 128) return launch_attn_fwd<128>(q, ldq, k, ldk, v, ldv, p, s);
-    if (head_dim == 64) return launch_attn_fwd<64>(q, ldq, k, ldk, v, ldv, p, s);
+    if (head_dim == 128) return launch_attn_fwd<128>(q, ldq, k, ldk, v, ldv, p, s, q_bs, k_bs, v_bs);
+    if (head_dim == 64) return launch_attn_fwd<64>(q, ldq, k, ldk, v, ldv, p, s, q_bs, k_bs, v_bs);
     fprintf(stderr, "unidisc_b200: attention supports head_dim 64 and 128 (got %d)\n", head_dim);
     return -1;
 }
@@ -911,9 +915,10 @@ extern "C" int ud_attn_fwd(const void* q, const void* k, long long ldqk, const v
     return attn_fwd_entry(q, ldqk, k, ldqk, v, ldv, o, ldo, lse, sample_ids, B, N, N, H, head_dim, scale, stream);
 }
 
-extern "C" int ud_attn_fwd_kv(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
-                              long long ldo, float* lse, int B, int Nq, int Nk, int H, int head_dim, float scale, void* stream) {
-    return attn_fwd_entry(q, ldq, k, ldk, v, ldv, o, ldo, lse, nullptr, B, Nq, Nk, H, head_dim, scale, stream);
+extern "C" int ud_attn_fwd_kv(const void* q, long long ldq, long long q_bs, const void* k, long long ldk, long long k_bs,
+                              const void* v, long long ldv, long long v_bs, void* o, long long ldo, long long o_bs, float* lse, int B,
+                              int Nq, int Nk, int H, int head_dim, float scale, void* stream) {
+    return attn_fwd_entry(q, ldq, k, ldk, v, ldv, o, ldo, lse, nullptr, B, Nq, Nk, H, head_dim, scale, stream, q_bs, k_bs, v_bs, o_bs);
 }
 
 extern "C" int ud_attn_bwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const void* o,

@@ -164,8 +164,13 @@ class ThinDDP(nn.Module):
             torch.cuda.current_stream().wait_event(self._done_event)   # optimizer waits on ONE event
 
 
-class FusedAdamW:
+class FusedAdamW(torch.optim.Optimizer):
     """AdamW over the DIT's flat fp32 buffers (torch.optim.AdamW semantics, single param group like the reference).
+
+    It IS a `torch.optim.Optimizer` (one param group holding the module's parameters), so the reference's
+    `hydra.utils.instantiate(config.lr_scheduler, optimizer=optimizer)` (model_setup.py:426, LambdaLR warm-up) drives it:
+    lr / betas / eps / weight_decay are read from `param_groups[0]` at every step.  The moments live in two flat buffers
+    (`exp_avg`, `exp_avg_sq`, the layout of DIT._flat_p), exposed per parameter as views through `state[p]`.
 
     `overlap=True` (default on CUDA) streams the optimizer around the compute-bound GEMM phases instead of running it as
     one exposed HBM-bound block between backward and forward:
@@ -180,18 +185,26 @@ class FusedAdamW:
     def __init__(self, module, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=None, overlap=None):
         self.ddp = module if isinstance(module, ThinDDP) else None
         self.module = module.module if isinstance(module, ThinDDP) else module
+        self.module._ensure_ready()           # parameters become views of the flat buffer BEFORE the param group captures them
+        super().__init__([p for _, p in self.module.named_parameters()],
+                         dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         if self.ddp is None:
             # handed the bare DIT although a ThinDDP wraps it: its grad_ready_hook must stay in place (replacing it would
             # silently switch the gradient all-reduce off), so the optimizer chains behind it
             owner = getattr(getattr(self.module, "grad_ready_hook", None), "__self__", None)
             if isinstance(owner, ThinDDP):
                 self.ddp = owner
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.step_count = 0
         p = self.module.flat_params
         self.exp_avg = torch.zeros_like(p)
         self.exp_avg_sq = torch.zeros_like(p)
+        offs = getattr(self.module, "_offs", None)
+        if offs is not None:                  # per-parameter views of the flat moments (torch.optim state layout)
+            for n, q in self.module.named_parameters():
+                o, k = offs[n], q.numel()
+                self.state[q] = dict(step=torch.zeros(()), exp_avg=self.exp_avg[o:o + k].view(q.shape),
+                                     exp_avg_sq=self.exp_avg_sq[o:o + k].view(q.shape))
         self._sumsq = torch.zeros(1, device=p.device)
         self._scale = torch.ones(1, device=p.device)
         self._norm = None
@@ -211,8 +224,10 @@ class FusedAdamW:
         if self.overlap and self.max_grad_norm is not None:
             if self.ddp is not None:
                 self.ddp.post_bucket_hook = self._on_bucket_final
-                if bool(int(os.environ.get("UD_DDP_FUSED_SUMSQ", "0"))) and self.ddp.bf16_compress and self.ddp.world > 1:
-                    self.ddp.sumsq_target = self._sumsq        # grad_unpack adds the squares; the hook only counts the bucket
+                if bool(int(os.environ.get("UD_DDP_FUSED_SUMSQ", "1"))) and self.ddp.bf16_compress and self.ddp.world > 1 \
+                        and self._sumsq.is_cuda:
+                    # the decompression kernel that writes the all-reduced gradient also sums its squares: no separate pass
+                    self.ddp.sumsq_target = self._sumsq        # the hook below then only counts the bucket
             else:
                 prev = self.module.grad_ready_hook
                 if prev is not None and not getattr(prev, "_ud_fused_adamw", False):
@@ -270,6 +285,12 @@ class FusedAdamW:
                     ops.sumsq(g[lo:hi], self._sumsq, 0 if block_idx == -1 else self.sumsq_ctas)
         self._buckets_seen += 1
 
+    # hyper-parameters live in param_groups[0] (what LR schedulers mutate)
+    lr = property(lambda self: self.param_groups[0]["lr"], lambda self, v: self.param_groups[0].__setitem__("lr", v))
+    betas = property(lambda self: self.param_groups[0]["betas"])
+    eps = property(lambda self: self.param_groups[0]["eps"])
+    weight_decay = property(lambda self: self.param_groups[0]["weight_decay"])
+
     def zero_grad(self, set_to_none: bool = True):
         self.module._force_fresh_grads = True     # next backward overwrites the GEMM grads and re-zeroes the rest
 
@@ -288,12 +309,22 @@ class FusedAdamW:
         if not partial_ok:
             self._sumsq.zero_()
             ops.sumsq(g, self._sumsq)
+        if self.ddp is not None and self.ddp.world > 1:
+            # every rank sums the SAME all-reduced gradient, but with float atomics in a different order: the last bits of the
+            # norm (and with them the clip coefficient and, from then on, the replicas) could differ.  One 4-byte all-reduce
+            # (MAX) pins the value, so parameters stay bit-identical across ranks like under torch DDP + clip_grad_norm_.
+            dist.all_reduce(self._sumsq, op=dist.ReduceOp.MAX, group=self.ddp.pg)
         self._norm = self._sumsq.sqrt()
         torch.clamp(self.max_grad_norm / (self._norm + 1e-6), max=1.0, out=self._scale)
         return self._scale
 
     @torch.no_grad()
-    def step(self):
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self._step_impl()
+        return loss
+
+    def _step_impl(self):
         m = self.module
         p, g = m._flat_p, m._flat_g              # (not the properties: they would refresh the bf16 shadow we are about to rewrite)
         self.step_count += 1
@@ -329,12 +360,38 @@ class FusedAdamW:
         m.mark_weights_updated(shadow_is_current=True)
 
     def state_dict(self):
+        """Flat layout (step, exp_avg, exp_avg_sq over DIT._flat_p) + the param group's hyper-parameters.  `to_torch_state_dict`
+        gives the per-parameter torch.optim.AdamW layout (reference optimizer checkpoints)."""
         self.join()                                # the moments may still be in flight on the optimizer stream
         return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, lr=self.lr, betas=self.betas,
                     eps=self.eps, weight_decay=self.weight_decay)
 
     def load_state_dict(self, sd):
         self.join()
+        if "state" in sd and "param_groups" in sd:                 # a torch.optim.AdamW checkpoint (per-parameter state)
+            params = self.param_groups[0]["params"]
+            for idx, st in sd["state"].items():
+                mine = self.state[params[int(idx)]]
+                mine["exp_avg"].copy_(st["exp_avg"])
+                mine["exp_avg_sq"].copy_(st["exp_avg_sq"])
+                self.step_count = int(st["step"])
+            for k in ("lr", "betas", "eps", "weight_decay"):
+                if k in sd["param_groups"][0]:
+                    self.param_groups[0][k] = sd["param_groups"][0][k]
+            return
         self.step_count = sd["step"]
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in sd:
+                self.param_groups[0][k] = sd[k]
+
+    def to_torch_state_dict(self):
+        """The same state in torch.optim.AdamW's state_dict layout (loadable by the reference's optimizer)."""
+        self.join()
+        params = self.param_groups[0]["params"]
+        state = {i: dict(step=torch.tensor(float(self.step_count)), exp_avg=self.state[p]["exp_avg"].clone(),
+                         exp_avg_sq=self.state[p]["exp_avg_sq"].clone()) for i, p in enumerate(params)}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(params)))
+        return dict(state=state, param_groups=[group])

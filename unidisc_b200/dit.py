@@ -139,6 +139,16 @@ class _DiTFunction(torch.autograd.Function):
         return torch.zeros_like(module._anchor), None, None, None, None, None, None, None
 
 
+class TextFullImageSelfMask:
+    """Stands in for the FlexAttention BlockMask the reference builds for step 1 of an inference attention-caching cycle
+    (`get_block_mask(txt_batch_attn_dropout=False, img_batch_attn_dropout=True)`, model_utils.py:721-738,
+    model_eval.py:2329-2338): text queries attend to every token, image queries to image tokens only.  The layout is the static
+    one of the shipped configs: the first `txt_length` tokens are text."""
+
+    def __init__(self, txt_length: int):
+        self.txt_length = int(txt_length)
+
+
 class DIT(nn.Module):
     def __init__(self, config, vocab_size: int, text_vocab_size: int, mask_index: int, dtype=None, device=None,
                  static_img_sl=None, static_txt_sl=None, **kwargs):
@@ -180,6 +190,7 @@ class DIT(nn.Module):
         self.dropout = float(g(m, "dropout", 0.0))
         self.dropout_seed = int(g(config, "seed", 42))
         self._dropout_calls = 0
+        self._dropout_rank = None
         self.txt_length, self.img_length, self.total_length = m.txt_length, m.img_length, m.length
         self.multimodal_batches = True
         self.rope_2d = True
@@ -224,6 +235,7 @@ class DIT(nn.Module):
         self._flat_g = None
         self._flat_bf16 = None
         self._shadow_dirty = True
+        self._shadow_versions = -1
         self._anchor = None
         self.training_graph_enabled = True
         self.grad_ready_hook = None                # thin-DDP / optimizer: hook(block) when that bucket's flat grads are final
@@ -232,6 +244,10 @@ class DIT(nn.Module):
         self.grad_sumsq_acc = None                 # FusedAdamW (N=1): fp32 scalar the wgrad GEMM epilogues add sum(dW^2) into
         self._last_bwd_fused_sumsq = False
         self._grads_attached = False
+        self._kv_cache = None                      # inference attention caching (set_flex_attention_cache)
+        # additive key: with eval.attention_caching the reference's text-only steps write the cache but attend to the LOCAL text
+        # K/V (dit.py:798-812); True makes them attend to the cached image K/V as its comment describes
+        self.cache_attend_cached = bool(g(g(config, "eval"), "attention_caching_attend_cache", False))
         if device is not None:
             self.to(device)
 
@@ -239,10 +255,20 @@ class DIT(nn.Module):
     # reference API stubs
     # ------------------------------------------------------------------------------------------------------------
     def reset_kv_cache(self, *a, **k):
-        raise NotImplementedError("unidisc_b200.DIT: KV cache is not implemented (model.use_kv_cache)")
+        raise NotImplementedError("unidisc_b200.DIT: the causal start_pos KV cache (model.use_kv_cache, dit.py:588-600) belongs to the "
+                                  "autoregressive parameterisation, which is off the hot path; use set_flex_attention_cache")
 
-    def set_flex_attention_cache(self, *a, **k):
-        raise NotImplementedError("unidisc_b200.DIT: FlexAttention image-KV cache is not implemented")
+    def set_flex_attention_cache(self, batch_size, seq_len, device=None, dtype=None):
+        """reference dit.py:610-614 / 1320-1322: allocate the per-block K/V cache of an inference attention-caching cycle
+        (model_eval.py:2297-2367).  K is cached AFTER q/k-LayerNorm + RoPE, V as projected: bf16 [B*seq_len, D] per block."""
+        dev = device if device is not None else self.vocab_embed.embedding.device
+        D = self.hidden_size
+        self._kv_cache = dict(B=int(batch_size), N=int(seq_len),
+                              k=[torch.zeros((batch_size * seq_len, D), device=dev, dtype=bf16) for _ in range(self.n_blocks)],
+                              v=[torch.zeros((batch_size * seq_len, D), device=dev, dtype=bf16) for _ in range(self.n_blocks)])
+
+    def clear_flex_attention_cache(self):
+        self._kv_cache = None
 
     # ------------------------------------------------------------------------------------------------------------
     # flat parameter / gradient storage
@@ -323,13 +349,29 @@ class DIT(nn.Module):
                 self._top["d_w_" + key], self._top["d_b_" + key] = gr(n + ".weight"), gr(n + ".bias")
         self._grad_views = {n: gr(n) for n in self._names}
 
+    def _param_versions(self):
+        """Sum of the autograd version counters of all parameters: changes whenever a parameter is written in place through
+        the Parameter itself (`p.mul_()`, `p.copy_()`, torch.optim steps); writes through `p.data` are invisible to it."""
+        return sum(p._version for p in self.parameters())
+
     def _ensure_ready(self):
         first = self.blocks[0].attention.attn_qkv.weight
         if self._flat_p is None or first.data_ptr() != self._flat_p.data_ptr() or first.device != self._flat_p.device:
             self._flatten()
-        if self._shadow_dirty:
+        # The tensor cores read the bf16 SHADOW of the fp32 master weights.  It is refreshed when (a) a backward ran (an optimizer
+        # step is expected), (b) load_state_dict / mark_weights_updated / train() / eval() was called — the reference swaps EMA
+        # weights in with `ema.copy_to(params)` (writes through p.data) right before switching to eval and restores them before
+        # train (model_eval.py:164-166, model_utils.py:338-345) — or (c) any parameter's version counter moved.
+        v = self._param_versions()
+        if self._shadow_dirty or v != self._shadow_versions:
             ops.cast_bf16(self._flat_p, self._flat_bf16)
             self._shadow_dirty = False
+            self._shadow_versions = v
+
+    def train(self, mode: bool = True):
+        if self._flat_p is not None:
+            self._shadow_dirty = True          # EMA swap / restore happens around mode switches (see _ensure_ready)
+        return super().train(mode)
 
     def wait_param_events(self, which=None):
         """Order the current stream after the streamed optimizer update (FusedAdamW overlap mode): bucket `which`
@@ -349,8 +391,11 @@ class DIT(nn.Module):
         return super().state_dict(*a, **k)
 
     def mark_weights_updated(self, shadow_is_current: bool = False):
-        """Call after the fp32 parameters changed (optimizer step / load_state_dict)."""
+        """Call after the fp32 parameters changed behind the module's back — e.g. written through `p.data` outside a mode
+        switch (EMA swaps, manual re-initialisation).  FusedAdamW passes shadow_is_current=True: it writes both copies."""
         self._shadow_dirty = not shadow_is_current
+        if shadow_is_current:
+            self._shadow_versions = self._param_versions()
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -403,11 +448,28 @@ class DIT(nn.Module):
                 x_img_emb=None, modality=None, start_pos=None, block_mask=None, update_cache_slice=None, sample_ids=None):
         """Returns logits [B,N,V] in bf16 (what the reference returns under its outer bf16 autocast, model.py:693-729).
         `sigma` is used only with `time_conditioning` (off in every shipped training config)."""
-        if label is not None or x_cond is not None or continuous_mode or x_img_emb is not None or start_pos is not None \
-                or update_cache_slice is not None:
-            raise NotImplementedError("unidisc_b200.DIT.forward: label/x_cond/continuous/kv-cache arguments are not supported")
+        if label is not None or x_cond is not None or continuous_mode or x_img_emb is not None or start_pos is not None:
+            raise NotImplementedError("unidisc_b200.DIT.forward: label/x_cond/continuous/start_pos arguments are not supported")
         if attention_mask is not None:
             raise NotImplementedError("unidisc_b200.DIT.forward: dense attention_mask is not supported (model.use_attention_mask)")
+        cache_op = None
+        if self._kv_cache is not None and not self.training:
+            # the three steps of the reference's caching cycle, told apart exactly like dit.py:798-810
+            if indices.shape[1] != self._kv_cache["N"]:
+                if update_cache_slice is None:
+                    raise ValueError("attention caching: a shortened sequence needs update_cache_slice")
+                cache_op = ("update", update_cache_slice)
+            elif isinstance(block_mask, TextFullImageSelfMask):
+                if update_cache_slice is None:
+                    raise ValueError("attention caching: the cache-filling step needs update_cache_slice")
+                cache_op = ("store", block_mask.txt_length)
+            if cache_op is not None and torch.is_grad_enabled():
+                raise RuntimeError("unidisc_b200.DIT: attention caching is an inference path; call under torch.no_grad()")
+            block_mask = None if sample_ids is None else block_mask
+        elif update_cache_slice is not None or isinstance(block_mask, TextFullImageSelfMask):
+            raise ValueError("unidisc_b200.DIT.forward: update_cache_slice / caching masks need set_flex_attention_cache() and eval mode")
+        if block_mask is True and sample_ids is None:
+            block_mask = None                          # the reference's "full attention" marker (dit.py:808-811)
         if block_mask is not None and sample_ids is None:
             raise NotImplementedError("unidisc_b200.DIT.forward: FlexAttention block_mask objects are not supported; pass sample_ids")
         if self.require_sample_ids and sample_ids is None:
@@ -424,6 +486,10 @@ class DIT(nn.Module):
         # here a non-None `block_mask` switches the attention kernels' document mask on and the mask itself is derived
         # from `sample_ids` on the fly.  Without require_sample_ids, passing sample_ids alone also enables it.
         doc_mask = sample_ids is not None and (block_mask is not None or not self.require_sample_ids)
+        if cache_op is not None:
+            logits, _ = self._forward_impl(indices, modality, sample_ids, save=False, doc_mask=doc_mask,
+                                           sigma=sigma if self.time_conditioning else None, cache_op=cache_op)
+            return logits
         return _DiTFunction.apply(self._anchor, self, indices, modality, sample_ids, save, doc_mask,
                                   sigma if self.time_conditioning else None)
 
@@ -497,7 +563,33 @@ class DIT(nn.Module):
         T["d_w_sm0"].addmm_(dh1.t(), C["e"].float())
         T["d_b_sm0"].add_(dh1.sum(0))
 
-    def _forward_impl(self, indices, modality, sample_ids, save, doc_mask=True, sigma=None):
+    def _cached_attention(self, i, qk, qkv, B, N, scale, cache_op):
+        """Attention of block i inside an inference caching cycle (reference dit.py:793-812)."""
+        D, H, hd = self.hidden_size, self.n_heads, self.head_dim
+        C = self._kv_cache
+        q, k, v = qk[:, :D], qk[:, D:], qkv[:, 2 * D:]
+        if cache_op[0] == "store":
+            # step 1: text queries see every key, image queries see image keys only; this step's K / V become the cache
+            T = cache_op[1]
+            o = torch.empty((B * N, D), device=qk.device, dtype=bf16)
+            if T > 0:
+                ops.attn_fwd_kv(q, k, v, B, T, N, H, hd, scale, o=o, q_bs=N * 2 * D, k_bs=N * 2 * D, v_bs=N * 3 * D, o_bs=N * D)
+            if N - T > 0:
+                ops.attn_fwd_kv(q[T:], k[T:], v[T:], B, N - T, N - T, H, hd, scale, o=o[T:], q_bs=N * 2 * D, k_bs=N * 2 * D,
+                                v_bs=N * 3 * D, o_bs=N * D)
+            C["k"][i].copy_(k)
+            C["v"][i].copy_(v)
+            return o
+        # steps 2..: the shortened (text-only) sequence writes its K / V into the cache's slice ...
+        sl = cache_op[1]
+        Nc = C["N"]
+        C["k"][i].view(C["B"], Nc, D)[:B, sl] = k.reshape(B, N, D)
+        C["v"][i].view(C["B"], Nc, D)[:B, sl] = v.reshape(B, N, D)
+        if self.cache_attend_cached:            # ... and attends to the whole cache (fresh text + cached image K / V)
+            return ops.attn_fwd_kv(q, C["k"][i], C["v"][i], B, N, Nc, H, hd, scale)[0]
+        return ops.attn_fwd(q, k, v, B, N, H, hd, scale)[0]       # reference dataflow: local K / V (dit.py:812)
+
+    def _forward_impl(self, indices, modality, sample_ids, save, doc_mask=True, sigma=None, cache_op=None):
         B, N = indices.shape
         M, D, H, hd, V = B * N, self.hidden_size, self.n_heads, self.head_dim, self.vocab_size
         T = self._top
@@ -524,6 +616,11 @@ class DIT(nn.Module):
                                             Ecount=T.get("Ecount"), tc=self._tc(C, norm_block=0))
         # training-mode dropout of the MLP branch (dit.py:1024-1031): Philox mask keyed by (seed, call counter * L + block)
         p_drop = self.dropout if self.training else 0.0
+        if self._dropout_rank is None:
+            # the reference seeds every rank with seed + rank (main.py:1062): data-parallel replicas draw independent masks
+            import torch.distributed as dist
+            self._dropout_rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+            self.dropout_seed += self._dropout_rank
         self._dropout_calls += 1
         drop_base = self._dropout_calls * self.n_blocks
         saved = dict(ids=ids, mod=mod, sid=sid, cos=cos, sin=sin, B=B, N=N, x0=x, rstd0=rstd0, blocks=[], p_drop=p_drop,
@@ -538,7 +635,10 @@ class DIT(nn.Module):
                 self._dbg_fwd_events.append(e)
             qkv = ops.gemm(h, W["wqkv"])
             qk, stats = ops.qk_ln_rope_fwd(qkv, W["gq"], W["bq"], W["gk"], W["bk"], cos, sin, hd)
-            o, lse = ops.attn_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, N, H, hd, scale, sample_ids=sid)
+            if cache_op is not None:
+                o, lse = self._cached_attention(i, qk, qkv, B, N, scale, cache_op), None
+            else:
+                o, lse = ops.attn_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, N, H, hd, scale, sample_ids=sid)
             a = ops.gemm(o, W["wout"])
             x1, h2, ra, rx1 = ops.norm_residual_fwd(a, x, W["npre"], W["n2"], tc=self._tc(C, norm_block=i, mlp=True))
             u, gl = ops.gemm(h2, W["w1"], epi=L.EPI_BF16_GELU, bias=W["b1"])

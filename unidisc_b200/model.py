@@ -25,7 +25,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import noise_schedule, ops
-from .dit import DIT, _wrap_cfg
+from .dit import DIT, TextFullImageSelfMask, _wrap_cfg
 
 bf16 = torch.bfloat16
 
@@ -308,8 +308,18 @@ class Diffusion(nn.Module):
                             static_txt_sl=self.static_txt_sl, static_img_sl=self.static_img_sl)
         self.backbone.to(self.device)
         self.global_step = 0
+        self._backbone_kwargs = {}     # per-step backbone arguments of an attention-caching sampling run (block_mask, update_cache_slice)
         self.fast_rng = bool(_g(config.trainer, "b200_philox_rng", False))   # additive key: in-kernel Philox instead of torch.rand
         self._rng_offset = 0
+        self._rng_seed = None
+
+    def _philox_seed(self):
+        """in-kernel Philox key: config.seed + rank (the reference seeds every rank with seed + rank, main.py:1062)"""
+        if self._rng_seed is None:
+            import torch.distributed as dist
+            rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+            self._rng_seed = int(_g(self.config, "seed", 42)) + rank
+        return self._rng_seed
 
     # ------------------------------------------------------------------------------------------------------------
     # training side
@@ -341,7 +351,7 @@ class Diffusion(nn.Module):
             # one kernel: xt = (rand < move_chance) ? mask : x      (model.py:439,579)
             if self.fast_rng:
                 self._rng_offset += 1
-                xt, move = ops.q_xt(x, move_chance, self.mask_index, rand=None, seed=int(_g(self.config, "seed", 42)),
+                xt, move = ops.q_xt(x, move_chance, self.mask_index, rand=None, seed=self._philox_seed(),
                                     offset=self._rng_offset, return_move=True)
             else:
                 rnd = torch.rand(*x.shape, device=x.device)
@@ -496,7 +506,7 @@ class Diffusion(nn.Module):
         tv = self.text_vocab_size if _g(self.config.model, "force_argmax_valid_indices", False) else -1
         return ops.ddpm_update_logits(x, lc, modality.reshape(-1).contiguous(), mc_t.float().contiguous(), mc_s.float().contiguous(),
                                       self.mask_index, tv, self.vocab_size, logits_uncond=lu, cfg_w=w, u=u,
-                                      seed=int(_g(self.config, "seed", 42)), offset=self._rng_offset)
+                                      seed=self._philox_seed(), offset=self._rng_offset)
 
     @torch.no_grad()
     def _ddpm_update(self, x, t, dt, **kwargs):                                      # reference model_eval.py:2042-2070
@@ -571,10 +581,11 @@ class Diffusion(nn.Module):
         cfg = _g(_g(self.config, "eval"), "cfg", None)
         use_cfg = cfg is not None and x0_unmask is not None and bool(x0_unmask.any())
         kw = dict(sample_ids=sample_ids) if sample_ids is not None else {}
+        kw.update(self._backbone_kwargs)
         if use_cfg:
             x_uncond = torch.where(x0_unmask, torch.full_like(x, self.mask_index), x)
             if sample_ids is not None:
-                kw = dict(sample_ids=torch.cat([sample_ids, sample_ids], 0))
+                kw["sample_ids"] = torch.cat([sample_ids, sample_ids], 0)
             lg = self.backbone(torch.cat([x, x_uncond], 0), None if sigma is None else torch.cat([sigma, sigma], 0),
                                modality=torch.cat([modality, modality], 0), **kw)
             ldv = lg.stride(1)
@@ -611,7 +622,7 @@ class Diffusion(nn.Module):
         out, _, _ = ops.maskgit_update(x, lc, modality.reshape(-1).contiguous(), t.reshape(-1).float().contiguous(), sched, self.mask_index,
                                        tv, self.vocab_size, r_temp=float(r_temp), logits_uncond=lu, cfg_w=w,
                                        e_noise=None if e_noise is None else e_noise.reshape(-1, e_noise.shape[-1]), gumbel=gumbel,
-                                       seed=int(_g(self.config, "seed", 42)), offset=self._rng_offset)
+                                       seed=self._philox_seed(), offset=self._rng_offset)
         return out, 1
 
     @torch.no_grad()
@@ -651,25 +662,64 @@ class Diffusion(nn.Module):
         dt = (1 - eps) / num_steps
         p_cache, nfe = None, 0
         parity = bool(kwargs.get("parity_noise", False))
-        for i in range(num_steps):
-            t = timesteps[i] * torch.ones(B, 1, device=self.device)
-            if self.sampler == "maskgit":
-                x, n = self._maskgit_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, schedule=schedule, step=i, modality=modality,
-                                            sample_ids=sample_ids)
-            elif self.sampler == "first_hitting":                                    # model_eval.py:2373-2374
-                x, n = self._first_hitting_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, schedule=schedule, step=i, modality=modality)
-            elif self.sampler == "ddpm":
-                x, n = self._ddpm_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, modality=modality, parity_noise=parity)
-            elif self.sampler == "ddpm_cache":
-                p_cache, x_next, n = self._ddpm_caching_update(x, t, dt, p_x0=p_cache, x0=x0, x0_unmask=x0_unmask,
-                                                               modality=modality, parity_noise=parity, sample_ids=sample_ids)
-                if p_cache is not None and (not torch.equal(x_next, x) or self.time_conditioning):
-                    p_cache = None
-                x = x_next
-            else:
-                raise NotImplementedError(f"sampling.predictor={self.sampler}")
-            nfe += n
-            x = torch.where(x0_unmask, x0, x)
+        # ---- inference attention caching (eval.attention_caching, reference model_eval.py:2297-2367): cycles of `ratio` steps —
+        # one full joint step, one step that stores the image K/V (image queries see image keys only), then text-only steps ----
+        ev = _g(self.config, "eval")
+        caching = bool(_g(ev, "attention_caching", False))
+        ratio = int(_g(ev, "attention_caching_txt_to_img_ratio", 10))
+        txt_sl = self.static_txt_sl
+        full, sliced = {}, False
+        if caching:
+            if sample_ids is not None:
+                raise NotImplementedError("attention caching assumes the static [text | image] layout (no sample_ids)")
+            use_cfg = _g(ev, "cfg", None) is not None and bool(x0_unmask.any())
+            self.backbone.set_flex_attention_cache(B * (2 if use_cfg else 1), N, self.device)
+
+        def restore(key, new):                                                       # model_eval.py:2314-2317
+            full[key][:, txt_sl] = new
+            return full[key]
+
+        try:
+            for i in range(num_steps):
+                t = timesteps[i] * torch.ones(B, 1, device=self.device)
+                if caching:
+                    if i % ratio == 0:
+                        if sliced:
+                            x, x0, x0_unmask, modality = restore("x", x), restore("x0", x0), restore("x0_unmask", x0_unmask), full["modality"]
+                            full, sliced, p_cache = {}, False, None
+                        self._backbone_kwargs = dict(block_mask=True, update_cache_slice=None)
+                    elif (i - 1) % ratio == 0:
+                        self._backbone_kwargs = dict(block_mask=TextFullImageSelfMask(self.config.model.txt_length),
+                                                     update_cache_slice=slice(0, N))
+                    else:
+                        self._backbone_kwargs = dict(block_mask=True, update_cache_slice=txt_sl)
+                        if not sliced:
+                            full.update(x=x.clone(), x0=x0.clone(), x0_unmask=x0_unmask.clone(), modality=modality)
+                            x, x0, x0_unmask, modality = (v[:, txt_sl].contiguous() for v in (x, x0, x0_unmask, modality))
+                            sliced, p_cache = True, None
+                if self.sampler == "maskgit":
+                    x, n = self._maskgit_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, schedule=schedule, step=i, modality=modality,
+                                                sample_ids=sample_ids)
+                elif self.sampler == "first_hitting":                                # model_eval.py:2373-2374
+                    x, n = self._first_hitting_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, schedule=schedule, step=i, modality=modality)
+                elif self.sampler == "ddpm":
+                    x, n = self._ddpm_update(x, t, dt, x0=x0, x0_unmask=x0_unmask, modality=modality, parity_noise=parity)
+                elif self.sampler == "ddpm_cache":
+                    p_cache, x_next, n = self._ddpm_caching_update(x, t, dt, p_x0=p_cache, x0=x0, x0_unmask=x0_unmask,
+                                                                   modality=modality, parity_noise=parity, sample_ids=sample_ids)
+                    if p_cache is not None and (not torch.equal(x_next, x) or self.time_conditioning):
+                        p_cache = None
+                    x = x_next
+                else:
+                    raise NotImplementedError(f"sampling.predictor={self.sampler}")
+                nfe += n
+                x = torch.where(x0_unmask, x0, x)
+            if sliced:                                                               # model_eval.py:2425-2438
+                x, x0, x0_unmask, modality = restore("x", x), restore("x0", x0), restore("x0_unmask", x0_unmask), full["modality"]
+        finally:
+            self._backbone_kwargs = {}
+            if caching:
+                self.backbone.clear_flex_attention_cache()
         if _g(_g(self.config, "sampling"), "noise_removal", True):                   # model_eval.py:2440-2446
             t_last = timesteps[-1] * torch.ones(B, 1, device=self.device)
             lg = self.backbone(x, self._sampling_sigma(t_last), modality=modality,

@@ -144,14 +144,16 @@ def attn_fwd(q, k, v, B, N, H, head_dim, scale, sample_ids=None, o=None):
     return o, lse
 
 
-def attn_fwd_kv(q, k, v, B, Nq, Nk, H, head_dim, scale, o=None):
-    """partial-query attention against cached K/V: q [B*Nq, >=H*hd], k/v [B*Nk, >=H*hd] bf16 views. Returns o [B*Nq, H*hd], lse."""
+def attn_fwd_kv(q, k, v, B, Nq, Nk, H, head_dim, scale, o=None, q_bs=0, k_bs=0, v_bs=0, o_bs=0):
+    """partial-query attention: Nq query tokens per sample against Nk key/value tokens, no mask.  q / k / v / o are 2-D bf16
+    views whose row 0 is the first token of sample 0; `*_bs` = elements between consecutive samples (0 = dense rows * stride),
+    which lets sub-ranges of a sequence (text queries, cached image keys) be used in place.  Returns o, lse [B,H,Nq]."""
     D = H * head_dim
     if o is None:
         o = torch.empty((B * Nq, D), device=q.device, dtype=bf16)
     lse = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32)
-    call("ud_attn_fwd_kv", P(q), q.stride(0), P(k), k.stride(0), P(v), v.stride(0), P(o), o.stride(0), P(lse), B, Nq, Nk, H, head_dim,
-         scale, stream())
+    call("ud_attn_fwd_kv", P(q), q.stride(0), q_bs, P(k), k.stride(0), k_bs, P(v), v.stride(0), v_bs, P(o), o.stride(0), o_bs, P(lse),
+         B, Nq, Nk, H, head_dim, scale, stream())
     return o, lse
 
 
