@@ -678,22 +678,24 @@ def main():
             for b_, r_, s_, e_ in rows:
                 print(f"[ddp timeline] {b_:3d} {r_:8.2f} {s_:8.2f} {e_:8.2f} {e_ - s_:7.2f}", file=sys.stderr)
 
-    # ---- roofline of the dominant kernel: the tcgen05 GEMM (MLP up-projection shape of this workload), timed live ----
+    # ---- roofline of the dominant kernel family: the tcgen05 GEMM exactly as the model launches it for the MLP up-projection
+    #      (mlp.0: bias + GELU-tanh epilogue writing u and gelu(u), reference dit.py:917-919), timed live over rotated operands ----
     pk = peaks()
     M = B * N
     sets = []
     for i in range(4):                                                # rotate operand sets (> L2) between launches
         sets.append((torch.randn(M, D, device=dev).to(torch.bfloat16), torch.randn(4 * D, D, device=dev).to(torch.bfloat16),
-                     torch.empty(M, 4 * D, device=dev, dtype=torch.bfloat16)))
-    for a, b_, c in sets:
-        ops.gemm(a, b_, out=c)
+                     torch.empty(M, 4 * D, device=dev, dtype=torch.bfloat16), torch.empty(M, 4 * D, device=dev, dtype=torch.bfloat16)))
+    bias_r = torch.randn(4 * D, device=dev).to(torch.bfloat16)
+    for a, b_, c, g_ in sets:
+        ops.gemm(a, b_, out=c, epi=Lb.EPI_BF16_GELU, bias=bias_r, aux=g_)
     torch.cuda.synchronize()
     iters = 24
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for i in range(iters):
-        a, b_, c = sets[i % 4]
-        ops.gemm(a, b_, out=c)
+        a, b_, c, g_ = sets[i % 4]
+        ops.gemm(a, b_, out=c, epi=Lb.EPI_BF16_GELU, bias=bias_r, aux=g_)
     g1.record()
     torch.cuda.synchronize()
     gemm_ms = g0.elapsed_time(g1) / iters
@@ -702,9 +704,9 @@ def main():
     # DRAM traffic of that kernel (dram__bytes_read + dram__bytes_write of one launch) from the committed `ncu --set full` capture
     gemm_traffic, gemm_traffic_src = None, None
     try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_roofline_ncu.json")))
-        if (M, 4 * D, D) == (10240, 8192, 2048):
-            gemm_traffic, gemm_traffic_src = cap["traffic_bytes"], "profiles/r01_gemm_roofline_ncu.json (ncu --set full, one launch)"
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_roofline_ncu.json")))
+        if [M, 4 * D, D] == list(cap.get("shape", [])):
+            gemm_traffic, gemm_traffic_src = cap["traffic_bytes"], "profiles/r02_gemm_roofline_ncu.json (ncu --set full, one launch)"
     except Exception:  # noqa: BLE001
         pass
 
@@ -762,10 +764,11 @@ def main():
                      loss=loss_e2e),
             gpu_launches=n_launch // max(args.steps, 1),
             clocks=clocks,
-            roofline=dict(bound="tensor", kernel=f"gemm_kernel<K-major,K-major> M={M} N={4*D} K={D} (MLP up-projection)",
+            roofline=dict(bound="tensor", kernel=f"gemm2_kernel<K-major,K-major,256,EPI_BF16_GELU> M={M} N={4*D} K={D} (mlp.0: bias + GELU epilogue, "
+                                                 "as launched by the model)",
                           achieved=gemm_tflops, peak=pk["bf16_tflops"], unit="TFLOP/s", frac=gemm_tflops / pk["bf16_tflops"],
                           peak_source=pk["source"] + " (burst: kernel timed alone)", traffic=gemm_traffic, traffic_source=gemm_traffic_src,
-                          algorithmic_bytes=2 * (M * D + 4 * D * D + M * 4 * D), ms_per_launch=gemm_ms),
+                          algorithmic_bytes=2 * (M * D + 4 * D * D + 2 * M * 4 * D), ms_per_launch=gemm_ms),
             step_model_tflops_per_gpu=model_tflops_per_gpu,
             step_frac_of_sustained_peak=model_tflops_per_gpu / pk["bf16_tflops_sustained"],
             flops_per_token_fwd_bwd=fpt,

@@ -28,11 +28,14 @@ enum {
     UD_EPI_BF16_DGELU = 2, /* C bf16 = acc * gelu_tanh'(aux)  (aux = saved u)           autograd of the above */
     UD_EPI_F32 = 3,        /* C fp32 = acc ; aux (optional) = fp32 device scalar += sum C^2   weight gradient (+ its share of the
                               gradient norm of clip_grad_norm_, model.py:1518; needs M > 128) */
-    UD_EPI_F32_ACC = 4     /* C fp32 += acc                                             weight gradient accumulation (.grad +=) */
+    UD_EPI_F32_ACC = 4,    /* C fp32 += acc                                             weight gradient accumulation (.grad +=) */
+    UD_EPI_BF16_SCALED = 5 /* C bf16 = bf16(bf16(acc) * alpha), alpha = *aux (device fp32)   weight gradient written straight in the wire
+                              format of torch's bf16 compress hook (`buffer.to(bf16).div_(world)`, main.py:643-648): the DDP
+                              bucket is all-reduced in place, no fp32 store + compression pass.  (ta, tb) = (1, 1) only */
 };
 /* C[M,N] = sum_k A(m,k) B(n,k).  ta=0: A is [M,K] (lda);  ta=1: A is [K,M] (lda).  tb=0: B is [N,K];  tb=1: B is [K,N].
  * Supported (ta,tb): (0,0) forward, (0,1) dgrad, (1,1) wgrad.  A,B bf16, 16-byte aligned, lda/ldb multiples of 8.
- * bias: bf16 [N] or NULL.  bn_hint: 128 / 256 / 0 (auto). */
+ * bias: bf16 [N] or NULL.  bn_hint: 128 / 256 / 0 (auto).  One kernel family: persistent CTA pairs (cta_group::2), any M. */
 int ud_gemm_bf16(int ta, int tb, int M, int N, int K, const void* A, long long lda, const void* B, long long ldb, void* C,
                  long long ldc, int epi, const void* bias, void* aux, long long ld_aux, int bn_hint, void* stream);
 

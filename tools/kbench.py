@@ -94,9 +94,10 @@ def main():
         t = timeit(lambda: ops.colsum(dy, db))
         print(f"colsum [M,4D]     {t*1e3:8.1f} us  {(M*4*D*2)/t/1e6:7.1f} GB/s")
     if "roof" in which:
-        # exactly bench.py's roofline kernel: plain bf16 GEMM at the MLP up-projection shape (for the ncu traffic capture)
-        a, b, c = rb(M, D), rb(4 * D, D), torch.empty(M, 4 * D, device=dev, dtype=bf16)
-        t = timeit(lambda: ops.gemm(a, b, out=c), iters=10)
+        # exactly bench.py's roofline kernel: the mlp.0 GEMM with bias + GELU epilogue (for the ncu traffic capture)
+        a, b, c, g = rb(M, D), rb(4 * D, D), torch.empty(M, 4 * D, device=dev, dtype=bf16), torch.empty(M, 4 * D, device=dev, dtype=bf16)
+        bias = rb(4 * D)
+        t = timeit(lambda: ops.gemm(a, b, out=c, epi=L.EPI_BF16_GELU, bias=bias, aux=g), iters=10)
         print(f"gemm roofline {M}x{4*D}x{D} {t*1e3:8.1f} us  {2*M*4*D*D/t/1e9:7.1f} TFLOP/s")
     if "gemm" in which:
         shapes = [("qkv fwd", 0, 0, M, 3 * D, D, L.EPI_BF16), ("out fwd", 0, 0, M, D, D, L.EPI_BF16), ("mlp1 gelu", 0, 0, M, 4 * D, D, L.EPI_BF16_GELU),

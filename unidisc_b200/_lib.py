@@ -64,7 +64,7 @@ def adaln(sel, img, shift=None, scale=None, gate=None, ld=0, tokens_per_sample=1
     s = AdaLN(P(sel), P(img), P(shift), P(scale), P(gate), ld, tokens_per_sample, P(d_shift), P(d_scale), P(d_gate), ld_d)
     return C.cast(C.pointer(s), _vp), s
 
-EPI_BF16, EPI_BF16_GELU, EPI_BF16_DGELU, EPI_F32, EPI_F32_ACC = 0, 1, 2, 3, 4
+EPI_BF16, EPI_BF16_GELU, EPI_BF16_DGELU, EPI_F32, EPI_F32_ACC, EPI_BF16_SCALED = 0, 1, 2, 3, 4, 5
 
 
 class UnidiscB200Error(RuntimeError):

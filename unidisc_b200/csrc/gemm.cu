@@ -90,116 +90,6 @@ struct WorkIter {
     }
 };
 
-template <int BN>
-struct GemmCfg {
-    static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-// Epilogue for one 32-column chunk of one accumulator row held in registers (shared by the 1-CTA and 2-CTA kernels).
-template <int EPI>
-UD_DEVINL void epilogue_chunk(const uint32_t (&r)[32], int row, bool row_ok, int col0, const GemmParams& p) {
-    const bool full = (col0 + 32 <= p.N);
-    if constexpr (EPI == UD_EPI_F32 || EPI == UD_EPI_F32_ACC) {
-        float* cp = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
-        if (row_ok) {
-            if (full) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                    if constexpr (EPI == UD_EPI_F32_ACC) {
-                        float4 o = *reinterpret_cast<float4*>(cp + 4 * j);
-                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                    }
-                    *reinterpret_cast<float4*>(cp + 4 * j) = v;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (col0 + j < p.N) {
-                        float v = __uint_as_float(r[j]);
-                        if constexpr (EPI == UD_EPI_F32_ACC) v += cp[j];
-                        cp[j] = v;
-                    }
-                }
-            }
-        }
-    } else {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
-            if (full) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + j);
-                    v[8 * j + 0] += bf16lo(b.x); v[8 * j + 1] += bf16hi(b.x);
-                    v[8 * j + 2] += bf16lo(b.y); v[8 * j + 3] += bf16hi(b.y);
-                    v[8 * j + 4] += bf16lo(b.z); v[8 * j + 5] += bf16hi(b.z);
-                    v[8 * j + 6] += bf16lo(b.w); v[8 * j + 7] += bf16hi(b.w);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
-            }
-        }
-        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
-        __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ld_aux + col0;
-        if (row_ok) {
-            if constexpr (EPI == UD_EPI_BF16_DGELU) {
-                // C = acc * gelu'(u), u = aux (bf16 pre-activation saved by the forward)
-                if (full) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 u = ldg_stream(reinterpret_cast<const uint4*>(xp) + j);
-                        v[8 * j + 0] *= gelu_tanh_grad(bf16lo(u.x)); v[8 * j + 1] *= gelu_tanh_grad(bf16hi(u.x));
-                        v[8 * j + 2] *= gelu_tanh_grad(bf16lo(u.y)); v[8 * j + 3] *= gelu_tanh_grad(bf16hi(u.y));
-                        v[8 * j + 4] *= gelu_tanh_grad(bf16lo(u.z)); v[8 * j + 5] *= gelu_tanh_grad(bf16hi(u.z));
-                        v[8 * j + 6] *= gelu_tanh_grad(bf16lo(u.w)); v[8 * j + 7] *= gelu_tanh_grad(bf16hi(u.w));
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.N) v[j] *= gelu_tanh_grad(__bfloat162float(xp[j]));
-                }
-            }
-            if (full) {
-                uint32_t o[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *(reinterpret_cast<uint4*>(cp) + j) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                if constexpr (EPI == UD_EPI_BF16_GELU) {
-                    uint32_t g[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        g[j] = pack_bf16x2(gelu_tanh(bf16lo(o[j])), gelu_tanh(bf16hi(o[j])));
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *(reinterpret_cast<uint4*>(xp) + j) = make_uint4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (col0 + j < p.N) {
-                        __nv_bfloat16 ub = __float2bfloat16_rn(v[j]);
-                        cp[j] = ub;
-                        if constexpr (EPI == UD_EPI_BF16_GELU) xp[j] = __float2bfloat16_rn(gelu_tanh(__bfloat162float(ub)));
-                    }
-                }
-            }
-        }
-    }
-}
-
-
 // Warp-cooperative store of a [32 rows x 128 bytes] slab whose row `lane` is held by thread `lane` as 8 x 16-byte units.
 // Row-per-thread stores touch 32 different 128-byte lines per instruction with 16 bytes each: ncu showed the L1->XBAR
 // request path 73 % busy and twice the payload in sector traffic (each 16-byte store occupies a 32-byte sector slot).
@@ -241,6 +131,7 @@ struct EpiRegs {
     char* C;
     char* aux;
     const __nv_bfloat16* bias;
+    float alpha;
 };
 template <int EPI>
 UD_DEVINL void epilogue_chunk2(const uint32_t (&r)[32], int row, bool row_ok, int col0, const EpiRegs& e, const float* bias_s,
@@ -282,6 +173,10 @@ UD_DEVINL void epilogue_chunk2(const uint32_t (&r)[32], int row, bool row_ok, in
                 const float4 b = *reinterpret_cast<const float4*>(bias_s + 4 * j);     // broadcast LDS.128 (zero beyond N)
                 v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
+        }
+        if constexpr (EPI == UD_EPI_BF16_SCALED) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]) * e.alpha;
         }
         __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(e.C) + (long long)row * e.ldc + col0;
         __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(e.aux) + (long long)row * e.ld_aux + col0;
@@ -328,146 +223,6 @@ UD_DEVINL void epilogue_chunk2(const uint32_t (&r)[32], int row, bool row_ok, in
         }
     }
 }
-
-template <bool A_MN, bool B_MN, int BN, int EPI>
-__global__ void __launch_bounds__(192, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full = empty_bar + STAGES;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int num_kb = (p.K + BK - 1) / BK;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tma_a);
-        tma_prefetch_desc(&tma_b);
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 4);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                int tm, tn;
-                tile_coords(tile, p.num_m_tiles, p.num_n_tiles, tm, tn);
-                const int m0 = tm * BM;
-                const int n0 = tn * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-                    uint8_t* sb = sa + Cfg::A_BYTES;
-                    mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                    const int k0 = kb * BK;
-                    if constexpr (!A_MN) {
-                        tma_load_2d(sa, &tma_a, &full_bar[s], k0, m0);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tma_a, &full_bar[s], m0 + 64 * j, k0);
-                    }
-                    if constexpr (!B_MN) {
-                        tma_load_2d(sb, &tma_b, &full_bar[s], k0, n0);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, &full_bar[s], n0 + 64 * j, k0);
-                    }
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== UMMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
-            int s = 0;
-            uint32_t ph = 0;
-            int as = 0;
-            uint32_t aph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[as], aph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                    const uint32_t sb = sa + Cfg::A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * (UMMA_K * 128), 8192, 1024)
-                                                 : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
-                        const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), 8192, 1024)
-                                                 : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
-                        umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
-                    umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above retire
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
-                }
-                umma_commit(&tmem_full[as]);     // accumulator complete -> epilogue
-                if (++as == 2) { as = 0; aph ^= 1; }
-            }
-        }
-    } else {
-        // ===================== epilogue warps (2..5) =====================
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
-        int as = 0;
-        uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            int tm, tn;
-            tile_coords(tile, p.num_m_tiles, p.num_n_tiles, tm, tn);
-            const int m0 = tm * BM;
-            const int n0 = tn * BN;
-            mbar_wait(&tmem_full[as], aph);
-            tc_fence_after();
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < p.M;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = n0 + c * 32;
-                if (col0 >= p.N) break;  // warp-uniform
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + as * BN + c * 32 + ((uint32_t)(q * 32) << 16), r);
-                tmem_ld_wait();
-                epilogue_chunk<EPI>(r, row, row_ok, col0, p);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
-            if (++as == 2) { as = 0; aph ^= 1; }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------
 // 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BN tile.  Each CTA stages its own 128 rows of A
@@ -622,6 +377,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         e.N = p.N; e.ldc = p.ldc; e.ld_aux = p.ld_aux; e.C = reinterpret_cast<char*>(p.C); e.aux = reinterpret_cast<char*>(p.aux);
         e.bias = p.bias;
         const bool has_bias = (EPI != UD_EPI_F32 && EPI != UD_EPI_F32_ACC) && e.bias != nullptr;
+        float alpha = 1.f;                     // UD_EPI_BF16_SCALED: C = bf16(bf16(acc) * alpha), alpha = *aux (1 / world size)
+        if constexpr (EPI == UD_EPI_BF16_SCALED) alpha = *reinterpret_cast<const float*>(e.aux);
+        e.alpha = alpha;
         float ssq = 0.f;                       // UD_EPI_F32 + aux: sum of squares of everything this thread stores (gradient norm)
         WorkIter it(p, cluster_id, num_clusters, num_kb);
         WorkItem w;
@@ -638,27 +396,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             // GELU-backward reads the saved pre-activations u[row, n0 + ...]: issued here, BEFORE waiting for the accumulator, as
             // coalesced loads (8 lanes x 16 B per row, 4 rows per instruction); transposed to row-per-thread through the
             // warp's shared-memory buffer at the point of use.
-            constexpr int NSLAB = (CH / 2 > 0) ? CH / 2 : 1;
-            uint4 pre[NSLAB][8];
+            // (one 64-column slab is in flight at a time: the next slab's loads are issued while the current one is processed —
+            //  holding all of a 256-wide tile's pre-activations cost 64 registers and spilled, see -Xptxas -v)
+            uint4 pre[8];
             bool aux_coal = false;
+            const int rows_v = max(0, min(32, p.M - (m0 + q * 32)));
+            auto prefetch_pre = [&](int sl) {
+                const int uu = lane & 7, r0 = lane >> 3;
+                const int col0 = n0 + (c_lo + 2 * sl) * 32;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + r0;
+                    pre[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (rr < rows_v && col0 + 64 <= e.N)
+                        pre[i] = ldg_stream(reinterpret_cast<const uint4*>(
+                            e.aux + ((long long)(m0 + q * 32 + rr) * e.ld_aux + col0) * 2 + uu * 16));
+                }
+            };
             if constexpr (EPI == UD_EPI_BF16_DGELU) {
                 aux_coal = (e.ld_aux & 7) == 0;
-                if (w.kind != 2 && aux_coal) {
-                    const int rows_v = max(0, min(32, p.M - (m0 + q * 32)));
-                    const int uu = lane & 7, r0 = lane >> 3;
-#pragma unroll
-                    for (int sl = 0; sl < NSLAB; ++sl) {
-                        const int col0 = n0 + (c_lo + 2 * sl) * 32;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rr = i * 4 + r0;
-                            pre[sl][i] = make_uint4(0u, 0u, 0u, 0u);
-                            if (rr < rows_v && col0 + 64 <= e.N)
-                                pre[sl][i] = ldg_stream(reinterpret_cast<const uint4*>(
-                                    e.aux + ((long long)(m0 + q * 32 + rr) * e.ld_aux + col0) * 2 + uu * 16));
-                        }
-                    }
-                }
+                if (w.kind != 2 && aux_coal) prefetch_pre(0);
             }
             if (has_bias) {
                 // this tile's bias, fp32, in shared memory (one barrier per work item: a buffer is rewritten two items later,
@@ -750,42 +507,47 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                         }
                     }
                 } else {
-                    // bf16 outputs: two chunks = 64 columns = 128 bytes per row = one slab
+                    // bf16 outputs: two chunks = 64 columns = 128 bytes per row = one slab.  Only ONE 32-column chunk of the
+                    // accumulator is live at a time (the fused GELU / GELU' epilogues need ~60 more registers than the plain one).
                     const bool coal = ((e.ldc & 7) == 0) && (EPI != UD_EPI_BF16_GELU || (e.ld_aux & 7) == 0);
 #pragma unroll
                     for (int sl = 0; sl < CH / 2; ++sl) {
                         const int cc = c_lo + 2 * sl, col0 = n0 + cc * 32;
                         if (col0 >= e.N) break;
-                        uint32_t r0[32], r1[32];
-                        tmem_ld_32x32b_x32(tacc + cc * 32, r0);
-                        if (col0 + 32 < e.N) tmem_ld_32x32b_x32(tacc + (cc + 1) * 32, r1);
-                        tmem_ld_wait();
-                        add_partials(r0, cc);
-                        if (col0 + 32 < e.N) add_partials(r1, cc + 1);
                         if (coal && col0 + 64 <= e.N) {
                             uint4 u[8];
-                            uint4 xg[8];                                     // this row's 64 pre-activations (GELU-backward)
                             if constexpr (EPI == UD_EPI_BF16_DGELU) {
                                 if (aux_coal) {
+                                    // transpose this slab's pre-activations to row-per-thread through the warp's smem buffer, then
+                                    // put the NEXT slab's loads in flight
                                     const int uu = lane & 7, r0q = lane >> 3;
 #pragma unroll
                                     for (int i = 0; i < 8; ++i) {
                                         const int rr = i * 4 + r0q;
-                                        *reinterpret_cast<uint4*>(sbuf + rr * 128 + ((uu ^ (rr & 7)) << 4)) = pre[sl][i];
+                                        *reinterpret_cast<uint4*>(sbuf + rr * 128 + ((uu ^ (rr & 7)) << 4)) = pre[i];
                                     }
                                     __syncwarp();
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) xg[j] = *reinterpret_cast<const uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
-                                    __syncwarp();
-                                } else if (row_ok) {
-                                    const uint4* xr = reinterpret_cast<const uint4*>(e.aux + ((long long)row * e.ld_aux + col0) * 2);
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) xg[j] = xr[j];
+                                    if (sl + 1 < CH / 2) prefetch_pre(sl + 1);
                                 }
                             }
 #pragma unroll
                             for (int hch = 0; hch < 2; ++hch) {
-                                const uint32_t(&r)[32] = hch == 0 ? r0 : r1;
+                                uint32_t r[32];
+                                tmem_ld_32x32b_x32(tacc + (cc + hch) * 32, r);
+                                uint4 xg[4];                                 // this row's 32 pre-activations of the chunk (GELU-backward)
+                                if constexpr (EPI == UD_EPI_BF16_DGELU) {
+                                    if (aux_coal) {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j)
+                                            xg[j] = *reinterpret_cast<const uint4*>(sbuf + lane * 128 + (((4 * hch + j) ^ (lane & 7)) << 4));
+                                    } else if (row_ok) {
+                                        const uint4* xr = reinterpret_cast<const uint4*>(e.aux + ((long long)row * e.ld_aux + col0 + 32 * hch) * 2);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) xg[j] = xr[j];
+                                    }
+                                }
+                                tmem_ld_wait();
+                                add_partials(r, cc + hch);
                                 float v[32];
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -797,10 +559,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                                         v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                                     }
                                 }
+                                if constexpr (EPI == UD_EPI_BF16_SCALED) {
+                                    // torch's bf16 compress hook: buffer.to(bf16).div_(world) — round, scale, round
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]) * alpha;
+                                }
                                 if constexpr (EPI == UD_EPI_BF16_DGELU) {
 #pragma unroll
                                     for (int j = 0; j < 4; ++j) {
-                                        const uint4 x = xg[4 * hch + j];
+                                        const uint4 x = xg[j];
                                         v[8 * j + 0] *= gelu_tanh_grad(bf16lo(x.x)); v[8 * j + 1] *= gelu_tanh_grad(bf16hi(x.x));
                                         v[8 * j + 2] *= gelu_tanh_grad(bf16lo(x.y)); v[8 * j + 3] *= gelu_tanh_grad(bf16hi(x.y));
                                         v[8 * j + 4] *= gelu_tanh_grad(bf16lo(x.z)); v[8 * j + 5] *= gelu_tanh_grad(bf16hi(x.z));
@@ -812,22 +579,34 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                                     u[4 * hch + j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                             }
+                            if constexpr (EPI == UD_EPI_BF16_DGELU) __syncwarp();      // every lane has read its pre-activation row
                             store_slab_coalesced<false>(sbuf, u, lane, e.C + ((long long)row_base * e.ldc + col0) * 2, e.ldc * 2, rows_ok);
                             if constexpr (EPI == UD_EPI_BF16_GELU) {
-                                uint4 g[8];
+                                // g = gelu(u) in place (u has been staged to shared memory by the store above)
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
-                                    g[j] = make_uint4(pack_bf16x2(gelu_tanh(bf16lo(u[j].x)), gelu_tanh(bf16hi(u[j].x))),
+                                    u[j] = make_uint4(pack_bf16x2(gelu_tanh(bf16lo(u[j].x)), gelu_tanh(bf16hi(u[j].x))),
                                                       pack_bf16x2(gelu_tanh(bf16lo(u[j].y)), gelu_tanh(bf16hi(u[j].y))),
                                                       pack_bf16x2(gelu_tanh(bf16lo(u[j].z)), gelu_tanh(bf16hi(u[j].z))),
                                                       pack_bf16x2(gelu_tanh(bf16lo(u[j].w)), gelu_tanh(bf16hi(u[j].w))));
-                                store_slab_coalesced<false>(sbuf, g, lane, e.aux + ((long long)row_base * e.ld_aux + col0) * 2, e.ld_aux * 2,
+                                store_slab_coalesced<false>(sbuf, u, lane, e.aux + ((long long)row_base * e.ld_aux + col0) * 2, e.ld_aux * 2,
                                                             rows_ok);
                             }
                         } else {
-                            epilogue_chunk2<EPI>(r0, row, row_ok, col0, e, has_bias ? bias_s + cc * 32 : nullptr, nullptr);
-                            if (col0 + 32 < e.N)
-                                epilogue_chunk2<EPI>(r1, row, row_ok, col0 + 32, e, has_bias ? bias_s + (cc + 1) * 32 : nullptr, nullptr);
+                            if constexpr (EPI == UD_EPI_BF16_DGELU) {
+                                if (aux_coal && sl + 1 < CH / 2) prefetch_pre(sl + 1);
+                            }
+                            uint32_t r[32];
+                            tmem_ld_32x32b_x32(tacc + cc * 32, r);
+                            tmem_ld_wait();
+                            add_partials(r, cc);
+                            epilogue_chunk2<EPI>(r, row, row_ok, col0, e, has_bias ? bias_s + cc * 32 : nullptr, nullptr);
+                            if (col0 + 32 < e.N) {
+                                tmem_ld_32x32b_x32(tacc + (cc + 1) * 32, r);
+                                tmem_ld_wait();
+                                add_partials(r, cc + 1);
+                                epilogue_chunk2<EPI>(r, row, row_ok, col0 + 32, e, has_bias ? bias_s + (cc + 1) * 32 : nullptr, nullptr);
+                            }
                         }
                     }
                 }
@@ -933,46 +712,6 @@ int sm_count() {
     return n;
 }
 
-template <bool A_MN, bool B_MN, int BN, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
-    auto kern = gemm_kernel<A_MN, B_MN, BN, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        UD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
-    int tiles = p.num_m_tiles * p.num_n_tiles;
-    int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-    UD_CUDA_CHECK(cudaGetLastError());
-    return 0;
-}
-
-template <bool A_MN, bool B_MN, int BN>
-static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
-    switch (epi) {
-        case UD_EPI_BF16: return launch_gemm<A_MN, B_MN, BN, UD_EPI_BF16>(ta, tb, p, s);
-        case UD_EPI_BF16_GELU: return launch_gemm<A_MN, B_MN, BN, UD_EPI_BF16_GELU>(ta, tb, p, s);
-        case UD_EPI_BF16_DGELU: return launch_gemm<A_MN, B_MN, BN, UD_EPI_BF16_DGELU>(ta, tb, p, s);
-        case UD_EPI_F32: return launch_gemm<A_MN, B_MN, BN, UD_EPI_F32>(ta, tb, p, s);
-        case UD_EPI_F32_ACC: return launch_gemm<A_MN, B_MN, BN, UD_EPI_F32_ACC>(ta, tb, p, s);
-    }
-    fprintf(stderr, "unidisc_b200: unknown GEMM epilogue %d\n", epi);
-    return -4;
-}
-
-template <int BN>
-static int dispatch_major(int ta_, int tb_, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                          cudaStream_t s) {
-    if (!ta_ && !tb_) return dispatch_epi<false, false, BN>(epi, ta, tb, p, s);
-    if (!ta_ && tb_) return dispatch_epi<false, true, BN>(epi, ta, tb, p, s);
-    if (ta_ && tb_) return dispatch_epi<true, true, BN>(epi, ta, tb, p, s);
-    fprintf(stderr, "unidisc_b200: GEMM layout (ta=1,tb=0) is not used by the DiT path and not built\n");
-    return -5;
-}
-
-
 // stream-K workspace: one slot per cluster + arrival counters, cached per stream (GEMMs on different streams may overlap)
 struct SkWorkspace { float* ws = nullptr; int* flags = nullptr; };
 static int get_sk_workspace(cudaStream_t stream, SkWorkspace& out) {
@@ -1037,6 +776,9 @@ static int dispatch_epi2(int epi, const CUtensorMap& ta, const CUtensorMap& tb, 
         case UD_EPI_BF16_DGELU: return launch_gemm2<A_MN, B_MN, BN, UD_EPI_BF16_DGELU>(ta, tb, p, s);
         case UD_EPI_F32: return launch_gemm2<A_MN, B_MN, BN, UD_EPI_F32>(ta, tb, p, s);
         case UD_EPI_F32_ACC: return launch_gemm2<A_MN, B_MN, BN, UD_EPI_F32_ACC>(ta, tb, p, s);
+        case UD_EPI_BF16_SCALED:
+            if constexpr (A_MN && B_MN) return launch_gemm2<A_MN, B_MN, BN, UD_EPI_BF16_SCALED>(ta, tb, p, s);
+            break;
     }
     return -4;
 }
@@ -1057,12 +799,11 @@ extern "C" int ud_gemm_bf16(int ta, int tb, int M, int N, int K, const void* A, 
                             void* stream) {
     using namespace ud;
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    // bn_hint: 0 = auto, 128 / 256 = tile width; +1024 forces the single-CTA kernel (A/B testing, tiny problems)
-    const bool force_1cta = (bn_hint & 1024) != 0;
+    // bn_hint: 0 = auto, 128 / 256 = tile width (other bits are ignored: the single-CTA kernel family of round 1 is gone, the
+    // CTA-pair kernel covers every M — rows beyond M are TMA zero-fill and never stored)
     int BN = bn_hint & 1023;
-    const bool two_cta = !force_1cta && M > 128;
-    const int TM = two_cta ? 256 : BM;
-    const int units = two_cta ? sm_count() / 2 : sm_count();
+    constexpr int TM = 256;
+    const int units = sm_count() / 2;
     if (BN != 128 && BN != 256) {
         // 256-wide tiles run ~1.6x faster per flop than 128-wide ones (operand traffic from L2 per flop, measured on B200:
         // ~1560 vs ~950 TFLOP/s), so only fall back to 128 when wave quantisation costs more than that.
@@ -1078,17 +819,20 @@ extern "C" int ud_gemm_bf16(int ta, int tb, int M, int N, int K, const void* A, 
     if (!ta) rc = make_tmap_2d_bf16(&tmA, A, M, K, lda, BM, 64);
     else rc = make_tmap_2d_bf16(&tmA, A, K, M, lda, 64, 64);
     if (rc) return rc;
-    const int b_rows = two_cta ? BN / 2 : BN;
-    if (!tb) rc = make_tmap_2d_bf16(&tmB, B, N, K, ldb, b_rows, 64);
+    if (!tb) rc = make_tmap_2d_bf16(&tmB, B, N, K, ldb, BN / 2, 64);
     else rc = make_tmap_2d_bf16(&tmB, B, K, N, ldb, 64, 64);
     if (rc) return rc;
     if ((reinterpret_cast<uintptr_t>(C) & 15) || (ldc % 4) != 0) {
         fprintf(stderr, "unidisc_b200: GEMM output needs a 16-byte aligned base and ldc %% 4 == 0\n");
         return -6;
     }
-    if (aux != nullptr && (epi == UD_EPI_F32_ACC || (epi == UD_EPI_F32 && !two_cta))) {
-        fprintf(stderr, "unidisc_b200: the fused sum of squares (aux with an fp32 epilogue) needs UD_EPI_F32 and M > 128\n");
+    if (aux != nullptr && epi == UD_EPI_F32_ACC) {
+        fprintf(stderr, "unidisc_b200: the fused sum of squares (aux with an fp32 epilogue) needs UD_EPI_F32\n");
         return -7;
+    }
+    if (epi == UD_EPI_BF16_SCALED && (aux == nullptr || !(ta && tb))) {
+        fprintf(stderr, "unidisc_b200: UD_EPI_BF16_SCALED is the weight-gradient epilogue (ta = tb = 1) and needs aux = device fp32 scale\n");
+        return -8;
     }
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
@@ -1098,10 +842,6 @@ extern "C" int ud_gemm_bf16(int ta, int tb, int M, int N, int K, const void* A, 
     p.num_m_tiles = (M + TM - 1) / TM;
     p.num_n_tiles = (N + BN - 1) / BN;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (two_cta) {
-        if (BN == 256) return dispatch_major2<256>(ta, tb, epi, tmA, tmB, p, s);
-        return dispatch_major2<128>(ta, tb, epi, tmA, tmB, p, s);
-    }
-    if (BN == 256) return dispatch_major<256>(ta, tb, epi, tmA, tmB, p, s);
-    return dispatch_major<128>(ta, tb, epi, tmA, tmB, p, s);
+    if (BN == 256) return dispatch_major2<256>(ta, tb, epi, tmA, tmB, p, s);
+    return dispatch_major2<128>(ta, tb, epi, tmA, tmB, p, s);
 }

@@ -84,6 +84,14 @@ class ThinDDP(nn.Module):
         self._stage = None
         self._comm_stream = None
         self._done_event = None
+        # GEMM-weight gradients never exist in fp32 before the all-reduce: the wgrad GEMM epilogue writes bf16(bf16(dW) / world)
+        # into this buffer (DIT.attach_grad_stage), which is all-reduced in place and decompressed into the fp32 gradient
+        self._wstage = None
+        if self.world > 1 and bf16_compress and module.flat_grads.is_cuda and hasattr(module, "attach_grad_stage") \
+                and not bool(int(os.environ.get("UD_DDP_NO_WGRAD_STAGE", "0"))):
+            self._wstage = torch.zeros(module._big_end, device=module.flat_grads.device, dtype=bf16)
+            self._alpha = torch.full((1,), 1.0 / self.world, device=module.flat_grads.device, dtype=torch.float32)
+            module.attach_grad_stage(self._wstage, self._alpha, lambda: self._sync)
         module.grad_ready_hook = self._on_grads_ready
         self.post_bucket_hook = None       # FusedAdamW: hook(block_idx, ranges, on_side_stream) once a bucket's gradients are final
         self.bytes_on_wire_per_step = 0
@@ -140,11 +148,15 @@ class ThinDDP(nn.Module):
             if dbg:
                 c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 c0.record(self._comm_stream)
+            staged = self._wstage is not None and getattr(self.module, "_last_bwd_staged", False)
             for lo, hi in self._ranges_by_block.get(block_idx, []):
                 seg = g[lo:hi]
                 if self.bf16_compress:
-                    st = self._stage[: hi - lo]
-                    self._pack(seg, st, 1.0 / self.world)
+                    if staged and hi <= self._wstage.numel():
+                        st = self._wstage[lo:hi]                 # already in wire format (wgrad GEMM epilogue)
+                    else:
+                        st = self._stage[: hi - lo]
+                        self._pack(seg, st, 1.0 / self.world)
                     dist.all_reduce(st, group=self.pg)
                     self._unpack(st, seg)
                     self.bytes_on_wire_per_step += 2 * (hi - lo)

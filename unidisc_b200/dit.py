@@ -245,6 +245,14 @@ class DIT(nn.Module):
         self._last_bwd_fused_sumsq = False
         self._grads_attached = False
         self._kv_cache = None                      # inference attention caching (set_flex_attention_cache)
+        # ThinDDP (world > 1): weight gradients are written by the wgrad GEMM epilogue straight into a bf16 staging buffer in the
+        # wire format of the bf16 compress hook (attach_grad_stage); _last_bwd_staged tells the DDP hook which path the last
+        # backward took
+        self._ddp_stage = None
+        self._ddp_alpha = None
+        self._ddp_sync_fn = None
+        self._stage_views = None
+        self._last_bwd_staged = False
         # additive key: with eval.attention_caching the reference's text-only steps write the cache but attend to the LOCAL text
         # K/V (dit.py:798-812); True makes them attend to the cached image K/V as its comment describes
         self.cache_attend_cached = bool(g(g(config, "eval"), "attention_caching_attend_cache", False))
@@ -401,6 +409,18 @@ class DIT(nn.Module):
         r = super().load_state_dict(*a, **k)
         self._shadow_dirty = True
         return r
+
+    def attach_grad_stage(self, stage, alpha, sync_fn):
+        """ThinDDP: `stage` = bf16 buffer covering the GEMM-weight part of the flat gradient layout ([0, _big_end)), `alpha` = device
+        fp32 scalar 1 / world, `sync_fn()` -> True when the running backward is the one whose gradients get all-reduced."""
+        self._ensure_ready()
+        named = dict(self.named_parameters())
+        o = self._offs
+        sv = lambda n: stage[o[n]: o[n] + named[n].numel()].view(named[n].shape)
+        self._stage_views = dict(head=sv("output_layer.linear.weight"), blocks=[
+            dict(wqkv=sv(f"blocks.{i}.attention.attn_qkv.weight"), wout=sv(f"blocks.{i}.attention.attn_out.weight"),
+                 w1=sv(f"blocks.{i}.mlp.0.weight"), w2=sv(f"blocks.{i}.mlp.2.weight")) for i in range(self.n_blocks)])
+        self._ddp_stage, self._ddp_alpha, self._ddp_sync_fn = stage, alpha, sync_fn
 
     def _attach_grads(self):
         """Make p.grad a view of the flat gradient buffer.  Returns True if the gradients were (re)created — i.e. the
@@ -665,8 +685,19 @@ class DIT(nn.Module):
         wacc = L.EPI_F32 if fresh else L.EPI_F32_ACC
         # gradient-norm fusion: when the weight gradients are written (not accumulated) their squares are summed by the GEMM
         # epilogue that stores them, so the optimizer never re-reads the 5.6 GB of GEMM-weight gradients for clip_grad_norm_
-        gacc = self.grad_sumsq_acc if (fresh and self.hidden_size > 128) else None      # (the fused epilogue needs M > 128)
+        gacc = self.grad_sumsq_acc if fresh else None
         self._last_bwd_fused_sumsq = gacc is not None
+        # data parallel: the synchronising backward writes bf16(bf16(dW) / world) into the all-reduce staging buffer (no fp32
+        # store, no compression pass); accumulation micro-steps keep the fp32 path
+        staged = fresh and self._ddp_stage is not None and self._ddp_sync_fn()
+        self._last_bwd_staged = staged
+
+        def wgrad(dy, x, dst, stage_dst, **shape):
+            if staged:
+                ops.gemm(dy, x, ta=True, tb=True, epi=L.EPI_BF16_SCALED, out=stage_dst, aux=self._ddp_alpha, **shape)
+            else:
+                ops.gemm(dy, x, ta=True, tb=True, epi=wacc, out=dst, aux=gacc, **shape)
+        SV = self._stage_views
         # logits gradient in the padded [M, Vp] layout (produced in place by the fused SUBS-NLL backward when possible)
         if dlogits.dtype == bf16 and dlogits.dim() == 3 and dlogits.stride() == (N * self.Vp, self.Vp, 1):
             dl = dlogits.as_strided((M, self.Vp), (self.Vp, 1))[:, :V]
@@ -675,7 +706,7 @@ class DIT(nn.Module):
             buf[:, :V].copy_(dlogits.reshape(M, V))
             dl = buf[:, :V]
         # head
-        ops.gemm(dl, S["hf"], ta=True, tb=True, M=V, N=D, K=M, epi=wacc, out=T["d_wh"], aux=gacc)
+        wgrad(dl, S["hf"], T["d_wh"], SV["head"] if staged else None, M=V, N=D, K=M)
         ops.colsum(dl, T["d_bh"], M, V)
         dh = ops.gemm(dl, T["wh"], tb=True, M=M, N=D, K=V)
         S["logits_buf"] = None
@@ -708,9 +739,10 @@ class DIT(nn.Module):
             if C is not None and i == self.n_blocks - 1:
                 self._adaln_param_grads(C, self.n_blocks)                 # final layer's shift / scale are complete
             # MLP
-            ops.gemm(dd, A["g"], ta=True, tb=True, epi=wacc, out=W["d_w2"], aux=gacc)
+            SB = SV["blocks"][i] if staged else None
+            wgrad(dd, A["g"], W["d_w2"], SB and SB["w2"])
             du = ops.gemm(dd, W["w2"], tb=True, epi=L.EPI_BF16_DGELU, aux=A["u"])
-            ops.gemm(du, A["h2"], ta=True, tb=True, epi=wacc, out=W["d_w1"], aux=gacc)
+            wgrad(du, A["h2"], W["d_w1"], SB and SB["w1"])
             ops.colsum(du, W["d_b1"])
             dh2 = ops.gemm(du, W["w1"], tb=True)
             # x1 = x + rms(a)*w_pre ; h2 = rms(x1)*w_n2
@@ -721,7 +753,7 @@ class DIT(nn.Module):
                 # block i+1's six chunks are final (its norm1 modulation was differentiated by this iteration's first kernel)
                 self._adaln_param_grads(C, i + 1)
             # attention
-            ops.gemm(da, A["o"], ta=True, tb=True, epi=wacc, out=W["d_wout"], aux=gacc)
+            wgrad(da, A["o"], W["d_wout"], SB and SB["wout"])
             do = ops.gemm(da, W["wout"], tb=True)
             dqk = torch.empty((M, 2 * D), device=do.device, dtype=bf16)
             dqkv = torch.empty((M, 3 * D), device=do.device, dtype=bf16)
@@ -731,7 +763,7 @@ class DIT(nn.Module):
                          B, N, H, hd, scale, sample_ids=S["sid"])
             ops.qk_ln_rope_bwd(dqk, qkv, A["stats"], W["gq"], W["gk"], S["cos"], S["sin"], dqkv, W["d_gq"], W["d_bq"], W["d_gk"],
                                W["d_bk"], hd)
-            ops.gemm(dqkv, A["h"], ta=True, tb=True, epi=wacc, out=W["d_wqkv"], aux=gacc)
+            wgrad(dqkv, A["h"], W["d_wqkv"], SB and SB["wqkv"])
             dh = ops.gemm(dqkv, W["wqkv"], tb=True)
             S["blocks"][i] = None      # release this block's activations
             pending.append(i)

@@ -30,6 +30,8 @@ def gemm(a, b, *, ta=False, tb=False, M=None, N=None, K=None, out=None, epi=L.EP
         out = torch.empty((M, N), device=a.device, dtype=torch.float32 if fp32_out else bf16)
     _chk(out.stride(-1) == 1, "gemm output must be row-major")
     _chk(out.dtype == (torch.float32 if fp32_out else bf16), "gemm output dtype mismatch")
+    if epi == L.EPI_BF16_SCALED:
+        _chk(aux is not None and aux.dtype == torch.float32 and ta and tb, "EPI_BF16_SCALED: wgrad layout + device fp32 scale in aux")
     if epi == L.EPI_BF16_GELU and aux is None:
         aux = torch.empty((M, N), device=a.device, dtype=bf16)
     call("ud_gemm_bf16", int(ta), int(tb), M, N, K, P(a), a.stride(0), P(b), b.stride(0), P(out), out.stride(0), epi,
