@@ -147,7 +147,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     uint64_t* pv_done = bars + 11;     // 1
     uint64_t* k_empty = bars + 12;     // 2   K stage free as soon as Q.K^T of that tile retired (long before P.V):
                                        //     the next K tile is prefetched under the softmax instead of after it
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* all_done = bars + 14;    // 1   every MMA of this CTA has retired (completes exactly ONCE: the epilogue's wait cannot
+                                       //     alias an earlier phase the way a parity wait on the per-tile pv_done barrier can
+                                       //     when two completions are still outstanding)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
     __shared__ int sid_k[2 * 128];            // [stage][128]
     __shared__ float xch[2 * 2 * 128];        // [stage][warpgroup][row]: partial row maxima (and final row sums)
     __shared__ DocTiles tl;                   // active key tiles of this query tile (document mask only)
@@ -165,6 +168,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256);
         }
         mbar_init(pv_done, 1);
+        mbar_init(all_done, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
@@ -237,6 +241,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                         umma_ts(tO, tP0 + s * 64 + ks * 8, desc_mnmajor(aV, ks), idesc_pv, acc0 | (ks != 0));
                     umma_commit(&v_empty[s]);
                     umma_commit(pv_done);
+                    if (j + 1 == T) umma_commit(all_done);
                 }
                 __syncwarp();
             }
@@ -348,7 +353,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         xs[wg * 128 + rloc] = l;
         named_bar_sync(1, 256);
         const float lt = xs[rloc] + xs[128 + rloc];
-        if (T > 0) mbar_wait(pv_done, (T - 1) & 1);
+        if (T > 0) mbar_wait(all_done, 0);
         tc_fence_after();
         const float inv = lt > 0.f ? 1.0f / lt : 0.f;
         __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)row * p.ldo + h * HD + wg * (HD / 2);
@@ -481,7 +486,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
     uint64_t* p_rdy = dp_full + 2;           // 2   bf16 P^T written over S^T        (softmax warpgroup -> tensor pipe)
     uint64_t* ds_rdy = p_rdy + 2;            // 2   bf16 dS^T written over dP^T
     uint64_t* acc_done = ds_rdy + 2;         // 2
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_done + 2);
+    uint64_t* all_done = acc_done + 2;       // 1   every MMA of this CTA has retired.  Completes exactly ONCE, so the epilogue's wait
+                                             //     cannot alias an earlier phase: a parity wait on acc_done[] by the warpgroup that
+                                             //     does not own that buffer passed early whenever two completions were still
+                                             //     outstanding (rare, timing dependent: wrong dK / dV)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(all_done + 1);
     __shared__ __align__(16) float s_lse[4 * 64];   // per-column metadata of the streamed sub-tile: [warpgroup][2 slots][64]
     __shared__ __align__(16) float s_dlt[4 * 64];   // (two alternating slots per warpgroup: a fast thread may already publish
     __shared__ __align__(16) int s_sid[4 * 64];     //  sub-tile i+2 while a slow one still reads sub-tile i)
@@ -500,6 +509,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             mbar_init(&s_full[s], 1); mbar_init(&dp_full[s], 1); mbar_init(&p_rdy[s], 128); mbar_init(&ds_rdy[s], 128);
             mbar_init(&acc_done[s], 1);
         }
+        mbar_init(all_done, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
@@ -587,6 +597,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                     for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, acc0 | (ks != 0));
                     umma_commit(&st_empty[s]);
                     umma_commit(&acc_done[bf]);
+                    if (i + 1 == T2) umma_commit(all_done);
                 }
                 __syncwarp();
                 if (i + 2 < T2) {
@@ -752,7 +763,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             mbar_arrive(&ds_rdy[bf]);
         }
         // ---- write the accumulators (the two warpgroups split the work) ----
-        if (T2 > 0) mbar_wait(&acc_done[(T2 - 1) & 1], ((T2 - 1) >> 1) & 1);
+        if (T2 > 0) mbar_wait(all_done, 0);
         tc_fence_after();
         {
             // MODE0: warpgroup 0 stores dK (Acc0), warpgroup 1 stores dV (Acc1).  MODE1: each stores half of dQ's columns.

@@ -464,6 +464,7 @@ class DIT(nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     # forward / backward
     # ------------------------------------------------------------------------------------------------------------
+    @torch.compiler.disable
     def forward(self, indices, sigma=None, label=None, x_cond=None, attention_mask=None, continuous_mode=False,
                 x_img_emb=None, modality=None, start_pos=None, block_mask=None, update_cache_slice=None, sample_ids=None):
         """Returns logits [B,N,V] in bf16 (what the reference returns under its outer bf16 autocast, model.py:693-729).
@@ -609,6 +610,28 @@ class DIT(nn.Module):
             return ops.attn_fwd_kv(q, C["k"][i], C["v"][i], B, N, Nc, H, hd, scale)[0]
         return ops.attn_fwd(q, k, v, B, N, H, hd, scale)[0]       # reference dataflow: local K / V (dit.py:812)
 
+    def _block_forward(self, i, x, h, cos, sin, sid, B, N, C, p_drop, drop_base, cache_op=None):
+        """DDiTBlock.forward (reference dit.py:948-1033) as 8 launches; returns (x_out, h_next, activations for backward)."""
+        D, H, hd = self.hidden_size, self.n_heads, self.head_dim
+        W, T = self._blk[i], self._top
+        scale = 1.0 / math.sqrt(hd)
+        w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
+        qkv = ops.gemm(h, W["wqkv"])
+        qk, stats = ops.qk_ln_rope_fwd(qkv, W["gq"], W["bq"], W["gk"], W["bk"], cos, sin, hd)
+        if cache_op is not None:
+            o, lse = self._cached_attention(i, qk, qkv, B, N, scale, cache_op), None
+        else:
+            o, lse = ops.attn_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, N, H, hd, scale, sample_ids=sid)
+        a = ops.gemm(o, W["wout"])
+        x1, h2, ra, rx1 = ops.norm_residual_fwd(a, x, W["npre"], W["n2"], tc=self._tc(C, norm_block=i, mlp=True))
+        u, gl = ops.gemm(h2, W["w1"], epi=L.EPI_BF16_GELU, bias=W["b1"])
+        d = ops.gemm(gl, W["w2"], bias=W["b2"])
+        x2, h_next, rd, rx2 = ops.norm_residual_fwd(d, x1, W["npost"], w_next, p_drop=p_drop, seed=self.dropout_seed,
+                                                    offset=drop_base + i, tc=self._tc(C, norm_block=i + 1, gate_block=i))
+        rec = dict(h=h, qkv=qkv, qk=qk, stats=stats, o=o, lse=lse, a=a, ra=ra, x1=x1, rx1=rx1, h2=h2, u=u, g=gl, d=d, rd=rd, x2=x2,
+                   rx2=rx2)
+        return x2, h_next, rec
+
     def _forward_impl(self, indices, modality, sample_ids, save, doc_mask=True, sigma=None, cache_op=None):
         B, N = indices.shape
         M, D, H, hd, V = B * N, self.hidden_size, self.n_heads, self.head_dim, self.vocab_size
@@ -645,29 +668,19 @@ class DIT(nn.Module):
         drop_base = self._dropout_calls * self.n_blocks
         saved = dict(ids=ids, mod=mod, sid=sid, cos=cos, sin=sin, B=B, N=N, x0=x, rstd0=rstd0, blocks=[], p_drop=p_drop,
                      drop_base=drop_base, ordinal=ordinal, C=C) if save else None
-        for i, W in enumerate(self._blk):
-            w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
+        ckpt = save and self.use_gradient_checkpointing and self.training
+        for i in range(self.n_blocks):
             if i + 1 < self.n_blocks:
                 self.wait_param_events(i + 1)  # this block's last kernel applies the next block's norm1 weight
             if self._dbg_fwd_events is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
                 self._dbg_fwd_events.append(e)
-            qkv = ops.gemm(h, W["wqkv"])
-            qk, stats = ops.qk_ln_rope_fwd(qkv, W["gq"], W["bq"], W["gk"], W["bk"], cos, sin, hd)
-            if cache_op is not None:
-                o, lse = self._cached_attention(i, qk, qkv, B, N, scale, cache_op), None
-            else:
-                o, lse = ops.attn_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, N, H, hd, scale, sample_ids=sid)
-            a = ops.gemm(o, W["wout"])
-            x1, h2, ra, rx1 = ops.norm_residual_fwd(a, x, W["npre"], W["n2"], tc=self._tc(C, norm_block=i, mlp=True))
-            u, gl = ops.gemm(h2, W["w1"], epi=L.EPI_BF16_GELU, bias=W["b1"])
-            d = ops.gemm(gl, W["w2"], bias=W["b2"])
-            x2, h_next, rd, rx2 = ops.norm_residual_fwd(d, x1, W["npost"], w_next, p_drop=p_drop, seed=self.dropout_seed,
-                                                        offset=drop_base + i, tc=self._tc(C, norm_block=i + 1, gate_block=i))
+            x2, h_next, rec = self._block_forward(i, x, h, cos, sin, sid, B, N, C, p_drop, drop_base, cache_op)
             if save:
-                saved["blocks"].append(dict(h=h, qkv=qkv, qk=qk, stats=stats, o=o, lse=lse, a=a, ra=ra, x1=x1, rx1=rx1, h2=h2,
-                                            u=u, g=gl, d=d, rd=rd, x2=x2, rx2=rx2))
+                # trainer.use_gradient_checkpointing (reference dit.py:1485-1490 wraps every block in torch.utils.checkpoint):
+                # keep only the block's inputs; the backward re-runs the block's forward (same Philox dropout mask)
+                saved["blocks"].append(dict(ckpt=True, x=x, h=h) if ckpt else rec)
             x, h = x2, h_next
         buf = torch.empty((M, self.Vp), device=x.device, dtype=bf16)
         self.wait_param_events()               # head (last bucket) => everything; the events are dropped
@@ -729,6 +742,8 @@ class DIT(nn.Module):
             C["d_c"] = torch.zeros(C["c"].shape, device=C["c"].device, dtype=torch.float32)
         for i in range(self.n_blocks - 1, -1, -1):
             W, A = self._blk[i], S["blocks"][i]
+            if A.get("ckpt"):      # gradient checkpointing: rebuild this block's activations from its saved inputs
+                _, _, A = self._block_forward(i, A["x"], A["h"], S["cos"], S["sin"], S["sid"], B, N, C, S["p_drop"], S["drop_base"])
             w_next = self._blk[i + 1]["n1"] if i + 1 < self.n_blocks else T["nf"]
             d_wnext = self._blk[i + 1]["d_n1"] if i + 1 < self.n_blocks else T["d_nf"]
             # x2 = x1 + rms(d)*w_post ; h_next = rms(x2)*w_next
@@ -746,7 +761,6 @@ class DIT(nn.Module):
             ops.colsum(du, W["d_b1"])
             dh2 = ops.gemm(du, W["w1"], tb=True)
             # x1 = x + rms(a)*w_pre ; h2 = rms(x1)*w_n2
-            x_in = S["blocks"][i - 1]["x2"] if i > 0 else S["x0"]
             g_res, da = ops.norm_residual_bwd(g_res, dh2, A["x1"], A["rx1"], W["n2"], A["a"], A["ra"], W["npre"], W["d_n2"], W["d_npre"],
                                               tc=self._tc(C, norm_block=i, mlp=True, bwd=True))
             if C is not None and i + 1 < self.n_blocks:
@@ -767,7 +781,7 @@ class DIT(nn.Module):
             dh = ops.gemm(dqkv, W["wqkv"], tb=True)
             S["blocks"][i] = None      # release this block's activations
             pending.append(i)
-            del x_in
+            del A
         # first norm + embedding
         g0 = ops.rmsnorm_bwd(g_res, dh, S["x0"], S["rstd0"], self._blk[0]["n1"], self._blk[0]["d_n1"],
                              tc=self._tc(C, norm_block=0, bwd=True))
