@@ -93,6 +93,26 @@ def main():
         db = torch.zeros(4 * D, device=dev)
         t = timeit(lambda: ops.colsum(dy, db))
         print(f"colsum [M,4D]     {t*1e3:8.1f} us  {(M*4*D*2)/t/1e6:7.1f} GB/s")
+    if "sampler" in which:
+        # vocabulary-pass kernels of BASELINE configs[3] (B=64, N=1280, all rows masked, bf16 logits resident): fused absorbing
+        # update and MaskGIT draw + selection, in-kernel Philox noise
+        Bs, V, tv, mi = 64, 48385, 32001, 32000
+        Vp = (V + 63) // 64 * 64
+        lg = torch.empty(Bs * N, Vp, device=dev, dtype=bf16)
+        for c in range(0, Bs * N, 8192):
+            lg[c:c + 8192].normal_(0, 3)
+        xs = torch.full((Bs, N), mi, dtype=torch.int64, device=dev)
+        mods = torch.cat([torch.zeros(Bs, 256, dtype=torch.int64), torch.ones(Bs, 1024, dtype=torch.int64)], 1).to(dev).view(-1)
+        tt = torch.full((Bs,), 0.7, device=dev)
+        num = torch.full((Bs,), 20, dtype=torch.int32, device=dev)
+        alg = Bs * (256 * tv + 1024 * (V - tv)) * 2 + Bs * N * 16
+        t = timeit(lambda: ops.ddpm_update_logits(xs, lg, mods, tt, tt - 0.01, mi, tv, V, seed=1, offset=1), iters=10)
+        print(f"ddpm_update_logits (fused, Philox) {t*1e3:8.1f} us  {alg/t/1e6:7.1f} GB/s")
+        t = timeit(lambda: ops.maskgit_update(xs, lg, mods, tt, num, mi, tv, V, seed=1, offset=1), iters=10)
+        print(f"maskgit_update (draw + select)     {t*1e3:8.1f} us  {alg/t/1e6:7.1f} GB/s")
+        t = timeit(lambda: ops.subs_argmax(lg, xs.view(-1), mods, V, tv, mi), iters=10)
+        print(f"subs_argmax (noise removal)        {t*1e3:8.1f} us  {alg/t/1e6:7.1f} GB/s")
+        del lg
     if "roof" in which:
         # exactly bench.py's roofline kernel: the mlp.0 GEMM with bias + GELU epilogue (for the ncu traffic capture)
         a, b, c, g = rb(M, D), rb(4 * D, D), torch.empty(M, 4 * D, device=dev, dtype=bf16), torch.empty(M, 4 * D, device=dev, dtype=bf16)

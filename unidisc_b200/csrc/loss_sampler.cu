@@ -401,7 +401,17 @@ __global__ void subs_argmax_kernel(const __nv_bfloat16* __restrict__ logits, lon
         const MaxSum t = block_ms(row_lse_bf16(row, lo, hi, mask_index), sm);
         const float lse = t.m + logf(t.s);
         ArgMax a = {-INFINITY, 0x7fffffff};
-        for (int v = lo + threadIdx.x; v < hi; v += blockDim.x)
+        const int lo_al = min(hi, (lo + 7) & ~7), hi_al = max(lo_al, hi & ~7);
+        for (int v = lo + threadIdx.x; v < lo_al; v += blockDim.x)
+            if (v != mask_index) am_upd(a, __bfloat162float(row[v]) - lse, v);
+        for (int v = lo_al + threadIdx.x * 8; v < hi_al; v += blockDim.x * 8) {      // second pass over the row: L2-resident
+            const uint4 t = *reinterpret_cast<const uint4*>(row + v);
+            const float f[8] = {bf16lo(t.x), bf16hi(t.x), bf16lo(t.y), bf16hi(t.y), bf16lo(t.z), bf16hi(t.z), bf16lo(t.w), bf16hi(t.w)};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (v + i != mask_index) am_upd(a, f[i] - lse, v + i);
+        }
+        for (int v = hi_al + threadIdx.x; v < hi; v += blockDim.x)
             if (v != mask_index) am_upd(a, __bfloat162float(row[v]) - lse, v);
         a = block_argmax(a, smv, smi);
         if (threadIdx.x == 0) out[r] = a.i;
