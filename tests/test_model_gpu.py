@@ -507,3 +507,87 @@ def test_backbone_under_torch_compile():
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
     assert torch.allclose(m.flat_grads, g_ref, rtol=1e-4, atol=1e-6)
+
+
+def test_fused_adamw_is_a_torch_optimizer_lr_scheduler_and_state_dicts():
+    """FusedAdamW behind the reference's optimizer plumbing: LambdaLR warm-up (`hydra.utils.instantiate(lr_scheduler, optimizer=...)`,
+    model_setup.py:426) drives it through param_groups, the update matches torch.optim.AdamW under the same schedule, the state
+    converts to / from torch.optim.AdamW's per-parameter state_dict layout, and a plain torch optimizer stepping the same
+    parameters is noticed by the bf16 shadow (version counters)."""
+    from oracle import restated as R
+    from unidisc_b200.config import make_config
+    from unidisc_b200.ddp import FusedAdamW
+    from unidisc_b200.model import Diffusion
+    cfg = make_config("small", hidden_size=128, n_blocks=2, n_heads=2, txt_length=64, img_length=64, image_vocab_size=63, text_vocab_size=97)
+    torch.manual_seed(0)
+    model = Diffusion(cfg, device=dev())
+    model.train()
+    net = model.backbone
+    opt = FusedAdamW(net, lr=1e-3, weight_decay=0.01, max_grad_norm=None, overlap=False)
+    assert isinstance(opt, torch.optim.Optimizer) and len(opt.param_groups) == 1
+    warm = lambda step: min(1.0, (step + 1) / 4)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, warm)
+    ref_params = [torch.nn.Parameter(p.detach().clone()) for p in net.parameters()]
+    ref_opt = torch.optim.AdamW(ref_params, lr=1e-3, weight_decay=0.01)
+    ref_sched = torch.optim.lr_scheduler.LambdaLR(ref_opt, warm)
+    ids, modality = R.synthetic_batch(2, 64, 64, model.text_vocab_size, model.vocab_size, seed=1)
+    batch = dict(input_ids=ids.to(dev()), modality=modality.to(dev()))
+    for it in range(3):
+        torch.manual_seed(30 + it)
+        model.compute_loss(batch).loss.backward()
+        for rp, p in zip(ref_params, net.parameters()):
+            rp.grad = p.grad.detach().clone()
+        assert abs(opt.param_groups[0]["lr"] - ref_opt.param_groups[0]["lr"]) < 1e-12 and opt.lr == 1e-3 * warm(it)
+        opt.step(); sched.step(); opt.zero_grad()
+        ref_opt.step(); ref_sched.step()
+        for rp, p in zip(ref_params, net.parameters()):
+            assert torch.allclose(p.detach(), rp.detach(), rtol=1e-4, atol=1e-6)
+    # state in torch.optim.AdamW's layout: loadable by a torch optimizer over the same parameter list, and back
+    tsd = opt.to_torch_state_dict()
+    ref2 = torch.optim.AdamW([torch.nn.Parameter(p.detach().clone()) for p in net.parameters()], lr=1.0)
+    ref2.load_state_dict(tsd)
+    st_ref = ref_opt.state_dict()["state"]
+    for i in range(len(ref_params)):
+        assert torch.allclose(tsd["state"][i]["exp_avg"], st_ref[i]["exp_avg"], rtol=1e-4, atol=1e-7)
+        assert torch.allclose(tsd["state"][i]["exp_avg_sq"], st_ref[i]["exp_avg_sq"], rtol=1e-4, atol=1e-9)
+    opt2 = FusedAdamW(net, lr=5e-4, overlap=False)
+    opt2.load_state_dict(ref_opt.state_dict())
+    assert opt2.step_count == 3 and torch.allclose(opt2.exp_avg, opt.exp_avg, rtol=1e-4, atol=1e-7)
+    # a stock torch optimizer on the same module: in-place parameter updates must reach the bf16 operand copies
+    with torch.no_grad():
+        before = net(ids.to(dev()), None, modality=modality.to(dev())).float()
+    sgd = torch.optim.SGD(net.parameters(), lr=0.5)
+    torch.manual_seed(50)
+    model.compute_loss(batch).loss.backward()
+    sgd.step()
+    with torch.no_grad():
+        after = net(ids.to(dev()), None, modality=modality.to(dev())).float()
+    assert torch.equal(net.flat_params_bf16, net.flat_params.to(bf16))
+    assert (after - before).abs().max() > 1e-3
+
+
+def test_ema_swap_reaches_the_tensor_cores():
+    """reference eval flow (model_eval.py:164-166, model_utils.py:338-345): `ema.copy_to(params)` writes through p.data, then the
+    model is switched to eval — the forward must run with the swapped weights, and with the restored ones after train()."""
+    from oracle import restated as R
+    from unidisc_b200.config import make_config
+    from unidisc_b200.dit import DIT
+    cfg = make_config("small", hidden_size=128, n_blocks=2, n_heads=2, txt_length=64, img_length=64, image_vocab_size=63, text_vocab_size=97)
+    torch.manual_seed(0)
+    m = DIT(cfg, vocab_size=160, text_vocab_size=97, mask_index=96).to(dev())
+    m.train()
+    ids, mod = R.synthetic_batch(2, 64, 64, 97, 160, seed=1)
+    ids, mod = ids.to(dev()), mod.to(dev())
+    with torch.no_grad():
+        base = m(ids, None, modality=mod).float()
+        stored = [p.detach().clone() for p in m.parameters()]
+        for p in m.parameters():                               # ema.copy_to: param.data.copy_(shadow)
+            p.data.copy_(p.data * 0.5)
+        m.eval()
+        swapped = m(ids, None, modality=mod).float()
+        for p, s0 in zip(m.parameters(), stored):              # ema.restore
+            p.data.copy_(s0)
+        m.train()
+        restored = m(ids, None, modality=mod).float()
+    assert (swapped - base).abs().max() > 1e-2
+    assert torch.equal(restored, base)

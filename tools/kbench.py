@@ -80,6 +80,8 @@ def main():
         gi, da = ops.norm_residual_bwd(g, dh, xo, rx, w, a, ra, w, dwn, dwa)
         t = timeit(lambda: ops.norm_residual_bwd(g, dh, xo, rx, w, a, ra, w, dwn, dwa, g_in=gi, da=da))
         print(f"norm_residual_bwd {t*1e3:8.1f} us  {(M*D*(4+2+4+2+4+2))/t/1e6:7.1f} GB/s")
+        t = timeit(lambda: ops.norm_residual_bwd(g, dh, xo, rx, w, a, ra, w, dwn, dwa, g_in=gi, da=da, p_drop=0.1, seed=1, offset=3))
+        print(f"norm_residual_bwd (dropout 0.1) {t*1e3:8.1f} us  {(M*D*(4+2+4+2+4+2))/t/1e6:7.1f} GB/s")
         qkv = rb(M, 3 * D)
         cos, sin = torch.rand(M, hd // 2, device=dev), torch.rand(M, hd // 2, device=dev)
         t = timeit(lambda: ops.qk_ln_rope_fwd(qkv, w, w, w, w, cos, sin, hd))

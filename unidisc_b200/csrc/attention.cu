@@ -187,15 +187,23 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             mbar_expect_tx(q_full, S::TILE_BYTES);
 #pragma unroll
             for (int bx = 0; bx < S::NBOX; ++bx) tma_load_3d(sQ + bx * S::BOX_BYTES, &tm_q, q_full, h * HD + bx * 64, q0, b);
-            for (int jj = 0; jj < T; ++jj) {
+            // K(jj+1) is requested BEFORE V(jj): its stage is free as soon as QK^T(jj-1) retired, whereas V(jj) has to wait for
+            // P.V(jj-2) — issued in program order behind V, the K tile would arrive a whole tile later than it could
+            auto load_k = [&](int jj) {
                 const int j = tile_of(jj);
                 const int s = jj & 1;
-                const uint32_t ph = (jj >> 1) & 1;
-                mbar_wait(&k_empty[s], ph ^ 1);
+                mbar_wait(&k_empty[s], ((jj >> 1) & 1) ^ 1);
                 mbar_expect_tx(&k_full[s], S::TILE_BYTES);
 #pragma unroll
                 for (int bx = 0; bx < S::NBOX; ++bx)
                     tma_load_3d(sK + s * S::TILE_BYTES + bx * S::BOX_BYTES, &tm_k, &k_full[s], h * HD + bx * 64, j * ATT_BKV, b);
+            };
+            load_k(0);
+            for (int jj = 0; jj < T; ++jj) {
+                const int j = tile_of(jj);
+                const int s = jj & 1;
+                const uint32_t ph = (jj >> 1) & 1;
+                if (jj + 1 < T) load_k(jj + 1);
                 mbar_wait(&v_empty[s], ph ^ 1);
                 mbar_expect_tx(&v_full[s], S::TILE_BYTES);
 #pragma unroll
@@ -451,17 +459,23 @@ attn_fwd5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             mbar_expect_tx(q_full, S::TILE_BYTES);
 #pragma unroll
             for (int bx = 0; bx < S::NBOX; ++bx) tma_load_3d(sQ + bx * S::BOX_BYTES, &tm_q, q_full, h * HD + bx * 64, q0, b);
-            for (int jj = 0; jj < T; ++jj) {
-                const int j = tile_of(jj);
-                const uint32_t ph = jj & 1;
-                mbar_wait(k_empty, ph ^ 1);
+            // K(jj+1) is requested before V(jj) would force it to wait: the K stage is free once QK^T(jj) retired (while the
+            // softmax of tile jj runs), the V stage only once P.V(jj-1) retired
+            auto load_k = [&](int jj) {
+                mbar_wait(k_empty, (jj & 1) ^ 1);
                 mbar_expect_tx(k_full, S::TILE_BYTES);
 #pragma unroll
-                for (int bx = 0; bx < S::NBOX; ++bx) tma_load_3d(sK + bx * S::BOX_BYTES, &tm_k, k_full, h * HD + bx * 64, j * ATT_BKV, b);
-                mbar_wait(v_empty, ph ^ 1);
+                for (int bx = 0; bx < S::NBOX; ++bx)
+                    tma_load_3d(sK + bx * S::BOX_BYTES, &tm_k, k_full, h * HD + bx * 64, tile_of(jj) * ATT_BKV, b);
+            };
+            load_k(0);
+            for (int jj = 0; jj < T; ++jj) {
+                const int j = tile_of(jj);
+                mbar_wait(v_empty, (jj & 1) ^ 1);
                 mbar_expect_tx(v_full, S::TILE_BYTES);
 #pragma unroll
                 for (int bx = 0; bx < S::NBOX; ++bx) tma_load_3d(sV + bx * S::BOX_BYTES, &tm_v, v_full, h * HD + bx * 64, j * ATT_BKV, b);
+                if (jj + 1 < T) load_k(jj + 1);
             }
         }
     } else if (warp == 1) {

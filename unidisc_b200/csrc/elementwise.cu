@@ -207,7 +207,7 @@ __global__ void norm_residual_fwd_kernel(const __nv_bfloat16* __restrict__ a, co
 
 // backward of the fused kernel (see header).  HAS_BRANCH=false degenerates to a plain RMSNorm backward.
 template <bool HAS_BRANCH, int R, bool DROP>
-__global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const __nv_bfloat16* __restrict__ dh,
+UD_DEVINL void norm_residual_bwd_body(const float* __restrict__ g_out, const __nv_bfloat16* __restrict__ dh,
                                          const float* __restrict__ x_out, const float* __restrict__ rstd_x,
                                          const float* __restrict__ w_n, const __nv_bfloat16* __restrict__ a,
                                          const float* __restrict__ rstd_a, const float* __restrict__ w_a,
@@ -291,6 +291,24 @@ __global__ void norm_residual_bwd_kernel(const float* __restrict__ g_out, const 
             if (db_a != nullptr) atomicAdd(db_a + c + i, acc_b.v[i]);
         }
     }
+}
+
+#define UD_NRB_PARAMS                                                                                                     \
+    const float *__restrict__ g_out, const __nv_bfloat16 *__restrict__ dh, const float *__restrict__ x_out,                 \
+        const float *__restrict__ rstd_x, const float *__restrict__ w_n, const __nv_bfloat16 *__restrict__ a,               \
+        const float *__restrict__ rstd_a, const float *__restrict__ w_a, float *__restrict__ g_in,                          \
+        __nv_bfloat16 *__restrict__ da, float *__restrict__ dw_n, float *__restrict__ dw_a, float *__restrict__ db_a,       \
+        int rows, int D, uint32_t drop_thresh, float inv_keep, uint64_t seed, uint64_t offset
+#define UD_NRB_ARGS g_out, dh, x_out, rstd_x, w_n, a, rstd_a, w_a, g_in, da, dw_n, dw_a, db_a, rows, D, drop_thresh, inv_keep, seed, offset
+// Without dropout the body fits 64 registers (two 512-thread CTAs per SM).  The dropout variant (Philox mask) takes 80 unbounded,
+// i.e. ONE CTA per SM: it gets explicit launch bounds (64 registers, 68 bytes of spills) to keep two CTAs resident.
+template <bool HAS_BRANCH, int R, bool DROP>
+__global__ void norm_residual_bwd_kernel(UD_NRB_PARAMS) {
+    norm_residual_bwd_body<HAS_BRANCH, R, DROP>(UD_NRB_ARGS);
+}
+template <bool HAS_BRANCH, int R>
+__global__ void __launch_bounds__(512, 2) norm_residual_bwd_drop_kernel(UD_NRB_PARAMS) {
+    norm_residual_bwd_body<HAS_BRANCH, R, true>(UD_NRB_ARGS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1119,7 +1137,7 @@ extern "C" int ud_norm_residual_bwd(const float* g_out, const void* dh, const fl
         return 0;
     }
     if (p_drop > 0.f)
-        norm_residual_bwd_kernel<true, 2, true><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, db_a, rows, D,
+        norm_residual_bwd_drop_kernel<true, 2><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, db_a, rows, D,
                                                                                    dropout_thresh(p_drop), 1.0f / (1.0f - p_drop), seed, offset);
     else
         norm_residual_bwd_kernel<true, 2, false><<<grid, D / 4, 0, STREAM(stream)>>>(g_out, CBF(dh), x_out, rstd_x, w_n, CBF(a), rstd_a, w_a, g_in, BF(da), dw_n, dw_a, db_a, rows, D, 0u, 1.f, 0, 0);
