@@ -120,6 +120,12 @@ UD_DEVINL uint64_t desc_kmajor(uint32_t tile_base, int ks) {
 UD_DEVINL uint64_t desc_mnmajor(uint32_t tile_base, int ks) {
     return make_smem_desc_sw128(tile_base + ks * 2048, 128 * 128, 1024);
 }
+UD_DEVINL uint64_t desc_kmajor64(uint32_t tile_base, int ks) {   // [64 rows][HD] as HD/64 boxes of [64][64]
+    return make_smem_desc_sw128(tile_base + (ks >> 2) * (64 * 128) + (ks & 3) * 32, 16, 1024);
+}
+UD_DEVINL uint64_t desc_mnmajor64(uint32_t tile_base, int ks) {  // MN-major view: k-step = 16 rows, MN chunks 8 KB apart
+    return make_smem_desc_sw128(tile_base + ks * 2048, 64 * 128, 1024);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Forward v3: the v1 dataflow (one 128-query tile per CTA, double-buffered S and P in TMEM so QK^T of tile j+1 runs under
@@ -654,6 +660,268 @@ attn_fwd5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// Forward v6: v3's dataflow (double-buffered S so that Q.K^T of tile j+1 runs under the softmax of tile j, and the softmax warps
+// never wait for P.V) at HALF the key-tile width, which makes everything small enough for TWO CTAs per SM:
+//   key tiles of 64: S0[64] S1[64] O[HD] = 256 TMEM columns, Q + 2 x (K, V) 64-row stages = 96 KB of shared memory (hd = 128);
+//   four softmax warps, one thread per query row: the 64 scores of a tile live in registers for ONE pass (no second TMEM read as
+//   in v5, no cross-warp exchange of row maxima as in v3); bf16 P overwrites the first 32 columns of its S buffer.
+// The softmax warps of a CTA run back to back (their only waits are S(j) — computed a tile ahead — and the rare lazy rescale),
+// two CTAs share each SM's MUFU, and the tensor pipe / TMA of one CTA fill the gaps of the other.
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(192, 2)
+attn_fwd6_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+    constexpr int BKV = 64;
+    constexpr int QTILE = 128 * HD * 2;          // bytes of the Q tile
+    constexpr int KTILE = BKV * HD * 2;          // bytes of one K (or V) stage
+    constexpr int NBOX = HD / 64;
+    constexpr int QBOX = 128 * 128, KBOX = BKV * 128;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + QTILE;                    // [2] stages
+    uint8_t* sV = sK + 2 * KTILE;                // [2] stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * KTILE);
+    uint64_t* q_full = bars;           // 1
+    uint64_t* k_full = bars + 1;       // 2
+    uint64_t* v_full = bars + 3;       // 2
+    uint64_t* k_empty = bars + 5;      // 2   K stage free once Q.K^T of that tile retired
+    uint64_t* v_empty = bars + 7;      // 2   V stage free once P.V of that tile retired
+    uint64_t* s_full = bars + 9;       // 2
+    uint64_t* p_full = bars + 11;      // 2   128 arrivals
+    uint64_t* pv_done = bars + 13;     // 1   completes once per tile; waited only in step (lazy rescale)
+    uint64_t* all_done = bars + 14;    // 1   completes once
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
+    __shared__ int sid_k[2 * BKV];            // [stage][64]
+    __shared__ DocTiles tl;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
+    const int Tall = (p.Nk + BKV - 1) / BKV;
+    const bool use_ids = p.sample_ids != nullptr;
+    constexpr uint32_t TCOLS = (128 + HD <= 256) ? 256 : 512;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1); mbar_init(&v_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_empty[s], 1);
+            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128);
+        }
+        mbar_init(pv_done, 1); mbar_init(all_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TCOLS>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+    const uint32_t tS0 = tmem, tO0 = tmem + 128;        // S_s = tS0 + 64 s
+    if (use_ids) doc_tile_list<BKV>(p.sample_ids + (long long)b * p.N, p.N, q0, Tall, tl);
+    const int T = use_ids ? tl.n : Tall;
+    auto tile_of = [&](int jj) { return use_ids ? (int)tl.idx[jj] : jj; };
+
+    if (warp == 0) {
+        if (lane == 0 && T > 0) {
+            mbar_expect_tx(q_full, QTILE);
+#pragma unroll
+            for (int bx = 0; bx < NBOX; ++bx) tma_load_3d(sQ + bx * QBOX, &tm_q, q_full, h * HD + bx * 64, q0, b);
+            auto load_k = [&](int jj) {
+                const int s = jj & 1;
+                mbar_wait(&k_empty[s], ((jj >> 1) & 1) ^ 1);
+                mbar_expect_tx(&k_full[s], KTILE);
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx)
+                    tma_load_3d(sK + s * KTILE + bx * KBOX, &tm_k, &k_full[s], h * HD + bx * 64, tile_of(jj) * BKV, b);
+            };
+            load_k(0);
+            for (int jj = 0; jj < T; ++jj) {
+                const int s = jj & 1;
+                if (jj + 1 < T) load_k(jj + 1);       // K first: its stage frees a tile earlier than the V stage
+                mbar_wait(&v_empty[s], ((jj >> 1) & 1) ^ 1);
+                mbar_expect_tx(&v_full[s], KTILE);
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx)
+                    tma_load_3d(sV + s * KTILE + bx * KBOX, &tm_v, &v_full[s], h * HD + bx * 64, tile_of(jj) * BKV, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (T > 0) {
+            const uint32_t leader = elect_one();
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, false, false);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
+            const uint32_t aQ = smem_u32(sQ);
+            auto issue_s = [&](int j) {
+                const int s = j & 1;
+                mbar_wait(&k_full[s], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t aK = smem_u32(sK + s * KTILE);
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks)
+                        umma_ss(tS0 + s * 64, desc_kmajor(aQ, ks), desc_kmajor64(aK, ks), idesc_s, ks != 0);
+                    umma_commit(&s_full[s]);
+                    umma_commit(&k_empty[s]);
+                }
+                __syncwarp();
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < T; ++j) {
+                if (j + 1 < T) issue_s(j + 1);        // into the other S buffer (its P was consumed by P.V(j-1), issued earlier)
+                const int s = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(&v_full[s], ph);
+                mbar_wait(&p_full[s], ph);
+                tc_fence_after();
+                const uint32_t aV = smem_u32(sV + s * KTILE);
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < BKV / 16; ++ks)
+                        umma_ts(tO0, tS0 + s * 64 + ks * 8, desc_mnmajor64(aV, ks), idesc_pv, (uint32_t)(j != 0) | (uint32_t)(ks != 0));
+                    umma_commit(&v_empty[s]);
+                    umma_commit(pv_done);
+                    if (j + 1 == T) umma_commit(all_done);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int qd = warp & 3;
+        const int rloc = qd * 32 + lane;          // row inside the tile == TMEM lane
+        const int row = q0 + rloc;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const uint32_t tO = tO0 + lane_off;
+        const int tid128 = threadIdx.x - 64;
+        int sid_q = 0;
+        if (use_ids) sid_q = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
+        const float scl = p.scale_log2;
+        const int Ntok = p.Nk;
+        float m_used = -INFINITY, l = 0.f;
+        for (int jj = 0; jj < T; ++jj) {
+            const int j = tile_of(jj);
+            const int s = jj & 1;
+            const uint32_t ph = (jj >> 1) & 1;
+            const bool use_mask = use_ids && !tl.nomask[jj];
+            const int kbase = j * BKV;
+            const bool tail = kbase + BKV > Ntok;
+            if (use_mask) {
+                if (tid128 < BKV) {
+                    const int kk = kbase + tid128;
+                    sid_k[s * BKV + tid128] = kk < Ntok ? (int)p.sample_ids[(long long)b * Ntok + kk] : -2;
+                }
+                named_bar_sync(1, 128);
+            }
+            mbar_wait(&s_full[s], ph);
+            tc_fence_after();
+            const uint32_t tS = tS0 + s * 64 + lane_off;
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(tS, r0);
+            tmem_ld_32x32b_x32(tS + 32, r1);
+            tmem_ld_wait();
+            if (use_mask) {
+                const int* sk = sid_k + s * BKV;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (!(kbase + i < Ntok && sk[i] == sid_q && sid_q != -1)) r0[i] = 0xff800000u;
+                    if (!(kbase + 32 + i < Ntok && sk[32 + i] == sid_q && sid_q != -1)) r1[i] = 0xff800000u;
+                }
+            } else if (tail) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (kbase + i >= Ntok) r0[i] = 0xff800000u;
+                    if (kbase + 32 + i >= Ntok) r1[i] = 0xff800000u;
+                }
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(r1[i])); mx3 = fmaxf(mx3, __uint_as_float(r1[i + 1]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scl;
+            const float m_new = fmaxf(m_used, mx);
+            const bool grow = m_new > m_used + 8.0f;
+            if (__any_sync(0xffffffffu, grow)) {
+                const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_new);
+                if (jj > 0) {
+                    mbar_wait(pv_done, (jj - 1) & 1);          // O must be quiescent before it is rescaled
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < HD / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tO + c * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tmem_st_32x32b_x32(tO + c * 32, r);
+                    }
+                    tmem_st_wait();
+                }
+                l *= alpha;
+                m_used = m_new;
+            }
+            const float mref = (m_used == -INFINITY) ? 0.f : m_used;
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float a0 = ex2(fmaf(__uint_as_float(r0[2 * i]), scl, -mref)), a1 = ex2(fmaf(__uint_as_float(r0[2 * i + 1]), scl, -mref));
+                l0 += a0 + a1;
+                r0[i] = pack_bf16x2(a0, a1);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float b0 = ex2(fmaf(__uint_as_float(r1[2 * i]), scl, -mref)), b1 = ex2(fmaf(__uint_as_float(r1[2 * i + 1]), scl, -mref));
+                l1 += b0 + b1;
+                r0[16 + i] = pack_bf16x2(b0, b1);
+            }
+            l += l0 + l1;
+            tmem_st_32x32b_x32(tS, r0);                   // P over the first 32 columns of this S buffer
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_full[s]);
+        }
+        // ---- epilogue: O / l, lse ----
+        if (T > 0) mbar_wait(all_done, 0);
+        tc_fence_after();
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)row * p.ldo + h * HD;
+#pragma unroll
+        for (int c = 0; c < HD / 32; ++c) {
+            uint32_t r[32];
+            if (T > 0) {
+                tmem_ld_32x32b_x32(tO + c * 32, r);
+                tmem_ld_wait();
+            }
+            if (inv == 0.f) {                              // fully masked row (padding): O holds no mass / was never written
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = 0u;
+            }
+            if (row < p.N) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 o4;
+                    o4.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
+                    o4.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
+                    o4.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
+                    o4.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = o4;
+                }
+            }
+        }
+        if (row < p.N) p.lse[((long long)b * p.H + h) * p.N + row] = l > 0.f ? (m_used + log2f(l)) * LN2 : INFINITY;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TCOLS>(tmem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // delta[b,h,n] = sum_d o[n,d] * do[n,d]   (softmax backward row term)
 // ------------------------------------------------------------------------------------------------
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, long long ldo,
@@ -723,12 +991,6 @@ struct AttnBwd2Smem {
     static constexpr int NBOX = HD / 64;
     static constexpr int BYTES = 2 * FIX_BYTES + NST * 2 * SUB_BYTES + 1024 + 4096;
 };
-UD_DEVINL uint64_t desc_kmajor64(uint32_t tile_base, int ks) {   // [64 rows][HD] as HD/64 boxes of [64][64]
-    return make_smem_desc_sw128(tile_base + (ks >> 2) * (64 * 128) + (ks & 3) * 32, 16, 1024);
-}
-UD_DEVINL uint64_t desc_mnmajor64(uint32_t tile_base, int ks) {  // MN-major view: k-step = 16 rows, MN chunks 8 KB apart
-    return make_smem_desc_sw128(tile_base + ks * 2048, 64 * 128, 1024);
-}
 
 template <int HD, int MODE>
 __global__ void __launch_bounds__(320, 1)
@@ -1106,15 +1368,21 @@ static int launch_attn_fwd(const void* q, long long ldq, const void* k, long lon
     const int smem3 = attn_smem_bytes<HD>(5);
     static bool attr3 = false;
     const int smem5 = 3 * AttnSmem<HD>::TILE_BYTES + 1024 + 256;
+    CUtensorMap tk64, tv64;
+    if ((rc = make_head_tmap(&tk64, k, ldk, p.B, p.Nk, D, 64, k_bs))) return rc;
+    if ((rc = make_head_tmap(&tv64, v, ldv, p.B, p.Nk, D, 64, v_bs))) return rc;
     if (!attr3) {
+        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd6_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
         UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
         UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd5_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
         attr3 = true;
     }
-    static const int variant = getenv("UD_ATTN_FWD") ? atoi(getenv("UD_ATTN_FWD")) : 5;   // A/B switch: 3 = one CTA/SM, double-buffered S; 5 = two CTAs/SM
+    // A/B switch: 3 = one CTA/SM, double-buffered 128-key S; 5 = two CTAs/SM, single S; 6 = two CTAs/SM, double-buffered 64-key S
+    static const int variant = getenv("UD_ATTN_FWD") ? atoi(getenv("UD_ATTN_FWD")) : 6;
     dim3 grid3((p.N + ATT_BQ - 1) / ATT_BQ, p.H, p.B);
     if (variant == 3) attn_fwd3_kernel<HD><<<grid3, 320, smem3, stream>>>(tq, tk, tv, p);
-    else attn_fwd5_kernel<HD><<<grid3, 192, smem5, stream>>>(tq, tk, tv, p);
+    else if (variant == 5) attn_fwd5_kernel<HD><<<grid3, 192, smem5, stream>>>(tq, tk, tv, p);
+    else attn_fwd6_kernel<HD><<<grid3, 192, smem5, stream>>>(tq, tk64, tv64, p);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
