@@ -404,267 +404,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
-// Forward v5: TWO CTAs per SM instead of one CTA with double-buffered scores.  Every resource of a CTA is halved — one S
-// buffer (bf16 P is written over its first 64 columns), one K and one V stage (96 KB of shared memory for hd = 128, 256 TMEM
-// columns), six warps (TMA, MMA, four softmax warps: one thread per query row, the whole 128-column row in two 64-column
-// passes, no cross-warp exchange) — so that two independent CTAs are resident per SM and the hardware interleaves them: one
-// CTA's softmax runs under the other's tensor-core work and K/V loads without any cross-tile protocol inside the kernel.
-// (v3 keeps both S buffers in ONE CTA whose eight softmax warps march in lock-step: ncu shows tensor pipe 37 %, XU 37 %, issue
-// 32 % — nothing saturated, the S -> softmax -> P -> PV chain is latency bound.)
-//   per CTA, key tile j:  K(j+1) is loaded while softmax(j) / PV(j) run (K stage free once QK^T(j) retired),
-//                         V(j+1) while QK^T(j+1) / softmax(j+1) run (V stage free once PV(j) retired).
-// ------------------------------------------------------------------------------------------------
-template <int HD>
-__global__ void __launch_bounds__(192, 2)
-attn_fwd5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                 const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
-    using S = AttnSmem<HD>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + S::TILE_BYTES;
-    uint8_t* sV = sK + S::TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + S::TILE_BYTES);
-    uint64_t* q_full = bars;           // K / V / S / P barriers complete once per key tile: phase parity = jj & 1
-    uint64_t* k_full = bars + 1;
-    uint64_t* v_full = bars + 2;
-    uint64_t* k_empty = bars + 3;
-    uint64_t* v_empty = bars + 4;
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_full = bars + 6;       // 128 arrivals
-    uint64_t* pv_done = bars + 7;
-    uint64_t* all_done = bars + 8;     // completes once
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
-    __shared__ int sid_k[2 * 128];            // [jj & 1][128]
-    __shared__ DocTiles tl;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
-    const int Tall = (p.Nk + ATT_BKV - 1) / ATT_BKV;
-    const bool use_ids = p.sample_ids != nullptr;
-    constexpr uint32_t TCOLS = (128 + HD <= 256) ? 256 : 512;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
-        mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(k_empty, 1); mbar_init(v_empty, 1);
-        mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(pv_done, 1); mbar_init(all_done, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<TCOLS>(tmem_ptr_smem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_ptr_smem;
-    const uint32_t tS0 = tmem, tO0 = tmem + 128;
-    if (use_ids) doc_tile_list<ATT_BKV>(p.sample_ids + (long long)b * p.N, p.N, q0, Tall, tl);
-    const int T = use_ids ? tl.n : Tall;
-    auto tile_of = [&](int jj) { return use_ids ? (int)tl.idx[jj] : jj; };
-
-    if (warp == 0) {
-        if (lane == 0 && T > 0) {
-            mbar_expect_tx(q_full, S::TILE_BYTES);
-#pragma unroll
-            for (int bx = 0; bx < S::NBOX; ++bx) tma_load_3d(sQ + bx * S::BOX_BYTES, &tm_q, q_full, h * HD + bx * 64, q0, b);
-            // K(jj+1) is requested before V(jj) would force it to wait: the K stage is free once QK^T(jj) retired (while the
-            // softmax of tile jj runs), the V stage only once P.V(jj-1) retired
-            auto load_k = [&](int jj) {
-                mbar_wait(k_empty, (jj & 1) ^ 1);
-                mbar_expect_tx(k_full, S::TILE_BYTES);
-#pragma unroll
-                for (int bx = 0; bx < S::NBOX; ++bx)
-                    tma_load_3d(sK + bx * S::BOX_BYTES, &tm_k, k_full, h * HD + bx * 64, tile_of(jj) * ATT_BKV, b);
-            };
-            load_k(0);
-            for (int jj = 0; jj < T; ++jj) {
-                const int j = tile_of(jj);
-                mbar_wait(v_empty, (jj & 1) ^ 1);
-                mbar_expect_tx(v_full, S::TILE_BYTES);
-#pragma unroll
-                for (int bx = 0; bx < S::NBOX; ++bx) tma_load_3d(sV + bx * S::BOX_BYTES, &tm_v, v_full, h * HD + bx * 64, j * ATT_BKV, b);
-                if (jj + 1 < T) load_k(jj + 1);
-            }
-        }
-    } else if (warp == 1) {
-        if (T > 0) {
-            const uint32_t leader = elect_one();
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
-            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
-            mbar_wait(q_full, 0);
-            for (int jj = 0; jj < T; ++jj) {
-                const uint32_t ph = jj & 1;
-                mbar_wait(k_full, ph);
-                tc_fence_after();
-                if (leader) {           // S(jj) overwrites the columns P(jj-1) was read from: in-order execution after PV(jj-1)
-#pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tS0, desc_kmajor(aQ, ks), desc_kmajor(aK, ks), idesc_s, ks != 0);
-                    umma_commit(s_full);
-                    umma_commit(k_empty);
-                }
-                __syncwarp();
-                mbar_wait(v_full, ph);
-                mbar_wait(p_full, ph);
-                tc_fence_after();
-                if (leader) {
-#pragma unroll
-                    for (int ks = 0; ks < ATT_BKV / 16; ++ks)
-                        umma_ts(tO0, tS0 + ks * 8, desc_mnmajor(aV, ks), idesc_pv, (uint32_t)(jj != 0) | (uint32_t)(ks != 0));
-                    umma_commit(v_empty);
-                    umma_commit(pv_done);
-                    if (jj + 1 == T) umma_commit(all_done);
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        const int qd = warp & 3;
-        const int rloc = qd * 32 + lane;          // row inside the tile == TMEM lane
-        const int row = q0 + rloc;
-        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const uint32_t tS = tS0 + lane_off, tO = tO0 + lane_off;
-        const int tid128 = threadIdx.x - 64;
-        int sid_q = 0;
-        if (use_ids) sid_q = row < p.N ? (int)p.sample_ids[(long long)b * p.N + row] : -1;
-        const float scl = p.scale_log2;
-        const int Ntok = p.Nk;
-        float m_used = -INFINITY, l = 0.f;
-        for (int jj = 0; jj < T; ++jj) {
-            const int j = tile_of(jj);
-            const uint32_t ph = jj & 1;
-            const bool use_mask = use_ids && !tl.nomask[jj];     // this tile pair needs the per-element document mask
-            const int kbase = j * ATT_BKV;
-            const bool tail = kbase + ATT_BKV > Ntok;
-            const int* sk = sid_k + (jj & 1) * 128;
-            if (use_mask) {
-                const int kk = kbase + tid128;
-                sid_k[(jj & 1) * 128 + tid128] = kk < Ntok ? (int)p.sample_ids[(long long)b * Ntok + kk] : -2;
-                named_bar_sync(1, 128);
-            }
-            mbar_wait(s_full, ph);
-            tc_fence_after();
-            auto mask_chunk = [&](uint32_t (&r)[32], int c0) {      // c0 = first column of the chunk inside the tile
-                if (use_mask) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (!(kbase + c0 + i < Ntok && sk[c0 + i] == sid_q && sid_q != -1)) r[i] = 0xff800000u;
-                } else if (tail) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (kbase + c0 + i >= Ntok) r[i] = 0xff800000u;
-                }
-            };
-            // ---- pass 1: row maximum over the 128 columns (two loads in flight per wait) ----
-            float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                uint32_t r0[32], r1[32];
-                tmem_ld_32x32b_x32(tS + hf * 64, r0);
-                tmem_ld_32x32b_x32(tS + hf * 64 + 32, r1);
-                tmem_ld_wait();
-                mask_chunk(r0, hf * 64);
-                mask_chunk(r1, hf * 64 + 32);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r1[i])); }
-            }
-            const float mx = fmaxf(mx0, mx1) * scl;
-            const float m_new = fmaxf(m_used, mx);
-            const bool grow = m_new > m_used + 8.0f;
-            if (__any_sync(0xffffffffu, grow)) {
-                // lazy rescale of the accumulator (only when the running max grew by more than 2^8)
-                const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_new);
-                if (jj > 0) {
-                    mbar_wait(pv_done, ph ^ 1);               // P.V of the previous tile retired: O quiescent
-                    tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < HD / 32; ++c) {
-                        uint32_t r[32];
-                        tmem_ld_32x32b_x32(tO + c * 32, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                        tmem_st_32x32b_x32(tO + c * 32, r);
-                    }
-                    tmem_st_wait();
-                }
-                l *= alpha;
-                m_used = m_new;
-            }
-            const float mref = (m_used == -INFINITY) ? 0.f : m_used;
-            // ---- pass 2: P = 2^(S * scale - m) as bf16 over the first 64 columns of the S buffer (64 columns at a time: the
-            //      packed chunk lands on S columns that were already consumed) ----
-            float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                uint32_t r0[32], r1[32];
-                tmem_ld_32x32b_x32(tS + hf * 64, r0);
-                tmem_ld_32x32b_x32(tS + hf * 64 + 32, r1);
-                tmem_ld_wait();
-                mask_chunk(r0, hf * 64);
-                mask_chunk(r1, hf * 64 + 32);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float a0 = ex2(fmaf(__uint_as_float(r0[2 * i]), scl, -mref)), a1 = ex2(fmaf(__uint_as_float(r0[2 * i + 1]), scl, -mref));
-                    l0 += a0 + a1;
-                    r0[i] = pack_bf16x2(a0, a1);
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float b0 = ex2(fmaf(__uint_as_float(r1[2 * i]), scl, -mref)), b1 = ex2(fmaf(__uint_as_float(r1[2 * i + 1]), scl, -mref));
-                    l1 += b0 + b1;
-                    r0[16 + i] = pack_bf16x2(b0, b1);
-                }
-                tmem_st_32x32b_x32(tS + hf * 32, r0);
-            }
-            l += l0 + l1;
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(p_full);
-        }
-        // ---- epilogue: O / l, lse ----
-        if (T > 0) mbar_wait(all_done, 0);
-        tc_fence_after();
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
-        __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)row * p.ldo + h * HD;
-#pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-            uint32_t r[32];
-            if (T > 0) {
-                tmem_ld_32x32b_x32(tO + c * 32, r);
-                tmem_ld_wait();
-            }
-            if (inv == 0.f) {                              // fully masked row (padding): O holds no mass / was never written
-#pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = 0u;
-            }
-            if (row < p.N) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 o4;
-                    o4.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
-                    o4.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
-                    o4.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
-                    o4.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = o4;
-                }
-            }
-        }
-        if (row < p.N) p.lse[((long long)b * p.H + h) * p.N + row] = l > 0.f ? (m_used + log2f(l)) * LN2 : INFINITY;
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<TCOLS>(tmem);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Forward v6: v3's dataflow (double-buffered S so that Q.K^T of tile j+1 runs under the softmax of tile j, and the softmax warps
 // never wait for P.V) at HALF the key-tile width, which makes everything small enough for TWO CTAs per SM:
 //   key tiles of 64: S0[64] S1[64] O[HD] = 256 TMEM columns, Q + 2 x (K, V) 64-row stages = 96 KB of shared memory (hd = 128);
-//   four softmax warps, one thread per query row: the 64 scores of a tile live in registers for ONE pass (no second TMEM read as
-//   in v5, no cross-warp exchange of row maxima as in v3); bf16 P overwrites the first 32 columns of its S buffer.
+//   four softmax warps, one thread per query row: the 64 scores of a tile live in registers for ONE pass (no cross-warp
+//   exchange of row maxima as in v3); bf16 P overwrites the first 32 columns of its S buffer.
 // The softmax warps of a CTA run back to back (their only waits are S(j) — computed a tile ahead — and the rare lazy rescale),
 // two CTAs share each SM's MUFU, and the tensor pipe / TMA of one CTA fill the gaps of the other.
 // ------------------------------------------------------------------------------------------------
@@ -1374,14 +1118,12 @@ static int launch_attn_fwd(const void* q, long long ldq, const void* k, long lon
     if (!attr3) {
         UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd6_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
         UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd5_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
         attr3 = true;
     }
-    // A/B switch: 3 = one CTA/SM, double-buffered 128-key S; 5 = two CTAs/SM, single S; 6 = two CTAs/SM, double-buffered 64-key S
+    // A/B switch: 3 = one CTA/SM, double-buffered 128-key S (round 1); 6 = two CTAs/SM, double-buffered 64-key S (default)
     static const int variant = getenv("UD_ATTN_FWD") ? atoi(getenv("UD_ATTN_FWD")) : 6;
     dim3 grid3((p.N + ATT_BQ - 1) / ATT_BQ, p.H, p.B);
     if (variant == 3) attn_fwd3_kernel<HD><<<grid3, 320, smem3, stream>>>(tq, tk, tv, p);
-    else if (variant == 5) attn_fwd5_kernel<HD><<<grid3, 192, smem5, stream>>>(tq, tk, tv, p);
     else attn_fwd6_kernel<HD><<<grid3, 192, smem5, stream>>>(tq, tk64, tv64, p);
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
