@@ -130,7 +130,8 @@ int ud_attn_fwd(const void* q, const void* k, long long ldqk, const void* v, lon
 int ud_attn_fwd_kv(const void* q, long long ldq, long long q_bs, const void* k, long long ldk, long long k_bs, const void* v,
                    long long ldv, long long v_bs, void* o, long long ldo, long long o_bs, float* lse, int B, int Nq, int Nk, int H,
                    int head_dim, float scale, void* stream);
-/* backward: writes dq,dk (bf16, ld lddqk) and dv (bf16, ld lddv).  delta: fp32 [B,H,N] scratch. */
+/* backward: writes dq,dk (bf16, ld lddqk) and dv (bf16, ld lddv).  delta: fp32 scratch of 2*B*H*N floats
+ * ([0] rowsum(dO*O), [1] lse in the exp2 domain; both produced by the kernel's own first pass). */
 int ud_attn_bwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const void* o, const void* d_o,
                 long long ldo, const float* lse, float* delta, void* dq, void* dk, long long lddqk, void* dv, long long lddv,
                 const int64_t* sample_ids, int B, int N, int H, int head_dim, float scale, void* stream);

@@ -121,6 +121,13 @@ __global__ void k_mma_seq(long long* out, int reps) {
                 for (int ks = 0; ks < 8; ++ks) umma_ss(tptr, kmaj(fa, ks, 128), kmaj(sa, ks, 128), id128, ks != 0);
                 for (int ks = 0; ks < 8; ++ks) umma_ss(tptr + 128, kmaj(fb, ks, 128), kmaj(sb, ks, 128), id128, ks != 0);
             }
+            if (VAR == 6 || VAR == 7) {   // scores with the fixed operand (A) in TMEM: only the 64-row B tile is read from smem
+                for (int ks = 0; ks < 8; ++ks) umma_ts(tS, tptr + 384 + ks * 8, kmaj(sa, ks, 64), id64, ks != 0);
+                for (int ks = 0; ks < 8; ++ks) umma_ts(tD, tptr + 448 + ks * 8, kmaj(sb, ks, 64), id64, ks != 0);
+            }
+            if (VAR == 7) {
+                for (int ks = 0; ks < 4; ++ks) umma_ts(tptr + 256, tD + ks * 8, mnmaj(sa, ks, 64), idacc, 1);
+            }
             if (VAR == 1 || VAR == 5) {
                 for (int ks = 0; ks < 8; ++ks) umma_ts(tptr + 256, tptr + ks * 8, mnmaj(sb, ks, 128), idacc, 1);
                 for (int ks = 0; ks < 8; ++ks) umma_ts(tptr + 384, tptr + 128 + ks * 8, mnmaj(sa, ks, 128), idacc, 1);
@@ -204,6 +211,8 @@ int main() {
         run(k_mma_seq<1>, "128q sub-tile: 16 SS N=128 + 16 TS N=128");
         run(k_mma_seq<4>, "  SS part: 16 x 128x128x16");
         run(k_mma_seq<5>, "  TS part: 16 x 128x128x16 (B MN-major)");
+        run(k_mma_seq<6>, "dQ scores, A in TMEM: 16 TS 128x64x16 (B K-major)");
+        run(k_mma_seq<7>, "dQ sub-tile, A in TMEM: 16 TS N=64 + 4 TS N=128");
     }
     k_mbar_pingpong<<<sms, 64>>>(d, 1000); cudaDeviceSynchronize();
     cudaMemcpy(h.data(), d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);

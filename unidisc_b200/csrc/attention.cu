@@ -17,6 +17,21 @@
 #include "common.cuh"
 #include "unidisc_b200.h"
 
+// ------------------------------------------------------------------------------------------------
+// Debug only (-DUD_ATTN_TRACE, tools/attn_trace.py builds its own library with it; the product build never defines it):
+// one CTA writes clock64() stamps of its pipeline events into a global table [event][iteration].
+// ------------------------------------------------------------------------------------------------
+#ifdef UD_ATTN_TRACE
+static long long* g_attn_trace_host = nullptr;           // handed to the kernels through their parameter block (no load on the stamp path)
+extern "C" int ud_attn_set_trace(void* buf) { g_attn_trace_host = static_cast<long long*>(buf); return 0; }
+// UD_TR_INIT evaluates the CTA test once (special-register reads cost tens of cycles each: not on the stamp path)
+#define UD_TR_INIT const bool ud_tr_on = (blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 2)
+#define UD_TR(cond, ev, it) do { if (ud_tr_on && (cond) && (it) < 64) p.trace[(ev) * 64 + (it)] = clock64(); } while (0)
+#else
+#define UD_TR_INIT do { } while (0)
+#define UD_TR(cond, ev, it) do { } while (0)
+#endif
+
 namespace ud {
 
 static constexpr int ATT_BQ = 128;
@@ -29,6 +44,38 @@ UD_DEVINL float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100): one instruction for two adjacent scores.  The softmax loops of
+// all attention kernels are bound by instruction issue (tools/attn_trace.py), not by a pipe, so halving their FMA-pipe
+// instruction count is worth more than any per-pipe balancing.
+UD_DEVINL uint64_t f2pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+UD_DEVINL void f2unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+UD_DEVINL uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+UD_DEVINL uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+UD_DEVINL uint64_t fsub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+UD_DEVINL uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// (Measured and rejected: computing every 4th exponential with a cubic polynomial on the FMA pipe, the FlashAttention-4 trick.
+// MUFU.EX2 is not the limiter of these softmax loops, instruction issue is: the 8 extra FMA/ALU instructions per offloaded
+// exponential made the forward 6 % and the backward 1-4 % slower.)
 
 struct AttnParams {
     int B, N, H;       // N = number of QUERY tokens per sample
@@ -50,15 +97,17 @@ struct AttnParams {
 // softmax instantiation.
 // ------------------------------------------------------------------------------------------------
 static constexpr int MAX_DOC_TILES = 512;
-struct DocTiles {
+template <int CAP>
+struct DocTilesT {
     int n;
-    uint16_t idx[MAX_DOC_TILES];
-    uint8_t nomask[MAX_DOC_TILES];
-    uint8_t code[MAX_DOC_TILES];
+    uint16_t idx[CAP];
+    uint8_t nomask[CAP];
+    uint8_t code[CAP];
 };
+using DocTiles = DocTilesT<MAX_DOC_TILES>;
 
-template <int SUB_ROWS>
-UD_DEVINL void doc_tile_list(const int64_t* __restrict__ ids, int N, int f0, int nsub, DocTiles& tl) {   // whole CTA
+template <int SUB_ROWS, class TL>
+UD_DEVINL void doc_tile_list(const int64_t* __restrict__ ids, int N, int f0, int nsub, TL& tl) {   // whole CTA
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     int fmn = 0x7fffffff, fmx = -1;
     bool funi = true;
@@ -607,20 +656,30 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 m_used = m_new;
             }
             const float mref = (m_used == -INFINITY) ? 0.f : m_used;
-            float l0 = 0.f, l1 = 0.f;
+            // two scores per FFMA2 / FADD2 (the pairs are adjacent TMEM columns = adjacent registers)
+            const uint64_t scl2 = f2pack(scl, scl), nm2 = f2pack(-mref, -mref);
+            uint64_t l2a = 0ull, l2b = 0ull;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float a0 = ex2(fmaf(__uint_as_float(r0[2 * i]), scl, -mref)), a1 = ex2(fmaf(__uint_as_float(r0[2 * i + 1]), scl, -mref));
-                l0 += a0 + a1;
+                float x0, x1;
+                f2unpack(ffma2(f2pack(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1])), scl2, nm2), x0, x1);
+                const float a0 = ex2(x0), a1 = ex2(x1);
+                l2a = fadd2(l2a, f2pack(a0, a1));
                 r0[i] = pack_bf16x2(a0, a1);
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float b0 = ex2(fmaf(__uint_as_float(r1[2 * i]), scl, -mref)), b1 = ex2(fmaf(__uint_as_float(r1[2 * i + 1]), scl, -mref));
-                l1 += b0 + b1;
+                float x0, x1;
+                f2unpack(ffma2(f2pack(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1])), scl2, nm2), x0, x1);
+                const float b0 = ex2(x0), b1 = ex2(x1);
+                l2b = fadd2(l2b, f2pack(b0, b1));
                 r0[16 + i] = pack_bf16x2(b0, b1);
             }
-            l += l0 + l1;
+            {
+                float s0, s1;
+                f2unpack(fadd2(l2a, l2b), s0, s1);
+                l += s0 + s1;
+            }
             tmem_st_32x32b_x32(tS, r0);                   // P over the first 32 columns of this S buffer
             tmem_st_wait();
             tc_fence_before();
@@ -669,7 +728,8 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 // delta[b,h,n] = sum_d o[n,d] * do[n,d]   (softmax backward row term)
 // ------------------------------------------------------------------------------------------------
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, long long ldo,
-                                  float* __restrict__ delta, int B, int N, int H, int HD) {
+                                  float* __restrict__ delta, int B, int N, int H, int HD,
+                                  const float* __restrict__ lse = nullptr, float* __restrict__ lse2 = nullptr) {
     // one warp per (token, head)
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -688,6 +748,8 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
     if (lane == 0) {
         const int bb = (int)(tok / N), n = (int)(tok % N);
         delta[((long long)bb * H + hh) * N + n] = acc;
+        // the v3 dK/dV kernel reads the per-query log-sum-exp already in the exp2 domain (one FFMA + EX2 per score)
+        if (lse2 != nullptr) lse2[((long long)bb * H + hh) * N + n] = -lse[((long long)bb * H + hh) * N + n] * 1.4426950408889634f;
     }
 }
 
@@ -712,12 +774,16 @@ struct AttnBwdParams {
     long long ld0, ld1;
     const int64_t* sample_ids;
     int safe_order;
+    const float* lse2;    // v3: -lse * log2(e) (added by the FFMA in front of exp2), written by the delta pass (second half of the caller's delta scratch)
     // v2 dQ kernel only: it forms delta = rowsum(dO * O) for its own 128 query rows (and publishes it for the dK/dV kernel,
     // which runs after it), so no separate pass over O and dO is launched
     const __nv_bfloat16* o;
     const __nv_bfloat16* d_o;
     long long ldo;
     float* delta_out;
+#ifdef UD_ATTN_TRACE
+    long long* trace;
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -770,6 +836,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
     const int t0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int T2all = (p.N + 63) / 64;
     const bool use_ids = p.sample_ids != nullptr;
+    UD_TR_INIT;
+    UD_TR(threadIdx.x == 0, 17, 0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_fa); tma_prefetch_desc(&tm_fb); tma_prefetch_desc(&tm_sa); tma_prefetch_desc(&tm_sb);
@@ -806,6 +874,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 const int s = i % NST;
                 const int sub = sub_of(i);
                 mbar_wait(&st_empty[s], ((i / NST) & 1) ^ 1);
+                UD_TR(true, 13, i);
                 mbar_expect_tx(&st_full[s], 2 * S::SUB_BYTES);
                 uint8_t* sa = sST + s * 2 * S::SUB_BYTES;
                 uint8_t* sb = sa + S::SUB_BYTES;
@@ -827,6 +896,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 const int s = i % NST, bf = i & 1;
                 mbar_wait(&st_full[s], (i / NST) & 1);
                 tc_fence_after();
+                UD_TR(leader, 0, i);
                 const uint32_t aSA = smem_u32(sST + s * 2 * S::SUB_BYTES), aSB = aSA + S::SUB_BYTES;
                 const uint32_t tSc = tmem + bf * 128, tDp = tSc + 64;
                 if (leader) {
@@ -839,9 +909,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                     for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tDp, desc_kmajor(aFB, ks), desc_kmajor64(aSB, ks), idesc_sc, ks != 0);
                     umma_commit(&dp_full[bf]);
                 }
+                UD_TR(leader, 1, i);
                 __syncwarp();
             };
             mbar_wait(f_full, 0);
+            UD_TR(leader, 17, 1);
             issue_scores(0);
             if (T2 > 1) issue_scores(1);
             for (int i = 0; i < T2; ++i) {
@@ -854,6 +926,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                     // dV += P^T dO as soon as P^T is stored: it runs while the warpgroup still forms dS^T
                     mbar_wait(&p_rdy[bf], ph);
                     tc_fence_after();
+                    UD_TR(leader, 2, i);
                     if (leader) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc1, tSc + ks * 8, desc_mnmajor64(aSB, ks), idesc_acc, acc0 | (ks != 0));
@@ -862,6 +935,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 }
                 mbar_wait(&ds_rdy[bf], ph);
                 tc_fence_after();
+                UD_TR(leader, 3, i);
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) umma_ts(tAcc0, tDp + ks * 8, desc_mnmajor64(aSA, ks), idesc_acc, acc0 | (ks != 0));
@@ -869,6 +943,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                     umma_commit(&acc_done[bf]);
                     if (i + 1 == T2) umma_commit(all_done);
                 }
+                UD_TR(leader, 4, i);
                 __syncwarp();
                 if (i + 2 < T2) {
                     // scores(i+2) overwrite the columns the accumulation MMAs above read P / dS from.  tcgen05.mma issued by
@@ -923,7 +998,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             if ((MODE == 0 || use_ids) && tid128 < 64 && ii < T2) {
                 const int cidx = sub_of(ii) * 64 + tid128;
                 if (MODE == 0) {
-                    pf_lse = cidx < Ntok ? p.lse[bh * Ntok + cidx] * LOG2E : INFINITY;
+                    pf_lse = cidx < Ntok ? -p.lse[bh * Ntok + cidx] * LOG2E : -INFINITY;      // negated: added by the FFMA
                     pf_dlt = cidx < Ntok ? p.delta[bh * Ntok + cidx] : 0.f;
                 }
                 if (use_ids) pf_sid = cidx < Ntok ? (int)p.sample_ids[(long long)b * Ntok + cidx] : -2;
@@ -941,8 +1016,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 named_bar_sync(1 + wg, 128);
                 fetch_meta(ii + 2);
             }
+            UD_TR(tid128 == 0, 14, ii);
             mbar_wait(&s_full[bf], (ii >> 1) & 1);
             tc_fence_after();
+            UD_TR(tid128 == 0, 5, ii);
             // masks are needed only on edge tiles and on tile pairs that straddle a document boundary / hold padding
             const bool doc_mask = use_ids && !tl.nomask[ii];
             const bool slow = doc_mask || (i * 64 + 64 > Ntok) || !row_ok;
@@ -950,24 +1027,28 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             tmem_ld_32x32b_x32(tSc + lane_off, rsA);
             tmem_ld_32x32b_x32(tSc + 32 + lane_off, rsB);
             tmem_ld_wait();
+            UD_TR(tid128 == 0, 6, ii);
             // phase 1: P = exp(S * scale - lse), kept in fp32 in rsA / rsB (in place) and packed to bf16 in pk.  Interior tiles
             // take the mask-free instantiation (no per-element compare / select instructions).
             auto phase1 = [&](uint32_t (&rs)[32], int c, auto slow_tag) {
                 constexpr bool SLOW = decltype(slow_tag)::value;
+                const uint64_t scl2 = f2pack(scl, scl), nl_row2 = f2pack(-lse_row, -lse_row);
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
-                    float l4[4];
+                    uint64_t nl2[2] = {nl_row2, nl_row2};                      // -lse of the two column pairs
                     if (MODE == 0) {
                         const float4 lv = *reinterpret_cast<const float4*>(&s_lse[ms + c * 32 + e4 * 4]);
-                        l4[0] = lv.x; l4[1] = lv.y; l4[2] = lv.z; l4[3] = lv.w;
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) l4[u] = lse_row;
+                        nl2[0] = f2pack(lv.x, lv.y); nl2[1] = f2pack(lv.z, lv.w);
                     }
                     float pv[4];
 #pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        float x0, x1;
+                        f2unpack(ffma2(f2pack(__uint_as_float(rs[e4 * 4 + 2 * h2]), __uint_as_float(rs[e4 * 4 + 2 * h2 + 1])), scl2, nl2[h2]), x0, x1);
+                        pv[2 * h2] = ex2(x0); pv[2 * h2 + 1] = ex2(x1);
+                    }
+#pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        float pr = ex2(fmaf(__uint_as_float(rs[e4 * 4 + u]), scl, -l4[u]));
                         if (SLOW) {
                             const int col = c * 32 + e4 * 4 + u;
                             bool ok = row_ok && (i * 64 + col < Ntok);
@@ -975,10 +1056,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                                 const int sq = s_sid[ms + col];
                                 ok = ok && sq == sid_row && sid_row != -1;
                             }
-                            if (!ok) pr = 0.f;
+                            if (!ok) pv[u] = 0.f;
                         }
-                        pv[u] = pr;
-                        rs[e4 * 4 + u] = __float_as_uint(pr);
+                        rs[e4 * 4 + u] = __float_as_uint(pv[u]);
                     }
                     if (MODE == 0) {
                         pk[c * 16 + e4 * 2] = pack_bf16x2(pv[0], pv[1]);
@@ -993,48 +1073,55 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                 phase1(rsA, 0, std::false_type{});
                 phase1(rsB, 1, std::false_type{});
             }
+            UD_TR(tid128 == 0, 7, ii);
             if (MODE == 0) {
                 tmem_st_32x32b_x32(tSc + lane_off, pk);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_rdy[bf]);
+                UD_TR(tid128 == 0, 8, ii);
             }
             // phase 2: dS = P * (dP - delta)
             mbar_wait(&dp_full[bf], (ii >> 1) & 1);
             tc_fence_after();
+            UD_TR(tid128 == 0, 9, ii);
             uint32_t rdA[32], rdB[32];
             tmem_ld_32x32b_x32(tDp + lane_off, rdA);
             tmem_ld_32x32b_x32(tDp + 32 + lane_off, rdB);
             tmem_ld_wait();
+            UD_TR(tid128 == 0, 10, ii);
             auto phase2 = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c) {
+                const uint64_t d_row2 = f2pack(dlt_row, dlt_row);
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
-                    float d4[4];
+                    uint64_t d2[2] = {d_row2, d_row2};
                     if (MODE == 0) {
                         const float4 dv = *reinterpret_cast<const float4*>(&s_dlt[ms + c * 32 + e4 * 4]);
-                        d4[0] = dv.x; d4[1] = dv.y; d4[2] = dv.z; d4[3] = dv.w;
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) d4[u] = dlt_row;
+                        d2[0] = f2pack(dv.x, dv.y); d2[1] = f2pack(dv.z, dv.w);
                     }
-                    float dvv[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        dvv[u] = __uint_as_float(rs[e4 * 4 + u]) * (__uint_as_float(rd[e4 * 4 + u]) - d4[u]);
-                    pk[c * 16 + e4 * 2] = pack_bf16x2(dvv[0], dvv[1]);
-                    pk[c * 16 + e4 * 2 + 1] = pack_bf16x2(dvv[2], dvv[3]);
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int e = e4 * 4 + 2 * h2;
+                        float v0, v1;
+                        f2unpack(fmul2(f2pack(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1])),
+                                       fsub2(f2pack(__uint_as_float(rd[e]), __uint_as_float(rd[e + 1])), d2[h2])), v0, v1);
+                        pk[c * 16 + e4 * 2 + h2] = pack_bf16x2(v0, v1);
+                    }
                 }
             };
             phase2(rsA, rdA, 0);
             phase2(rsB, rdB, 1);
+            UD_TR(tid128 == 0, 11, ii);
             tmem_st_32x32b_x32(tDp + lane_off, pk);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&ds_rdy[bf]);
+            UD_TR(tid128 == 0, 12, ii);
         }
         // ---- write the accumulators (the two warpgroups split the work) ----
         if (T2 > 0) mbar_wait(all_done, 0);
         tc_fence_after();
+        UD_TR(tid128 == 0, 15, wg);
         {
             // MODE0: warpgroup 0 stores dK (Acc0), warpgroup 1 stores dV (Acc1).  MODE1: each stores half of dQ's columns.
             // TMEM gives every thread one ROW; the bf16 rows are staged in the (now idle) fixed-operand tiles with the
@@ -1079,7 +1166,454 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                     *reinterpret_cast<uint4*>(base + (long long)rr * ldo + ch * 8) = v;
                 }
             }
+            UD_TR(tid128 == 0, 16, wg);
         }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward v3.  Measured on the v2 kernels with in-kernel clock stamps (tools/attn_trace.py) and tools/ubench: a 128xNx16
+// tcgen05.mma costs ~47 cycles at N=64 against ~65 at N=128 whether its A operand comes from shared memory or TMEM, so the
+// 64-row streamed sub-tiles of v2 pay 72 % of the tensor time for 50 % of the work, and every sub-tile costs four
+// warpgroup <-> tensor-pipe hand-offs.  v3 streams full 128-row tiles (all MMAs are 128x128x16) and lets BOTH softmax
+// warpgroups work on every tile, each on 64 of its 128 columns:
+//   dK/dV kernel (CTA owns key tile j, streams query tiles i), TMEM = St/Pt[128] | dPt/dSt[128] | dK[HD] | dV[HD]
+//       issue order  dV(i), St(i+1), dK(i), dPt(i+1):  St(i+1) runs under the dS arithmetic of tile i
+//   dQ kernel (CTA owns query tile i, streams key tiles j),   TMEM = S0[128] | S1[128] | dP[128] | dQ[HD]
+//       S is double buffered (dS is written over the S it came from), dP single buffered but released as soon as the
+//       warpgroups hold it in registers:  issue order  dP(j+1), dQ(j), S(j+2)
+// The streamed operand that is read twice a tile apart (Q_i: St(i) ... dK(i);  K_j: S(j) ... dQ(j)) sits in a 3-deep ring,
+// the other one (dO_i / V_j) in a 2-deep ring: 2 fixed + 5 streamed 32 KB tiles = the whole 227 KB.  Per-column metadata
+// (log-sum-exp in the exp2 domain, delta, sample ids) is read straight from global memory with warp-uniform 16-byte loads
+// (L1 hits): no shared staging, no named barriers in the loop.
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+struct AttnBwd3Smem {
+    static constexpr int TILE = 128 * HD * 2;
+    static constexpr int NA = 3, NB = 2;
+    static constexpr int NBOX = HD / 64;
+    static constexpr int NTILE = 2 + NA + NB;
+    static constexpr int META = 2048;                    // barriers, TMEM pointer, document tile list
+    static constexpr int BYTES = NTILE * TILE + 1024 + META;
+};
+static constexpr int MAX_DOC_TILES3 = 256;
+using DocTiles3 = DocTilesT<MAX_DOC_TILES3>;
+
+// TMEM column (relative to the tile's first column) of the bf16 A operand of reduction step ks: warpgroup w = ks / 4 packs its
+// 64 probabilities into the first 32 columns of its own 64-column half
+UD_DEVINL uint32_t bwd3_pcol(int ks) { return (uint32_t)((ks >> 2) * 64 + (ks & 3) * 8); }
+
+// one elected lane per warp signals on behalf of its 32 rows (after every lane's TMEM stores / loads have completed)
+UD_DEVINL void warp_arrive(uint64_t* bar, int lane) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+// P = exp2(S * scl - lse) over this thread's 64 columns (fp32 kept in rs*, for the dS product); SLOW applies the edge /
+// document masks.  COLMETA: lse varies per column (dK/dV kernel) and is read from lse_col; else lse_row.
+template <bool COLMETA, bool SLOW>
+UD_DEVINL void bwd3_probs(uint32_t (&rsA)[32], uint32_t (&rsB)[32], uint32_t (&pk)[32], float scl, float lse_row,
+                          const float* __restrict__ nlse_col, int col0, int Ntok, bool row_ok, bool doc_mask, int sid_row,
+                          const int64_t* __restrict__ sid_col) {
+    const uint64_t scl2 = f2pack(scl, scl), nl_row2 = f2pack(-lse_row, -lse_row);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t (&rs)[32] = c == 0 ? rsA : rsB;
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+            uint64_t nl2[2] = {nl_row2, nl_row2};                  // -lse (exp2 domain) of the two column pairs
+            if (COLMETA) {
+                if (!SLOW) {
+                    const float4 lv = __ldg(reinterpret_cast<const float4*>(nlse_col + c * 32 + e4 * 4));
+                    nl2[0] = f2pack(lv.x, lv.y); nl2[1] = f2pack(lv.z, lv.w);
+                } else {
+                    float l4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) l4[u] = (col0 + c * 32 + e4 * 4 + u < Ntok) ? __ldg(nlse_col + c * 32 + e4 * 4 + u) : -INFINITY;
+                    nl2[0] = f2pack(l4[0], l4[1]); nl2[1] = f2pack(l4[2], l4[3]);
+                }
+            }
+            float pv[4];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                float x0, x1;
+                f2unpack(ffma2(f2pack(__uint_as_float(rs[e4 * 4 + 2 * h2]), __uint_as_float(rs[e4 * 4 + 2 * h2 + 1])), scl2, nl2[h2]), x0, x1);
+                pv[2 * h2] = ex2(x0); pv[2 * h2 + 1] = ex2(x1);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (SLOW) {
+                    const int col = col0 + c * 32 + e4 * 4 + u;
+                    bool ok = row_ok && col < Ntok;
+                    if (doc_mask && ok) ok = (int)__ldg(sid_col + c * 32 + e4 * 4 + u) == sid_row && sid_row != -1;
+                    if (!ok) pv[u] = 0.f;
+                }
+                rs[e4 * 4 + u] = __float_as_uint(pv[u]);
+            }
+            if (COLMETA) {       // dK/dV kernel: the bf16 probabilities are an MMA operand themselves
+                pk[c * 16 + e4 * 2] = pack_bf16x2(pv[0], pv[1]);
+                pk[c * 16 + e4 * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+            }
+        }
+    }
+}
+
+// dS = P * (dP - delta) for the 32-column chunk c of this thread's 64 columns, packed to bf16 pairs
+template <bool COLMETA, bool SLOW>
+UD_DEVINL void bwd3_ds(const uint32_t (&rs)[32], const uint32_t (&rd)[32], uint32_t (&pk)[32], int c, float dlt_row,
+                       const float* __restrict__ dlt_col, int col0, int Ntok) {
+    const uint64_t d_row2 = f2pack(dlt_row, dlt_row);
+#pragma unroll
+    for (int e4 = 0; e4 < 8; ++e4) {
+        uint64_t d2[2] = {d_row2, d_row2};
+        if (COLMETA) {
+            if (!SLOW) {
+                const float4 dv = __ldg(reinterpret_cast<const float4*>(dlt_col + c * 32 + e4 * 4));
+                d2[0] = f2pack(dv.x, dv.y); d2[1] = f2pack(dv.z, dv.w);
+            } else {
+                float d4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) d4[u] = (col0 + c * 32 + e4 * 4 + u < Ntok) ? __ldg(dlt_col + c * 32 + e4 * 4 + u) : 0.f;
+                d2[0] = f2pack(d4[0], d4[1]); d2[1] = f2pack(d4[2], d4[3]);
+            }
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int e = e4 * 4 + 2 * h2;
+            float v0, v1;
+            f2unpack(fmul2(f2pack(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1])),
+                           fsub2(f2pack(__uint_as_float(rd[e]), __uint_as_float(rd[e + 1])), d2[h2])), v0, v1);
+            pk[c * 16 + e4 * 2 + h2] = pack_bf16x2(v0, v1);
+        }
+    }
+}
+
+// accumulator -> bf16 rows staged (XOR-swizzled 16-byte chunks) in an idle fixed-operand tile -> coalesced global stores.
+// One warpgroup (128 threads, thread = row) writes columns [c_lo*32, c_hi*32) of a [128][HD] accumulator.
+template <int HD>
+UD_DEVINL void bwd3_store_acc(uint32_t tA, uint32_t lane_off, uint8_t* stg, int rloc, int tid128, int bar_id, int c_lo, int c_hi,
+                              float sc, bool zero, __nv_bfloat16* base, long long ldo, int rows_left) {
+    constexpr int CPR = HD * 2 / 16;
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tA + c * 32 + lane_off, r);
+        tmem_ld_wait();
+        if (zero) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = 0u;
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 o4;
+            o4.x = pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) * sc, __uint_as_float(r[8 * q4 + 1]) * sc);
+            o4.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * sc, __uint_as_float(r[8 * q4 + 3]) * sc);
+            o4.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * sc, __uint_as_float(r[8 * q4 + 5]) * sc);
+            o4.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * sc, __uint_as_float(r[8 * q4 + 7]) * sc);
+            const int ch = c * 4 + q4;
+            *reinterpret_cast<uint4*>(stg + rloc * (HD * 2) + ((ch ^ (rloc & (CPR - 1))) << 4)) = o4;
+        }
+    }
+    named_bar_sync(bar_id, 128);
+    const int chunks_w = (c_hi - c_lo) * 4, chunk0 = c_lo * 4;
+#pragma unroll 4
+    for (int it = 0; it < chunks_w; ++it) {
+        const int idx = it * 128 + tid128;
+        const int rr = idx / chunks_w, ch = chunk0 + idx % chunks_w;
+        if (rr < rows_left) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * (HD * 2) + ((ch ^ (rr & (CPR - 1))) << 4));
+            *reinterpret_cast<uint4*>(base + (long long)rr * ldo + ch * 8) = v;
+        }
+    }
+}
+
+// MODE 0: dK/dV (fixed K_j, V_j; ring A = Q_i, ring B = dO_i).  MODE 1: dQ (fixed Q_i, dO_i; ring A = K_j, ring B = V_j).
+template <int HD, int MODE>
+__global__ void __launch_bounds__(320, 1)
+attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fb,
+                 const __grid_constant__ CUtensorMap tm_ra, const __grid_constant__ CUtensorMap tm_rb, const AttnBwdParams p) {
+    using S = AttnBwd3Smem<HD>;
+    constexpr int NA = S::NA, NB = S::NB, TILE = S::TILE;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sFA = smem;
+    uint8_t* sFB = sFA + TILE;
+    uint8_t* sRA = sFB + TILE;                  // [NA]
+    uint8_t* sRB = sRA + NA * TILE;             // [NB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRB + NB * TILE);
+    uint64_t* f_full = bars;                   // 1
+    uint64_t* a_full = bars + 1;               // NA
+    uint64_t* a_empty = a_full + NA;           // NA
+    uint64_t* b_full = a_empty + NA;           // NB
+    uint64_t* b_empty = b_full + NB;           // NB
+    uint64_t* s_full = b_empty + NB;           // 2 (MODE 0 uses [0])   scores in TMEM
+    uint64_t* dp_full = s_full + 2;            // 1
+    uint64_t* p_rdy = dp_full + 1;             // 1   MODE 0: bf16 P^T stored          MODE 1: dP copied to registers (buffer free)
+    uint64_t* ds_rdy = p_rdy + 1;              // 1   bf16 dS stored
+    uint64_t* all_done = ds_rdy + 1;           // 1   completes exactly once (see v2)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(all_done + 1);
+    DocTiles3& tl = *reinterpret_cast<DocTiles3*>(tmem_ptr_smem + 4);
+    static_assert((1 + 2 * NA + 2 * NB + 6) * 8 + 16 + sizeof(DocTiles3) <= S::META, "metadata area too small");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int Tall = (p.N + 127) / 128;
+    const bool use_ids = p.sample_ids != nullptr;
+    UD_TR_INIT;
+    UD_TR(threadIdx.x == 0, 17, 0);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_fa); tma_prefetch_desc(&tm_fb); tma_prefetch_desc(&tm_ra); tma_prefetch_desc(&tm_rb);
+        mbar_init(f_full, 1);
+        for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(dp_full, 1);
+        mbar_init(p_rdy, 8); mbar_init(ds_rdy, 8);
+        mbar_init(all_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+    // MODE 0: R0 = St/Pt, R1 = dPt/dSt, accumulators dK | dV.   MODE 1: S0, S1, dP, accumulator dQ.
+    const uint32_t tR0 = tmem, tR1 = tmem + 128;
+    const uint32_t tAcc0 = MODE == 0 ? tmem + 256 : tmem + 384;       // dK | dQ
+    const uint32_t tAcc1 = tmem + 256 + HD;                            // dV (MODE 0)
+    const uint32_t tDP = MODE == 0 ? tR1 : tmem + 256;
+    if (use_ids) doc_tile_list<128>(p.sample_ids + (long long)b * p.N, p.N, t0, Tall, tl);
+    const int T = use_ids ? tl.n : Tall;
+    auto tile_of = [&](int ii) { return use_ids ? (int)tl.idx[ii] : ii; };
+
+    if (warp == 0) {
+        if (lane == 0 && T > 0) {
+            mbar_expect_tx(f_full, 2 * TILE);
+#pragma unroll
+            for (int bx = 0; bx < S::NBOX; ++bx) {
+                tma_load_3d(sFA + bx * (128 * 128), &tm_fa, f_full, h * HD + bx * 64, t0, b);
+                tma_load_3d(sFB + bx * (128 * 128), &tm_fb, f_full, h * HD + bx * 64, t0, b);
+            }
+            for (int i = 0; i < T; ++i) {
+                const int sa = i % NA, sb = i % NB, t = tile_of(i);
+                mbar_wait(&a_empty[sa], ((i / NA) & 1) ^ 1);
+                UD_TR(true, 13, i);
+                mbar_expect_tx(&a_full[sa], TILE);
+#pragma unroll
+                for (int bx = 0; bx < S::NBOX; ++bx)
+                    tma_load_3d(sRA + sa * TILE + bx * (128 * 128), &tm_ra, &a_full[sa], h * HD + bx * 64, t * 128, b);
+                mbar_wait(&b_empty[sb], ((i / NB) & 1) ^ 1);
+                mbar_expect_tx(&b_full[sb], TILE);
+#pragma unroll
+                for (int bx = 0; bx < S::NBOX; ++bx)
+                    tma_load_3d(sRB + sb * TILE + bx * (128 * 128), &tm_rb, &b_full[sb], h * HD + bx * 64, t * 128, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (T > 0) {
+            const uint32_t leader = elect_one();
+            constexpr uint32_t idesc_sc = make_idesc_bf16(128, 128, false, false);
+            constexpr uint32_t idesc_acc = make_idesc_bf16(128, HD, false, true);
+            const uint32_t aFA = smem_u32(sFA), aFB = smem_u32(sFB), aRA = smem_u32(sRA), aRB = smem_u32(sRB);
+            // scores of tile i from ring A (MODE 0: St = K_j Q_i^T -> R0;  MODE 1: S = Q_i K_j^T -> S[i & 1])
+            auto issue_s = [&](int i) {
+                const int sa = i % NA;
+                mbar_wait(&a_full[sa], (i / NA) & 1);
+                tc_fence_after();
+                UD_TR(leader, 0, i);
+                const uint32_t tS = MODE == 0 ? tR0 : tmem + (i & 1) * 128;
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tS, desc_kmajor(aFA, ks), desc_kmajor(aRA + sa * TILE, ks), idesc_sc, ks != 0);
+                    umma_commit(&s_full[MODE == 0 ? 0 : (i & 1)]);
+                }
+                UD_TR(leader, 1, i);
+                __syncwarp();
+            };
+            // dP of tile i from ring B (MODE 0: dPt = V_j dO_i^T;  MODE 1: dP = dO_i V_j^T).  MODE 1: the last read of V_j.
+            auto issue_dp = [&](int i) {
+                const int sb = i % NB;
+                mbar_wait(&b_full[sb], (i / NB) & 1);
+                tc_fence_after();
+                UD_TR(leader, 18, i);
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks) umma_ss(tDP, desc_kmajor(aFB, ks), desc_kmajor(aRB + sb * TILE, ks), idesc_sc, ks != 0);
+                    umma_commit(dp_full);
+                    if (MODE == 1) umma_commit(&b_empty[sb]);
+                }
+                UD_TR(leader, 19, i);
+                __syncwarp();
+            };
+            mbar_wait(f_full, 0);
+            UD_TR(leader, 17, 1);
+            issue_s(0);
+            issue_dp(0);
+            if (MODE == 1 && T > 1) issue_s(1);
+            for (int i = 0; i < T; ++i) {
+                const int sa = i % NA, sb = i % NB;
+                const uint32_t ph = i & 1;
+                const uint32_t acc0 = i != 0;
+                if (MODE == 0) {
+                    mbar_wait(p_rdy, ph);
+                    tc_fence_after();
+                    UD_TR(leader, 2, i);
+                    if (leader) {
+                        // dV += Pt dO_i  (reduction over the 128 queries of the tile; dO_i re-read MN-major).  Last read of dO_i.
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) umma_ts(tAcc1, tR0 + bwd3_pcol(ks), desc_mnmajor(aRB + sb * TILE, ks), idesc_acc, acc0 | (ks != 0));
+                        umma_commit(&b_empty[sb]);
+                    }
+                    __syncwarp();
+                    // St(i+1) overwrites Pt(i): tcgen05.mma issued by one thread execute in issue order (as v2 relies on)
+                    if (i + 1 < T) issue_s(i + 1);
+                } else {
+                    if (i + 1 < T) {
+                        mbar_wait(p_rdy, ph);            // both warpgroups hold dP(i) in registers
+                        tc_fence_after();
+                        UD_TR(leader, 2, i);
+                        issue_dp(i + 1);
+                    }
+                }
+                mbar_wait(ds_rdy, ph);
+                tc_fence_after();
+                UD_TR(leader, 3, i);
+                if (leader) {
+                    // MODE 0: dK += dSt Q_i.   MODE 1: dQ += dS K_j.   Last read of the ring-A tile.
+                    const uint32_t tA = MODE == 0 ? tR1 : tmem + (i & 1) * 128;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) umma_ts(tAcc0, tA + bwd3_pcol(ks), desc_mnmajor(aRA + sa * TILE, ks), idesc_acc, acc0 | (ks != 0));
+                    umma_commit(&a_empty[sa]);
+                    if (i + 1 == T) umma_commit(all_done);
+                }
+                UD_TR(leader, 4, i);
+                __syncwarp();
+                if (MODE == 0) {
+                    if (i + 1 < T) issue_dp(i + 1);      // overwrites dSt(i) after dK(i) has read it (issue order)
+                } else {
+                    if (i + 2 < T) issue_s(i + 2);       // overwrites dS(i) after dQ(i) has read it
+                }
+            }
+        }
+    } else {
+        // two warpgroups (warps 2-5, 6-9); thread = accumulator row (MODE 0: key, MODE 1: query); warpgroup w handles the 64
+        // streamed columns [64w, 64w+64) of every tile
+        const int wg = (warp - 2) >> 2;
+        const int qd = warp & 3;
+        const int rloc = qd * 32 + lane;
+        const int row = t0 + rloc;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const int tid128 = (threadIdx.x - 64) & 127;
+        const long long bh = (long long)b * p.H + h;
+        const int Ntok = p.N;
+        const bool row_ok = row < Ntok;
+        int sid_row = 0;
+        if (use_ids) sid_row = row_ok ? (int)p.sample_ids[(long long)b * Ntok + row] : -1;
+        float lse_row = 0.f, dlt_row = 0.f;
+        if (MODE == 1 && row_ok) {
+            lse_row = p.lse[bh * Ntok + row] * LOG2E;
+            dlt_row = p.delta[bh * Ntok + row];
+        }
+        const float scl = p.scale_log2;
+        const uint32_t cb = (uint32_t)(wg * 64);
+        const bool vec_ok = (Ntok & 3) == 0;           // 16-byte metadata loads need aligned per-head rows
+        // MODE 0: the per-column metadata of a tile (64 lse2 + 64 delta floats per warpgroup = four 128-byte lines) is pulled into
+        // L1 one tile ahead by lanes 0-3 of every warp, so the warp-uniform loads in the softmax loops hit L1 (~35 cycles) instead
+        // of paying an L2 / DRAM round trip per tile on the critical path
+        auto prefetch_meta = [&](int ii) {
+            if (MODE == 0 && ii < T && lane < 4) {
+                const int c0 = tile_of(ii) * 128 + wg * 64 + (lane & 1) * 32;
+                if (c0 < Ntok) {
+                    const float* src = ((lane & 2) ? p.delta : p.lse2) + bh * Ntok + c0;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
+                }
+            }
+        };
+        prefetch_meta(0);
+        for (int ii = 0; ii < T; ++ii) {
+            prefetch_meta(ii + 1);
+            const int t = tile_of(ii);
+            const int col0 = t * 128 + wg * 64;       // first streamed index (MODE 0: query, MODE 1: key) of this warpgroup
+            const bool doc_mask = use_ids && !tl.nomask[ii];
+            const bool slow = doc_mask || (t * 128 + 128 > Ntok) || !row_ok || (MODE == 0 && !vec_ok);
+            const float* lse_col = MODE == 0 ? p.lse2 + bh * Ntok + col0 : nullptr;
+            const float* dlt_col = MODE == 0 ? p.delta + bh * Ntok + col0 : nullptr;
+            const int64_t* sid_col = use_ids ? p.sample_ids + (long long)b * Ntok + col0 : nullptr;
+            const uint32_t tS = (MODE == 0 ? tR0 : tmem + (ii & 1) * 128) + cb;
+            UD_TR(tid128 == 0, 14, ii + 32 * wg);
+            mbar_wait(&s_full[MODE == 0 ? 0 : (ii & 1)], MODE == 0 ? (ii & 1) : ((ii >> 1) & 1));
+            tc_fence_after();
+            UD_TR(tid128 == 0, 5, ii + 32 * wg);
+            uint32_t rsA[32], rsB[32], pk[32];
+            tmem_ld_32x32b_x32(tS + lane_off, rsA);
+            tmem_ld_32x32b_x32(tS + 32 + lane_off, rsB);
+            tmem_ld_wait();
+            UD_TR(tid128 == 0, 6, ii + 32 * wg);
+            if (slow) bwd3_probs<MODE == 0, true>(rsA, rsB, pk, scl, lse_row, lse_col, col0, Ntok, row_ok, doc_mask, sid_row, sid_col);
+            else bwd3_probs<MODE == 0, false>(rsA, rsB, pk, scl, lse_row, lse_col, col0, Ntok, row_ok, doc_mask, sid_row, sid_col);
+            UD_TR(tid128 == 0, 7, ii + 32 * wg);
+            if (MODE == 0) {
+                tmem_st_32x32b_x32(tS + lane_off, pk);
+                tmem_st_wait();
+                warp_arrive(p_rdy, lane);
+                UD_TR(tid128 == 0, 8, ii + 32 * wg);
+            }
+            mbar_wait(dp_full, ii & 1);
+            tc_fence_after();
+            UD_TR(tid128 == 0, 9, ii + 32 * wg);
+            if (MODE == 0) {
+                // one 32-column chunk of dPt at a time (the fp32 probabilities stay live: register budget)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t rd[32];
+                    tmem_ld_32x32b_x32(tDP + cb + c * 32 + lane_off, rd);
+                    tmem_ld_wait();
+                    if (slow) bwd3_ds<true, true>(c == 0 ? rsA : rsB, rd, pk, c, dlt_row, dlt_col, col0, Ntok);
+                    else bwd3_ds<true, false>(c == 0 ? rsA : rsB, rd, pk, c, dlt_row, dlt_col, col0, Ntok);
+                }
+                UD_TR(tid128 == 0, 11, ii + 32 * wg);
+            } else {
+                uint32_t rdA[32], rdB[32];
+                tmem_ld_32x32b_x32(tDP + cb + lane_off, rdA);
+                tmem_ld_32x32b_x32(tDP + cb + 32 + lane_off, rdB);
+                tmem_ld_wait();
+                warp_arrive(p_rdy, lane);              // dP buffer may be overwritten by dP(j+1)
+                UD_TR(tid128 == 0, 10, ii + 32 * wg);
+                if (slow) { bwd3_ds<false, true>(rsA, rdA, pk, 0, dlt_row, dlt_col, col0, Ntok); bwd3_ds<false, true>(rsB, rdB, pk, 1, dlt_row, dlt_col, col0, Ntok); }
+                else { bwd3_ds<false, false>(rsA, rdA, pk, 0, dlt_row, dlt_col, col0, Ntok); bwd3_ds<false, false>(rsB, rdB, pk, 1, dlt_row, dlt_col, col0, Ntok); }
+                UD_TR(tid128 == 0, 11, ii + 32 * wg);
+            }
+            // MODE 0: dSt over dPt (R1).  MODE 1: dS over the S buffer it came from.
+            tmem_st_32x32b_x32((MODE == 0 ? tR1 + cb : tS) + lane_off, pk);
+            tmem_st_wait();
+            warp_arrive(ds_rdy, lane);
+            UD_TR(tid128 == 0, 12, ii + 32 * wg);
+        }
+        if (T > 0) mbar_wait(all_done, 0);
+        tc_fence_after();
+        UD_TR(tid128 == 0, 15, wg);
+        const int rows_left = Ntok - t0;
+        if (MODE == 0) {
+            // warpgroup 0 stores dK (scaled), warpgroup 1 stores dV
+            const uint32_t tA = wg == 0 ? tAcc0 : tAcc1;
+            __nv_bfloat16* base = (wg == 0 ? p.out0 : p.out1) + ((long long)b * Ntok + t0) * (wg == 0 ? p.ld0 : p.ld1) + h * HD;
+            bwd3_store_acc<HD>(tA, lane_off, wg == 0 ? sFA : sFB, rloc, tid128, 1 + wg, 0, HD / 32, wg == 0 ? p.scale : 1.0f, T == 0,
+                               base, wg == 0 ? p.ld0 : p.ld1, rows_left);
+        } else {
+            // each warpgroup stores half of dQ's columns
+            __nv_bfloat16* base = p.out0 + ((long long)b * Ntok + t0) * p.ld0 + h * HD;
+            bwd3_store_acc<HD>(tAcc0, lane_off, wg == 0 ? sFA : sFB, rloc, tid128, 1 + wg, wg * (HD / 64), (wg + 1) * (HD / 64), p.scale,
+                               T == 0, base, p.ld0, rows_left);
+        }
+        UD_TR(tid128 == 0, 16, wg);
     }
 
     tc_fence_before();
@@ -1133,14 +1667,20 @@ template <int HD>
 static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const void* v, long long ldv, const void* d_o,
                            long long ldo, AttnBwdParams p, __nv_bfloat16* dq, __nv_bfloat16* dk, long long lddqk,
                            __nv_bfloat16* dv, long long lddv, cudaStream_t stream) {
-    // The dQ kernel can form delta itself (UD_ATTN_FUSED_DELTA=1), but measured at B8 H16 N1280 hd128 the per-thread row reads
+    // Default: the v3 dQ kernel (128-row streamed tiles, double-buffered S) with the v2 dK/dV kernel (64-row sub-tiles, two
+    // sub-tiles in flight) -- the faster of each pair at B8 H16 N1280 hd128.  UD_ATTN_BWD=2 / 3 force one generation for both.
+    static const int gen = getenv("UD_ATTN_BWD") != nullptr ? atoi(getenv("UD_ATTN_BWD")) : 0;
+    static const bool dq_v3 = gen != 2, dkv_v3 = gen == 3;
+    // The v2 dQ kernel can form delta itself (UD_ATTN_FUSED_DELTA=1), but measured at B8 H16 N1280 hd128 the per-thread row reads
     // delay every CTA's first sub-tile: 458.6 us fused vs 445.4 us with the separate 33 us pass, so the pass stays the default.
-    static const bool sep_delta = getenv("UD_ATTN_FUSED_DELTA") == nullptr;
+    static const bool sep_delta = dq_v3 || getenv("UD_ATTN_FUSED_DELTA") == nullptr;
     if (sep_delta) {
         const long long warps = (long long)p.B * p.N * p.H;
         const int threads = 256;
         const long long blocks = (warps * 32 + threads - 1) / threads;
-        attn_delta_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p.o, p.d_o, p.ldo, p.delta_out, p.B, p.N, p.H, HD);
+        p.lse2 = dkv_v3 ? p.delta_out + warps : nullptr;         // second half of the caller's scratch (v3 dK/dV kernel only)
+        attn_delta_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p.o, p.d_o, p.ldo, p.delta_out, p.B, p.N, p.H, HD, p.lse,
+                                                                    const_cast<float*>(p.lse2));
         UD_CUDA_CHECK(cudaGetLastError());
         p.o = nullptr;                        // kernels read p.delta
     }
@@ -1156,21 +1696,38 @@ static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const v
     p0.out0 = dk; p0.ld0 = lddqk; p0.out1 = dv; p0.ld1 = lddv;
     AttnBwdParams p1 = p;
     p1.out0 = dq; p1.ld0 = lddqk; p1.out1 = nullptr; p1.ld1 = 0;
-    if ((rc = make_head_tmap(&tq64, q, ldqk, p.B, p.N, D, 64))) return rc;
-    if ((rc = make_head_tmap(&tk64, k, ldqk, p.B, p.N, D, 64))) return rc;
-    if ((rc = make_head_tmap(&tv64, v, ldv, p.B, p.N, D, 64))) return rc;
-    if ((rc = make_head_tmap(&tdo64, d_o, ldo, p.B, p.N, D, 64))) return rc;
-    const int smem = AttnBwd2Smem<HD>::BYTES;
-    static bool attr2 = false;
-    if (!attr2) {
-        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2_kernel<HD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2_kernel<HD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr2 = true;
+#ifdef UD_ATTN_TRACE
+    p0.trace = p1.trace = g_attn_trace_host;
+    const char* only = getenv("UD_ATTN_TRACE_ONLY");      // tools/attn_trace.py: one kernel stamps the table at a time
+    const bool run_dq = only == nullptr || only[1] == 'q', run_dkv = only == nullptr || only[1] == 'k';
+#else
+    constexpr bool run_dq = true, run_dkv = true;
+#endif
+    const int smem3 = AttnBwd3Smem<HD>::BYTES, smem2 = AttnBwd2Smem<HD>::BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd3_kernel<HD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd3_kernel<HD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2_kernel<HD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        UD_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd2_kernel<HD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        attr_set = true;
     }
-    // dQ first: it also produces delta, which the dK/dV kernel reads per streamed query column
-    attn_bwd2_kernel<HD, 1><<<grid, 320, smem, stream>>>(tq, tdo, tk64, tv64, p1);
+    if (!dq_v3 || !dkv_v3) {
+        if ((rc = make_head_tmap(&tq64, q, ldqk, p.B, p.N, D, 64))) return rc;
+        if ((rc = make_head_tmap(&tk64, k, ldqk, p.B, p.N, D, 64))) return rc;
+        if ((rc = make_head_tmap(&tv64, v, ldv, p.B, p.N, D, 64))) return rc;
+        if ((rc = make_head_tmap(&tdo64, d_o, ldo, p.B, p.N, D, 64))) return rc;
+    }
+    // dQ first (the fused-delta variant of the v2 dQ kernel also produces delta, which the dK/dV kernel reads)
+    if (run_dq) {
+        if (dq_v3) attn_bwd3_kernel<HD, 1><<<grid, 320, smem3, stream>>>(tq, tdo, tk, tv, p1);
+        else attn_bwd2_kernel<HD, 1><<<grid, 320, smem2, stream>>>(tq, tdo, tk64, tv64, p1);
+    }
     UD_CUDA_CHECK(cudaGetLastError());
-    attn_bwd2_kernel<HD, 0><<<grid, 320, smem, stream>>>(tk, tv, tq64, tdo64, p0);
+    if (run_dkv) {
+        if (dkv_v3) attn_bwd3_kernel<HD, 0><<<grid, 320, smem3, stream>>>(tk, tv, tq, tdo, p0);
+        else attn_bwd2_kernel<HD, 0><<<grid, 320, smem2, stream>>>(tk, tv, tq64, tdo64, p0);
+    }
     UD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1218,8 +1775,8 @@ extern "C" int ud_attn_bwd(const void* q, const void* k, long long ldqk, const v
                            void* dv, long long lddv, const int64_t* sample_ids, int B, int N, int H, int head_dim, float scale,
                            void* stream) {
     if (B <= 0 || N <= 0) return 0;
-    if (sample_ids != nullptr && (N + 63) / 64 > MAX_DOC_TILES) {
-        fprintf(stderr, "unidisc_b200: document-masked attention needs N <= %d\n", MAX_DOC_TILES * 64);
+    if (sample_ids != nullptr && (N + 127) / 128 > MAX_DOC_TILES3) {
+        fprintf(stderr, "unidisc_b200: document-masked attention needs N <= %d\n", MAX_DOC_TILES3 * 128);
         return -1;
     }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -1237,6 +1794,7 @@ extern "C" int ud_attn_bwd(const void* q, const void* k, long long ldqk, const v
     p.out0 = p.out1 = nullptr;
     p.ld0 = p.ld1 = 0;
     p.safe_order = getenv("UD_ATTN_BWD_SAFE") != nullptr;
+    p.lse2 = nullptr;
     auto* dqp = reinterpret_cast<__nv_bfloat16*>(dq);
     auto* dkp = reinterpret_cast<__nv_bfloat16*>(dk);
     auto* dvp = reinterpret_cast<__nv_bfloat16*>(dv);

@@ -162,7 +162,7 @@ def attn_fwd_kv(q, k, v, B, Nq, Nk, H, head_dim, scale, o=None, q_bs=0, k_bs=0, 
 def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, N, H, head_dim, scale, sample_ids=None):
     _chk(dq.stride(0) == dk.stride(0), "dq and dk must share a row stride")
     _chk(o.stride(0) == do.stride(0), "o and do must share a row stride")
-    delta = torch.empty((B, H, N), device=q.device, dtype=torch.float32)
+    delta = torch.empty((2, B, H, N), device=q.device, dtype=torch.float32)   # [0] delta, [1] lse * log2(e) (kernel scratch)
     call("ud_attn_bwd", P(q), P(k), q.stride(0), P(v), v.stride(0), P(o), P(do), o.stride(0), P(lse), P(delta), P(dq), P(dk),
          dq.stride(0), P(dv), dv.stride(0), P(sample_ids), B, N, H, head_dim, scale, stream())
     return dq, dk, dv
