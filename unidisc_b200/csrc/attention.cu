@@ -47,6 +47,11 @@ UD_DEVINL float ex2(float x) {
 // Packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100): one instruction for two adjacent scores.  The softmax loops of
 // all attention kernels are bound by instruction issue (tools/attn_trace.py), not by a pipe, so halving their FMA-pipe
 // instruction count is worth more than any per-pipe balancing.
+UD_DEVINL float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 UD_DEVINL uint64_t f2pack(float lo, float hi) {
     uint64_t r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -627,11 +632,14 @@ attn_fwd6_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     if (kbase + 32 + i >= Ntok) r1[i] = 0xff800000u;
                 }
             }
+            // row maximum with 3-input FMNMX3: one instruction per two scores
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
-                mx2 = fmaxf(mx2, __uint_as_float(r1[i])); mx3 = fmaxf(mx3, __uint_as_float(r1[i + 1]));
+            for (int i = 0; i < 32; i += 4) {
+                mx0 = fmax3(mx0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+                mx1 = fmax3(mx1, __uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3]));
+                mx2 = fmax3(mx2, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+                mx3 = fmax3(mx3, __uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3]));
             }
             const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scl;
             const float m_new = fmaxf(m_used, mx);
@@ -1538,6 +1546,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             }
         };
         prefetch_meta(0);
+        uint32_t rsA[32], rsB[32], pk[32];
         for (int ii = 0; ii < T; ++ii) {
             prefetch_meta(ii + 1);
             const int t = tile_of(ii);
@@ -1549,10 +1558,11 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             const int64_t* sid_col = use_ids ? p.sample_ids + (long long)b * Ntok + col0 : nullptr;
             const uint32_t tS = (MODE == 0 ? tR0 : tmem + (ii & 1) * 128) + cb;
             UD_TR(tid128 == 0, 14, ii + 32 * wg);
+            // (requesting S(ii+1) at the end of tile ii, to hide the TMEM read latency, was measured: it only moves the ~340 cycles
+            //  from the head of a tile to its tail, where they delay the dS hand-off instead)
             mbar_wait(&s_full[MODE == 0 ? 0 : (ii & 1)], MODE == 0 ? (ii & 1) : ((ii >> 1) & 1));
             tc_fence_after();
             UD_TR(tid128 == 0, 5, ii + 32 * wg);
-            uint32_t rsA[32], rsB[32], pk[32];
             tmem_ld_32x32b_x32(tS + lane_off, rsA);
             tmem_ld_32x32b_x32(tS + 32 + lane_off, rsB);
             tmem_ld_wait();
@@ -1669,11 +1679,14 @@ static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const v
                            __nv_bfloat16* dv, long long lddv, cudaStream_t stream) {
     // Default: the v3 dQ kernel (128-row streamed tiles, double-buffered S) with the v2 dK/dV kernel (64-row sub-tiles, two
     // sub-tiles in flight) -- the faster of each pair at B8 H16 N1280 hd128.  UD_ATTN_BWD=2 / 3 force one generation for both.
+    // Packed (document-masked) batches keep the v2 dQ kernel: its per-column sample ids come from shared memory, v3 reads them
+    // from global memory on every masked tile (cfg5: 88.4 vs 83.8 ms per step).
     static const int gen = getenv("UD_ATTN_BWD") != nullptr ? atoi(getenv("UD_ATTN_BWD")) : 0;
-    static const bool dq_v3 = gen != 2, dkv_v3 = gen == 3;
+    const bool dq_v3 = gen == 3 || (gen != 2 && p.sample_ids == nullptr);
+    static const bool dkv_v3 = gen == 3;
     // The v2 dQ kernel can form delta itself (UD_ATTN_FUSED_DELTA=1), but measured at B8 H16 N1280 hd128 the per-thread row reads
     // delay every CTA's first sub-tile: 458.6 us fused vs 445.4 us with the separate 33 us pass, so the pass stays the default.
-    static const bool sep_delta = dq_v3 || getenv("UD_ATTN_FUSED_DELTA") == nullptr;
+    const bool sep_delta = dq_v3 || getenv("UD_ATTN_FUSED_DELTA") == nullptr;
     if (sep_delta) {
         const long long warps = (long long)p.B * p.N * p.H;
         const int threads = 256;
