@@ -107,16 +107,18 @@ def main():
         t0 = int(t[17, 0])
         print(f"\n=== {val} kernel, CTA (3,5,2): cycles since CTA start; fixed tiles landed at {int(t[17, 1]) - t0}")
         print("sub " + " ".join(f"{c:>7d}" for c in COLS))
-        for i in range(min(args.iters, 32)):
+        for i in range(min(args.iters, 16)):
             if int(t[0, i]) == 0 and int(t[5, i]) == 0:
                 break
             print(f"{i:3d} " + " ".join(f"{(int(t[c, i]) - t0) if int(t[c, i]) else 0:7d}" for c in COLS))
-        if int(t[5, 32]) != 0:       # v3 kernels: the second warpgroup stamps its own rows (offset 32)
-            print("second warpgroup (warpgroup events only):")
-            for i in range(32, 64):
+        for g in (1, 2, 3):          # v3 kernels: warpgroup g stamps its own rows at offset 16 * g (v2: both share offset 0)
+            if int(t[5, 16 * g]) == 0:
+                continue
+            print(f"warpgroup {g} (warpgroup events only):")
+            for i in range(16 * g, 16 * g + 16):
                 if int(t[5, i]) == 0:
                     break
-                print(f"{i - 32:3d} " + " ".join(f"{(int(t[c, i]) - t0) if int(t[c, i]) else 0:7d}" for c in COLS))
+                print(f"{i - 16 * g:3d} " + " ".join(f"{(int(t[c, i]) - t0) if int(t[c, i]) else 0:7d}" for c in COLS))
         print(f"epilogue: all_done seen wg0 {int(t[15, 0]) - t0} wg1 {int(t[15, 1]) - t0}; stores done wg0 {int(t[16, 0]) - t0} "
               f"wg1 {int(t[16, 1]) - t0}")
         print("legend: " + "; ".join(f"{c}={EVENTS[c]}" for c in COLS))

@@ -1214,9 +1214,10 @@ struct AttnBwd3Smem {
 static constexpr int MAX_DOC_TILES3 = 256;
 using DocTiles3 = DocTilesT<MAX_DOC_TILES3>;
 
-// TMEM column (relative to the tile's first column) of the bf16 A operand of reduction step ks: warpgroup w = ks / 4 packs its
-// 64 probabilities into the first 32 columns of its own 64-column half
-UD_DEVINL uint32_t bwd3_pcol(int ks) { return (uint32_t)((ks >> 2) * 64 + (ks & 3) * 8); }
+// TMEM column (relative to the tile's first column) of the bf16 A operand of reduction step ks: each warpgroup packs its CW
+// probabilities into the first CW/2 columns of its own CW-column slice of the tile
+template <int CW>   // CW = streamed columns per warpgroup (64 with two warpgroups, 32 with four)
+UD_DEVINL uint32_t bwd3_pcol(int ks) { return (uint32_t)((ks / (CW / 16)) * CW + (ks % (CW / 16)) * 8); }
 
 // one elected lane per warp signals on behalf of its 32 rows (after every lane's TMEM stores / loads have completed)
 UD_DEVINL void warp_arrive(uint64_t* bar, int lane) {
@@ -1225,58 +1226,54 @@ UD_DEVINL void warp_arrive(uint64_t* bar, int lane) {
     if (lane == 0) mbar_arrive(bar);
 }
 
-// P = exp2(S * scl - lse) over this thread's 64 columns (fp32 kept in rs*, for the dS product); SLOW applies the edge /
-// document masks.  COLMETA: lse varies per column (dK/dV kernel) and is read from lse_col; else lse_row.
-template <bool COLMETA, bool SLOW>
-UD_DEVINL void bwd3_probs(uint32_t (&rsA)[32], uint32_t (&rsB)[32], uint32_t (&pk)[32], float scl, float lse_row,
+// P = exp2(S * scl - lse) for the 32-column chunk c of this thread's columns (fp32 kept in rs, for the dS product); SLOW applies
+// the edge / document masks.  COLMETA: lse varies per column (dK/dV kernel) and is read (negated, exp2 domain) from nlse_col.
+template <bool COLMETA, bool SLOW, int NPK>
+UD_DEVINL void bwd3_probs(uint32_t (&rs)[32], uint32_t (&pk)[NPK], int c, float scl, float lse_row,
                           const float* __restrict__ nlse_col, int col0, int Ntok, bool row_ok, bool doc_mask, int sid_row,
                           const int64_t* __restrict__ sid_col) {
     const uint64_t scl2 = f2pack(scl, scl), nl_row2 = f2pack(-lse_row, -lse_row);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint32_t (&rs)[32] = c == 0 ? rsA : rsB;
+    for (int e4 = 0; e4 < 8; ++e4) {
+        uint64_t nl2[2] = {nl_row2, nl_row2};                  // -lse of the two column pairs
+        if (COLMETA) {
+            if (!SLOW) {
+                const float4 lv = __ldg(reinterpret_cast<const float4*>(nlse_col + c * 32 + e4 * 4));
+                nl2[0] = f2pack(lv.x, lv.y); nl2[1] = f2pack(lv.z, lv.w);
+            } else {
+                float l4[4];
 #pragma unroll
-        for (int e4 = 0; e4 < 8; ++e4) {
-            uint64_t nl2[2] = {nl_row2, nl_row2};                  // -lse (exp2 domain) of the two column pairs
-            if (COLMETA) {
-                if (!SLOW) {
-                    const float4 lv = __ldg(reinterpret_cast<const float4*>(nlse_col + c * 32 + e4 * 4));
-                    nl2[0] = f2pack(lv.x, lv.y); nl2[1] = f2pack(lv.z, lv.w);
-                } else {
-                    float l4[4];
+                for (int u = 0; u < 4; ++u) l4[u] = (col0 + c * 32 + e4 * 4 + u < Ntok) ? __ldg(nlse_col + c * 32 + e4 * 4 + u) : -INFINITY;
+                nl2[0] = f2pack(l4[0], l4[1]); nl2[1] = f2pack(l4[2], l4[3]);
+            }
+        }
+        float pv[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) l4[u] = (col0 + c * 32 + e4 * 4 + u < Ntok) ? __ldg(nlse_col + c * 32 + e4 * 4 + u) : -INFINITY;
-                    nl2[0] = f2pack(l4[0], l4[1]); nl2[1] = f2pack(l4[2], l4[3]);
-                }
-            }
-            float pv[4];
+        for (int h2 = 0; h2 < 2; ++h2) {
+            float x0, x1;
+            f2unpack(ffma2(f2pack(__uint_as_float(rs[e4 * 4 + 2 * h2]), __uint_as_float(rs[e4 * 4 + 2 * h2 + 1])), scl2, nl2[h2]), x0, x1);
+            pv[2 * h2] = ex2(x0); pv[2 * h2 + 1] = ex2(x1);
+        }
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-                float x0, x1;
-                f2unpack(ffma2(f2pack(__uint_as_float(rs[e4 * 4 + 2 * h2]), __uint_as_float(rs[e4 * 4 + 2 * h2 + 1])), scl2, nl2[h2]), x0, x1);
-                pv[2 * h2] = ex2(x0); pv[2 * h2 + 1] = ex2(x1);
+        for (int u = 0; u < 4; ++u) {
+            if (SLOW) {
+                const int col = col0 + c * 32 + e4 * 4 + u;
+                bool ok = row_ok && col < Ntok;
+                if (doc_mask && ok) ok = (int)__ldg(sid_col + c * 32 + e4 * 4 + u) == sid_row && sid_row != -1;
+                if (!ok) pv[u] = 0.f;
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (SLOW) {
-                    const int col = col0 + c * 32 + e4 * 4 + u;
-                    bool ok = row_ok && col < Ntok;
-                    if (doc_mask && ok) ok = (int)__ldg(sid_col + c * 32 + e4 * 4 + u) == sid_row && sid_row != -1;
-                    if (!ok) pv[u] = 0.f;
-                }
-                rs[e4 * 4 + u] = __float_as_uint(pv[u]);
-            }
-            if (COLMETA) {       // dK/dV kernel: the bf16 probabilities are an MMA operand themselves
-                pk[c * 16 + e4 * 2] = pack_bf16x2(pv[0], pv[1]);
-                pk[c * 16 + e4 * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
-            }
+            rs[e4 * 4 + u] = __float_as_uint(pv[u]);
+        }
+        if (COLMETA) {       // dK/dV kernel: the bf16 probabilities are an MMA operand themselves
+            pk[c * 16 + e4 * 2] = pack_bf16x2(pv[0], pv[1]);
+            pk[c * 16 + e4 * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
         }
     }
 }
 
 // dS = P * (dP - delta) for the 32-column chunk c of this thread's 64 columns, packed to bf16 pairs
-template <bool COLMETA, bool SLOW>
-UD_DEVINL void bwd3_ds(const uint32_t (&rs)[32], const uint32_t (&rd)[32], uint32_t (&pk)[32], int c, float dlt_row,
+template <bool COLMETA, bool SLOW, int NPK>
+UD_DEVINL void bwd3_ds(const uint32_t (&rs)[32], const uint32_t (&rd)[32], uint32_t (&pk)[NPK], int c, float dlt_row,
                        const float* __restrict__ dlt_col, int col0, int Ntok) {
     const uint64_t d_row2 = f2pack(dlt_row, dlt_row);
 #pragma unroll
@@ -1344,12 +1341,17 @@ UD_DEVINL void bwd3_store_acc(uint32_t tA, uint32_t lane_off, uint8_t* stg, int 
 }
 
 // MODE 0: dK/dV (fixed K_j, V_j; ring A = Q_i, ring B = dO_i).  MODE 1: dQ (fixed Q_i, dO_i; ring A = K_j, ring B = V_j).
+// NWG softmax warpgroups share every tile, 128 / NWG columns each.  (Measured for the dQ kernel, whose warpgroups are the
+// bottleneck: FOUR warpgroups of 32 columns each -- half the arithmetic per hand-off, four warps per SM sub-partition, 96
+// registers -- are 2 % slower than two: 415.6 vs 406.0 us for the whole backward.)
+template <int MODE> struct Bwd3Cfg { static constexpr int NWG = 2; static constexpr int THREADS = 64 + 128 * NWG; };
 template <int HD, int MODE>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(Bwd3Cfg<MODE>::THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fb,
                  const __grid_constant__ CUtensorMap tm_ra, const __grid_constant__ CUtensorMap tm_rb, const AttnBwdParams p) {
     using S = AttnBwd3Smem<HD>;
     constexpr int NA = S::NA, NB = S::NB, TILE = S::TILE;
+    constexpr int NWG = Bwd3Cfg<MODE>::NWG, CW = 128 / NWG, NCH = CW / 32;      // columns / 32-column chunks per warpgroup
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sFA = smem;
@@ -1384,7 +1386,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
         for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(dp_full, 1);
-        mbar_init(p_rdy, 8); mbar_init(ds_rdy, 8);
+        mbar_init(p_rdy, 4 * NWG); mbar_init(ds_rdy, 4 * NWG);
         mbar_init(all_done, 1);
         fence_barrier_init();
     }
@@ -1477,7 +1479,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                     if (leader) {
                         // dV += Pt dO_i  (reduction over the 128 queries of the tile; dO_i re-read MN-major).  Last read of dO_i.
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) umma_ts(tAcc1, tR0 + bwd3_pcol(ks), desc_mnmajor(aRB + sb * TILE, ks), idesc_acc, acc0 | (ks != 0));
+                        for (int ks = 0; ks < 8; ++ks) umma_ts(tAcc1, tR0 + bwd3_pcol<CW>(ks), desc_mnmajor(aRB + sb * TILE, ks), idesc_acc, acc0 | (ks != 0));
                         umma_commit(&b_empty[sb]);
                     }
                     __syncwarp();
@@ -1498,7 +1500,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
                     // MODE 0: dK += dSt Q_i.   MODE 1: dQ += dS K_j.   Last read of the ring-A tile.
                     const uint32_t tA = MODE == 0 ? tR1 : tmem + (i & 1) * 128;
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) umma_ts(tAcc0, tA + bwd3_pcol(ks), desc_mnmajor(aRA + sa * TILE, ks), idesc_acc, acc0 | (ks != 0));
+                    for (int ks = 0; ks < 8; ++ks) umma_ts(tAcc0, tA + bwd3_pcol<CW>(ks), desc_mnmajor(aRA + sa * TILE, ks), idesc_acc, acc0 | (ks != 0));
                     umma_commit(&a_empty[sa]);
                     if (i + 1 == T) umma_commit(all_done);
                 }
@@ -1512,8 +1514,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             }
         }
     } else {
-        // two warpgroups (warps 2-5, 6-9); thread = accumulator row (MODE 0: key, MODE 1: query); warpgroup w handles the 64
-        // streamed columns [64w, 64w+64) of every tile
+        // NWG warpgroups of four warps; thread = accumulator row (MODE 0: key, MODE 1: query); warpgroup w handles the CW streamed
+        // columns [CW*w, CW*w + CW) of every tile, as NCH chunks of 32
         const int wg = (warp - 2) >> 2;
         const int qd = warp & 3;
         const int rloc = qd * 32 + lane;
@@ -1531,81 +1533,90 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             dlt_row = p.delta[bh * Ntok + row];
         }
         const float scl = p.scale_log2;
-        const uint32_t cb = (uint32_t)(wg * 64);
+        const uint32_t cb = (uint32_t)(wg * CW);
         const bool vec_ok = (Ntok & 3) == 0;           // 16-byte metadata loads need aligned per-head rows
-        // MODE 0: the per-column metadata of a tile (64 lse2 + 64 delta floats per warpgroup = four 128-byte lines) is pulled into
-        // L1 one tile ahead by lanes 0-3 of every warp, so the warp-uniform loads in the softmax loops hit L1 (~35 cycles) instead
+        // MODE 0: the per-column metadata of a tile (CW lse2 + CW delta floats per warpgroup, 128-byte lines) is pulled into L1 one
+        // tile ahead by the first lanes of every warp, so the warp-uniform loads in the softmax loops hit L1 (~35 cycles) instead
         // of paying an L2 / DRAM round trip per tile on the critical path
         auto prefetch_meta = [&](int ii) {
-            if (MODE == 0 && ii < T && lane < 4) {
-                const int c0 = tile_of(ii) * 128 + wg * 64 + (lane & 1) * 32;
+            if (MODE == 0 && ii < T && lane < 2 * NCH) {
+                const int c0 = tile_of(ii) * 128 + wg * CW + (lane % NCH) * 32;
                 if (c0 < Ntok) {
-                    const float* src = ((lane & 2) ? p.delta : p.lse2) + bh * Ntok + c0;
+                    const float* src = ((lane >= NCH) ? p.delta : p.lse2) + bh * Ntok + c0;
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
                 }
             }
         };
         prefetch_meta(0);
-        uint32_t rsA[32], rsB[32], pk[32];
+        uint32_t rs[NCH][32], pk[NCH * 16];
+        auto store_pk = [&](uint32_t taddr) {
+            if constexpr (NCH == 2) tmem_st_32x32b_x32(taddr, pk); else tmem_st_32x32b_x16(taddr, pk);
+        };
         for (int ii = 0; ii < T; ++ii) {
             prefetch_meta(ii + 1);
             const int t = tile_of(ii);
-            const int col0 = t * 128 + wg * 64;       // first streamed index (MODE 0: query, MODE 1: key) of this warpgroup
+            const int col0 = t * 128 + wg * CW;       // first streamed index (MODE 0: query, MODE 1: key) of this warpgroup
             const bool doc_mask = use_ids && !tl.nomask[ii];
             const bool slow = doc_mask || (t * 128 + 128 > Ntok) || !row_ok || (MODE == 0 && !vec_ok);
             const float* lse_col = MODE == 0 ? p.lse2 + bh * Ntok + col0 : nullptr;
             const float* dlt_col = MODE == 0 ? p.delta + bh * Ntok + col0 : nullptr;
             const int64_t* sid_col = use_ids ? p.sample_ids + (long long)b * Ntok + col0 : nullptr;
             const uint32_t tS = (MODE == 0 ? tR0 : tmem + (ii & 1) * 128) + cb;
-            UD_TR(tid128 == 0, 14, ii + 32 * wg);
+            UD_TR(tid128 == 0, 14, ii + 16 * wg);
             // (requesting S(ii+1) at the end of tile ii, to hide the TMEM read latency, was measured: it only moves the ~340 cycles
             //  from the head of a tile to its tail, where they delay the dS hand-off instead)
             mbar_wait(&s_full[MODE == 0 ? 0 : (ii & 1)], MODE == 0 ? (ii & 1) : ((ii >> 1) & 1));
             tc_fence_after();
-            UD_TR(tid128 == 0, 5, ii + 32 * wg);
-            tmem_ld_32x32b_x32(tS + lane_off, rsA);
-            tmem_ld_32x32b_x32(tS + 32 + lane_off, rsB);
+            UD_TR(tid128 == 0, 5, ii + 16 * wg);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(tS + c * 32 + lane_off, rs[c]);
             tmem_ld_wait();
-            UD_TR(tid128 == 0, 6, ii + 32 * wg);
-            if (slow) bwd3_probs<MODE == 0, true>(rsA, rsB, pk, scl, lse_row, lse_col, col0, Ntok, row_ok, doc_mask, sid_row, sid_col);
-            else bwd3_probs<MODE == 0, false>(rsA, rsB, pk, scl, lse_row, lse_col, col0, Ntok, row_ok, doc_mask, sid_row, sid_col);
-            UD_TR(tid128 == 0, 7, ii + 32 * wg);
+            UD_TR(tid128 == 0, 6, ii + 16 * wg);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (slow) bwd3_probs<MODE == 0, true>(rs[c], pk, c, scl, lse_row, lse_col, col0, Ntok, row_ok, doc_mask, sid_row, sid_col);
+                else bwd3_probs<MODE == 0, false>(rs[c], pk, c, scl, lse_row, lse_col, col0, Ntok, row_ok, doc_mask, sid_row, sid_col);
+            }
+            UD_TR(tid128 == 0, 7, ii + 16 * wg);
             if (MODE == 0) {
-                tmem_st_32x32b_x32(tS + lane_off, pk);
+                store_pk(tS + lane_off);
                 tmem_st_wait();
                 warp_arrive(p_rdy, lane);
-                UD_TR(tid128 == 0, 8, ii + 32 * wg);
+                UD_TR(tid128 == 0, 8, ii + 16 * wg);
             }
             mbar_wait(dp_full, ii & 1);
             tc_fence_after();
-            UD_TR(tid128 == 0, 9, ii + 32 * wg);
+            UD_TR(tid128 == 0, 9, ii + 16 * wg);
             if (MODE == 0) {
                 // one 32-column chunk of dPt at a time (the fp32 probabilities stay live: register budget)
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < NCH; ++c) {
                     uint32_t rd[32];
                     tmem_ld_32x32b_x32(tDP + cb + c * 32 + lane_off, rd);
                     tmem_ld_wait();
-                    if (slow) bwd3_ds<true, true>(c == 0 ? rsA : rsB, rd, pk, c, dlt_row, dlt_col, col0, Ntok);
-                    else bwd3_ds<true, false>(c == 0 ? rsA : rsB, rd, pk, c, dlt_row, dlt_col, col0, Ntok);
+                    if (slow) bwd3_ds<true, true>(rs[c], rd, pk, c, dlt_row, dlt_col, col0, Ntok);
+                    else bwd3_ds<true, false>(rs[c], rd, pk, c, dlt_row, dlt_col, col0, Ntok);
                 }
-                UD_TR(tid128 == 0, 11, ii + 32 * wg);
+                UD_TR(tid128 == 0, 11, ii + 16 * wg);
             } else {
-                uint32_t rdA[32], rdB[32];
-                tmem_ld_32x32b_x32(tDP + cb + lane_off, rdA);
-                tmem_ld_32x32b_x32(tDP + cb + 32 + lane_off, rdB);
+                uint32_t rd[NCH][32];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(tDP + cb + c * 32 + lane_off, rd[c]);
                 tmem_ld_wait();
                 warp_arrive(p_rdy, lane);              // dP buffer may be overwritten by dP(j+1)
-                UD_TR(tid128 == 0, 10, ii + 32 * wg);
-                if (slow) { bwd3_ds<false, true>(rsA, rdA, pk, 0, dlt_row, dlt_col, col0, Ntok); bwd3_ds<false, true>(rsB, rdB, pk, 1, dlt_row, dlt_col, col0, Ntok); }
-                else { bwd3_ds<false, false>(rsA, rdA, pk, 0, dlt_row, dlt_col, col0, Ntok); bwd3_ds<false, false>(rsB, rdB, pk, 1, dlt_row, dlt_col, col0, Ntok); }
-                UD_TR(tid128 == 0, 11, ii + 32 * wg);
+                UD_TR(tid128 == 0, 10, ii + 16 * wg);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    if (slow) bwd3_ds<false, true>(rs[c], rd[c], pk, c, dlt_row, dlt_col, col0, Ntok);
+                    else bwd3_ds<false, false>(rs[c], rd[c], pk, c, dlt_row, dlt_col, col0, Ntok);
+                }
+                UD_TR(tid128 == 0, 11, ii + 16 * wg);
             }
             // MODE 0: dSt over dPt (R1).  MODE 1: dS over the S buffer it came from.
-            tmem_st_32x32b_x32((MODE == 0 ? tR1 + cb : tS) + lane_off, pk);
+            store_pk((MODE == 0 ? tR1 + cb : tS) + lane_off);
             tmem_st_wait();
             warp_arrive(ds_rdy, lane);
-            UD_TR(tid128 == 0, 12, ii + 32 * wg);
+            UD_TR(tid128 == 0, 12, ii + 16 * wg);
         }
         if (T > 0) mbar_wait(all_done, 0);
         tc_fence_after();
@@ -1618,10 +1629,11 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_fa, const __grid_constan
             bwd3_store_acc<HD>(tA, lane_off, wg == 0 ? sFA : sFB, rloc, tid128, 1 + wg, 0, HD / 32, wg == 0 ? p.scale : 1.0f, T == 0,
                                base, wg == 0 ? p.ld0 : p.ld1, rows_left);
         } else {
-            // each warpgroup stores half of dQ's columns
+            // the 32-column chunks of dQ are dealt round-robin to the warpgroups (disjoint chunks of one staging tile)
+            constexpr int NC = HD / 32, PER = (NC + NWG - 1) / NWG;
+            const int c_lo = min(wg * PER, NC), c_hi = min(c_lo + PER, NC);
             __nv_bfloat16* base = p.out0 + ((long long)b * Ntok + t0) * p.ld0 + h * HD;
-            bwd3_store_acc<HD>(tAcc0, lane_off, wg == 0 ? sFA : sFB, rloc, tid128, 1 + wg, wg * (HD / 64), (wg + 1) * (HD / 64), p.scale,
-                               T == 0, base, p.ld0, rows_left);
+            bwd3_store_acc<HD>(tAcc0, lane_off, sFA, rloc, tid128, 1 + wg, c_lo, c_hi, p.scale, T == 0, base, p.ld0, rows_left);
         }
         UD_TR(tid128 == 0, 16, wg);
     }
@@ -1733,12 +1745,12 @@ static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const v
     }
     // dQ first (the fused-delta variant of the v2 dQ kernel also produces delta, which the dK/dV kernel reads)
     if (run_dq) {
-        if (dq_v3) attn_bwd3_kernel<HD, 1><<<grid, 320, smem3, stream>>>(tq, tdo, tk, tv, p1);
+        if (dq_v3) attn_bwd3_kernel<HD, 1><<<grid, Bwd3Cfg<1>::THREADS, smem3, stream>>>(tq, tdo, tk, tv, p1);
         else attn_bwd2_kernel<HD, 1><<<grid, 320, smem2, stream>>>(tq, tdo, tk64, tv64, p1);
     }
     UD_CUDA_CHECK(cudaGetLastError());
     if (run_dkv) {
-        if (dkv_v3) attn_bwd3_kernel<HD, 0><<<grid, 320, smem3, stream>>>(tk, tv, tq, tdo, p0);
+        if (dkv_v3) attn_bwd3_kernel<HD, 0><<<grid, Bwd3Cfg<0>::THREADS, smem3, stream>>>(tk, tv, tq, tdo, p0);
         else attn_bwd2_kernel<HD, 0><<<grid, 320, smem2, stream>>>(tk, tv, tq64, tdo64, p0);
     }
     UD_CUDA_CHECK(cudaGetLastError());
