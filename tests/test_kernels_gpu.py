@@ -338,9 +338,11 @@ def test_qk_ln_rope_fwd_bwd(ops, D, hd):
         assert torch.allclose(got, p.grad, rtol=2e-3, atol=3e-3), (nm, (got - p.grad).abs().max())
 
 
-def test_colsum(ops):
-    M, N = 1000, 777
-    buf = rnd(M, 784, seed=1, dtype=bf16)
+@pytest.mark.parametrize("N,ld", [(777, 784), (777, 779), (2048, 2048), (8, 8)])
+def test_colsum(ops, N, ld):
+    # ld % 8 == 0 takes the 16-byte kernel (the last vector's padding columns must not be summed), otherwise the 4-byte one
+    M = 1000
+    buf = rnd(M, ld, seed=1, dtype=bf16)
     db = torch.zeros(N, device=dev())
     ops.colsum(buf[:, :N], db, M, N)
     torch.cuda.synchronize()

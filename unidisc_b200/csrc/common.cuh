@@ -361,16 +361,24 @@ UD_DEVINL float philox_uniform(uint64_t seed, uint64_t offset, uint64_t idx) {
     return (float)(w >> 8) * (1.0f / 16777216.0f);
 }
 
-// dropout keep-scales for the 4 consecutive hidden columns [4*cg, 4*cg+4) of token row `row`: one Philox call per
-// 16-byte column group.  keep with probability 1-p (u32 >= thresh), kept values are scaled by 1/(1-p) like F.dropout.
+// dropout keep-scales for the 4 consecutive hidden columns [4*cg, 4*cg+4) of token row `row`.  One Philox call yields 4 x 32
+// random bits = the 16-bit draws of a column group for TWO rows (2r, 2r+1): the row kernels that process row pairs call
+// dropout_bits once per pair (the 10 Philox rounds were ~10 % of their instructions).  keep with probability 1-p
+// (u16 >= p * 65536), kept values are scaled by 1/(1-p) like F.dropout.
+UD_DEVINL uint4 dropout_bits(uint64_t seed, uint64_t offset, uint32_t row_pair, uint32_t cg) {
+    return philox4x32_10(make_uint4(row_pair, cg, (uint32_t)offset, (uint32_t)(offset >> 32)),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+UD_DEVINL void dropout_pick(const uint4& r, uint32_t odd_row, uint32_t thresh, float inv_keep, float (&ks)[4]) {
+    const uint32_t sh = odd_row * 16u, t16 = thresh >> 16;
+    ks[0] = ((r.x >> sh) & 0xffffu) >= t16 ? inv_keep : 0.f;
+    ks[1] = ((r.y >> sh) & 0xffffu) >= t16 ? inv_keep : 0.f;
+    ks[2] = ((r.z >> sh) & 0xffffu) >= t16 ? inv_keep : 0.f;
+    ks[3] = ((r.w >> sh) & 0xffffu) >= t16 ? inv_keep : 0.f;
+}
 UD_DEVINL void dropout_scales4(uint64_t seed, uint64_t offset, uint32_t row, uint32_t cg, uint32_t thresh, float inv_keep,
                                float (&ks)[4]) {
-    const uint4 r = philox4x32_10(make_uint4(row, cg, (uint32_t)offset, (uint32_t)(offset >> 32)),
-                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    ks[0] = r.x >= thresh ? inv_keep : 0.f;
-    ks[1] = r.y >= thresh ? inv_keep : 0.f;
-    ks[2] = r.z >= thresh ? inv_keep : 0.f;
-    ks[3] = r.w >= thresh ? inv_keep : 0.f;
+    dropout_pick(dropout_bits(seed, offset, row >> 1, cg), row & 1u, thresh, inv_keep, ks);
 }
 inline uint32_t dropout_thresh(float p) {
     double t = (double)p * 4294967296.0;
