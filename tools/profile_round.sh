@@ -12,9 +12,11 @@ cap() {  # name regex skip kbench-section
   rm -f gpurun_out/prof_$1.ncu-rep
 }
 cap gemm_roof 'gemm2_kernel<\(bool\)0, \(bool\)0, \(int\)256, \(int\)1>' 3 roof
-cap attn_fwd 'attn_fwd3_kernel' 3 attn
-cap attn_bwd_dq 'attn_bwd2_kernel<\(int\)128, \(int\)1>' 3 attn
+cap attn_fwd 'attn_fwd6_kernel' 3 attn
+cap attn_bwd_dq 'attn_bwd3_kernel<\(int\)128, \(int\)1>' 3 attn
 cap attn_bwd_dkv 'attn_bwd2_kernel<\(int\)128, \(int\)0>' 3 attn
-cap sampler 'ddpm_update_logits_fast_kernel' 2 sampler
+cap qkln_bwd 'qk_ln_rope_bwd_tma_kernel' 2 rows
+cap norm_bwd 'norm_residual_bwd_tma_kernel<\(int\)2, \(bool\)1' 2 rows
+[ "$2" = "nosampler" ] || cap sampler 'ddpm_update_logits_fast_kernel' 2 sampler
 wc -l gpurun_out/${TAG}_launches.csv
 ls -la gpurun_out/${TAG}_ncu_full_*.csv
