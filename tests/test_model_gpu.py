@@ -485,6 +485,38 @@ def test_gradient_checkpointing_matches_plain_backward():
     assert g0.abs().sum() > 0
 
 
+def test_masked_head_matches_full_head():
+    """trainer.b200_masked_head (additive, default true): the output projection, the fused SUBS NLL and their backward run on the
+    masked, attended token rows only.  An unmasked token's log-probability is exactly 0 under SUBS (reference model.py:621-658)
+    and padded tokens are multiplied by the attention mask, so the loss is identical and the gradients agree up to the summation
+    order of the weight-gradient GEMM (its reduction now runs over the selected rows)."""
+    from oracle import restated as R
+    from unidisc_b200.config import make_config
+    from unidisc_b200.model import Diffusion
+    outs = []
+    for masked in (False, True):
+        cfg = make_config("small", hidden_size=256, n_blocks=2, n_heads=4, txt_length=64, img_length=64, image_vocab_size=255,
+                          text_vocab_size=257, dropout=0.0, trainer__b200_masked_head=masked)
+        torch.manual_seed(0)
+        model = Diffusion(cfg, device=dev())
+        model.train()
+        ids, mod = R.synthetic_batch(4, 64, 64, model.text_vocab_size, model.vocab_size, seed=3)
+        am = torch.ones_like(ids, dtype=torch.bool)
+        am[1, 100:] = False                          # padding: masked-but-unattended rows must not reach the head either
+        batch = dict(input_ids=ids.to(dev()), modality=mod.to(dev()), attention_mask=am.to(dev()))
+        torch.manual_seed(11)
+        out = model.compute_loss(batch)
+        out.loss.backward()
+        torch.cuda.synchronize()
+        outs.append((out.loss.detach().clone(), out.nlls.detach().clone(), model.backbone.flat_grads.clone(), model._last_head_rows))
+    assert outs[0][3] is None and 0 < outs[1][3] < 4 * 128
+    assert torch.equal(outs[0][1], outs[1][1])                   # per-token NLLs: the same kernel on the same logits rows
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=0)
+    g0, g1 = outs[0][2], outs[1][2]
+    assert torch.allclose(g0, g1, rtol=2e-3, atol=2e-6), (g0 - g1).abs().max()
+    assert g0.abs().sum() > 0
+
+
 def test_backbone_under_torch_compile():
     """trainer.compile (reference model_setup.py:705-707 compiles the backbone): DIT.forward is marked torch.compiler.disable, so a
     compiled wrapper calls the CUDA path as an opaque region — same logits and gradients as eager."""

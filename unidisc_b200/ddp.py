@@ -112,6 +112,16 @@ class ThinDDP(nn.Module):
     def forward(self, *a, **k):
         return self.module(*a, **k)
 
+    def __getattr__(self, name):
+        # like accelerate's unwrapped access: attributes the wrapper does not have (require_sample_ids, Vp, supports_head_rows,
+        # set_flex_attention_cache, ...) are those of the wrapped backbone, so `self.backbone = ThinDDP(self.backbone)` is enough
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            if name == "module":
+                raise
+            return getattr(super().__getattr__("module"), name)
+
     @contextlib.contextmanager
     def no_sync(self):
         old, self._sync = self._sync, False

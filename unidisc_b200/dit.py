@@ -123,8 +123,9 @@ class DDitFinalLayer(nn.Module):                                     # parameter
 # ----------------------------------------------------------------------------------------------------------------
 class _DiTFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, module, indices, modality, sample_ids, save, doc_mask, sigma):
-        logits, saved = module._forward_impl(indices, modality, sample_ids, save=save, doc_mask=doc_mask, sigma=sigma)
+    def forward(ctx, anchor, module, indices, modality, sample_ids, save, doc_mask, sigma, head_rows=None):
+        logits, saved = module._forward_impl(indices, modality, sample_ids, save=save, doc_mask=doc_mask, sigma=sigma,
+                                             head_rows=head_rows)
         ctx.module = module
         ctx.saved = saved
         return logits
@@ -136,7 +137,7 @@ class _DiTFunction(torch.autograd.Function):
             raise RuntimeError("unidisc_b200.DIT: backward called on a forward that did not save activations")
         module._backward_impl(saved, dlogits)
         ctx.saved = None
-        return torch.zeros_like(module._anchor), None, None, None, None, None, None, None
+        return torch.zeros_like(module._anchor), None, None, None, None, None, None, None, None
 
 
 class TextFullImageSelfMask:
@@ -231,6 +232,7 @@ class DIT(nn.Module):
         self.register_buffer("rotary_sin_emb_txt", st.contiguous(), persistent=False)
 
         self.Vp = (vocab_size + 63) // 64 * 64     # logits row pitch (TMA / 16-byte vector stores)
+        self.supports_head_rows = True             # forward(head_rows=...): output projection of a subset of the token rows
         self._flat_p = None
         self._flat_g = None
         self._flat_bf16 = None
@@ -466,9 +468,14 @@ class DIT(nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     @torch.compiler.disable
     def forward(self, indices, sigma=None, label=None, x_cond=None, attention_mask=None, continuous_mode=False,
-                x_img_emb=None, modality=None, start_pos=None, block_mask=None, update_cache_slice=None, sample_ids=None):
+                x_img_emb=None, modality=None, start_pos=None, block_mask=None, update_cache_slice=None, sample_ids=None,
+                head_rows=None):
         """Returns logits [B,N,V] in bf16 (what the reference returns under its outer bf16 autocast, model.py:693-729).
-        `sigma` is used only with `time_conditioning` (off in every shipped training config)."""
+        `sigma` is used only with `time_conditioning` (off in every shipped training config).
+        `head_rows` (additive, default None = reference behaviour): int64 indices into the B*N token rows; the output projection
+        is then evaluated for those rows only and the result is [1, len(head_rows), V].  The SUBS loss needs logits of MASKED
+        positions only (model.py:621-658: an unmasked token's log-probability is exactly 0), so `Diffusion.compute_loss` passes
+        the masked rows: same loss, same gradients, about half the head GEMM work."""
         if label is not None or x_cond is not None or continuous_mode or x_img_emb is not None or start_pos is not None:
             raise NotImplementedError("unidisc_b200.DIT.forward: label/x_cond/continuous/start_pos arguments are not supported")
         if attention_mask is not None:
@@ -508,11 +515,15 @@ class DIT(nn.Module):
         # from `sample_ids` on the fly.  Without require_sample_ids, passing sample_ids alone also enables it.
         doc_mask = sample_ids is not None and (block_mask is not None or not self.require_sample_ids)
         if cache_op is not None:
+            if head_rows is not None:
+                raise ValueError("head_rows is a training-path argument (no attention caching)")
             logits, _ = self._forward_impl(indices, modality, sample_ids, save=False, doc_mask=doc_mask,
                                            sigma=sigma if self.time_conditioning else None, cache_op=cache_op)
             return logits
+        if head_rows is not None and (head_rows.dtype != torch.int64 or head_rows.dim() != 1 or head_rows.numel() == 0):
+            raise ValueError("head_rows: a non-empty 1-D int64 tensor of token-row indices is required")
         return _DiTFunction.apply(self._anchor, self, indices, modality, sample_ids, save, doc_mask,
-                                  sigma if self.time_conditioning else None)
+                                  sigma if self.time_conditioning else None, head_rows)
 
     # ------------------------------------------------------------------------------------------------------------
     # time conditioning (reference dit.py:415-449, 1378-1379, 966-967, 1083-1087).  The conditioning network acts on one
@@ -632,7 +643,7 @@ class DIT(nn.Module):
                    rx2=rx2)
         return x2, h_next, rec
 
-    def _forward_impl(self, indices, modality, sample_ids, save, doc_mask=True, sigma=None, cache_op=None):
+    def _forward_impl(self, indices, modality, sample_ids, save, doc_mask=True, sigma=None, cache_op=None, head_rows=None):
         B, N = indices.shape
         M, D, H, hd, V = B * N, self.hidden_size, self.n_heads, self.head_dim, self.vocab_size
         T = self._top
@@ -682,11 +693,23 @@ class DIT(nn.Module):
                 # keep only the block's inputs; the backward re-runs the block's forward (same Philox dropout mask)
                 saved["blocks"].append(dict(ckpt=True, x=x, h=h) if ckpt else rec)
             x, h = x2, h_next
-        buf = torch.empty((M, self.Vp), device=x.device, dtype=bf16)
         self.wait_param_events()               # head (last bucket) => everything; the events are dropped
+        if head_rows is not None:
+            # output projection of the requested token rows only (the masked positions: the only logits the SUBS loss reads)
+            hq = h.index_select(0, head_rows)
+            Mh = hq.shape[0]
+            buf = torch.empty((Mh, self.Vp), device=x.device, dtype=bf16)
+            ops.gemm(hq, T["wh"], N=V, out=buf[:, :V], bias=T["bh"])
+            if save:
+                saved["hf"] = hq
+                saved["head_rows"] = head_rows
+                saved["logits_buf"] = buf
+            return buf.view(1, Mh, self.Vp)[:, :, :V], saved
+        buf = torch.empty((M, self.Vp), device=x.device, dtype=bf16)
         ops.gemm(h, T["wh"], N=V, out=buf[:, :V], bias=T["bh"])
         if save:
             saved["hf"] = h
+            saved["head_rows"] = None
             saved["logits_buf"] = buf
         return buf.view(B, N, self.Vp)[:, :, :V], saved
 
@@ -711,17 +734,23 @@ class DIT(nn.Module):
             else:
                 ops.gemm(dy, x, ta=True, tb=True, epi=wacc, out=dst, aux=gacc, **shape)
         SV = self._stage_views
-        # logits gradient in the padded [M, Vp] layout (produced in place by the fused SUBS-NLL backward when possible)
-        if dlogits.dtype == bf16 and dlogits.dim() == 3 and dlogits.stride() == (N * self.Vp, self.Vp, 1):
-            dl = dlogits.as_strided((M, self.Vp), (self.Vp, 1))[:, :V]
+        # logits gradient in the padded [Mh, Vp] layout (produced in place by the fused SUBS-NLL backward when possible);
+        # Mh = M, or the number of head rows when the forward projected a subset of the token rows
+        rows = S.get("head_rows")
+        Mh = M if rows is None else S["hf"].shape[0]
+        if dlogits.dtype == bf16 and dlogits.dim() == 3 and dlogits.stride() == (dlogits.shape[1] * self.Vp, self.Vp, 1) \
+                and dlogits.shape[0] * dlogits.shape[1] == Mh:
+            dl = dlogits.as_strided((Mh, self.Vp), (self.Vp, 1))[:, :V]
         else:
-            buf = torch.zeros((M, self.Vp), device=dlogits.device, dtype=bf16)
-            buf[:, :V].copy_(dlogits.reshape(M, V))
+            buf = torch.zeros((Mh, self.Vp), device=dlogits.device, dtype=bf16)
+            buf[:, :V].copy_(dlogits.reshape(Mh, V))
             dl = buf[:, :V]
         # head
-        wgrad(dl, S["hf"], T["d_wh"], SV["head"] if staged else None, M=V, N=D, K=M)
-        ops.colsum(dl, T["d_bh"], M, V)
-        dh = ops.gemm(dl, T["wh"], tb=True, M=M, N=D, K=V)
+        wgrad(dl, S["hf"], T["d_wh"], SV["head"] if staged else None, M=V, N=D, K=Mh)
+        ops.colsum(dl, T["d_bh"], Mh, V)
+        dh = ops.gemm(dl, T["wh"], tb=True, M=Mh, N=D, K=V)
+        if rows is not None:                         # rows without logits received no gradient from the head
+            dh = torch.zeros((M, D), device=dh.device, dtype=dh.dtype).index_copy_(0, rows, dh)
         S["logits_buf"] = None
         # Gradient buckets that are final are handed to the DDP hook right BEFORE the next attention backward: the
         # all-reduce chain (pack -> NCCL -> unpack, ~0.4 ms) then runs next to the attention / row kernels, whose many

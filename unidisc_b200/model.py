@@ -427,10 +427,29 @@ class Diffusion(nn.Module):
         # model.py:876-878: packed batches hand the backbone sample_ids + the document BlockMask (here: a flag, the mask is
         # evaluated inside the attention kernels from sample_ids)
         flex = bool(_g(self.config.trainer, "interleaved_training_flex_attention", False))
-        logits = self.backbone(xt, None if not self.time_conditioning else sigma, modality=modality,
-                               sample_ids=batch.get("sample_ids", None) if (flex or self.backbone.require_sample_ids) else None,
-                               block_mask=True if flex else None)
-        log_p_theta = self._log_p_x0(logits, xt, x0, modality)                       # model.py:787 + :967, fused
+        # Additive key trainer.b200_masked_head (default true): the SUBS parameterisation gives every UNMASKED token log p = 0
+        # exactly (model.py:621-658) and padding is multiplied by the attention mask below, so only the masked, attended rows
+        # need logits.  The output projection (7 % of the step's FLOPs over all rows), the fused NLL and their backward then run
+        # on those rows only: same loss, same gradients.  Costs one device->host read of the row count per step.
+        head_rows = None
+        if bool(_g(self.config.trainer, "b200_masked_head", True)) and getattr(self.backbone, "supports_head_rows", False):
+            sel = ((xt == self.mask_index) & attention_mask.bool()).reshape(-1)
+            rows = sel.nonzero(as_tuple=False).squeeze(1)
+            if 0 < rows.numel() < sel.numel():
+                head_rows = rows
+        bb_kwargs = dict(modality=modality,
+                         sample_ids=batch.get("sample_ids", None) if (flex or self.backbone.require_sample_ids) else None,
+                         block_mask=True if flex else None)
+        if head_rows is None:
+            logits = self.backbone(xt, None if not self.time_conditioning else sigma, **bb_kwargs)
+            log_p_theta = self._log_p_x0(logits, xt, x0, modality)                   # model.py:787 + :967, fused
+        else:
+            logits = self.backbone(xt, None if not self.time_conditioning else sigma, head_rows=head_rows, **bb_kwargs)
+            take = lambda a: a.reshape(-1).index_select(0, head_rows)[None]
+            lp = self._log_p_x0(logits, take(xt), take(x0), take(modality))           # [1, rows]
+            log_p_theta = torch.zeros(x0.numel(), device=x0.device, dtype=lp.dtype).index_copy(0, head_rows, lp.reshape(-1))
+            log_p_theta = log_p_theta.view(x0.shape)
+        self._last_head_rows = None if head_rows is None else int(head_rows.numel())
         std_weighting = (dsigma / torch.expm1(sigma))[:, None]                       # model.py:975
         loss = -log_p_theta * std_weighting
         gamma = _g(self.config.trainer, "softmin_snr", None)
