@@ -474,6 +474,8 @@ def main():
     ap.add_argument("--predictor", default="ddpm_cache", choices=["ddpm_cache", "ddpm", "maskgit"], help="sampling workload only")
     ap.add_argument("--sampling-steps", type=int, default=64, help="sampling workload only")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch")
+    ap.add_argument("--no-split-head", action="store_true", help="training workloads: trainer.b200_split_head=false (masked rows x the "
+                    "whole vocabulary instead of text rows x text vocabulary + image rows x image vocabulary)")
     ap.add_argument("--full-head", action="store_true", help="training workloads: trainer.b200_masked_head=false, i.e. project ALL "
                     "token rows onto the vocabulary like the reference (A/B; the default projects only the masked rows the loss reads)")
     args = ap.parse_args()
@@ -512,7 +514,7 @@ def main():
     extra = dict(hidden_size=256, n_blocks=2, n_heads=4) if small else {}
     if packed:       # reference configs/experiments/*interleaved*: sample ids from the packing collate + FlexAttention document mask
         extra.update(data__require_sample_ids=True, trainer__interleaved=True, trainer__interleaved_training_flex_attention=True)
-    extra.update(trainer__b200_masked_head=not args.full_head)
+    extra.update(trainer__b200_masked_head=not args.full_head, trainer__b200_split_head=not args.no_split_head)
     cfg = make_config(preset, txt_length=txt, img_length=img, dropout=args.dropout, image_vocab_size=IMAGE_VOCAB if not small else 255,
                       text_vocab_size=TEXT_VOCAB if not small else 257, **extra)
     torch.manual_seed(0)
@@ -570,7 +572,7 @@ def main():
             if packed:
                 batch["sample_ids"] = sid_d
         losses = model.compute_loss(batch)
-        head_rows_seen.append(model._last_head_rows if model._last_head_rows is not None else B * N)
+        head_rows_seen.append((model._last_head_rows if model._last_head_rows is not None else B * N, model._last_head_split))
         losses.loss.backward()
         opt.step()
         opt.zero_grad()
@@ -751,9 +753,11 @@ def main():
     e2e_v = tok_step / (ms_e2e / args.steps * 1e-3)
     # FLOPs actually executed: the output projection (2*D*V per token, x3 for forward + two backward GEMMs) runs on the masked
     # rows only unless --full-head; utilisation is reported on the EXECUTED count, the nominal model count is given beside it
-    recent = head_rows_seen[-2 * args.steps:] or [B * N]
-    head_frac = sum(recent) / (len(recent) * B * N)
-    fpt_exec = fpt - 3 * 2 * D * V * (1.0 - head_frac)
+    recent = head_rows_seen[-2 * args.steps:] or [(B * N, None)]
+    head_frac = sum(r for r, _ in recent) / (len(recent) * B * N)
+    # vocabulary columns per projected row: all V, or (split head) the text block for text rows and the image block for image rows
+    head_cols = sum((mt * tv + (r - mt) * (V - tv // 8 * 8)) if mt else r * V for r, mt in recent) / max(sum(r for r, _ in recent), 1)
+    fpt_exec = fpt - 3 * 2 * D * (V - head_frac * head_cols)
     model_tflops_per_gpu = value / world * fpt_exec / 1e12
 
     if rank == 0:
@@ -770,7 +774,8 @@ def main():
                         global_batch=world * B, vocab=V, parallelism=f"dp{world}", optimizer="AdamW+clip(1.0)", optimizer_schedule="streamed" if opt.overlap else "blocking",
                         dropout=args.dropout,
                         head=("output projection + SUBS NLL on the masked, attended token rows only (exact: an unmasked token's log p is 0 "
-                              f"under SUBS, reference model.py:621-658); mean {head_frac:.3f} of the rows" if head_frac < 1.0
+                              f"under SUBS, reference model.py:621-658); mean {head_frac:.3f} of the rows x {head_cols:.0f} of {V} vocabulary columns "
+                              "(text rows x text block, image rows x image block: force_argmax_valid_indices)" if head_frac < 1.0
                               else "output projection on all token rows (--full-head, the reference's dataflow)"),
                         **(dict(packing="documents = text U[32,512] + image {256,1024} tokens, tail padding; "
                                                               f"mean attended keys per query {attn_pairs:.0f} of {N}") if packed else {}),
@@ -786,7 +791,7 @@ def main():
                           algorithmic_bytes=2 * (M * D + 4 * D * D + 2 * M * 4 * D), ms_per_launch=gemm_ms),
             step_model_tflops_per_gpu=model_tflops_per_gpu,
             step_frac_of_sustained_peak=model_tflops_per_gpu / pk["bf16_tflops_sustained"],
-            flops_per_token_fwd_bwd=fpt_exec, flops_per_token_fwd_bwd_nominal=fpt, head_rows_fraction=head_frac,
+            flops_per_token_fwd_bwd=fpt_exec, flops_per_token_fwd_bwd_nominal=fpt, head_rows_fraction=head_frac, head_cols_per_row=head_cols,
             cpu_baseline=cpu,
             sampler=sampler_info,
         )

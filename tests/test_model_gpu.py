@@ -489,14 +489,16 @@ def test_masked_head_matches_full_head():
     """trainer.b200_masked_head (additive, default true): the output projection, the fused SUBS NLL and their backward run on the
     masked, attended token rows only.  An unmasked token's log-probability is exactly 0 under SUBS (reference model.py:621-658)
     and padded tokens are multiplied by the attention mask, so the loss is identical and the gradients agree up to the summation
-    order of the weight-gradient GEMM (its reduction now runs over the selected rows)."""
+    order of the weight-gradient GEMM (its reduction now runs over the selected rows).  trainer.b200_split_head additionally
+    projects text rows onto the text vocabulary and image rows onto the image vocabulary only (text_vocab_size = 257 here: the
+    image block starts at column 256, i.e. the two blocks overlap by one weight row)."""
     from oracle import restated as R
     from unidisc_b200.config import make_config
     from unidisc_b200.model import Diffusion
     outs = []
-    for masked in (False, True):
+    for masked, split in ((False, False), (True, False), (True, True)):
         cfg = make_config("small", hidden_size=256, n_blocks=2, n_heads=4, txt_length=64, img_length=64, image_vocab_size=255,
-                          text_vocab_size=257, dropout=0.0, trainer__b200_masked_head=masked)
+                          text_vocab_size=257, dropout=0.0, trainer__b200_masked_head=masked, trainer__b200_split_head=split)
         torch.manual_seed(0)
         model = Diffusion(cfg, device=dev())
         model.train()
@@ -508,13 +510,17 @@ def test_masked_head_matches_full_head():
         out = model.compute_loss(batch)
         out.loss.backward()
         torch.cuda.synchronize()
-        outs.append((out.loss.detach().clone(), out.nlls.detach().clone(), model.backbone.flat_grads.clone(), model._last_head_rows))
-    assert outs[0][3] is None and 0 < outs[1][3] < 4 * 128
-    assert torch.equal(outs[0][1], outs[1][1])                   # per-token NLLs: the same kernel on the same logits rows
-    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=0)
-    g0, g1 = outs[0][2], outs[1][2]
-    assert torch.allclose(g0, g1, rtol=2e-3, atol=2e-6), (g0 - g1).abs().max()
-    assert g0.abs().sum() > 0
+        outs.append((out.loss.detach().clone(), out.nlls.detach().clone(), model.backbone.flat_grads.clone(), model._last_head_rows,
+                     model._last_head_split))
+    assert outs[0][3] is None and 0 < outs[1][3] < 4 * 128 and outs[1][4] is None
+    assert outs[2][3] == outs[1][3] and 0 < outs[2][4] < outs[2][3]       # text rows first, then image rows
+    for k in (1, 2):
+        # per-token NLLs: the same kernel on the same logits (bit-identical unless the GEMM's stream-K split differs by shape)
+        assert torch.allclose(outs[0][1], outs[k][1], rtol=1e-3, atol=1e-3), (k, (outs[0][1] - outs[k][1]).abs().max())
+        assert torch.allclose(outs[0][0], outs[k][0], rtol=1e-4, atol=0)
+        g0, g1 = outs[0][2], outs[k][2]
+        assert torch.allclose(g0, g1, rtol=2e-3, atol=2e-6), (k, (g0 - g1).abs().max())
+    assert outs[0][2].abs().sum() > 0
 
 
 def test_backbone_under_torch_compile():

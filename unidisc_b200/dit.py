@@ -123,9 +123,9 @@ class DDitFinalLayer(nn.Module):                                     # parameter
 # ----------------------------------------------------------------------------------------------------------------
 class _DiTFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, module, indices, modality, sample_ids, save, doc_mask, sigma, head_rows=None):
+    def forward(ctx, anchor, module, indices, modality, sample_ids, save, doc_mask, sigma, head_rows=None, head_split=None):
         logits, saved = module._forward_impl(indices, modality, sample_ids, save=save, doc_mask=doc_mask, sigma=sigma,
-                                             head_rows=head_rows)
+                                             head_rows=head_rows, head_split=head_split)
         ctx.module = module
         ctx.saved = saved
         return logits
@@ -137,7 +137,7 @@ class _DiTFunction(torch.autograd.Function):
             raise RuntimeError("unidisc_b200.DIT: backward called on a forward that did not save activations")
         module._backward_impl(saved, dlogits)
         ctx.saved = None
-        return torch.zeros_like(module._anchor), None, None, None, None, None, None, None, None
+        return torch.zeros_like(module._anchor), None, None, None, None, None, None, None, None, None
 
 
 class TextFullImageSelfMask:
@@ -469,13 +469,18 @@ class DIT(nn.Module):
     @torch.compiler.disable
     def forward(self, indices, sigma=None, label=None, x_cond=None, attention_mask=None, continuous_mode=False,
                 x_img_emb=None, modality=None, start_pos=None, block_mask=None, update_cache_slice=None, sample_ids=None,
-                head_rows=None):
+                head_rows=None, head_split=None):
         """Returns logits [B,N,V] in bf16 (what the reference returns under its outer bf16 autocast, model.py:693-729).
         `sigma` is used only with `time_conditioning` (off in every shipped training config).
         `head_rows` (additive, default None = reference behaviour): int64 indices into the B*N token rows; the output projection
         is then evaluated for those rows only and the result is [1, len(head_rows), V].  The SUBS loss needs logits of MASKED
         positions only (model.py:621-658: an unmasked token's log-probability is exactly 0), so `Diffusion.compute_loss` passes
-        the masked rows: same loss, same gradients, about half the head GEMM work."""
+        the masked rows: same loss, same gradients, about half the head GEMM work.  A zero-argument callable returning
+        `(rows or None, split or None)` is resolved right before the output projection.
+        `head_split` (with head_rows): the first `head_split` head rows are TEXT tokens, the rest IMAGE tokens; text rows are then
+        projected onto the text vocabulary only and image rows onto the image vocabulary only (the other columns of the returned
+        rows are NOT written).  Exact whenever the loss restricts each token to its modality's vocabulary
+        (model.force_argmax_valid_indices: the reference adds -1e6 to the other logits, model.py:627-640)."""
         if label is not None or x_cond is not None or continuous_mode or x_img_emb is not None or start_pos is not None:
             raise NotImplementedError("unidisc_b200.DIT.forward: label/x_cond/continuous/start_pos arguments are not supported")
         if attention_mask is not None:
@@ -520,10 +525,14 @@ class DIT(nn.Module):
             logits, _ = self._forward_impl(indices, modality, sample_ids, save=False, doc_mask=doc_mask,
                                            sigma=sigma if self.time_conditioning else None, cache_op=cache_op)
             return logits
-        if head_rows is not None and (head_rows.dtype != torch.int64 or head_rows.dim() != 1 or head_rows.numel() == 0):
-            raise ValueError("head_rows: a non-empty 1-D int64 tensor of token-row indices is required")
+        if head_rows is not None and not callable(head_rows) \
+                and (head_rows.dtype != torch.int64 or head_rows.dim() != 1 or head_rows.numel() == 0):
+            raise ValueError("head_rows: a non-empty 1-D int64 tensor of token-row indices (or a callable returning "
+                             "(rows, split), resolved right before the output projection) is required")
+        if head_split is not None and (head_rows is None or callable(head_rows) or not 0 < int(head_split) < head_rows.numel()):
+            raise ValueError("head_split needs head_rows and 0 < head_split < len(head_rows)")
         return _DiTFunction.apply(self._anchor, self, indices, modality, sample_ids, save, doc_mask,
-                                  sigma if self.time_conditioning else None, head_rows)
+                                  sigma if self.time_conditioning else None, head_rows, head_split)
 
     # ------------------------------------------------------------------------------------------------------------
     # time conditioning (reference dit.py:415-449, 1378-1379, 966-967, 1083-1087).  The conditioning network acts on one
@@ -643,7 +652,7 @@ class DIT(nn.Module):
                    rx2=rx2)
         return x2, h_next, rec
 
-    def _forward_impl(self, indices, modality, sample_ids, save, doc_mask=True, sigma=None, cache_op=None, head_rows=None):
+    def _forward_impl(self, indices, modality, sample_ids, save, doc_mask=True, sigma=None, cache_op=None, head_rows=None, head_split=None):
         B, N = indices.shape
         M, D, H, hd, V = B * N, self.hidden_size, self.n_heads, self.head_dim, self.vocab_size
         T = self._top
@@ -694,15 +703,28 @@ class DIT(nn.Module):
                 saved["blocks"].append(dict(ckpt=True, x=x, h=h) if ckpt else rec)
             x, h = x2, h_next
         self.wait_param_events()               # head (last bucket) => everything; the events are dropped
+        if callable(head_rows):
+            # lazily resolved row selection: the caller's device -> host read of the row counts was enqueued before this forward,
+            # so by now it has long completed and the host never waits for the GPU (which is still working through the blocks)
+            head_rows, head_split = head_rows()
         if head_rows is not None:
             # output projection of the requested token rows only (the masked positions: the only logits the SUBS loss reads)
             hq = h.index_select(0, head_rows)
             Mh = hq.shape[0]
             buf = torch.empty((Mh, self.Vp), device=x.device, dtype=bf16)
-            ops.gemm(hq, T["wh"], N=V, out=buf[:, :V], bias=T["bh"])
+            if head_split is None:
+                ops.gemm(hq, T["wh"], N=V, out=buf[:, :V], bias=T["bh"])
+            else:
+                # text rows x text vocabulary, image rows x image vocabulary.  The image block starts at the text vocabulary size
+                # rounded DOWN to 8 columns (16-byte aligned output / bias / weight-slice pointers); the <= 7 extra columns are
+                # outside the image rows' valid range and ignored by the loss
+                Mt, tv, tv8 = int(head_split), self.text_vocab_size, self.text_vocab_size // 8 * 8
+                ops.gemm(hq[:Mt], T["wh"][:tv], N=tv, out=buf[:Mt, :tv], bias=T["bh"][:tv])
+                ops.gemm(hq[Mt:], T["wh"][tv8:], N=V - tv8, out=buf[Mt:, tv8:V], bias=T["bh"][tv8:])
             if save:
                 saved["hf"] = hq
                 saved["head_rows"] = head_rows
+                saved["head_split"] = head_split
                 saved["logits_buf"] = buf
             return buf.view(1, Mh, self.Vp)[:, :, :V], saved
         buf = torch.empty((M, self.Vp), device=x.device, dtype=bf16)
@@ -746,9 +768,24 @@ class DIT(nn.Module):
             buf[:, :V].copy_(dlogits.reshape(Mh, V))
             dl = buf[:, :V]
         # head
-        wgrad(dl, S["hf"], T["d_wh"], SV["head"] if staged else None, M=V, N=D, K=Mh)
-        ops.colsum(dl, T["d_bh"], Mh, V)
-        dh = ops.gemm(dl, T["wh"], tb=True, M=Mh, N=D, K=V)
+        split = S.get("head_split") if rows is not None else None
+        if split is None:
+            wgrad(dl, S["hf"], T["d_wh"], SV["head"] if staged else None, M=V, N=D, K=Mh)
+            ops.colsum(dl, T["d_bh"], Mh, V)
+            dh = ops.gemm(dl, T["wh"], tb=True, M=Mh, N=D, K=V)
+        else:
+            # the SUBS-NLL backward wrote every column of every head row (zeros outside a row's vocabulary range), so the two
+            # blocks can be multiplied independently.  Weight rows [tv8, tv) are covered by both weight-gradient GEMMs: the image
+            # one (whose rows have zero gradient there) runs first and the text one then stores / accumulates the real values.
+            Mt, tv, tv8 = int(split), self.text_vocab_size, self.text_vocab_size // 8 * 8
+            hq, dwh, st = S["hf"], T["d_wh"], (SV["head"] if staged else None)
+            wgrad(dl[Mt:, tv8:], hq[Mt:], dwh[tv8:], st[tv8:] if st is not None else None, M=V - tv8, N=D, K=Mh - Mt)
+            wgrad(dl[:Mt, :tv], hq[:Mt], dwh[:tv], st[:tv] if st is not None else None, M=tv, N=D, K=Mt)
+            ops.colsum(dl[Mt:, tv8:], T["d_bh"][tv8:], Mh - Mt, V - tv8)
+            ops.colsum(dl[:Mt, :tv], T["d_bh"][:tv], Mt, tv)
+            dh = torch.empty((Mh, D), device=dl.device, dtype=bf16)
+            ops.gemm(dl[:Mt, :tv], T["wh"][:tv], tb=True, M=Mt, N=D, K=tv, out=dh[:Mt])
+            ops.gemm(dl[Mt:, tv8:], T["wh"][tv8:], tb=True, M=Mh - Mt, N=D, K=V - tv8, out=dh[Mt:])
         if rows is not None:                         # rows without logits received no gradient from the head
             dh = torch.zeros((M, D), device=dh.device, dtype=dh.dtype).index_copy_(0, rows, dh)
         S["logits_buf"] = None

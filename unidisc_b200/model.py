@@ -431,25 +431,47 @@ class Diffusion(nn.Module):
         # exactly (model.py:621-658) and padding is multiplied by the attention mask below, so only the masked, attended rows
         # need logits.  The output projection (7 % of the step's FLOPs over all rows), the fused NLL and their backward then run
         # on those rows only: same loss, same gradients.  Costs one device->host read of the row count per step.
-        head_rows = None
+        # With model.force_argmax_valid_indices (each token restricted to its modality's vocabulary, model.py:627-640) the rows are
+        # ordered text first and every row is projected onto its own vocabulary block only (`head_split`).
+        resolve, picked = None, [None, None]
         if bool(_g(self.config.trainer, "b200_masked_head", True)) and getattr(self.backbone, "supports_head_rows", False):
             sel = ((xt == self.mask_index) & attention_mask.bool()).reshape(-1)
-            rows = sel.nonzero(as_tuple=False).squeeze(1)
-            if 0 < rows.numel() < sel.numel():
-                head_rows = rows
+            split_ok = bool(_g(self.config.model, "force_argmax_valid_indices", False)) and bool(_g(self.config.trainer, "b200_split_head", True))
+            is_img = modality.reshape(-1) != 0
+            sel_t, sel_i = sel & ~is_img, sel & is_img
+            # the two row counts travel to the host asynchronously; they are read right before the output projection, when the copy
+            # (enqueued ahead of the whole backbone forward) has long finished: the host never stalls on the GPU
+            if getattr(self, "_head_counts_host", None) is None:
+                self._head_counts_host = torch.empty(2, dtype=torch.int64, pin_memory=True)
+            self._head_counts_host.copy_(torch.stack([sel_t.sum(), sel_i.sum()]), non_blocking=True)
+            counts_ready = torch.cuda.Event()
+            counts_ready.record()
+
+            def resolve():
+                counts_ready.synchronize()
+                n_t, n_i = self._head_counts_host.tolist()
+                if 0 < n_t + n_i < sel.numel():
+                    if split_ok and n_t > 0 and n_i > 0:
+                        picked[0] = torch.cat([torch.nonzero_static(sel_t, size=n_t).squeeze(1), torch.nonzero_static(sel_i, size=n_i).squeeze(1)])
+                        picked[1] = n_t
+                    else:
+                        picked[0] = torch.nonzero_static(sel, size=n_t + n_i).squeeze(1)
+                return picked[0], picked[1]
         bb_kwargs = dict(modality=modality,
                          sample_ids=batch.get("sample_ids", None) if (flex or self.backbone.require_sample_ids) else None,
                          block_mask=True if flex else None)
+        logits = self.backbone(xt, None if not self.time_conditioning else sigma, **(dict(head_rows=resolve) if resolve else {}),
+                               **bb_kwargs)
+        head_rows, head_split = picked
         if head_rows is None:
-            logits = self.backbone(xt, None if not self.time_conditioning else sigma, **bb_kwargs)
             log_p_theta = self._log_p_x0(logits, xt, x0, modality)                   # model.py:787 + :967, fused
         else:
-            logits = self.backbone(xt, None if not self.time_conditioning else sigma, head_rows=head_rows, **bb_kwargs)
             take = lambda a: a.reshape(-1).index_select(0, head_rows)[None]
             lp = self._log_p_x0(logits, take(xt), take(x0), take(modality))           # [1, rows]
             log_p_theta = torch.zeros(x0.numel(), device=x0.device, dtype=lp.dtype).index_copy(0, head_rows, lp.reshape(-1))
             log_p_theta = log_p_theta.view(x0.shape)
         self._last_head_rows = None if head_rows is None else int(head_rows.numel())
+        self._last_head_split = head_split
         std_weighting = (dsigma / torch.expm1(sigma))[:, None]                       # model.py:975
         loss = -log_p_theta * std_weighting
         gamma = _g(self.config.trainer, "softmin_snr", None)
