@@ -709,9 +709,13 @@ class DIT(nn.Module):
             head_rows, head_split = head_rows()
         if head_rows is not None:
             # output projection of the requested token rows only (the masked positions: the only logits the SUBS loss reads)
-            hq = h.index_select(0, head_rows)
-            Mh = hq.shape[0]
-            buf = torch.empty((Mh, self.Vp), device=x.device, dtype=bf16)
+            # buffers are allocated at their all-rows size and sliced: the number of head rows changes every step, and a new
+            # maximum would send the caching allocator to cudaMalloc in the middle of the step (seen as a ~3 ms slower
+            # device-resident loop on some runs)
+            Mh = head_rows.numel()
+            hq = torch.empty((M, D), device=x.device, dtype=bf16)[:Mh]
+            torch.index_select(h, 0, head_rows, out=hq)
+            buf = torch.empty((M, self.Vp), device=x.device, dtype=bf16)[:Mh]
             if head_split is None:
                 ops.gemm(hq, T["wh"], N=V, out=buf[:, :V], bias=T["bh"])
             else:
@@ -772,7 +776,7 @@ class DIT(nn.Module):
         if split is None:
             wgrad(dl, S["hf"], T["d_wh"], SV["head"] if staged else None, M=V, N=D, K=Mh)
             ops.colsum(dl, T["d_bh"], Mh, V)
-            dh = ops.gemm(dl, T["wh"], tb=True, M=Mh, N=D, K=V)
+            dh = ops.gemm(dl, T["wh"], tb=True, M=Mh, N=D, K=V, out=torch.empty((M, D), device=dl.device, dtype=bf16)[:Mh])
         else:
             # the SUBS-NLL backward wrote every column of every head row (zeros outside a row's vocabulary range), so the two
             # blocks can be multiplied independently.  Weight rows [tv8, tv) are covered by both weight-gradient GEMMs: the image
@@ -783,7 +787,7 @@ class DIT(nn.Module):
             wgrad(dl[:Mt, :tv], hq[:Mt], dwh[:tv], st[:tv] if st is not None else None, M=tv, N=D, K=Mt)
             ops.colsum(dl[Mt:, tv8:], T["d_bh"][tv8:], Mh - Mt, V - tv8)
             ops.colsum(dl[:Mt, :tv], T["d_bh"][:tv], Mt, tv)
-            dh = torch.empty((Mh, D), device=dl.device, dtype=bf16)
+            dh = torch.empty((M, D), device=dl.device, dtype=bf16)[:Mh]
             ops.gemm(dl[:Mt, :tv], T["wh"][:tv], tb=True, M=Mt, N=D, K=tv, out=dh[:Mt])
             ops.gemm(dl[Mt:, tv8:], T["wh"][tv8:], tb=True, M=Mh - Mt, N=D, K=V - tv8, out=dh[Mt:])
         if rows is not None:                         # rows without logits received no gradient from the head
