@@ -207,8 +207,18 @@ def test_embed_rmsnorm(ops, D):
     assert torch.allclose(dE, dE_ref, rtol=1e-4, atol=1e-4) and torch.allclose(dEm, dEm_ref, rtol=1e-4, atol=1e-3)
 
 
+@pytest.fixture(params=["staged", "registers"])
+def row_kernel_variant(request, monkeypatch):
+    """the two heaviest row kernels exist twice: operands staged in shared memory by bulk async copies (default) and the
+    register-prefetch versions (UD_NORM_BWD=1 / UD_QKLN_BWD=1; also the fallback for D > 2048).  The launcher reads the switch per call."""
+    if request.param == "registers":
+        monkeypatch.setenv("UD_NORM_BWD", "1")
+        monkeypatch.setenv("UD_QKLN_BWD", "1")
+    return request.param
+
+
 @pytest.mark.parametrize("D", [128, 768, 2048])
-def test_norm_residual_fwd_bwd(ops, D):
+def test_norm_residual_fwd_bwd(ops, D, row_kernel_variant):
     rows = 257
     a = rnd(rows, D, seed=1, scale=2.0, dtype=bf16)
     x_in = rnd(rows, D, seed=2)
@@ -255,7 +265,7 @@ def test_norm_residual_fwd_bwd(ops, D):
 
 
 @pytest.mark.parametrize("D,p", [(256, 0.1), (2048, 0.1), (768, 0.5)])
-def test_norm_residual_dropout_fwd_bwd(ops, D, p):
+def test_norm_residual_dropout_fwd_bwd(ops, D, p, row_kernel_variant):
     """training-mode dropout of the branch (reference dit.py:229-253,1024-1031): the in-kernel Philox keep-scales are
     materialised with ud_dropout_scales and fed to the torch reference."""
     rows, seed, off = 515, 1234, 77
@@ -300,7 +310,7 @@ def test_norm_residual_dropout_fwd_bwd(ops, D, p):
 
 
 @pytest.mark.parametrize("D,hd", [(128, 64), (768, 64), (2048, 128), (128, 32)])
-def test_qk_ln_rope_fwd_bwd(ops, D, hd):
+def test_qk_ln_rope_fwd_bwd(ops, D, hd, row_kernel_variant):
     from oracle import restated as R
     rows, H = 200, D // hd
     qkv = rnd(rows, 3 * D, seed=1, scale=1.5, dtype=bf16)

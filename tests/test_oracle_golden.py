@@ -71,6 +71,39 @@ def test_subs_parameterization(golden_fns, golden_dit):
     assert np.array_equal(R.subs_parameterization(lg.bfloat16(), xt, mod, mi, tv).float().numpy(), g["subs_bf16_ref_xt"])
 
 
+def test_loss_reads_only_masked_rows_and_their_own_vocabulary_block(golden_fns, golden_dit):
+    """The claim behind trainer.b200_masked_head / b200_split_head, checked on the oracle that the test above pins bit-exactly to
+    the reference's `_subs_parameterization` (model.py:621-658) and loss (model.py:967-1057): the training loss does not depend on
+    the logits of unmasked or padded rows, nor on a row's logits outside its modality's vocabulary block -- the loss is bit-identical
+    when those entries are replaced by garbage, and its gradient there is exactly zero."""
+    g = golden_fns
+    tv, mi = int(golden_dit["cfg"][6]), int(golden_dit["cfg"][7])
+    lg0 = torch.from_numpy(g["subs_logits"]).float()
+    xt, mod = torch.from_numpy(g["subs_xt"]), torch.from_numpy(g["subs_modality"])
+    B, N, V = lg0.shape
+    gen = torch.Generator().manual_seed(5)
+    own = torch.where(mod == 0, torch.randint(0, tv - 1, (B, N), generator=gen), torch.randint(tv, V, (B, N), generator=gen))
+    x0 = torch.where(xt == mi, own, xt)
+    am = torch.ones(B, N, dtype=torch.bool)
+    am[0, N - 3:] = False
+    t = torch.linspace(0.2, 0.9, B)
+    masked = (xt == mi) & am
+    assert masked.any() and (~masked).any()
+    cols = torch.arange(V)
+    foreign = torch.where((mod == 0)[..., None], cols >= tv, cols < tv)                   # [B,N,V]: the other modality's block
+    unread = (~masked)[..., None] | foreign
+    for dtype in (torch.float32, torch.bfloat16):
+        lg = lg0.to(dtype).clone().requires_grad_(True)
+        loss = R.diffusion_loss(R.subs_parameterization(lg, xt, mod, mi, tv), x0, t, mod, am)["loss"]
+        loss.backward()
+        assert torch.isfinite(loss) and lg.grad[masked].abs().sum() > 0
+        assert torch.count_nonzero(lg.grad[unread]) == 0
+        junk = (torch.randn(lg0.shape, generator=gen) * 50).to(dtype)
+        lg2 = torch.where(unread, junk, lg0.to(dtype))
+        loss2 = R.diffusion_loss(R.subs_parameterization(lg2, xt, mod, mi, tv), x0, t, mod, am)["loss"]
+        assert torch.equal(loss2, loss.detach()), (dtype, float(loss2), float(loss))
+
+
 def test_compute_loss(golden_fns, golden_dit):
     g, gd = golden_fns, golden_dit
     cfg, P = _cfg(gd), _params(gd)

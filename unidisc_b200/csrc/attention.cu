@@ -1677,7 +1677,8 @@ static int launch_attn_fwd(const void* q, long long ldq, const void* k, long lon
         attr3 = true;
     }
     // A/B switch: 3 = one CTA/SM, double-buffered 128-key S (round 1); 6 = two CTAs/SM, double-buffered 64-key S (default)
-    static const int variant = getenv("UD_ATTN_FWD") ? atoi(getenv("UD_ATTN_FWD")) : 6;
+    const char* fwd_env = getenv("UD_ATTN_FWD");           // read per call (see UD_ATTN_BWD)
+    const int variant = fwd_env != nullptr ? atoi(fwd_env) : 6;
     dim3 grid3((p.N + ATT_BQ - 1) / ATT_BQ, p.H, p.B);
     if (variant == 3) attn_fwd3_kernel<HD><<<grid3, 320, smem3, stream>>>(tq, tk, tv, p);
     else attn_fwd6_kernel<HD><<<grid3, 192, smem5, stream>>>(tq, tk64, tv64, p);
@@ -1692,10 +1693,12 @@ static int launch_attn_bwd(const void* q, const void* k, long long ldqk, const v
     // Default: the v3 dQ kernel (128-row streamed tiles, double-buffered S) with the v2 dK/dV kernel (64-row sub-tiles, two
     // sub-tiles in flight) -- the faster of each pair at B8 H16 N1280 hd128.  UD_ATTN_BWD=2 / 3 force one generation for both.
     // Packed (document-masked) batches keep the v2 dQ kernel: its per-column sample ids come from shared memory, v3 reads them
-    // from global memory on every masked tile (cfg5: 88.4 vs 83.8 ms per step).
-    static const int gen = getenv("UD_ATTN_BWD") != nullptr ? atoi(getenv("UD_ATTN_BWD")) : 0;
+    // from global memory on every masked tile (cfg5, same box: 89.2 ms per step vs 90.7 with v3 forced).
+    // (read per call, not cached: tests/test_attention_gpu.py runs every generation kept in the library in one process)
+    const char* gen_env = getenv("UD_ATTN_BWD");
+    const int gen = gen_env != nullptr ? atoi(gen_env) : 0;
     const bool dq_v3 = gen == 3 || (gen != 2 && p.sample_ids == nullptr);
-    static const bool dkv_v3 = gen == 3;
+    const bool dkv_v3 = gen == 3;
     // The v2 dQ kernel can form delta itself (UD_ATTN_FUSED_DELTA=1), but measured at B8 H16 N1280 hd128 the per-thread row reads
     // delay every CTA's first sub-tile: 458.6 us fused vs 445.4 us with the separate 33 us pass, so the pass stays the default.
     const bool sep_delta = dq_v3 || getenv("UD_ATTN_FUSED_DELTA") == nullptr;

@@ -1458,7 +1458,8 @@ extern "C" int ud_norm_residual_bwd(const float* g_out, const void* dh, const fl
         return 0;
     }
     // default: operands staged in shared memory by bulk async copies; UD_NORM_BWD=1 selects the register kernels
-    static const bool tma_path = !(getenv("UD_NORM_BWD") != nullptr && atoi(getenv("UD_NORM_BWD")) == 1);
+    const char* sel_env = getenv("UD_NORM_BWD");            // read per call: the tests run both kernels in one process
+    const bool tma_path = !(sel_env != nullptr && atoi(sel_env) == 1);
     if (tma_path && D <= 2048 && D % 8 == 0) {
         constexpr int R = 2, NS = 2;
         const int smem = NS * R * D * 12;
@@ -1551,7 +1552,8 @@ extern "C" int ud_qk_ln_rope_bwd(const void* dqk, const void* qkv, const float* 
     if (head_dim != 32 && head_dim != 64 && head_dim != 128) return -1;
     // default: operands staged in shared memory by bulk async copies (see qk_ln_rope_bwd_tma_kernel); UD_QKLN_BWD=1 selects the
     // register-prefetch kernel
-    static const bool tma_path = !(getenv("UD_QKLN_BWD") != nullptr && atoi(getenv("UD_QKLN_BWD")) == 1);
+    const char* sel_env = getenv("UD_QKLN_BWD");            // read per call: the tests run both kernels in one process
+    const bool tma_path = !(sel_env != nullptr && atoi(sel_env) == 1);
     if (tma_path) {
         constexpr int R = 2, NS = 3;
         const unsigned slotB = (unsigned)((2 * D * 4 + 2 * (head_dim / 2) * 4 + 16 + 127) & ~127);

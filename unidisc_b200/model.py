@@ -123,6 +123,20 @@ def q_xt_general(x, move_chance, mask_index, trainer_cfg, *, backbone_training, 
     return xt, ignore, should_mask_txt, should_mask_img, move_indices
 
 
+def select_head_rows(sel_t: torch.Tensor, sel_i: torch.Tensor, n_t: int, n_i: int, split_ok: bool):
+    """Token rows the output projection has to be evaluated for, from the flat boolean selections of masked & attended TEXT rows
+    (`sel_t`) and IMAGE rows (`sel_i`) and their (host) counts.  Returns `(rows, split)`: `rows` int64, text rows first, or None when
+    nothing or everything is selected (the plain all-rows head is used); `split` = number of leading text rows when both
+    modalities are present and the loss restricts each row to its own vocabulary block (`split_ok`), else None."""
+    total = sel_t.numel()
+    if not 0 < n_t + n_i < total:
+        return None, None
+    if split_ok and n_t > 0 and n_i > 0:
+        rows = torch.cat([torch.nonzero_static(sel_t, size=n_t).squeeze(1), torch.nonzero_static(sel_i, size=n_i).squeeze(1)])
+        return rows, n_t
+    return torch.nonzero_static(sel_t | sel_i, size=n_t + n_i).squeeze(1), None
+
+
 class _SubsNLL(torch.autograd.Function):
     """log p_theta(x0 | xt) under the SUBS parameterisation, fused: logits are read once, the [B,N,V] log-prob tensor of
     the reference (model.py:621-658 + gather at :967) is never materialised.  Backward writes dlogits IN PLACE over the
@@ -450,12 +464,7 @@ class Diffusion(nn.Module):
             def resolve():
                 counts_ready.synchronize()
                 n_t, n_i = self._head_counts_host.tolist()
-                if 0 < n_t + n_i < sel.numel():
-                    if split_ok and n_t > 0 and n_i > 0:
-                        picked[0] = torch.cat([torch.nonzero_static(sel_t, size=n_t).squeeze(1), torch.nonzero_static(sel_i, size=n_i).squeeze(1)])
-                        picked[1] = n_t
-                    else:
-                        picked[0] = torch.nonzero_static(sel, size=n_t + n_i).squeeze(1)
+                picked[0], picked[1] = select_head_rows(sel_t, sel_i, n_t, n_i, split_ok)
                 return picked[0], picked[1]
         bb_kwargs = dict(modality=modality,
                          sample_ids=batch.get("sample_ids", None) if (flex or self.backbone.require_sample_ids) else None,
