@@ -610,6 +610,19 @@ def main():
     n_launch = launches[0]
     ms_e2e, loss_e2e = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    # The same step with the output projection on EVERY token row (the reference's dataflow), measured in the same process right
+    # after the product's default: the line carries both, so the sparse head's share of the result is visible in one run.
+    full_head_info = None
+    if not args.full_head and not small:
+        n_seen = len(head_rows_seen)
+        model.config.trainer["b200_masked_head"] = False
+        for _ in range(2):
+            step(False)
+        ms_full, _ = timed(False, args.steps)
+        model.config.trainer["b200_masked_head"] = True
+        del head_rows_seen[n_seen:]
+        full_head_info = dict(value=world * B * N / (ms_full / args.steps * 1e-3), unit="tokens/s", ms_per_step=ms_full / args.steps,
+                              note="trainer.b200_masked_head=false (logits for all B*N rows x all V columns, like the reference), same process")
     if os.environ.get("UD_PHASE_TIMING"):
         # debug: CUDA-event split of one step into forward+loss / backward / optimizer (rank 0, stderr)
         for _ in range(3):
@@ -791,6 +804,7 @@ def main():
                           algorithmic_bytes=2 * (M * D + 4 * D * D + 2 * M * 4 * D), ms_per_launch=gemm_ms),
             step_model_tflops_per_gpu=model_tflops_per_gpu,
             step_frac_of_sustained_peak=model_tflops_per_gpu / pk["bf16_tflops_sustained"],
+            full_head=full_head_info,
             flops_per_token_fwd_bwd=fpt_exec, flops_per_token_fwd_bwd_nominal=fpt, head_rows_fraction=head_frac, head_cols_per_row=head_cols,
             cpu_baseline=cpu,
             sampler=sampler_info,
